@@ -1,0 +1,145 @@
+"""Host-side mirror of ``PointSegment/helper_tool.py`` for the hot path: configs + ``DataProcessing.knn_search``.
+
+``DataProcessing.knn_search(support_pts, query_pts, k)`` keeps the reference signature and result
+(``helper_tool.py:84-94``: int32 ``[B, N2, k]``, neighbours ascending by distance) but runs the sm_100a
+kernel in ``csrc/knn.cu`` through the C-ABI ``pu_knn_batch``.  numpy in -> numpy out (host buffers are staged
+through pinned memory); CUDA torch tensors in -> CUDA torch tensor out (no host round trip).
+
+Tie rule (stated with every result): fp32 squared distance ``((dx*dx)+(dy*dy))+(dz*dz)``, ``d = q - p``, no
+FMA; ascending (distance, index).  On tie-free clouds this is bit-identical to nanoflann; on lattice clouds
+nanoflann orders/keeps equal-distance points in kd-tree visiting order, so only the distance rows are
+guaranteed identical.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class ConfigPancreas:
+    """Hyper-parameters of the Pancreas model (``helper_tool.py:52-75``)."""
+    k_n = 16
+    num_layers = 5
+    num_points = 180000
+    num_classes = 2
+    sub_grid_size = 0.01
+    batch_size = 1
+    val_batch_size = 1
+    sub_sampling_ratio = [4, 4, 4, 4, 2]
+    d_out = [16, 64, 128, 256, 512]
+    num_features = 4  # xyz + 1 intensity channel (runPancreas.py:125)
+    learning_rate = 1e-3
+    lr_decays = 0.95
+    name = "Pancreas"
+
+
+class ConfigBraTS:
+    """Hyper-parameters of the BraTS model (``helper_tool.py:21-51``); ``num_points`` follows BASELINE.json."""
+    k_n = 16
+    num_layers = 5
+    num_points = 180000
+    num_classes = 4
+    sub_grid_size = 0.01
+    batch_size = 4
+    val_batch_size = 1
+    sub_sampling_ratio = [4, 4, 4, 4, 2]
+    d_out = [16, 64, 128, 256, 512]
+    num_features = 7  # xyz + 4 MRI modalities (runBraTS.py:141)
+    learning_rate = 1e-4
+    lr_decays = 0.95
+    name = "BraTS20"
+
+
+_workspaces: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device: torch.device, slot: int = 0) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, slot); the C-ABI never allocates."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def knn_search_cuda(support: torch.Tensor, query: torch.Tensor, k: int, return_dist: bool = False):
+    """Device-resident entry: ``support [B,N1,3]``, ``query [B,N2,3]`` fp32 CUDA -> int32 ``[B,N2,k]`` CUDA."""
+    if not (support.is_cuda and query.is_cuda):
+        raise _lib.PointUnetError("knn_search_cuda needs CUDA tensors (there is no CPU fallback)")
+    if support.dim() != 3 or query.dim() != 3 or support.shape[2] != 3 or query.shape[2] != 3 \
+            or support.shape[0] != query.shape[0]:
+        raise ValueError(f"expected support [B,N1,3] and query [B,N2,3], got {tuple(support.shape)} / {tuple(query.shape)}")
+    same = support.data_ptr() == query.data_ptr() and support.shape == query.shape
+    support = support.contiguous().float()
+    query = support if same else query.contiguous().float()
+    B, N1, _ = support.shape
+    N2 = query.shape[1]
+    L = _lib.lib()
+    out = torch.empty((B, N2, k), dtype=torch.int32, device=support.device)
+    nbytes = L.pu_knn_workspace_bytes(B, N1, N2, k)
+    ws = workspace(nbytes, support.device)
+    with torch.cuda.device(support.device):
+        if return_dist:
+            dist = torch.empty((B, N2, k), dtype=torch.float32, device=support.device)
+            st = L.pu_knn_batch_dist(support.data_ptr(), query.data_ptr(), B, N1, N2, k, out.data_ptr(),
+                                     dist.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(support.device))
+            _lib.check(st, "pu_knn_batch_dist")
+            return out, dist
+        st = L.pu_knn_batch(support.data_ptr(), query.data_ptr(), B, N1, N2, k, out.data_ptr(), ws.data_ptr(),
+                            ws.numel(), _stream_ptr(support.device))
+        _lib.check(st, "pu_knn_batch")
+    return out
+
+
+def knn_last_stats(device=None) -> dict:
+    """Counters of the last KNN call on ``device``: candidate distance evaluations, buckets swept, box tests."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws = workspace(0, device)
+    arr = (ctypes.c_ulonglong * 3)()
+    _lib.check(_lib.lib().pu_knn_read_stats(ws.data_ptr(), arr, _stream_ptr(device)), "pu_knn_read_stats")
+    return dict(dist_evals=int(arr[0]), buckets=int(arr[1]), box_tests=int(arr[2]))
+
+
+class DataProcessing:
+    @staticmethod
+    def knn_search(support_pts, query_pts, k):
+        """
+        :param support_pts: points you have, B*N1*3
+        :param query_pts: points you want to know the neighbour index, B*N2*3
+        :param k: Number of neighbours in knn search
+        :return: neighbor_idx: neighboring points indexes, B*N2*k  (int32)
+
+        Same contract as ``helper_tool.py:84-94``.  numpy arrays are staged host->device->host; CUDA
+        tensors stay on the device.
+        """
+        if isinstance(support_pts, torch.Tensor) and support_pts.is_cuda:
+            return knn_search_cuda(support_pts, query_pts, int(k))
+        if not torch.cuda.is_available():
+            raise _lib.PointUnetError("DataProcessing.knn_search needs a CUDA device (no CPU fallback)")
+        same = support_pts is query_pts
+        s = torch.from_numpy(np.ascontiguousarray(support_pts, dtype=np.float32)).cuda(non_blocking=True)
+        q = s if same else torch.from_numpy(np.ascontiguousarray(query_pts, dtype=np.float32)).cuda(non_blocking=True)
+        return knn_search_cuda(s, q, int(k)).cpu().numpy()
+
+    @staticmethod
+    def get_class_weights(dataset_name):
+        """``helper_tool.py:172-184``: 1 / (class frequency + 0.02) with uniform pre-counted frequencies."""
+        if dataset_name == "BraTS20":
+            num_per_class = np.array([1, 1, 1, 1])
+        elif dataset_name == "BraTS_Block64":
+            num_per_class = np.array([1403, 22, 80, 11])
+        elif dataset_name == "Pancreas":
+            num_per_class = np.array([1, 1])
+        else:
+            raise ValueError(dataset_name)
+        weight = num_per_class / float(sum(num_per_class))
+        return np.expand_dims(1 / (weight + 0.02), axis=0)

@@ -1,0 +1,162 @@
+"""GPU parity tests: csrc/knn.cu through the C-ABI vs the oracle and the reference's golden vectors.
+
+Bar: bit-exact int32 indices under the stated tie rule (distance, then index).  Against nanoflann itself:
+bit-exact rows on tie-free clouds; on lattice clouds identical fp32 distance rows.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import knn as ok
+from point_unet_b200.helper_tool import DataProcessing as DP
+from point_unet_b200.helper_tool import knn_last_stats, knn_search_cuda
+from tests.golden.make_knn_golden import SMALL, make_cloud
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLD, "knn_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def checksums():
+    with open(os.path.join(GOLD, "knn_checksums.json")) as f:
+        return json.load(f)
+
+
+def gpu_knn(s, q, k, dist=False):
+    st = torch.from_numpy(s).cuda()
+    qt = st if q is s else torch.from_numpy(q).cuda()
+    r = knn_search_cuda(st, qt, k, return_dist=dist)
+    if dist:
+        return r[0].cpu().numpy(), r[1].cpu().numpy()
+    return r.cpu().numpy()
+
+
+def explain(got, want):
+    bad = np.argwhere((got != want).any(-1))
+    if len(bad) == 0:
+        return "equal"
+    b, i = bad[0]
+    return f"{len(bad)} rows differ; first row {b},{i}: got {got[b, i].tolist()} want {want[b, i].tolist()}"
+
+
+@pytest.mark.parametrize("kind,n,seed", SMALL)
+def test_small_vs_canonical_oracle_and_reference(golden, kind, n, seed):
+    tag = f"{kind}_{n}"
+    p = golden[tag + "_xyz"]
+    got, gd = gpu_knn(p, p, 16, dist=True)
+    can, cd = ok.knn_restated(p, p, 16, tie_rule=1, return_dist=True)
+    assert np.array_equal(got, can), explain(got, can)
+    assert np.array_equal(gd, cd)
+    ref = golden[tag + "_k16_self"]
+    assert np.array_equal(ok.knn_dists(p, p, got), ok.knn_dists(p, p, ref))  # distance rows == nanoflann's
+    if kind in ("uniform", "jitter"):
+        assert np.array_equal(got, ref), explain(got, ref)  # tie-free: bit-exact vs nanoflann
+    sub = np.ascontiguousarray(p[:, : n // 4])
+    got1 = gpu_knn(sub, p, 1)
+    assert np.array_equal(got1, ok.knn_restated(sub, p, 1, tie_rule=1)), "K=1 prefix"
+    if kind in ("uniform", "jitter"):
+        assert np.array_equal(got1, golden[tag + "_k1_prefix"])
+
+
+def test_ragged_tiny_and_cross(golden):
+    t = golden["tiny_xyz"]
+    got = gpu_knn(t, t, 16)
+    assert np.array_equal(got, golden["tiny_k16_self"]), explain(got, golden["tiny_k16_self"])  # N1 < K: zero tail
+    r = golden["ragged_xyz"]  # B=3, N=703 (not a multiple of 32), tie-free
+    assert np.array_equal(gpu_knn(r, r, 16), golden["ragged_k16_self"])
+    assert np.array_equal(gpu_knn(np.ascontiguousarray(r[:, :351]), r, 1), golden["ragged_k1_prefix"])
+    assert np.array_equal(gpu_knn(np.ascontiguousarray(r[:, :500]), np.ascontiguousarray(r[:, 100:]), 5),
+                          golden["ragged_k5_cross"])
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 8, 16, 17, 32])
+def test_every_k(k):
+    p = make_cloud("uniform", 5000, 77)[None]
+    q = make_cloud("uniform", 3000, 78)[None] * 1.2 - 0.1  # queries partly outside the support's bounding box
+    got = gpu_knn(p, q, k)
+    want = ok.knn_restated(p, q, k, tie_rule=1)
+    assert np.array_equal(got, want), explain(got, want)
+
+
+def test_duplicates_and_degenerate_clouds():
+    rng = np.random.default_rng(5)
+    base = rng.random((1, 400, 3), dtype=np.float32)
+    dup = np.concatenate([base, base, base[:, :100]], axis=1)  # every point 2-3 times: distance-0 ties
+    got = gpu_knn(dup, dup, 16)
+    assert np.array_equal(got, ok.knn_brute(dup, dup, 16))
+    flat = dup.copy()
+    flat[..., 2] = 0.25  # zero extent along z
+    assert np.array_equal(gpu_knn(flat, flat, 16), ok.knn_brute(flat, flat, 16))
+    same = np.full((1, 100, 3), 0.5, dtype=np.float32)  # all points identical
+    assert np.array_equal(gpu_knn(same, same, 16), ok.knn_brute(same, same, 16))
+    one = rng.random((2, 1, 3), dtype=np.float32)
+    assert np.array_equal(gpu_knn(one, one, 1), np.zeros((2, 1, 1), np.int32))
+
+
+def test_batched_equals_per_cloud():
+    p = np.stack([make_cloud("pancreas", 6000, s) for s in (1, 2, 3, 4, 5)])
+    got = gpu_knn(p, p, 16)
+    for b in range(5):
+        assert np.array_equal(got[b:b + 1], gpu_knn(p[b:b + 1].copy(), p[b:b + 1].copy(), 16))
+    assert np.array_equal(got, ok.knn_restated(p, p, 16, tie_rule=1))
+
+
+@pytest.mark.parametrize("tag", ["uniform_16384", "uniform_65536", "jitter_65536", "pancreas_65536", "uniform_180000",
+                                 "jitter_180000", "pancreas_180000", "brats_180000"])
+def test_large_vs_reference_checksums(checksums, tag):
+    c = checksums[tag]
+    p = make_cloud(c["kind"], c["n"], c["seed"])[None]
+    assert digest(p) == c["xyz"]
+    got = gpu_knn(p, p, 16)
+    sub = np.ascontiguousarray(p[:, : c["n"] // 4])
+    got1 = gpu_knn(sub, p, 1)
+    # under ANY tie rule the fp32 distance rows must equal those of the reference's neighbours
+    assert digest(ok.knn_dists(p, p, got)) == c["k16_self_dist"]
+    assert digest(ok.knn_dists(sub, p, got1)) == c["k1_prefix_dist"]
+    if c["kind"] in ("uniform", "jitter"):  # tie-free: bit-exact indices vs nanoflann
+        assert digest(got) == c["k16_self_idx"]
+        assert digest(got1) == c["k1_prefix_idx"]
+    else:  # lattice: bit-exact vs the canonical-rule oracle, no duplicate ids in a row
+        can = ok.knn_restated(p, p, 16, tie_rule=1)
+        assert np.array_equal(got, can), explain(got, can)
+        s = np.sort(got, axis=-1)
+        assert (np.diff(s, axis=-1) > 0).all()
+        assert np.array_equal(got1, ok.knn_restated(sub, p, 1, tie_rule=1))
+
+
+def test_one_million_points_properties():
+    n = 1_000_000
+    p = make_cloud("uniform", n, n)[None]
+    got, gd = gpu_knn(p, p, 16, dist=True)
+    assert (got[0, :, 0] == np.arange(n)).all()          # self first (uniform fp32 cloud has no duplicates)
+    assert (gd[0, :, 0] == 0).all() and (np.diff(gd, axis=-1) >= 0).all()
+    assert np.array_equal(gd, ok.knn_dists(p, p, got))   # reported distances are the reference arithmetic
+    sel = np.random.default_rng(0).choice(n, 20000, replace=False)
+    want = ok.knn_restated(p, np.ascontiguousarray(p[:, sel]), 16, tie_rule=1)
+    assert np.array_equal(got[:, sel], want)
+    st = knn_last_stats()
+    assert st["dist_evals"] > 16 * n
+
+
+def test_deterministic_and_numpy_boundary():
+    p = make_cloud("brats", 30000, 9)[None]
+    a = DP.knn_search(p, p, 16)  # numpy in -> numpy out, like helper_tool.py:84-94
+    b = DP.knn_search(p, p, 16)
+    assert isinstance(a, np.ndarray) and a.dtype == np.int32 and a.shape == (1, 30000, 16)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, ok.knn_restated(p, p, 16, tie_rule=1))
+    pd = p.astype(np.float64)  # the reference coerces to contiguous float32 (knn.pyx:95-96)
+    assert np.array_equal(DP.knn_search(pd, pd, 16), a)
