@@ -66,6 +66,85 @@ PU_API int pu_knn_batch_dist(const float *support, const float *query, int B, in
  * stats[0] = candidate distance evaluations, stats[1] = buckets visited, stats[2] = bucket box tests. */
 PU_API int pu_knn_read_stats(const void *workspace, unsigned long long *host_stats3, pu_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row gathers (channels-last).  rows_per_cloud = M*K; idx is int32 [B, rows_per_cloud] with values in
+ * [0, n_src); ld_* are row strides in floats (>= d) so outputs can land inside a concat buffer.
+ * ref: Network.gather_neighbour  PointSegment/RandLANet.py:377-386  (pc [B,N,d], idx [B,N,K] -> [B,N,K,d])
+ *      Network.nearest_interpolation  RandLANet.py:362-375          (K = 1)
+ * No index validation, like the reference (TF's GPU gather does not raise on out-of-range ids).
+ * ------------------------------------------------------------------------------------------ */
+PU_API int pu_gather_rows_fwd(const float *src, int ld_src, int n_src, const int32_t *idx, long long rows_per_cloud,
+                              int B, float *dst, int ld_dst, int d, pu_stream_t stream);
+/* Inverse neighbour lists for the scatter-free backward: offsets int32 [B*n_src + 1], perm int32
+ * [B*rows_per_cloud] (global row numbers, ascending inside each segment -> deterministic sums). */
+PU_API size_t pu_inverse_workspace_bytes(int B, long long rows_per_cloud);
+PU_API int pu_build_inverse(const int32_t *idx, long long rows_per_cloud, int B, int n_src, int32_t *offsets,
+                            int32_t *perm, void *workspace, size_t workspace_bytes, pu_stream_t stream);
+/* grad_src[j,:] (+)= sum over the inverse list of j of grad_out[row,:]   (gradient of any row gather) */
+PU_API int pu_segment_sum(const float *grad_out, int ld_go, const int32_t *offsets, const int32_t *perm,
+                          long long n_targets, float *grad_src, int ld_gs, int d, int accumulate, pu_stream_t stream);
+
+/* ref: Network.relative_pos_encoding  RandLANet.py:337-343
+ *   xyz [B,N,3], idx [B,N,K] -> out [B,N,K,10] = [dist, rel(3), tile(3), neighbour(3)]; no gradient (xyz is data). */
+PU_API int pu_relative_pos_encoding_fwd(const float *xyz, const int32_t *idx, int B, int N, int K, float *out,
+                                        pu_stream_t stream);
+
+/* ref: Network.random_sample  RandLANet.py:345-360   out[b,m,:] = max_k feat[b, pool_idx[b,m,k], :]
+ *   ties (uint8 [B*M, d], optional) = how many neighbours attain the max; the backward splits the gradient
+ *   evenly among exact ties like tf.reduce_max and walks the inverse list of pool_idx (scatter-free). */
+PU_API int pu_random_sample_fwd(const float *feat, int ld_f, int n_src, const int32_t *pool_idx, int B, int M, int K,
+                                float *out, int ld_o, unsigned char *ties, int d, pu_stream_t stream);
+PU_API int pu_random_sample_bwd(const float *feat, int ld_f, const float *out, int ld_o, const unsigned char *ties,
+                                const float *g_out, int ld_g, const int32_t *offsets, const int32_t *perm,
+                                long long n_targets, int K, float *g_feat, int ld_gf, int d, pu_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Shared MLP = 1x1 convolution over channels-last rows.
+ * ref: helper_tf_util.conv2d  PointSegment/helper_tf_util.py:115-170 ; conv2d_transpose :173-250 ;
+ *      tf.layers.dense RandLANet.py:114.   y[M,N] (+)= x[M,K] w[K,N] + bias.
+ *   stat_sum/stat_sq (optional, [pu_linear_row_tiles(M,N), N]) receive per-tile column sums of y and y^2;
+ *   pu_stats_finalize turns them into the batch-norm mean and BIASED variance (training mode, :166). */
+PU_API int pu_linear_row_tiles(long long M, int N);
+PU_API int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float *bias, float *y, int ldy,
+                         long long M, int K, int N, int accumulate, float *stat_sum, float *stat_sq,
+                         pu_stream_t stream);
+PU_API int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int C, long long count,
+                             float *mean, float *var, pu_stream_t stream);
+/* dw[K,N] (+)= x^T dy ; db[N] (+)= column sums of dy (db may be NULL).  Deterministic. */
+PU_API size_t pu_wgrad_workspace_bytes(long long M, int K, int N);
+PU_API int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, int K, int N, float *dw,
+                    float *db, int accumulate, void *workspace, size_t workspace_bytes, pu_stream_t stream);
+/* out = leaky_relu_slope(y*scale + shift [+ y2*scale2 + shift2]) per channel (slope 1 = no activation);
+ * the two-input form is the residual sum of dilated_res_block (RandLANet.py:317-321). */
+PU_API int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shift, const float *y2, int ldy2,
+                         const float *scale2, const float *shift2, float slope, long long R, int C, float *out,
+                         int ldo, pu_stream_t stream);
+/* dz = dout * (out > 0 ? 1 : slope) */
+PU_API int pu_act_bwd(const float *dout, int ldd, const float *out, int ldo, float slope, long long R, int C,
+                      float *dz, int ldz, pu_stream_t stream);
+/* batch-norm backward: pass 1 reduces sum(dz) and sum(dz*y) per channel into [pu_bn_bwd_reduce_blocks, C]
+ * partials (dz = dout * lrelu'(y*scale+shift)); pass 2 applies dy = ka*dz + kb + kc*y. */
+PU_API int pu_bn_bwd_reduce_blocks(long long R, int C);
+PU_API int pu_bn_bwd_reduce(const float *dout, int ldd, const float *y, int ldy, const float *scale,
+                            const float *shift, float slope, long long R, int C, float *part_dz, float *part_dzy,
+                            pu_stream_t stream);
+PU_API int pu_bn_bwd_apply(const float *dout, int ldd, const float *y, int ldy, const float *scale, const float *shift,
+                           float slope, const float *ka, const float *kb, const float *kc, long long R, int C,
+                           float *dy, int lddy, pu_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ref: Network.att_pooling  RandLANet.py:388-401 (up to f_agg; the trailing conv2d is pu_linear_fwd)
+ *   feature_set [P, K, d] (P = B*N points, row stride ldx), w [d,d] (tf.layers.dense kernel, no bias)
+ *   f_agg[p,c] = sum_k x[p,k,c] * softmax_k(x[p,k,:] w)[c]          -- one fused kernel, K must be 16.
+ * Backward: d_act [P*K, d] = s*(g*x - sum_k g*x*s), dx_direct [P*K, d] = g*s; the caller finishes with
+ *   dx = dx_direct + d_act w^T  (pu_linear_fwd, accumulate)  and  dw = x^T d_act  (pu_wgrad).
+ * ------------------------------------------------------------------------------------------ */
+PU_API int pu_att_pooling_fwd(const float *feature_set, int ldx, const float *w, long long P, int K, int d,
+                              float *f_agg, int ldo, pu_stream_t stream);
+PU_API int pu_att_pooling_bwd(const float *feature_set, int ldx, const float *w, const float *g_agg, int ldg,
+                              long long P, int K, int d, float *d_act, int ldda, float *dx_direct, int lddx,
+                              pu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

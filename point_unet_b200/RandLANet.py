@@ -1,0 +1,297 @@
+"""Host-side mirror of ``PointSegment/RandLANet.py`` for the hot path: the ``Network`` of RandLA-Net local
+feature aggregation, built on the sm_100a kernels in ``csrc/`` (see ``ops.py``).
+
+Same method names, argument order and tensor layouts as the reference (``[B,N,(K,)d]`` channels-last, the
+singleton axis-2 convention, int32 indices):
+
+    Network.gather_neighbour(pc, neighbor_idx)            RandLANet.py:377-386
+    Network.relative_pos_encoding(xyz, neigh_idx)         RandLANet.py:337-343
+    Network.att_pooling(feature_set, d_out, name, is_training)   RandLANet.py:388-401
+    Network.random_sample(feature, pool_idx)              RandLANet.py:345-360
+    Network.nearest_interpolation(feature, interp_idx)    RandLANet.py:362-375
+    Network.building_block / dilated_res_block / inference / get_loss   RandLANet.py:314-335, 110-152, 267-274
+
+Variables keep the reference's scope names (``Encoder_layer_0LFAatt_pooling_1fc/kernel`` ...), stored in the
+layouts of ``helper_tf_util.py``: conv2d kernels ``[Cin, Cout]`` (the 1x1 ``[1,1,Cin,Cout]`` squeezed),
+conv2d_transpose kernels ``[Cout, Cin]``, dense kernels ``[in, out]``.  ``tf_map`` (``runPancreas.py:124-145``)
+is ``build_pyramid`` here and runs the KNN kernel on the device.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .helper_tool import DataProcessing as DP
+from .helper_tool import knn_search_cuda
+
+
+def layer_table(cfg, num_features: int):
+    """[(scope, kind, Cin, Cout)] in graph order; kind in {dense, conv, convT, att_fc}."""
+    t = [("fc0", "dense", num_features, 8)]
+    d_in = 8
+    for i in range(cfg.num_layers):
+        d = cfg.d_out[i]
+        n = "Encoder_layer_%d" % i
+        t += [(n + "mlp1", "conv", d_in, d // 2),
+              (n + "LFAmlp1", "conv", 10, d // 2),
+              (n + "LFAatt_pooling_1fc", "att_fc", d, d),
+              (n + "LFAatt_pooling_1mlp", "conv", d, d // 2),
+              (n + "LFAmlp2", "conv", d // 2, d // 2),
+              (n + "LFAatt_pooling_2fc", "att_fc", d, d),
+              (n + "LFAatt_pooling_2mlp", "conv", d, d),
+              (n + "mlp2", "conv", d, 2 * d),
+              (n + "shortcut", "conv", d_in, 2 * d)]
+        d_in = 2 * d
+    t.append(("decoder_0", "conv", d_in, d_in))
+    enc_widths = [2 * cfg.d_out[0]] + [2 * d for d in cfg.d_out[:cfg.num_layers]]  # enc0, samp0..samp4
+    feat = d_in
+    for j in range(cfg.num_layers):
+        skip = enc_widths[-j - 2]
+        t.append(("Decoder_layer_%d" % j, "convT", skip + feat, skip))
+        feat = skip
+    t += [("fc1", "conv", feat, 64), ("fc2", "conv", 64, 32), ("fc", "conv_nobn", 32, cfg.num_classes)]
+    return t
+
+
+def init_params(cfg, num_features: int, seed: int = 0) -> dict:
+    """Reference initialisers as numpy fp32 (shared verbatim with the oracle):
+    conv kernels truncated_normal(std=sqrt(2/shape[-1])) rounded to 3 decimals (helper_tf_util.py:47-51; shape[-1]
+    is Cout for conv2d and Cin for conv2d_transpose), zero biases, glorot-uniform dense kernels, BN gamma=1 beta=0
+    moving_mean=0 moving_variance=1."""
+    rng = np.random.default_rng(seed)
+    p = {}
+
+    def trunc_normal(shape, std):
+        x = rng.standard_normal(shape)
+        bad = np.abs(x) > 2
+        while bad.any():
+            x[bad] = rng.standard_normal(int(bad.sum()))
+            bad = np.abs(x) > 2
+        return (np.round(x * std * 1000) / 1000).astype(np.float32)
+
+    def glorot(shape):
+        lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+        return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+    def bn(scope, c):
+        p[scope + "/bn/gamma"] = np.ones(c, np.float32)
+        p[scope + "/bn/beta"] = np.zeros(c, np.float32)
+        p[scope + "/bn/moving_mean"] = np.zeros(c, np.float32)
+        p[scope + "/bn/moving_variance"] = np.ones(c, np.float32)
+
+    for scope, kind, cin, cout in layer_table(cfg, num_features):
+        if kind == "dense":
+            p[scope + "/kernel"] = glorot((cin, cout))
+            p[scope + "/bias"] = np.zeros(cout, np.float32)
+            bn(scope, cout)
+        elif kind == "att_fc":
+            p[scope + "/kernel"] = glorot((cin, cout))
+        elif kind == "conv":
+            p[scope + "/weights"] = trunc_normal((cin, cout), math.sqrt(2.0 / cout))
+            p[scope + "/biases"] = np.zeros(cout, np.float32)
+            bn(scope, cout)
+        elif kind == "convT":
+            p[scope + "/weights"] = trunc_normal((cout, cin), math.sqrt(2.0 / cin))
+            p[scope + "/biases"] = np.zeros(cout, np.float32)
+            bn(scope, cout)
+        elif kind == "conv_nobn":
+            p[scope + "/weights"] = trunc_normal((cin, cout), math.sqrt(2.0 / cout))
+            p[scope + "/biases"] = np.zeros(cout, np.float32)
+    return p
+
+
+def build_pyramid(xyz: torch.Tensor, cfg) -> dict:
+    """``tf_map`` (runPancreas.py:124-145 / runBraTS.py:140-161) on the device: per level
+    ``neigh_idx = knn(xyz, xyz, k_n)``, ``sub = xyz[:, :N//ratio]``, ``sub_idx = neigh_idx[:, :N//ratio]``,
+    ``interp_idx = knn(sub, xyz, 1)``.  ``xyz`` is a CUDA ``[B,N,3]`` fp32 tensor; everything stays on the GPU."""
+    out = dict(xyz=[], neigh_idx=[], sub_idx=[], interp_idx=[])
+    xyz = xyz.contiguous().float()
+    for i in range(cfg.num_layers):
+        neigh = knn_search_cuda(xyz, xyz, cfg.k_n)
+        n_sub = xyz.shape[1] // cfg.sub_sampling_ratio[i]
+        sub_points = xyz[:, :n_sub, :].contiguous()
+        pool_i = neigh[:, :n_sub, :].contiguous()
+        up_i = knn_search_cuda(sub_points, xyz, 1)
+        out["xyz"].append(xyz)
+        out["neigh_idx"].append(neigh)
+        out["sub_idx"].append(pool_i)
+        out["interp_idx"].append(up_i)
+        xyz = sub_points
+    return out
+
+
+class Network(torch.nn.Module):
+    """RandLA-Net ``Network`` (RandLANet.py:19-152) on CUDA.  ``config`` mirrors ``helper_tool.Config*``."""
+
+    def __init__(self, config, num_features: int | None = None, seed: int = 0, device="cuda"):
+        super().__init__()
+        self.config = config
+        self.num_features = num_features if num_features is not None else config.num_features
+        self._names = {}
+        self.vars = torch.nn.ParameterDict()
+        self.stats = {}  # moving_mean / moving_variance (not trained)
+        self.load_numpy(init_params(config, self.num_features, seed), device)
+        self.class_weights = torch.tensor(DP.get_class_weights(config.name).reshape(-1), dtype=torch.float32,
+                                          device=device)
+        self.is_training = True
+
+    # -- variables -------------------------------------------------------------------------------
+    @staticmethod
+    def _key(name: str) -> str:
+        return name.replace("/", "__").replace(".", "_")
+
+    def load_numpy(self, params: dict, device="cuda"):
+        """Inject variables by reference name (the same dict feeds the oracle)."""
+        for name, arr in params.items():
+            t = torch.as_tensor(np.asarray(arr), dtype=torch.float32).to(device).contiguous()
+            if name.endswith("moving_mean") or name.endswith("moving_variance"):
+                self.stats[name] = t
+            else:
+                key = self._key(name)
+                self._names[name] = key
+                self.vars[key] = torch.nn.Parameter(t)
+
+    def v(self, name: str) -> torch.Tensor:
+        if name in self.stats:
+            return self.stats[name]
+        return self.vars[self._names[name]]
+
+    def named_variables(self):
+        """(reference name, tensor) for every trainable variable."""
+        return [(n, self.vars[k]) for n, k in self._names.items()]
+
+    def grads_numpy(self) -> dict:
+        return {n: (t.grad.detach().cpu().numpy() if t.grad is not None else None) for n, t in self.named_variables()}
+
+    # -- layers (helper_tf_util.py) --------------------------------------------------------------
+    def _bn_stats(self, scope, mean, var, count, is_training, fused_4d=True):
+        """Batch statistics in training (and the moving-average update, momentum 0.99, run with the step like
+        UPDATE_OPS at RandLANet.py:90,163); moving statistics at inference."""
+        mm, mv = self.stats[scope + "/bn/moving_mean"], self.stats[scope + "/bn/moving_variance"]
+        if not is_training:
+            return mm, mv
+        if torch.is_grad_enabled():
+            with torch.no_grad():
+                # TF's fused kernel (4-D NHWC inputs) feeds the UNBIASED variance to the moving average
+                unbias = count / max(count - 1, 1) if fused_4d else 1.0
+                mm.mul_(ops.BN_MOMENTUM).add_(mean, alpha=1 - ops.BN_MOMENTUM)
+                mv.mul_(ops.BN_MOMENTUM).add_(var * unbias, alpha=1 - ops.BN_MOMENTUM)
+        return mean, var
+
+    def conv2d(self, x, scope, bn=True, is_training=True, activation=True, transpose=False, dense_names=False):
+        """1x1 conv (+bias) [-> BN(0.99, 1e-6)] [-> LeakyReLU(0.2)]  (helper_tf_util.py:115-170 / :173-250)."""
+        wname, bname = ("/kernel", "/bias") if dense_names else ("/weights", "/biases")
+        w = self.v(scope + wname)
+        if transpose:
+            w = w.t()
+        b = self.v(scope + bname)
+        if not bn:
+            if activation:
+                raise NotImplementedError("activation without batch norm is not used by PointSegment")
+            return ops.linear(x, w, b)
+        rows_n = x.numel() // x.shape[-1]
+        if is_training:
+            y, mean, var = ops.linear(x, w, b, want_stats=True)
+        else:
+            y = ops.linear(x, w, b)
+            mean = var = None
+        mean, var = self._bn_stats(scope, mean, var, rows_n, is_training, fused_4d=not dense_names)
+        return ops.bn_act(y, mean, var, self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta"),
+                          slope=ops.LEAKY_SLOPE if activation else 1.0, training=is_training)
+
+    # -- LFA ops (RandLANet.py:337-401) ----------------------------------------------------------
+    @staticmethod
+    def gather_neighbour(pc, neighbor_idx):
+        return ops.gather_neighbour(pc, neighbor_idx)
+
+    @staticmethod
+    def relative_pos_encoding(xyz, neigh_idx):
+        return ops.relative_pos_encoding(xyz, neigh_idx)
+
+    @staticmethod
+    def random_sample(feature, pool_idx):
+        return ops.random_sample(feature, pool_idx)
+
+    @staticmethod
+    def nearest_interpolation(feature, interp_idx):
+        return ops.nearest_interpolation(feature, interp_idx)
+
+    def att_pooling(self, feature_set, d_out, name, is_training):
+        f_agg = ops.att_pool(feature_set, self.v(name + "fc/kernel"))
+        return self.conv2d(f_agg, name + "mlp", True, is_training, True)
+
+    def building_block(self, xyz, feature, neigh_idx, d_out, name, is_training):
+        f_xyz = self.relative_pos_encoding(xyz, neigh_idx)
+        f_xyz = self.conv2d(f_xyz, name + "mlp1", True, is_training)
+        f_neighbours = self.gather_neighbour(feature.squeeze(2), neigh_idx)
+        f_concat = torch.cat([f_neighbours, f_xyz], dim=-1)
+        f_pc_agg = self.att_pooling(f_concat, d_out // 2, name + "att_pooling_1", is_training)
+        f_xyz = self.conv2d(f_xyz, name + "mlp2", True, is_training)
+        f_neighbours = self.gather_neighbour(f_pc_agg.squeeze(2), neigh_idx)
+        f_concat = torch.cat([f_neighbours, f_xyz], dim=-1)
+        return self.att_pooling(f_concat, d_out, name + "att_pooling_2", is_training)
+
+    def dilated_res_block(self, feature, xyz, neigh_idx, d_out, name, is_training):
+        f_pc = self.conv2d(feature, name + "mlp1", True, is_training)
+        f_pc = self.building_block(xyz, f_pc, neigh_idx, d_out, name + "LFA", is_training)
+        # mlp2 / shortcut: BN without activation, then leaky_relu(sum)  (RandLANet.py:317-321), one fused kernel
+        outs = []
+        for x, scope in ((f_pc, name + "mlp2"), (feature, name + "shortcut")):
+            w, b = self.v(scope + "/weights"), self.v(scope + "/biases")
+            rows_n = x.numel() // x.shape[-1]
+            if is_training:
+                y, mean, var = ops.linear(x, w, b, want_stats=True)
+            else:
+                y, mean, var = ops.linear(x, w, b), None, None
+            mean, var = self._bn_stats(scope, mean, var, rows_n, is_training)
+            outs.append((y, mean, var, self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta")))
+        (y1, m1, v1, g1, b1), (y2, m2, v2, g2, b2) = outs
+        return ops.bn_act(y1, m1, v1, g1, b1, slope=ops.LEAKY_SLOPE, training=is_training,
+                          y2=y2, mean2=m2, var2=v2, gamma2=g2, beta2=b2)
+
+    def inference(self, inputs, is_training, dropout_mask=None):
+        """RandLANet.py:110-152.  ``inputs``: dict(xyz, neigh_idx, sub_idx, interp_idx: lists of 5; features [B,N,F])."""
+        cfg = self.config
+        feature = self.conv2d(inputs["features"], "fc0", True, is_training, True, dense_names=True)
+        feature = feature.unsqueeze(2)
+        f_encoder_list = []
+        for i in range(cfg.num_layers):
+            f_encoder_i = self.dilated_res_block(feature, inputs["xyz"][i], inputs["neigh_idx"][i], cfg.d_out[i],
+                                                 "Encoder_layer_" + str(i), is_training)
+            f_sampled_i = self.random_sample(f_encoder_i, inputs["sub_idx"][i])
+            feature = f_sampled_i
+            if i == 0:
+                f_encoder_list.append(f_encoder_i)
+            f_encoder_list.append(f_sampled_i)
+        feature = self.conv2d(f_encoder_list[-1], "decoder_0", True, is_training)
+        f_decoder_list = []
+        for j in range(cfg.num_layers):
+            f_interp_i = self.nearest_interpolation(feature, inputs["interp_idx"][-j - 1])
+            f_decoder_i = self.conv2d(torch.cat([f_encoder_list[-j - 2], f_interp_i], dim=3), "Decoder_layer_" + str(j),
+                                      True, is_training, transpose=True)
+            feature = f_decoder_i
+            f_decoder_list.append(f_decoder_i)
+        f_layer_fc1 = self.conv2d(f_decoder_list[-1], "fc1", True, is_training)
+        f_layer_fc2 = self.conv2d(f_layer_fc1, "fc2", True, is_training)
+        if is_training:
+            if dropout_mask is None:  # tf.nn.dropout(keep_prob=0.5) (helper_tf_util.py:571-573)
+                dropout_mask = (torch.rand_like(f_layer_fc2) < 0.5)
+            f_layer_drop = f_layer_fc2 * (dropout_mask.to(f_layer_fc2.dtype) * 2.0)
+        else:
+            f_layer_drop = f_layer_fc2
+        f_layer_fc3 = self.conv2d(f_layer_drop, "fc", False, is_training, activation=False)
+        return f_layer_fc3.squeeze(2)
+
+    def forward(self, inputs, dropout_mask=None):
+        return self.inference(inputs, self.is_training, dropout_mask)
+
+    def get_loss(self, logits, labels):
+        """RandLANet.py:62-84,267-274 (no ignored labels for Pancreas/BraTS): class-weighted CE, mean over points."""
+        C = logits.shape[-1]
+        logits = logits.reshape(-1, C)
+        labels = labels.reshape(-1).long()
+        w = self.class_weights[labels]
+        return (torch.nn.functional.cross_entropy(logits, labels, reduction="none") * w).mean()

@@ -1,0 +1,343 @@
+// lfa_ops.cu -- the HBM-bound building blocks of the RandLA-Net local-feature-aggregation stack.
+//
+//   gather_rows        Network.gather_neighbour   (PointSegment/RandLANet.py:377-386)  tf.batch_gather
+//                      Network.nearest_interpolation (:362-375)                        (K = 1)
+//   locse              Network.relative_pos_encoding (:337-343)
+//   random_sample      Network.random_sample (:345-360)  gather + reduce_max over K, fused
+//   inverse lists      (no reference counterpart: TF back-propagates gathers with unsorted_segment_sum,
+//                      i.e. atomics; here every gather gradient is a per-point SEGMENTED SUM over a
+//                      precomputed inverse neighbour list -- scatter-free and bit-deterministic)
+//
+// All tensors channels-last fp32; "rows" of d channels are moved as 128-bit vectors when d % 4 == 0 and the
+// row strides allow it.  Outputs take a row stride (ld) so a kernel can write straight into one half of a
+// concat buffer (tf.concat at RandLANet.py:328,333,138 never needs its own copy).
+#include <cub/device/device_radix_sort.cuh>
+#include <float.h>
+
+#include "common.cuh"
+
+namespace pu {
+namespace lfa {
+
+// ---------------------------------------------------------------------------------------------
+// out[b, r, 0:d] = src[b, idx[b, r], 0:d]        r in [0, R)   (R = M*K rows per cloud)
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ src, int ld_src, int n_src,
+                                                          const int32_t *__restrict__ idx, long long R, int B,
+                                                          float *__restrict__ dst, int ld_dst, int d) {
+    const int cpr = d / VEC;  // chunks per row
+    const long long total = (long long)B * R * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / cpr;
+        const int c = (int)(t - row * cpr) * VEC;
+        const int b = (int)(row / R);
+        const int j = idx[row];
+        const float *s = src + ((size_t)b * n_src + j) * ld_src + c;
+        float *o = dst + (size_t)row * ld_dst + c;
+        if (VEC == 4) {
+            st_stream_f4(reinterpret_cast<float4 *>(o), *reinterpret_cast<const float4 *>(s));
+        } else {
+            *o = *s;
+        }
+    }
+}
+
+// grad_src[b, j, 0:d] = sum over e in [off[b*n+j], off[b*n+j+1]) of grad_out[perm[e], 0:d]
+// (perm holds GLOBAL row numbers b*R + r, ascending inside a segment => fixed summation order)
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float *__restrict__ grad_out, int ld_go,
+                                                          const int32_t *__restrict__ off,
+                                                          const int32_t *__restrict__ perm, long long n_targets,
+                                                          float *__restrict__ grad_src, int ld_gs, int d,
+                                                          int accumulate) {
+    const int cpr = d / VEC;
+    const long long total = n_targets * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / cpr;
+        const int c = (int)(t - j * cpr) * VEC;
+        const int e0 = off[j], e1 = off[j + 1];
+        float *o = grad_src + (size_t)j * ld_gs + c;
+        if (VEC == 4) {
+            float4 acc = accumulate ? *reinterpret_cast<float4 *>(o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = e0; e < e1; ++e) {
+                const float4 g = ld_stream_f4(reinterpret_cast<const float4 *>(grad_out + (size_t)perm[e] * ld_go + c));
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            }
+            *reinterpret_cast<float4 *>(o) = acc;
+        } else {
+            float acc = accumulate ? *o : 0.f;
+            for (int e = e0; e < e1; ++e) acc += grad_out[(size_t)perm[e] * ld_go + c];
+            *o = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inverse neighbour lists: stable radix sort of (target = b*n + idx[row]) with payload row
+__global__ void __launch_bounds__(256) inv_keys_kernel(const int32_t *__restrict__ idx, long long R, int B, int n,
+                                                       unsigned *__restrict__ keys, unsigned *__restrict__ vals) {
+    const long long total = (long long)B * R;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / R);
+        keys[t] = (unsigned)b * (unsigned)n + (unsigned)idx[t];
+        vals[t] = (unsigned)t;
+    }
+}
+// off[k] = first sorted position whose key >= k, for k in [0, n_targets]; positions i in [0, total]
+__global__ void __launch_bounds__(256) inv_offsets_kernel(const unsigned *__restrict__ keys_sorted, long long total,
+                                                          long long n_targets, int32_t *__restrict__ off) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long prev = i == 0 ? -1 : (long long)keys_sorted[i - 1];
+        const long long cur = i == total ? n_targets : (long long)keys_sorted[i];
+        for (long long k = prev + 1; k <= cur; ++k) off[k] = (int32_t)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LocSE: out[b,n,k,:] = [ |p - q|, p - q (3), p (3), q (3) ]  with p = xyz[b,n], q = xyz[b, idx[b,n,k]]
+// One CTA = 256 (n,k) rows = 2560 contiguous floats, staged in shared memory and stored as float4.
+__global__ void __launch_bounds__(256) locse_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx,
+                                                    int N, int K, long long rows_total, float *__restrict__ out) {
+    __shared__ __align__(16) float s_out[256 * 10];
+    const long long row0 = (long long)blockIdx.x * 256;
+    const long long row = row0 + threadIdx.x;
+    if (row < rows_total) {
+        const long long pn = row / K;  // global point b*N + n
+        const int b = (int)(pn / N);
+        const int j = idx[row];
+        const float *p = xyz + (size_t)pn * 3;
+        const float *q = xyz + ((size_t)b * N + j) * 3;
+        const float px = p[0], py = p[1], pz = p[2], qx = q[0], qy = q[1], qz = q[2];
+        const float rx = px - qx, ry = py - qy, rz = pz - qz;
+        float *o = s_out + threadIdx.x * 10;
+        o[0] = sqrtf(rx * rx + ry * ry + rz * rz);
+        o[1] = rx; o[2] = ry; o[3] = rz;
+        o[4] = px; o[5] = py; o[6] = pz;
+        o[7] = qx; o[8] = qy; o[9] = qz;
+    }
+    __syncthreads();
+    const long long nrows = min((long long)256, rows_total - row0);
+    const int nvec = (int)(nrows * 10 / 4);  // row0*10 floats is a multiple of 4 (row0 % 256 == 0)
+    float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)row0 * 10);
+    for (int v = threadIdx.x; v < nvec; v += 256) st_stream_f4(o4 + v, reinterpret_cast<float4 *>(s_out)[v]);
+    for (int r = nvec * 4 + threadIdx.x; r < nrows * 10; r += 256) out[(size_t)row0 * 10 + r] = s_out[r];
+}
+
+// ---------------------------------------------------------------------------------------------
+// random_sample: out[b,m,c] = max_k feat[b, idx[b,m,k], c];  ties[b,m,c] = number of k attaining the max
+template <int VEC>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float *__restrict__ feat, int ld_f, int n_src,
+                                                          const int32_t *__restrict__ idx, int M, int K, int B,
+                                                          float *__restrict__ out, int ld_o,
+                                                          unsigned char *__restrict__ ties, int d) {
+    const int cpr = d / VEC;
+    const long long total = (long long)B * M * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long m = t / cpr;  // global output point b*M + m
+        const int c = (int)(t - m * cpr) * VEC;
+        const int b = (int)(m / M);
+        const int32_t *ix = idx + (size_t)m * K;
+        float best[VEC];
+        int cnt[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { best[v] = -FLT_MAX; cnt[v] = 0; }
+        for (int k = 0; k < K; ++k) {
+            const float *s = feat + ((size_t)b * n_src + ix[k]) * ld_f + c;
+            float x[VEC];
+            if (VEC == 4) {
+                const float4 v4 = *reinterpret_cast<const float4 *>(s);
+                x[0] = v4.x; x[1 % VEC] = v4.y; x[2 % VEC] = v4.z; x[3 % VEC] = v4.w;
+            } else {
+                x[0] = *s;
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (x[v] > best[v]) { best[v] = x[v]; cnt[v] = 1; }
+                else if (x[v] == best[v]) cnt[v]++;
+            }
+        }
+        float *o = out + (size_t)m * ld_o + c;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            o[v] = best[v];
+            if (ties) ties[(size_t)m * d + c + v] = (unsigned char)cnt[v];
+        }
+    }
+}
+
+// gradient of random_sample, scatter-free: every source point j walks its inverse list (edges e = m*K + k of
+// pool_idx that reference j) and takes g[m,c] / ties[m,c] wherever its own value is the maximum
+// (tf.reduce_max's gradient splits evenly among exact ties).
+template <int VEC>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restrict__ feat, int ld_f,
+                                                          const float *__restrict__ out, int ld_o,
+                                                          const unsigned char *__restrict__ ties,
+                                                          const float *__restrict__ g_out, int ld_g,
+                                                          const int32_t *__restrict__ off,
+                                                          const int32_t *__restrict__ perm, long long n_targets,
+                                                          int K, float *__restrict__ g_feat, int ld_gf, int d) {
+    const int cpr = d / VEC;
+    const long long total = n_targets * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / cpr;
+        const int c = (int)(t - j * cpr) * VEC;
+        float acc[VEC], x[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { acc[v] = 0.f; x[v] = feat[(size_t)j * ld_f + c + v]; }
+        const int e0 = off[j], e1 = off[j + 1];
+        for (int e = e0; e < e1; ++e) {
+            const long long m = perm[e] / K;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float o = out[(size_t)m * ld_o + c + v];
+                if (x[v] == o) acc[v] += g_out[(size_t)m * ld_g + c + v] / (float)ties[(size_t)m * d + c + v];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) g_feat[(size_t)j * ld_gf + c + v] = acc[v];
+    }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+    long long g = (total + block - 1) / block;
+    const long long cap = (long long)kNumSMs * 32;  // grid-stride loops; cap at 32 CTAs per SM
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+static inline bool vec4_ok(const void *p, int ld) { return (((uintptr_t)p) & 15) == 0 && (ld & 3) == 0; }
+
+}  // namespace lfa
+}  // namespace pu
+
+using namespace pu;
+using namespace pu::lfa;
+
+extern "C" {
+
+int pu_gather_rows_fwd(const float *src, int ld_src, int n_src, const int32_t *idx, long long rows_per_cloud, int B,
+                       float *dst, int ld_dst, int d, pu_stream_t stream) {
+    if (!src || !idx || !dst || B < 0 || rows_per_cloud < 0 || d < 1 || ld_src < d || ld_dst < d || n_src < 1)
+        return PU_ERR_INVALID_ARG;
+    if (B == 0 || rows_per_cloud == 0) return PU_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((d & 3) == 0 && vec4_ok(src, ld_src) && vec4_ok(dst, ld_dst)) {
+        gather_rows_kernel<4><<<grid_for((long long)B * rows_per_cloud * (d / 4)), 256, 0, st>>>(
+            src, ld_src, n_src, idx, rows_per_cloud, B, dst, ld_dst, d);
+    } else {
+        gather_rows_kernel<1><<<grid_for((long long)B * rows_per_cloud * d), 256, 0, st>>>(
+            src, ld_src, n_src, idx, rows_per_cloud, B, dst, ld_dst, d);
+    }
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_segment_sum(const float *grad_out, int ld_go, const int32_t *offsets, const int32_t *perm, long long n_targets,
+                   float *grad_src, int ld_gs, int d, int accumulate, pu_stream_t stream) {
+    if (!grad_out || !offsets || !perm || !grad_src || n_targets < 0 || d < 1 || ld_go < d || ld_gs < d)
+        return PU_ERR_INVALID_ARG;
+    if (n_targets == 0) return PU_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((d & 3) == 0 && vec4_ok(grad_out, ld_go) && vec4_ok(grad_src, ld_gs)) {
+        segment_sum_kernel<4><<<grid_for(n_targets * (d / 4)), 256, 0, st>>>(grad_out, ld_go, offsets, perm, n_targets,
+                                                                          grad_src, ld_gs, d, accumulate);
+    } else {
+        segment_sum_kernel<1><<<grid_for(n_targets * d), 256, 0, st>>>(grad_out, ld_go, offsets, perm, n_targets,
+                                                                    grad_src, ld_gs, d, accumulate);
+    }
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+size_t pu_inverse_workspace_bytes(int B, long long rows_per_cloud) {
+    if (B <= 0 || rows_per_cloud < 0) return 0;
+    const size_t n = (size_t)B * rows_per_cloud;
+    return 4 * align_up(n * 4, 256) + (8u << 20) + n;
+}
+
+int pu_build_inverse(const int32_t *idx, long long rows_per_cloud, int B, int n_src, int32_t *offsets, int32_t *perm,
+                     void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    if (!idx || !offsets || !perm || B < 0 || rows_per_cloud < 0 || n_src < 1) return PU_ERR_INVALID_ARG;
+    const long long total = (long long)B * rows_per_cloud, n_targets = (long long)B * n_src;
+    if (total >= (1ll << 31) || n_targets >= (1ll << 31)) return PU_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!workspace || workspace_bytes < pu_inverse_workspace_bytes(B, rows_per_cloud)) return PU_ERR_WORKSPACE;
+    char *ws = (char *)workspace;
+    const size_t seg = align_up((size_t)total * 4, 256);
+    unsigned *ka = (unsigned *)ws, *kb = (unsigned *)(ws + seg), *va = (unsigned *)(ws + 2 * seg),
+             *vb = (unsigned *)(ws + 3 * seg);
+    void *temp = ws + 4 * seg;
+    const size_t temp_reserved = workspace_bytes - 4 * seg;
+    if (total > 0) {
+        inv_keys_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, B, n_src, ka, va);
+        PU_LAUNCH_CHECK();
+        int bits = 1;
+        while ((1ll << bits) < n_targets) ++bits;
+        cub::DoubleBuffer<unsigned> dk(ka, kb), dv(va, vb);
+        size_t need = 0;
+        PU_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)total, 0, bits, st));
+        if (need > temp_reserved) return PU_ERR_WORKSPACE;
+        PU_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, need, dk, dv, (int)total, 0, bits, st));
+        count_launch(3);
+        PU_CUDA_TRY(cudaMemcpyAsync(perm, dv.Current(), (size_t)total * 4, cudaMemcpyDeviceToDevice, st));
+        inv_offsets_kernel<<<grid_for(total + 1), 256, 0, st>>>(dk.Current(), total, n_targets, offsets);
+        PU_LAUNCH_CHECK();
+    } else {
+        PU_CUDA_TRY(cudaMemsetAsync(offsets, 0, (size_t)(n_targets + 1) * 4, st));
+    }
+    return PU_OK;
+}
+
+int pu_relative_pos_encoding_fwd(const float *xyz, const int32_t *idx, int B, int N, int K, float *out,
+                                 pu_stream_t stream) {
+    if (!xyz || !idx || !out || B < 0 || N < 0 || K < 1) return PU_ERR_INVALID_ARG;
+    const long long rows = (long long)B * N * K;
+    if (rows == 0) return PU_OK;
+    if ((((uintptr_t)out) & 15) != 0) return PU_ERR_INVALID_ARG;
+    locse_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(xyz, idx, N, K, rows, out);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_random_sample_fwd(const float *feat, int ld_f, int n_src, const int32_t *pool_idx, int B, int M, int K,
+                         float *out, int ld_o, unsigned char *ties, int d, pu_stream_t stream) {
+    if (!feat || !pool_idx || !out || B < 0 || M < 0 || K < 1 || K > 255 || d < 1 || ld_f < d || ld_o < d || n_src < 1)
+        return PU_ERR_INVALID_ARG;
+    if (B == 0 || M == 0) return PU_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((d & 3) == 0 && vec4_ok(feat, ld_f) && vec4_ok(out, ld_o)) {
+        maxpool_fwd_kernel<4><<<grid_for((long long)B * M * (d / 4)), 256, 0, st>>>(feat, ld_f, n_src, pool_idx, M, K, B,
+                                                                                  out, ld_o, ties, d);
+    } else {
+        maxpool_fwd_kernel<1><<<grid_for((long long)B * M * d), 256, 0, st>>>(feat, ld_f, n_src, pool_idx, M, K, B, out,
+                                                                            ld_o, ties, d);
+    }
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_random_sample_bwd(const float *feat, int ld_f, const float *out, int ld_o, const unsigned char *ties,
+                         const float *g_out, int ld_g, const int32_t *offsets, const int32_t *perm,
+                         long long n_targets, int K, float *g_feat, int ld_gf, int d, pu_stream_t stream) {
+    if (!feat || !out || !ties || !g_out || !offsets || !perm || !g_feat || n_targets < 0 || K < 1 || d < 1)
+        return PU_ERR_INVALID_ARG;
+    if (n_targets == 0) return PU_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((d & 3) == 0) {
+        maxpool_bwd_kernel<4><<<grid_for(n_targets * (d / 4)), 256, 0, st>>>(feat, ld_f, out, ld_o, ties, g_out, ld_g,
+                                                                           offsets, perm, n_targets, K, g_feat, ld_gf, d);
+    } else {
+        maxpool_bwd_kernel<1><<<grid_for(n_targets * d), 256, 0, st>>>(feat, ld_f, out, ld_o, ties, g_out, ld_g, offsets,
+                                                                     perm, n_targets, K, g_feat, ld_gf, d);
+    }
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+}  // extern "C"

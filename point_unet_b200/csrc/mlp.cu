@@ -1,0 +1,656 @@
+// mlp.cu -- the contraction kernels of the PointSegment hot path (fp32 CUDA-core tiles).
+//
+//   pu_linear_fwd          helper_tf_util.conv2d / conv2d_transpose 1x1 (PointSegment/helper_tf_util.py:115-170,
+//                          173-250) and tf.layers.dense (RandLANet.py:114): y = x W + b, with the per-channel
+//                          batch-norm statistics (sum, sum of squares over all rows) accumulated in the epilogue.
+//   pu_att_pooling_fwd     Network.att_pooling (RandLANet.py:388-401) up to f_agg: FC (no bias), softmax over the
+//                          K neighbours per channel, weighted sum -- ONE kernel, the [B,N,K,d] activations /
+//                          scores / products of the reference never touch HBM.
+//   pu_att_pooling_bwd     its gradient: recomputes the scores tile, emits d(act) and the direct term g*s.
+//   pu_wgrad               dW = x^T dy (+ db), deterministic two-stage reduction over row chunks.
+//   pu_bn_act_* / pu_act_* batch-norm apply + LeakyReLU(0.2) forward/backward (helper_tf_util.py:166-169),
+//                          residual add of dilated_res_block (RandLANet.py:321).
+//
+// One tiled kernel template serves the three GEMM-shaped ops; they differ in the epilogue only.  Tile
+// 128 rows x 64 channels, 256 threads, 8x4 register micro-tile; 16 consecutive rows = the K=16 neighbours of one
+// point, held by two lanes (l, l^16) of one warp, so softmax over K is registers + one shuffle.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace pu {
+namespace mlp {
+
+enum { EPI_STORE = 0, EPI_ATT_FWD = 1, EPI_ATT_BWD = 2 };
+
+struct GemmParams {
+    const float *A; int lda;   // [M,K]
+    const float *B; int ldb;   // [K,N]
+    float *C; int ldc;         // [M,N]   (EPI_ATT_BWD: d(act))
+    const float *bias;         // [N] or null
+    long long M; int N, K;
+    int accumulate;            // C += A B
+    float *stat_sum, *stat_sq; // [gridDim.x, N] partial column sums of the stored value, or null
+    const float *X; int ldx;   // att: feature_set rows [M,N]
+    const float *G; int ldg;   // att bwd: upstream gradient [M/16, N]
+    float *OUT; int ldo;       // att fwd: f_agg [M/16, N];  att bwd: g * s  [M,N]
+};
+
+constexpr int BK = 16;
+
+template <int BM, int BN, int TM, int TN, int EPI>
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
+    constexpr int TX = BN / TN, TY = BM / TM;
+    static_assert(TX * TY == 256, "256 threads");
+    static_assert(TN == 4 && (TM % 4) == 0, "micro-tile");
+    constexpr int LDA_S = BM + 4;
+    __shared__ __align__(16) float As[BK][LDA_S];
+    __shared__ __align__(16) float Bs[BK][BN];
+
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const bool vecA = ((p.lda & 3) == 0) && ((((uintptr_t)p.A) & 15) == 0);
+    const bool vecB = ((p.ldb & 3) == 0) && ((((uintptr_t)p.B) & 15) == 0);
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        // A tile: BM rows x BK, stored k-major
+        for (int i = tid; i < BM * (BK / 4); i += 256) {
+            const int row = i / (BK / 4), kq = (i % (BK / 4)) * 4;
+            const long long gm = m0 + row;
+            const int gk = k0 + kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gm < p.M) {
+                const float *a = p.A + (size_t)gm * p.lda + gk;
+                if (vecA && gk + 3 < p.K) {
+                    v = *reinterpret_cast<const float4 *>(a);
+                } else {
+                    if (gk + 0 < p.K) v.x = a[0];
+                    if (gk + 1 < p.K) v.y = a[1];
+                    if (gk + 2 < p.K) v.z = a[2];
+                    if (gk + 3 < p.K) v.w = a[3];
+                }
+            }
+            As[kq + 0][row] = v.x; As[kq + 1][row] = v.y; As[kq + 2][row] = v.z; As[kq + 3][row] = v.w;
+        }
+        // B tile: BK x BN
+        for (int i = tid; i < BK * (BN / 4); i += 256) {
+            const int kr = i / (BN / 4), nq = (i % (BN / 4)) * 4;
+            const int gk = k0 + kr, gn = n0 + nq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < p.K) {
+                const float *b = p.B + (size_t)gk * p.ldb + gn;
+                if (vecB && gn + 3 < p.N) {
+                    v = *reinterpret_cast<const float4 *>(b);
+                } else {
+                    if (gn + 0 < p.N) v.x = b[0];
+                    if (gn + 1 < p.N) v.y = b[1];
+                    if (gn + 2 < p.N) v.z = b[2];
+                    if (gn + 3 < p.N) v.w = b[3];
+                }
+            }
+            *reinterpret_cast<float4 *>(&Bs[kr][nq]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(&As[k][ty * TM + i]);
+                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            }
+            {
+                const float4 v = *reinterpret_cast<const float4 *>(&Bs[k][tx * TN]);
+                b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    const int gn = n0 + tx * TN;
+    if constexpr (EPI == EPI_STORE) {
+        float cs[TN], cq[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+        float bj[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bj[j] = (p.bias && gn + j < p.N) ? p.bias[gn + j] : 0.f;
+        const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0) && (gn + 3 < p.N);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const long long gm = m0 + ty * TM + i;
+            if (gm >= p.M) continue;
+            float *c = p.C + (size_t)gm * p.ldc + gn;
+            float v[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) v[j] = acc[i][j] + bj[j];
+            if (vecC) {
+                if (p.accumulate) {
+                    const float4 o = *reinterpret_cast<const float4 *>(c);
+                    v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+                }
+                *reinterpret_cast<float4 *>(c) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (gn + j < p.N) {
+                        if (p.accumulate) v[j] += c[j];
+                        c[j] = v[j];
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
+        }
+        if (p.stat_sum) {  // per-CTA column partials (fixed order => deterministic)
+            float *red = &As[0][0];  // TY x BN x 2 floats <= BK*LDA_S
+            static_assert(TY * BN * 2 <= BK * LDA_S, "reduction scratch");
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                red[(ty * BN + tx * TN + j) * 2 + 0] = cs[j];
+                red[(ty * BN + tx * TN + j) * 2 + 1] = cq[j];
+            }
+            __syncthreads();
+            if (tid < BN && n0 + tid < p.N) {
+                float s = 0.f, q = 0.f;
+                for (int r = 0; r < TY; ++r) { s += red[(r * BN + tid) * 2]; q += red[(r * BN + tid) * 2 + 1]; }
+                p.stat_sum[(size_t)blockIdx.x * p.N + n0 + tid] = s;
+                p.stat_sq[(size_t)blockIdx.x * p.N + n0 + tid] = q;
+            }
+        }
+    } else {
+        // rows ty*8 .. ty*8+7 are one half of point (m0/16 + ty/2); the other half lives in lane ^ 16
+        static_assert(BM == 128 && TM == 8 && TX == 16, "att epilogue layout");
+        const long long pt = m0 / 16 + ty / 2;
+        const bool pt_ok = (m0 + ty * TM) < p.M && gn < p.N;
+        float cmax[TN], csum[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float m = acc[0][j];
+#pragma unroll
+            for (int i = 1; i < TM; ++i) m = fmaxf(m, acc[i][j]);
+            cmax[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < TM; ++i) { acc[i][j] = __expf(acc[i][j] - cmax[j]); s += acc[i][j]; }
+            csum[j] = s + __shfl_xor_sync(0xffffffffu, s, 16);
+        }
+        float x[TM][TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pt_ok) v = *reinterpret_cast<const float4 *>(p.X + (size_t)(m0 + ty * TM + i) * p.ldx + gn);
+            x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
+        }
+        if constexpr (EPI == EPI_ATT_FWD) {
+            float num[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < TM; ++i) s = fmaf(x[i][j], acc[i][j], s);
+                num[j] = s + __shfl_xor_sync(0xffffffffu, s, 16);
+            }
+            if (pt_ok && (ty & 1) == 0)
+                *reinterpret_cast<float4 *>(p.OUT + (size_t)pt * p.ldo + gn) =
+                    make_float4(num[0] / csum[0], num[1] / csum[1], num[2] / csum[2], num[3] / csum[3]);
+        } else {  // EPI_ATT_BWD
+            float g[TN] = {0.f, 0.f, 0.f, 0.f};
+            if (pt_ok) {
+                const float4 v = *reinterpret_cast<const float4 *>(p.G + (size_t)pt * p.ldg + gn);
+                g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+            }
+            float dot[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const float inv = 1.f / csum[j];
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    acc[i][j] *= inv;                      // s_k  (softmax score)
+                    s = fmaf(g[j] * x[i][j], acc[i][j], s);  // sum_k ds_k s_k,  ds_k = g x_k
+                }
+                dot[j] = s + __shfl_xor_sync(0xffffffffu, s, 16);
+            }
+            if (pt_ok) {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const size_t row = (size_t)(m0 + ty * TM + i);
+                    float da[TN], dx[TN];
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        da[j] = acc[i][j] * (g[j] * x[i][j] - dot[j]);
+                        dx[j] = g[j] * acc[i][j];
+                    }
+                    *reinterpret_cast<float4 *>(p.C + row * p.ldc + gn) = make_float4(da[0], da[1], da[2], da[3]);
+                    *reinterpret_cast<float4 *>(p.OUT + row * p.ldo + gn) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dW[K,N] = sum_r A[r,K]^T G[r,N]  (+ db[N] = sum_r G[r,N]); grid (k tiles, n tiles, row chunks);
+// each CTA writes its partial tile to part[chunk][K][N]; pu_wgrad then reduces over chunks in a fixed order.
+constexpr int WT = 64, WR = 16;
+__global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A, int lda, const float *__restrict__ G,
+                                                    int ldg, long long M, int K, int N, long long rows_per_chunk,
+                                                    float *__restrict__ part, float *__restrict__ db_part) {
+    __shared__ __align__(16) float As[WR][WT];
+    __shared__ __align__(16) float Gs[WR][WT];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int k0 = blockIdx.x * WT, n0 = blockIdx.y * WT;
+    const long long r_begin = (long long)blockIdx.z * rows_per_chunk;
+    const long long r_end = min(M, r_begin + rows_per_chunk);
+    const bool vecA = ((lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0);
+    const bool vecG = ((ldg & 3) == 0) && ((((uintptr_t)G) & 15) == 0);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (long long r0 = r_begin; r0 < r_end; r0 += WR) {
+        {   // 16 rows x 64 cols of each operand = 256 float4, one per thread
+            const int rr = tid / 16, cq = (tid % 16) * 4;
+            const long long gr = r0 + rr;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vg = va;
+            if (gr < r_end) {
+                const float *a = A + (size_t)gr * lda + k0 + cq;
+                if (vecA && k0 + cq + 3 < K) va = *reinterpret_cast<const float4 *>(a);
+                else {
+                    if (k0 + cq + 0 < K) va.x = a[0];
+                    if (k0 + cq + 1 < K) va.y = a[1];
+                    if (k0 + cq + 2 < K) va.z = a[2];
+                    if (k0 + cq + 3 < K) va.w = a[3];
+                }
+                const float *g = G + (size_t)gr * ldg + n0 + cq;
+                if (vecG && n0 + cq + 3 < N) vg = *reinterpret_cast<const float4 *>(g);
+                else {
+                    if (n0 + cq + 0 < N) vg.x = g[0];
+                    if (n0 + cq + 1 < N) vg.y = g[1];
+                    if (n0 + cq + 2 < N) vg.z = g[2];
+                    if (n0 + cq + 3 < N) vg.w = g[3];
+                }
+            }
+            *reinterpret_cast<float4 *>(&As[rr][cq]) = va;
+            *reinterpret_cast<float4 *>(&Gs[rr][cq]) = vg;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < WR; ++r) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[r][ty * 4]);
+            const float4 g = *reinterpret_cast<const float4 *>(&Gs[r][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+            if (ty == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dbacc[j] += gv[j];
+            }
+        }
+        __syncthreads();
+    }
+    float *o = part + (size_t)blockIdx.z * K * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gk = k0 + ty * 4 + i;
+        if (gk >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn < N) o[(size_t)gk * N + gn] = acc[i][j];
+        }
+    }
+    if (db_part && ty == 0 && blockIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn < N) db_part[(size_t)blockIdx.z * N + gn] = dbacc[j];
+        }
+    }
+}
+
+// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order)
+__global__ void __launch_bounds__(256) reduce_chunks_kernel(const float *__restrict__ part, int chunks, long long n,
+                                                            float *__restrict__ out, int accumulate) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += (double)part[(size_t)c * n + i];
+    out[i] = accumulate ? out[i] + (float)s : (float)s;
+}
+
+// mean/var (biased) per channel from per-tile partials, in double
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float *__restrict__ psum, const float *__restrict__ psq,
+                                                             int tiles, int C, double inv_count,
+                                                             float *__restrict__ mean, float *__restrict__ var) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int t = lane; t < tiles; t += 32) { s += (double)psum[(size_t)t * C + warp]; q += (double)psq[(size_t)t * C + warp]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+        const double m = s * inv_count;
+        double v = q * inv_count - m * m;
+        mean[warp] = (float)m;
+        var[warp] = (float)(v > 0.0 ? v : 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise: out = lrelu_slope(y*scale[c] + shift[c] (+ y2*scale2[c] + shift2[c])) ; mask = optional dropout scale
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict__ y, int ld_y, const float *__restrict__ scale,
+                                                         const float *__restrict__ shift, const float *__restrict__ y2,
+                                                         int ld_y2, const float *__restrict__ scale2,
+                                                         const float *__restrict__ shift2, float slope, long long R, int C,
+                                                         float *__restrict__ out, int ld_o) {
+    const int cq = C >> 2;
+    const long long total = R * cq;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / cq;
+        const int c = (int)(t - r * cq) * 4;
+        const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), sh = *reinterpret_cast<const float4 *>(shift + c);
+        float z[4] = {fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)};
+        if (y2) {
+            const float4 w = *reinterpret_cast<const float4 *>(y2 + (size_t)r * ld_y2 + c);
+            const float4 s2 = *reinterpret_cast<const float4 *>(scale2 + c), h2 = *reinterpret_cast<const float4 *>(shift2 + c);
+            z[0] += fmaf(w.x, s2.x, h2.x); z[1] += fmaf(w.y, s2.y, h2.y);
+            z[2] += fmaf(w.z, s2.z, h2.z); z[3] += fmaf(w.w, s2.w, h2.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * slope;
+        *reinterpret_cast<float4 *>(out + (size_t)r * ld_o + c) = make_float4(z[0], z[1], z[2], z[3]);
+    }
+}
+
+// dz = dout * (out > 0 ? 1 : slope)   -- gradient through the LeakyReLU given its OUTPUT (sign-preserving)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float *__restrict__ dout, int ld_d, const float *__restrict__ out,
+                                                      int ld_o, float slope, long long R, int C, float *__restrict__ dz,
+                                                      int ld_z) {
+    const int cq = C >> 2;
+    const long long total = R * cq;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / cq;
+        const int c = (int)(t - r * cq) * 4;
+        const float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + c);
+        const float4 o = *reinterpret_cast<const float4 *>(out + (size_t)r * ld_o + c);
+        *reinterpret_cast<float4 *>(dz + (size_t)r * ld_z + c) =
+            make_float4(o.x > 0.f ? g.x : g.x * slope, o.y > 0.f ? g.y : g.y * slope, o.z > 0.f ? g.z : g.z * slope,
+                        o.w > 0.f ? g.w : g.w * slope);
+    }
+}
+
+// BN backward, pass 1: per-channel partials of  sum(dz)  and  sum(dz * y)  with dz = dout * lrelu'(y*scale+shift).
+// grid = fixed number of CTAs; each CTA strides over rows; thread owns one float4 column group.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restrict__ dout, int ld_d,
+                                                            const float *__restrict__ y, int ld_y,
+                                                            const float *__restrict__ scale, const float *__restrict__ shift,
+                                                            float slope, long long R, int C, float *__restrict__ part_dz,
+                                                            float *__restrict__ part_dzy) {
+    extern __shared__ float sred[];  // [rows_in_flight][C][2]
+    const int cq = C >> 2;                 // column groups
+    const int rpb = 256 / cq > 0 ? 256 / cq : 1;  // rows processed concurrently by the CTA
+    const int my_c = (threadIdx.x % cq) * 4, my_r = threadIdx.x / cq;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (my_r < rpb) {
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + my_c), sh = *reinterpret_cast<const float4 *>(shift + my_c);
+        for (long long r = (long long)blockIdx.x * rpb + my_r; r < R; r += (long long)gridDim.x * rpb) {
+            const float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + my_c);
+            const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + my_c);
+            const float gz[4] = {fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : g.x * slope, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : g.y * slope,
+                                 fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : g.z * slope, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : g.w * slope};
+            const float yv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[j] += gz[j]; q[j] = fmaf(gz[j], yv[j], q[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sred[((size_t)my_r * C + my_c + j) * 2 + 0] = s[j];
+            sred[((size_t)my_r * C + my_c + j) * 2 + 1] = q[j];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < rpb; ++r) { a += sred[((size_t)r * C + c) * 2]; b += sred[((size_t)r * C + c) * 2 + 1]; }
+        part_dz[(size_t)blockIdx.x * C + c] = a;
+        part_dzy[(size_t)blockIdx.x * C + c] = b;
+    }
+}
+
+// BN backward, pass 2: dy = ka[c]*dz + kb[c] + kc[c]*y
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restrict__ dout, int ld_d, const float *__restrict__ y,
+                                                           int ld_y, const float *__restrict__ scale,
+                                                           const float *__restrict__ shift, float slope,
+                                                           const float *__restrict__ ka, const float *__restrict__ kb,
+                                                           const float *__restrict__ kc, long long R, int C,
+                                                           float *__restrict__ dy, int ld_dy) {
+    const int cq = C >> 2;
+    const long long total = R * cq;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / cq;
+        const int c = (int)(t - r * cq) * 4;
+        const float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + c);
+        const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), sh = *reinterpret_cast<const float4 *>(shift + c);
+        const float4 a = *reinterpret_cast<const float4 *>(ka + c), b = *reinterpret_cast<const float4 *>(kb + c),
+                     cc = *reinterpret_cast<const float4 *>(kc + c);
+        const float gz[4] = {fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : g.x * slope, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : g.y * slope,
+                             fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : g.z * slope, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : g.w * slope};
+        *reinterpret_cast<float4 *>(dy + (size_t)r * ld_dy + c) =
+            make_float4(fmaf(a.x, gz[0], fmaf(cc.x, v.x, b.x)), fmaf(a.y, gz[1], fmaf(cc.y, v.y, b.y)),
+                        fmaf(a.z, gz[2], fmaf(cc.z, v.z, b.z)), fmaf(a.w, gz[3], fmaf(cc.w, v.w, b.w)));
+    }
+}
+
+static inline int ew_grid(long long total) {
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+template <int EPI>
+static int launch_gemm(const GemmParams &p, cudaStream_t st) {
+    if (EPI == EPI_STORE && p.N <= 16) {
+        dim3 grid(ceil_div(p.M, 256), ceil_div(p.N, 16));
+        gemm_kernel<256, 16, 4, 4, EPI_STORE><<<grid, 256, 0, st>>>(p);
+    } else {
+        dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, 64));
+        gemm_kernel<128, 64, 8, 4, EPI><<<grid, 256, 0, st>>>(p);
+    }
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+}  // namespace mlp
+}  // namespace pu
+
+using namespace pu;
+using namespace pu::mlp;
+
+extern "C" {
+
+int pu_linear_row_tiles(long long M, int N) { return N <= 16 ? ceil_div(M, 256) : ceil_div(M, 128); }
+
+int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float *bias, float *y, int ldy, long long M,
+                  int K, int N, int accumulate, float *stat_sum, float *stat_sq, pu_stream_t stream) {
+    if (!x || !w || !y || M < 0 || K < 1 || N < 1 || ldx < K || ldw < N || ldy < N) return PU_ERR_INVALID_ARG;
+    if ((stat_sum == nullptr) != (stat_sq == nullptr)) return PU_ERR_INVALID_ARG;
+    if (M == 0) return PU_OK;
+    if (ceil_div(M, 128) > 2147483647LL) return PU_ERR_UNSUPPORTED;
+    GemmParams p{};
+    p.A = x; p.lda = ldx; p.B = w; p.ldb = ldw; p.C = y; p.ldc = ldy; p.bias = bias;
+    p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+    return launch_gemm<EPI_STORE>(p, (cudaStream_t)stream);
+}
+
+int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int C, long long count, float *mean,
+                      float *var, pu_stream_t stream) {
+    if (!stat_sum || !stat_sq || !mean || !var || tiles < 1 || C < 1 || count < 1) return PU_ERR_INVALID_ARG;
+    stats_finalize_kernel<<<ceil_div((long long)C * 32, 256), 256, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
+                                                                                          1.0 / (double)count, mean, var);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+static int att_args_ok(const float *x, int ldx, const float *w, long long P, int K, int d) {
+    if (!x || !w || P < 0 || d < 4 || (d & 3) || ldx < d || (ldx & 3) || (((uintptr_t)x) & 15)) return PU_ERR_INVALID_ARG;
+    if (K != 16) return PU_ERR_UNSUPPORTED;  // the tile layout pairs two 8-row halves per point
+    return PU_OK;
+}
+
+int pu_att_pooling_fwd(const float *feature_set, int ldx, const float *w, long long P, int K, int d, float *f_agg,
+                       int ldo, pu_stream_t stream) {
+    int rc = att_args_ok(feature_set, ldx, w, P, K, d);
+    if (rc != PU_OK) return rc;
+    if (!f_agg || ldo < d || (ldo & 3) || (((uintptr_t)f_agg) & 15)) return PU_ERR_INVALID_ARG;
+    if (P == 0) return PU_OK;
+    GemmParams p{};
+    p.A = feature_set; p.lda = ldx; p.B = w; p.ldb = d; p.M = P * K; p.N = d; p.K = d;
+    p.X = feature_set; p.ldx = ldx; p.OUT = f_agg; p.ldo = ldo;
+    return launch_gemm<EPI_ATT_FWD>(p, (cudaStream_t)stream);
+}
+
+int pu_att_pooling_bwd(const float *feature_set, int ldx, const float *w, const float *g_agg, int ldg, long long P,
+                       int K, int d, float *d_act, int ldda, float *dx_direct, int lddx, pu_stream_t stream) {
+    int rc = att_args_ok(feature_set, ldx, w, P, K, d);
+    if (rc != PU_OK) return rc;
+    if (!g_agg || !d_act || !dx_direct || ldg < d || ldda < d || lddx < d || ((ldg | ldda | lddx) & 3) ||
+        ((((uintptr_t)g_agg) | ((uintptr_t)d_act) | ((uintptr_t)dx_direct)) & 15))
+        return PU_ERR_INVALID_ARG;
+    if (P == 0) return PU_OK;
+    GemmParams p{};
+    p.A = feature_set; p.lda = ldx; p.B = w; p.ldb = d; p.M = P * K; p.N = d; p.K = d;
+    p.X = feature_set; p.ldx = ldx; p.G = g_agg; p.ldg = ldg; p.C = d_act; p.ldc = ldda; p.OUT = dx_direct; p.ldo = lddx;
+    return launch_gemm<EPI_ATT_BWD>(p, (cudaStream_t)stream);
+}
+
+static inline void wgrad_plan(long long M, int K, int N, int *chunks, long long *rows_per_chunk) {
+    const int tiles = ceil_div(K, WT) * ceil_div(N, WT);
+    long long want = ((long long)kNumSMs * 8 + tiles - 1) / tiles;  // ~8 CTAs per SM in total
+    long long max_chunks = (M + 255) / 256;                          // at least 256 rows per chunk
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    long long rpc = (M + want - 1) / want;
+    rpc = (rpc + WR - 1) / WR * WR;
+    *rows_per_chunk = rpc;
+    *chunks = (int)((M + rpc - 1) / rpc);
+    if (*chunks < 1) *chunks = 1;
+}
+
+size_t pu_wgrad_workspace_bytes(long long M, int K, int N) {
+    int chunks; long long rpc;
+    wgrad_plan(M, K, N, &chunks, &rpc);
+    return ((size_t)chunks * K * N + (size_t)chunks * N) * sizeof(float) + 256;
+}
+
+int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, int K, int N, float *dw, float *db,
+             int accumulate, void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    if (!x || !dy || !dw || M < 0 || K < 1 || N < 1 || ldx < K || lddy < N) return PU_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        if (!accumulate) {
+            PU_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)K * N * 4, st));
+            if (db) PU_CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)N * 4, st));
+        }
+        return PU_OK;
+    }
+    if (!workspace || workspace_bytes < pu_wgrad_workspace_bytes(M, K, N)) return PU_ERR_WORKSPACE;
+    int chunks; long long rpc;
+    wgrad_plan(M, K, N, &chunks, &rpc);
+    float *part = (float *)workspace;
+    float *db_part = db ? part + (size_t)chunks * K * N : nullptr;
+    dim3 grid(ceil_div(K, WT), ceil_div(N, WT), chunks);
+    wgrad_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
+    PU_LAUNCH_CHECK();
+    reduce_chunks_kernel<<<ceil_div((long long)K * N, 256), 256, 0, st>>>(part, chunks, (long long)K * N, dw, accumulate);
+    PU_LAUNCH_CHECK();
+    if (db) {
+        reduce_chunks_kernel<<<ceil_div(N, 256), 256, 0, st>>>(db_part, chunks, N, db, accumulate);
+        PU_LAUNCH_CHECK();
+    }
+    return PU_OK;
+}
+
+int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shift, const float *y2, int ldy2,
+                  const float *scale2, const float *shift2, float slope, long long R, int C, float *out, int ldo,
+                  pu_stream_t stream) {
+    if (!y || !scale || !shift || !out || R < 0 || C < 4 || (C & 3) || ((ldy | ldo) & 3) || ldy < C || ldo < C)
+        return PU_ERR_INVALID_ARG;
+    if (y2 && (!scale2 || !shift2 || (ldy2 & 3) || ldy2 < C)) return PU_ERR_INVALID_ARG;
+    if (R == 0) return PU_OK;
+    bn_act_fwd_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, scale, shift, y2, ldy2, scale2, shift2,
+                                                                            slope, R, C, out, ldo);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_act_bwd(const float *dout, int ldd, const float *out, int ldo, float slope, long long R, int C, float *dz, int ldz,
+               pu_stream_t stream) {
+    if (!dout || !out || !dz || R < 0 || C < 4 || (C & 3) || ((ldd | ldo | ldz) & 3)) return PU_ERR_INVALID_ARG;
+    if (R == 0) return PU_OK;
+    act_bwd_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dout, ldd, out, ldo, slope, R, C, dz, ldz);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_bn_bwd_reduce_blocks(long long R, int C) {
+    const int rpb = 256 / (C / 4) > 0 ? 256 / (C / 4) : 1;
+    long long g = (R + rpb - 1) / rpb;
+    const long long cap = (long long)kNumSMs * 8;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+int pu_bn_bwd_reduce(const float *dout, int ldd, const float *y, int ldy, const float *scale, const float *shift,
+                     float slope, long long R, int C, float *part_dz, float *part_dzy, pu_stream_t stream) {
+    if (!dout || !y || !scale || !shift || !part_dz || !part_dzy || R < 1 || C < 4 || (C & 3) || C > 1024 * 4 ||
+        ((ldd | ldy) & 3))
+        return PU_ERR_INVALID_ARG;
+    const int cq = C / 4;
+    if (cq > 256) return PU_ERR_UNSUPPORTED;
+    const int rpb = 256 / cq;
+    const size_t smem = (size_t)rpb * C * 2 * sizeof(float);
+    if (smem > 48 * 1024) return PU_ERR_UNSUPPORTED;
+    bn_bwd_reduce_kernel<<<pu_bn_bwd_reduce_blocks(R, C), 256, smem, (cudaStream_t)stream>>>(dout, ldd, y, ldy, scale, shift,
+                                                                                            slope, R, C, part_dz, part_dzy);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_bn_bwd_apply(const float *dout, int ldd, const float *y, int ldy, const float *scale, const float *shift,
+                    float slope, const float *ka, const float *kb, const float *kc, long long R, int C, float *dy,
+                    int lddy, pu_stream_t stream) {
+    if (!dout || !y || !scale || !shift || !ka || !kb || !kc || !dy || R < 0 || C < 4 || (C & 3) ||
+        ((ldd | ldy | lddy) & 3))
+        return PU_ERR_INVALID_ARG;
+    if (R == 0) return PU_OK;
+    bn_bwd_apply_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dout, ldd, y, ldy, scale, shift, slope, ka, kb,
+                                                                              kc, R, C, dy, lddy);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+}  // extern "C"

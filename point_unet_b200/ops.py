@@ -1,0 +1,462 @@
+"""PyTorch-facing operators of the PointSegment hot path, each a thin autograd shim over the C-ABI.
+
+Tensor layouts are the reference's (channels-last, fp32 features, int32 indices).  Every op runs a
+hand-written sm_100a kernel from ``libpointunet_b200.so`` on the current CUDA stream; there is no CPU or
+eager-PyTorch fallback (CPU tensors raise).  PyTorch supplies device memory, streams and autograd
+bookkeeping only; per-channel vectors of a few hundred floats (batch-norm scale/shift) are the one thing
+computed with torch ops.
+
+Reference interfaces mirrored (PointSegment/RandLANet.py): gather_neighbour :377-386,
+relative_pos_encoding :337-343, att_pooling :388-401, random_sample :345-360, nearest_interpolation :362-375;
+helper_tf_util.conv2d / conv2d_transpose (helper_tf_util.py:115-250).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import c_float, c_int, c_size_t, c_void_p
+from .helper_tool import workspace
+
+c_ll = ctypes.c_longlong
+
+_lib._OP_SIGS.update({
+    "pu_gather_rows_fwd": [c_void_p, c_int, c_int, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_void_p],
+    "pu_build_inverse": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "pu_segment_sum": [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p],
+    "pu_relative_pos_encoding_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "pu_random_sample_fwd": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                             c_void_p],
+    "pu_random_sample_bwd": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll,
+                             c_int, c_void_p, c_int, c_int, c_void_p],
+    "pu_linear_fwd": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
+                      c_void_p, c_void_p],
+    "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
+    "pu_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                 c_void_p],
+    "pu_bn_act_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_int,
+                      c_void_p, c_int, c_void_p],
+    "pu_act_bwd": [c_void_p, c_int, c_void_p, c_int, c_float, c_ll, c_int, c_void_p, c_int, c_void_p],
+    "pu_bn_bwd_reduce": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_int, c_void_p, c_void_p,
+                         c_void_p],
+    "pu_bn_bwd_apply": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                        c_ll, c_int, c_void_p, c_int, c_void_p],
+    "pu_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pu_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
+                           c_int, c_void_p],
+})
+
+LEAKY_SLOPE = 0.2  # helper_tf_util.py:169 (alpha is always 0.2, whatever activation_fn was passed)
+BN_EPS = 1e-6      # helper_tf_util.py:167
+BN_MOMENTUM = 0.99
+
+
+def _L():
+    L = _lib.lib()
+    if not getattr(L, "_pu_extra_declared", False):
+        _lib._declare_ops(L)
+        L.pu_inverse_workspace_bytes.restype = c_size_t
+        L.pu_inverse_workspace_bytes.argtypes = [c_int, c_ll]
+        L.pu_wgrad_workspace_bytes.restype = c_size_t
+        L.pu_wgrad_workspace_bytes.argtypes = [c_ll, c_int, c_int]
+        L.pu_linear_row_tiles.argtypes = [c_ll, c_int]
+        L.pu_bn_bwd_reduce_blocks.argtypes = [c_ll, c_int]
+        L._pu_extra_declared = True
+    return L
+
+
+def _stream(t: torch.Tensor):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.PointUnetError("point_unet_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def rows(t: torch.Tensor):
+    """View ``t[..., C]`` as a row-strided matrix: returns (tensor, R, C, ld).  Copies only if the layout
+    cannot be expressed as rows with one constant stride (e.g. a half of a concat buffer is fine)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    C = t.shape[-1]
+    ok = t.dim() >= 1 and (C == 1 or t.stride(-1) == 1)
+    if ok and t.dim() >= 2:
+        ld = t.stride(-2) if t.shape[-2] > 1 else max(C, t.stride(-2))
+        expect = ld * t.shape[-2]
+        for i in range(t.dim() - 3, -1, -1):
+            if t.shape[i] > 1 and t.stride(i) != expect:
+                ok = False
+                break
+            expect *= t.shape[i]
+        ok = ok and ld >= C
+    elif ok:
+        ld = C
+    if not ok:
+        t = t.contiguous()
+        ld = C
+    R = t.numel() // C if C > 0 else 0
+    return t, R, C, ld
+
+
+def _idx32(idx: torch.Tensor) -> torch.Tensor:
+    if idx.dtype != torch.int32:
+        idx = idx.to(torch.int32)
+    return idx.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# inverse neighbour lists (scatter-free backward)
+class InverseIndex:
+    """offsets/perm of an index tensor ``idx [B, M, K]`` pointing into ``n_src`` rows per cloud."""
+
+    def __init__(self, idx: torch.Tensor, n_src: int):
+        idx = _idx32(idx)
+        B = idx.shape[0]
+        R = idx[0].numel()
+        L = _L()
+        self.offsets = torch.empty(B * n_src + 1, dtype=torch.int32, device=idx.device)
+        self.perm = torch.empty(B * R, dtype=torch.int32, device=idx.device)
+        nbytes = L.pu_inverse_workspace_bytes(B, R)
+        ws = workspace(nbytes, idx.device, slot=1)
+        _lib.check(L.pu_build_inverse(idx.data_ptr(), R, B, n_src, self.offsets.data_ptr(), self.perm.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _stream(idx)), "pu_build_inverse")
+        self.n_targets = B * n_src
+
+
+_inverse_cache: dict = {}
+
+
+def inverse_of(idx: torch.Tensor, n_src: int) -> InverseIndex:
+    """Inverse list of ``idx``, cached per index tensor (the pyramid's indices are reused by every layer)."""
+    key = (idx.data_ptr(), tuple(idx.shape), idx._version, n_src, idx.device.index)
+    inv = _inverse_cache.get(key)
+    if inv is None:
+        if len(_inverse_cache) > 64:
+            _inverse_cache.clear()
+        inv = InverseIndex(idx, n_src)
+        _inverse_cache[key] = (inv, idx)  # keep idx alive so data_ptr stays unique
+        return inv
+    return inv[0]
+
+
+def clear_caches():
+    _inverse_cache.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``out[b, r, :] = src[b, idx[b, r], :]`` for ``src [B, n, d]`` and ``idx [B, ...]`` (raw, no autograd)."""
+    _need_cuda(src, idx)
+    idx = _idx32(idx)
+    B, n = src.shape[0], src.shape[1]
+    s, _, d, ld_s = rows(src)
+    Rpc = idx[0].numel() if B > 0 else 0
+    if out is None:
+        out = torch.empty(tuple(idx.shape) + (d,), dtype=torch.float32, device=src.device)
+    o, Ro, do, ld_o = rows(out)
+    assert o.data_ptr() == out.data_ptr() and do == d and Ro == B * Rpc, "gather_rows: bad output view"
+    _lib.check(_L().pu_gather_rows_fwd(s.data_ptr(), ld_s, n, idx.data_ptr(), Rpc, B, o.data_ptr(), ld_o, d, _stream(src)),
+               "pu_gather_rows_fwd")
+    return out
+
+
+def segment_sum(grad_out: torch.Tensor, inv: InverseIndex, d: int, out: torch.Tensor | None = None,
+                accumulate: bool = False) -> torch.Tensor:
+    g, R, dg, ld_g = rows(grad_out)
+    assert dg == d
+    if out is None:
+        out = torch.empty((inv.n_targets, d), dtype=torch.float32, device=grad_out.device)
+    o, Ro, do, ld_o = rows(out)
+    assert o.data_ptr() == out.data_ptr() and Ro == inv.n_targets
+    _lib.check(_L().pu_segment_sum(g.data_ptr(), ld_g, inv.offsets.data_ptr(), inv.perm.data_ptr(), inv.n_targets,
+                                   o.data_ptr(), ld_o, d, int(accumulate), _stream(grad_out)), "pu_segment_sum")
+    return out
+
+
+class _GatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, idx):
+        ctx.idx, ctx.shape = idx, src.shape
+        return gather_rows(src, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, n, d = ctx.shape
+        inv = inverse_of(ctx.idx, n)
+        return segment_sum(grad_out, inv, d).view(B, n, d), None
+
+
+def gather_neighbour(pc: torch.Tensor, neighbor_idx: torch.Tensor) -> torch.Tensor:
+    """RandLANet.py:377-386.  ``pc [B,N,d]``, ``neighbor_idx [B,N,K]`` -> ``[B,N,K,d]``."""
+    _need_cuda(pc, neighbor_idx)
+    if pc.requires_grad:
+        return _GatherFn.apply(pc, neighbor_idx)
+    return gather_rows(pc, neighbor_idx)
+
+
+def nearest_interpolation(feature: torch.Tensor, interp_idx: torch.Tensor) -> torch.Tensor:
+    """RandLANet.py:362-375.  ``feature [B,N,1,d]``, ``interp_idx [B,up,1]`` -> ``[B,up,1,d]``."""
+    _need_cuda(feature, interp_idx)
+    f = feature.squeeze(2)
+    out = _GatherFn.apply(f, interp_idx) if f.requires_grad else gather_rows(f, interp_idx)
+    return out  # idx [B,up,1] -> [B,up,1,d]
+
+
+def relative_pos_encoding(xyz: torch.Tensor, neigh_idx: torch.Tensor) -> torch.Tensor:
+    """RandLANet.py:337-343.  ``xyz [B,N,3]``, ``neigh_idx [B,N,K]`` -> ``[B,N,K,10]`` (no gradient: xyz is data)."""
+    _need_cuda(xyz, neigh_idx)
+    xyz = xyz.detach().contiguous().float()
+    idx = _idx32(neigh_idx)
+    B, N, K = idx.shape
+    out = torch.empty((B, N, K, 10), dtype=torch.float32, device=xyz.device)
+    _lib.check(_L().pu_relative_pos_encoding_fwd(xyz.data_ptr(), idx.data_ptr(), B, N, K, out.data_ptr(), _stream(xyz)),
+               "pu_relative_pos_encoding_fwd")
+    return out
+
+
+class _RandomSampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, pool_idx):
+        idx = _idx32(pool_idx)
+        B, n = feat.shape[0], feat.shape[1]
+        M, K = idx.shape[1], idx.shape[2]
+        f, _, d, ld_f = rows(feat)
+        out = torch.empty((B, M, d), dtype=torch.float32, device=feat.device)
+        ties = torch.empty((B * M, d), dtype=torch.uint8, device=feat.device)
+        _lib.check(_L().pu_random_sample_fwd(f.data_ptr(), ld_f, n, idx.data_ptr(), B, M, K, out.data_ptr(), d,
+                                             ties.data_ptr(), d, _stream(feat)), "pu_random_sample_fwd")
+        ctx.save_for_backward(f, out, ties)
+        ctx.idx, ctx.dims = pool_idx, (B, n, M, K, d, ld_f)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        f, out, ties = ctx.saved_tensors
+        B, n, M, K, d, ld_f = ctx.dims
+        inv = inverse_of(ctx.idx, n)
+        g, _, _, ld_g = rows(g_out)
+        g_feat = torch.empty((B, n, d), dtype=torch.float32, device=f.device)
+        _lib.check(_L().pu_random_sample_bwd(f.data_ptr(), ld_f, out.data_ptr(), d, ties.data_ptr(), g.data_ptr(), ld_g,
+                                             inv.offsets.data_ptr(), inv.perm.data_ptr(), inv.n_targets, K,
+                                             g_feat.data_ptr(), d, d, _stream(f)), "pu_random_sample_bwd")
+        return g_feat, None
+
+
+def random_sample(feature: torch.Tensor, pool_idx: torch.Tensor) -> torch.Tensor:
+    """RandLANet.py:345-360.  ``feature [B,N,1,d]``, ``pool_idx [B,N',K]`` -> ``[B,N',1,d]`` (max over K)."""
+    _need_cuda(feature, pool_idx)
+    return _RandomSampleFn.apply(feature.squeeze(2), pool_idx).unsqueeze(2)
+
+
+# ---------------------------------------------------------------------------------------------
+def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False):
+    """y = x w (+ bias) over rows; optionally the batch-norm mean / biased variance of y. (no autograd)"""
+    xr, M, K, ldx = rows(x)
+    assert w.dim() == 2 and w.shape[0] == K and w.is_contiguous()
+    N = w.shape[1]
+    if out is None:
+        out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
+    o, Mo, No, ldo = rows(out)
+    assert o.data_ptr() == out.data_ptr() and Mo == M and No == N
+    L = _L()
+    ssum = ssq = None
+    if want_stats:
+        tiles = L.pu_linear_row_tiles(M, N)
+        ssum = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
+        ssq = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
+    _lib.check(L.pu_linear_fwd(xr.data_ptr(), ldx, w.data_ptr(), N, bias.data_ptr() if bias is not None else None,
+                               o.data_ptr(), ldo, M, K, N, int(accumulate),
+                               ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None,
+                               _stream(x)), "pu_linear_fwd")
+    if not want_stats:
+        return out
+    mean = torch.empty(N, dtype=torch.float32, device=x.device)
+    var = torch.empty(N, dtype=torch.float32, device=x.device)
+    _lib.check(L.pu_stats_finalize(ssum.data_ptr(), ssq.data_ptr(), ssum.shape[0], N, M, mean.data_ptr(), var.data_ptr(),
+                                   _stream(x)), "pu_stats_finalize")
+    return out, mean, var
+
+
+def wgrad_raw(x, dy, want_db=False):
+    xr, M, K, ldx = rows(x)
+    gr, Mg, N, ldg = rows(dy)
+    assert M == Mg
+    L = _L()
+    dw = torch.empty((K, N), dtype=torch.float32, device=x.device)
+    db = torch.empty(N, dtype=torch.float32, device=x.device) if want_db else None
+    nbytes = L.pu_wgrad_workspace_bytes(M, K, N)
+    ws = workspace(nbytes, x.device, slot=2)
+    _lib.check(L.pu_wgrad(xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
+                          db.data_ptr() if want_db else None, 0, ws.data_ptr(), ws.numel(), _stream(x)), "pu_wgrad")
+    return dw, db
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x w + b with batch statistics of y as non-differentiable side outputs."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, want_stats):
+        w = w.contiguous()
+        res = linear_raw(x, w, bias, want_stats=want_stats)
+        y, mean, var = res if want_stats else (res, None, None)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        ctx.x_needs = x.requires_grad
+        if want_stats:
+            ctx.mark_non_differentiable(mean, var)
+            return y, mean, var
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *_):
+        x, w = ctx.saved_tensors
+        dx = None
+        if ctx.x_needs:
+            dx = linear_raw(dy, w.t().contiguous())
+            dx = dx.view(x.shape)
+        dw, db = wgrad_raw(x, dy, want_db=ctx.has_bias)
+        return dx, dw, db, None
+
+
+def linear(x, w, bias=None, want_stats=False):
+    """``y = x w + b`` over the last axis (1x1 conv / dense); with ``want_stats`` also returns the batch mean and
+    biased variance of ``y`` per channel (non-differentiable side outputs consumed by :func:`bn_act`)."""
+    _need_cuda(x, w)
+    return _LinearFn.apply(x, w, bias, want_stats)
+
+
+def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shift2=None):
+    yr, R, C, ldy = rows(y)
+    if out is None:
+        out = torch.empty(y.shape, dtype=torch.float32, device=y.device)
+    o, Ro, Co, ldo = rows(out)
+    assert o.data_ptr() == out.data_ptr() and Ro == R and Co == C
+    if y2 is not None:
+        y2r, R2, C2, ldy2 = rows(y2)
+        assert R2 == R and C2 == C
+    _lib.check(_L().pu_bn_act_fwd(yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+                                  y2r.data_ptr() if y2 is not None else None, ldy2 if y2 is not None else 0,
+                                  scale2.data_ptr() if y2 is not None else None,
+                                  shift2.data_ptr() if y2 is not None else None, float(slope), R, C, o.data_ptr(), ldo,
+                                  _stream(y)), "pu_bn_act_fwd")
+    return out
+
+
+def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training):
+    """Gradient of out = lrelu(BN(y)) wrt y, gamma, beta given dout (= dz when slope == 1)."""
+    dzr, R, C, ldd = rows(dz)
+    yr, Ry, Cy, ldy = rows(y)
+    assert R == Ry and C == Cy
+    L = _L()
+    blocks = L.pu_bn_bwd_reduce_blocks(R, C)
+    p1 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
+    p2 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
+    st = _stream(y)
+    _lib.check(L.pu_bn_bwd_reduce(dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+                                  float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st), "pu_bn_bwd_reduce")
+    sum_dz = p1.sum(0, dtype=torch.float64)
+    sum_dzy = p2.sum(0, dtype=torch.float64)
+    m64, i64, g64 = mean.double(), invstd.double(), gamma.double()
+    sum_dzxh = (sum_dzy - m64 * sum_dz) * i64          # sum dz * xhat
+    dgamma, dbeta = sum_dzxh.float(), sum_dz.float()
+    if training:
+        mdz, mdzx = sum_dz / R, sum_dzxh / R
+        ka = g64 * i64
+        kc = -g64 * i64 * i64 * mdzx
+        kb = -g64 * i64 * mdz - kc * m64
+    else:  # inference statistics are constants
+        ka, kb, kc = g64 * i64, torch.zeros_like(g64), torch.zeros_like(g64)
+    ka, kb, kc = ka.float().contiguous(), kb.float().contiguous(), kc.float().contiguous()
+    dy = torch.empty(y.shape, dtype=torch.float32, device=y.device)
+    _lib.check(L.pu_bn_bwd_apply(dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(), float(slope),
+                                 ka.data_ptr(), kb.data_ptr(), kc.data_ptr(), R, C, dy.data_ptr(), C, st),
+               "pu_bn_bwd_apply")
+    return dy, dgamma, dbeta
+
+
+class _BNActFn(torch.autograd.Function):
+    """out = leaky_relu_slope(BN(y) [+ BN2(y2)]) with batch statistics given as (mean, var) of y (and y2)."""
+
+    @staticmethod
+    def forward(ctx, y, mean, var, gamma, beta, slope, training, y2, mean2, var2, gamma2, beta2):
+        invstd = torch.rsqrt(var + BN_EPS)
+        scale = (gamma * invstd).contiguous()
+        shift = (beta - mean * scale).contiguous()
+        two = y2 is not None
+        if two:
+            invstd2 = torch.rsqrt(var2 + BN_EPS)
+            scale2 = (gamma2 * invstd2).contiguous()
+            shift2 = (beta2 - mean2 * scale2).contiguous()
+            res = _bn_act_fwd_raw(y, scale, shift, slope, y2=y2, scale2=scale2, shift2=shift2)
+            ctx.save_for_backward(y, scale, shift, gamma, mean, invstd, y2, scale2, shift2, gamma2, mean2, invstd2, res)
+        else:
+            res = _bn_act_fwd_raw(y, scale, shift, slope)
+            ctx.save_for_backward(y, scale, shift, gamma, mean, invstd)
+        ctx.two, ctx.slope, ctx.training = two, slope, training
+        return res
+
+    @staticmethod
+    def backward(ctx, dout):
+        none5 = (None,) * 5
+        if not ctx.two:
+            y, scale, shift, gamma, mean, invstd = ctx.saved_tensors
+            dy, dg, db = _bn_bwd_raw(dout, y, scale, shift, ctx.slope, gamma, mean, invstd, ctx.training)
+            return (dy, None, None, dg, db, None, None) + none5
+        y, scale, shift, gamma, mean, invstd, y2, scale2, shift2, gamma2, mean2, invstd2, res = ctx.saved_tensors
+        # through the activation first (sign of the output), then each BN branch without activation
+        dr, R, C, ldd = rows(dout)
+        rr, _, _, ldr = rows(res)
+        dz = torch.empty(res.shape, dtype=torch.float32, device=res.device)
+        _lib.check(_L().pu_act_bwd(dr.data_ptr(), ldd, rr.data_ptr(), ldr, float(ctx.slope), R, C, dz.data_ptr(), C,
+                                   _stream(res)), "pu_act_bwd")
+        dy, dg, db = _bn_bwd_raw(dz, y, scale, shift, 1.0, gamma, mean, invstd, ctx.training)
+        dy2, dg2, db2 = _bn_bwd_raw(dz, y2, scale2, shift2, 1.0, gamma2, mean2, invstd2, ctx.training)
+        return dy, None, None, dg, db, None, None, dy2, None, None, dg2, db2
+
+
+def bn_act(y, mean, var, gamma, beta, slope=LEAKY_SLOPE, training=True,
+           y2=None, mean2=None, var2=None, gamma2=None, beta2=None):
+    """``leaky_relu_slope(BN(y) [+ BN2(y2)])`` with the given per-channel statistics (batch stats in training,
+    moving stats at inference); ``slope=1`` means no activation (helper_tf_util.py:166-169)."""
+    _need_cuda(y)
+    return _BNActFn.apply(y, mean, var, gamma, beta, slope, training, y2, mean2, var2, gamma2, beta2)
+
+
+# ---------------------------------------------------------------------------------------------
+class _AttPoolFn(torch.autograd.Function):
+    """f_agg[p,c] = sum_k x[p,k,c] softmax_k(x[p,k,:] w)[c]   (RandLANet.py:394-398, one fused kernel)"""
+
+    @staticmethod
+    def forward(ctx, feature_set, w):
+        w = w.contiguous()
+        B, N, K, d = feature_set.shape
+        x, R, _, ldx = rows(feature_set)
+        out = torch.empty((B, N, 1, d), dtype=torch.float32, device=feature_set.device)
+        _lib.check(_L().pu_att_pooling_fwd(x.data_ptr(), ldx, w.data_ptr(), B * N, K, d, out.data_ptr(), d, _stream(x)),
+                   "pu_att_pooling_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.dims = (B, N, K, d, ldx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_agg):
+        x, w = ctx.saved_tensors
+        B, N, K, d, ldx = ctx.dims
+        g, _, _, ldg = rows(g_agg)
+        d_act = torch.empty((B * N * K, d), dtype=torch.float32, device=x.device)
+        dx = torch.empty((B, N, K, d), dtype=torch.float32, device=x.device)
+        _lib.check(_L().pu_att_pooling_bwd(x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
+                                           d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x)), "pu_att_pooling_bwd")
+        linear_raw(d_act, w.t().contiguous(), out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
+        dw, _ = wgrad_raw(x, d_act)
+        return dx, dw
+
+
+def att_pool(feature_set: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Fused FC + softmax over K + weighted sum: ``[B,N,K,d]`` x ``[d,d]`` -> ``[B,N,1,d]``."""
+    _need_cuda(feature_set, w)
+    return _AttPoolFn.apply(feature_set, w)

@@ -1,0 +1,241 @@
+"""GPU parity tests of the LFA building blocks and the full PointSegment network against the oracle restatement
+(oracle/randla_ref.py, run in fp64 on the CPU).  Tolerance (north_star): 1e-3 relative in fp32, measured per
+tensor as max|a-b| / max(max|b|, eps); pure data-movement ops must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import randla_ref as ref
+from point_unet_b200 import ops
+from point_unet_b200.helper_tool import ConfigBraTS, ConfigPancreas
+from point_unet_b200.RandLANet import Network, build_pyramid, init_params
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu() if isinstance(a, torch.Tensor) else torch.as_tensor(a).double()
+    b = b.detach().double().cpu() if isinstance(b, torch.Tensor) else torch.as_tensor(b).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+def rand_idx(B, M, K, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (B, M, K), generator=g, dtype=torch.int32)
+
+
+@pytest.mark.parametrize("d", [3, 8, 32, 64, 20])
+def test_gather_neighbour_fwd_bwd(d):
+    B, N, K = 2, 1003, 16
+    g = torch.Generator().manual_seed(d)
+    pc = torch.randn(B, N, d, generator=g)
+    idx = rand_idx(B, N, K, N, d + 1)
+    w = torch.randn(B, N, K, d, generator=g)
+    pc_ref = pc.double().requires_grad_(True)
+    out_ref = ref.gather_neighbour(pc_ref, idx)
+    (out_ref * w.double()).sum().backward()
+    pc_gpu = pc.cuda().requires_grad_(True)
+    out = ops.gather_neighbour(pc_gpu, idx.cuda())
+    assert out.shape == (B, N, K, d)
+    assert torch.equal(out.detach().cpu(), out_ref.detach().float())  # a copy: bit-exact
+    (out * w.cuda()).sum().backward()
+    assert rel_err(pc_gpu.grad, pc_ref.grad) < 1e-5
+    # determinism of the scatter-free backward
+    g1 = pc_gpu.grad.clone()
+    pc_gpu.grad = None
+    out = ops.gather_neighbour(pc_gpu, idx.cuda())
+    (out * w.cuda()).sum().backward()
+    assert torch.equal(g1, pc_gpu.grad)
+
+
+def test_relative_pos_encoding():
+    B, N, K = 3, 777, 16
+    g = torch.Generator().manual_seed(3)
+    xyz = torch.rand(B, N, 3, generator=g)
+    idx = rand_idx(B, N, K, N, 4)
+    idx[:, :, 0] = torch.arange(N, dtype=torch.int32)[None]  # self neighbour: sqrt(0) = 0
+    out = ops.relative_pos_encoding(xyz.cuda(), idx.cuda())
+    want = ref.relative_pos_encoding(xyz.double(), idx)
+    assert out.shape == (B, N, K, 10)
+    assert rel_err(out, want) < 1e-6
+    assert (out[:, :, 0, 0] == 0).all()
+    assert torch.equal(out[..., 4:7].cpu(), xyz[:, :, None, :].expand(B, N, K, 3))
+
+
+@pytest.mark.parametrize("d", [32, 128, 6])
+def test_random_sample_fwd_bwd(d):
+    B, N, M, K = 2, 1000, 250, 16
+    g = torch.Generator().manual_seed(10 + d)
+    feat = torch.randn(B, N, 1, d, generator=g)
+    feat[:, ::7] = feat[:, 3:4]  # exact ties between different points
+    idx = rand_idx(B, M, K, N, 11)
+    w = torch.randn(B, M, 1, d, generator=g)
+    f_ref = feat.double().requires_grad_(True)
+    o_ref = ref.random_sample(f_ref, idx)
+    (o_ref * w.double()).sum().backward()
+    f_gpu = feat.cuda().requires_grad_(True)
+    o = ops.random_sample(f_gpu, idx.cuda())
+    assert o.shape == (B, M, 1, d)
+    assert torch.equal(o.detach().cpu(), o_ref.detach().float())
+    (o * w.cuda()).sum().backward()
+    assert rel_err(f_gpu.grad, f_ref.grad) < 1e-5  # includes the even split among ties (tf.reduce_max gradient)
+
+
+def test_nearest_interpolation_fwd_bwd():
+    B, N, up, d = 2, 351, 703, 64
+    g = torch.Generator().manual_seed(20)
+    feat = torch.randn(B, N, 1, d, generator=g)
+    idx = rand_idx(B, up, 1, N, 21)
+    w = torch.randn(B, up, 1, d, generator=g)
+    f_ref = feat.double().requires_grad_(True)
+    o_ref = ref.nearest_interpolation(f_ref, idx)
+    (o_ref * w.double()).sum().backward()
+    f_gpu = feat.cuda().requires_grad_(True)
+    o = ops.nearest_interpolation(f_gpu, idx.cuda())
+    assert o.shape == (B, up, 1, d) and torch.equal(o.detach().cpu(), o_ref.detach().float())
+    (o * w.cuda()).sum().backward()
+    assert rel_err(f_gpu.grad, f_ref.grad) < 1e-5
+
+
+@pytest.mark.parametrize("rows,cin,cout", [(5000, 7, 8), (4096, 10, 8), (3001, 8, 16), (2000, 64, 128), (700, 1536, 512),
+                                            (9000, 32, 2), (1500, 160, 32)])
+def test_linear_and_wgrad(rows, cin, cout):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cin, cout, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    dy = torch.randn(rows, cout, generator=g)
+    xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = xr @ wr + br
+    (yr * dy.double()).sum().backward()
+    xg, wg, bg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y, mean, var = ops.linear(xg, wg, bg, want_stats=True)
+    assert rel_err(y, yr) < 1e-5
+    assert rel_err(mean, yr.mean(0)) < 1e-4 and rel_err(var, yr.var(0, unbiased=False)) < 1e-4
+    (y * dy.cuda()).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < 1e-5
+    assert rel_err(wg.grad, wr.grad) < 1e-4
+    assert rel_err(bg.grad, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("shape,cin,cout,act", [((2, 500, 16), 10, 8, True), ((2, 300, 1), 64, 128, False),
+                                               ((1, 1000, 16), 32, 32, True)])
+def test_conv2d_bn_act_vs_oracle(shape, cin, cout, act):
+    g = torch.Generator().manual_seed(cin * cout)
+    x = torch.randn(*shape, cin, generator=g)
+    p = {"s/weights": torch.randn(cin, cout, generator=g) * (2 / cout) ** 0.5, "s/biases": torch.randn(cout, generator=g) * 0.1,
+         "s/bn/gamma": torch.rand(cout, generator=g) + 0.5, "s/bn/beta": torch.randn(cout, generator=g) * 0.1}
+    dy = torch.randn(*shape, cout, generator=g)
+    pr = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    xr = x.double().requires_grad_(True)
+    yr = ref.conv2d(xr, pr, "s", True, True, act)
+    (yr * dy.double()).sum().backward()
+    pg = {k: v.cuda().requires_grad_(True) for k, v in p.items()}
+    xg = x.cuda().requires_grad_(True)
+    y, mean, var = ops.linear(xg, pg["s/weights"], pg["s/biases"], want_stats=True)
+    out = ops.bn_act(y, mean, var, pg["s/bn/gamma"], pg["s/bn/beta"], slope=0.2 if act else 1.0, training=True)
+    assert rel_err(out, yr) < TOL * 0.1
+    (out * dy.cuda()).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < TOL
+    for k in ("s/weights", "s/bn/gamma", "s/bn/beta"):
+        assert rel_err(pg[k].grad, pr[k].grad) < TOL, k
+    # the bias gradient through a batch norm is analytically zero: compare on the scale of the weight gradient
+    assert float(pg["s/biases"].grad.abs().max()) < 1e-3 * float(pr["s/weights"].grad.abs().max()) + 1e-4
+
+
+@pytest.mark.parametrize("d", [16, 64, 128, 32])
+def test_att_pool_fwd_bwd(d):
+    B, N, K = 2, 300, 16
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(B, N, K, d, generator=g)
+    w = torch.randn(d, d, generator=g) * (1.5 / d ** 0.5)
+    dy = torch.randn(B, N, 1, d, generator=g)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    keep = {}
+    pr = {"afc/kernel": wr, "amlp/weights": torch.eye(d).double(), "amlp/biases": torch.zeros(d).double(),
+          "amlp/bn/gamma": torch.ones(d).double(), "amlp/bn/beta": torch.zeros(d).double()}
+    ref.att_pooling(xr, pr, "a", True, None, keep)
+    agg_r = keep["af_agg"]
+    (agg_r * dy.double()).sum().backward()
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    agg = ops.att_pool(xg, wg)
+    assert agg.shape == (B, N, 1, d)
+    assert rel_err(agg, agg_r) < 1e-4
+    (agg * dy.cuda()).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < TOL
+    assert rel_err(wg.grad, wr.grad) < TOL
+    # strided input (a half of a wider buffer) takes the same path
+    wide = torch.zeros(B, N, K, 2 * d, device="cuda")
+    wide[..., :d] = x.cuda()
+    assert torch.equal(ops.att_pool(wide[..., :d], wg.detach()), agg.detach())
+
+
+def _small_cfg(base, n_points):
+    class Cfg(base):
+        num_points = n_points
+    return Cfg
+
+
+@pytest.mark.parametrize("base,n_points,B", [(ConfigPancreas, 16384, 2), (ConfigBraTS, 8192, 3)])
+def test_full_network_fwd_bwd_vs_oracle(base, n_points, B):
+    from point_unet_b200 import synthetic as syn
+    cfg = _small_cfg(base, n_points)
+    gen = syn.pancreas_cloud if base is ConfigPancreas else syn.brats_cloud
+    data = syn.batch(gen, B, n_points, seed0=40)
+    F = 3 + data["features"].shape[-1]
+    params = init_params(cfg, F, seed=1)
+    rng = np.random.default_rng(2)
+    for k in params:  # move gamma/beta off their trivial values so their gradients are exercised
+        if k.endswith("gamma"):
+            params[k] = (params[k] + rng.uniform(-0.3, 0.3, params[k].shape)).astype(np.float32)
+        if k.endswith("beta") or k.endswith("biases") or k.endswith("bias"):
+            params[k] = rng.uniform(-0.1, 0.1, params[k].shape).astype(np.float32)
+    net = Network(cfg, F, device="cuda")
+    net.load_numpy(params)
+    xyz = torch.from_numpy(data["xyz"]).cuda()
+    pyr = build_pyramid(xyz, cfg)
+    feats = torch.cat([xyz, torch.from_numpy(data["features"]).cuda()], dim=-1)  # runPancreas.py:125
+    labels = torch.from_numpy(data["labels"]).cuda()
+    mask = torch.from_numpy(rng.random((B, n_points, 1, 32)) < 0.5).cuda()
+    inputs = dict(pyr, features=feats)
+    logits = net.inference(inputs, True, dropout_mask=mask)
+    loss = net.get_loss(logits, labels)
+    loss.backward()
+
+    # oracle on the same indices, weights and dropout mask, fp64
+    p64 = {k: torch.from_numpy(v).double().requires_grad_(not k.split("/")[-1].startswith("moving")) for k, v in params.items()}
+    in64 = dict(xyz=[t.cpu().double() for t in pyr["xyz"]], neigh_idx=[t.cpu() for t in pyr["neigh_idx"]],
+                sub_idx=[t.cpu() for t in pyr["sub_idx"]], interp_idx=[t.cpu() for t in pyr["interp_idx"]],
+                features=feats.cpu().double())
+    upd = {}
+    logits_r = ref.inference(p64, in64, cfg, True, dropout_mask=mask.cpu(), upd=upd)
+    loss_r = ref.get_loss(logits_r, labels.cpu(), net.class_weights.cpu().numpy())
+    loss_r.backward()
+    assert logits.shape == (B, n_points, cfg.num_classes)
+    assert rel_err(logits, logits_r) < TOL
+    assert abs(float(loss) - float(loss_r)) < TOL * abs(float(loss_r))
+    worst = ("", 0.0)
+    for name, t in net.named_variables():
+        gr = p64[name].grad
+        assert t.grad is not None, name
+        if name.endswith("biases") and (name + "/x").replace("/biases/x", "/bn/gamma") in p64:
+            continue  # bias under a batch norm: analytically zero gradient, pure rounding noise on both sides
+        if name == "fc0/bias":
+            continue
+        e = rel_err(t.grad, gr)
+        if e > worst[1]:
+            worst = (name, e)
+    assert worst[1] < TOL, worst
+    # moving statistics follow momentum 0.99 from (0, 1)
+    mean0, var0, cnt = upd["fc0/bn"]
+    assert rel_err(net.stats["fc0/bn/moving_mean"], 0.01 * mean0) < 1e-3
+    assert rel_err(net.stats["fc0/bn/moving_variance"], 0.99 + 0.01 * var0) < 1e-3
+    # inference mode runs (moving statistics, no dropout) and is deterministic
+    with torch.no_grad():
+        a = net.inference(inputs, False)
+        b = net.inference(inputs, False)
+    assert torch.equal(a, b)
+    p_eval = {k: (net.stats[k].cpu().double() if k in net.stats else v.detach()) for k, v in p64.items()}
+    assert rel_err(a, ref.inference(p_eval, in64, cfg, False)) < TOL
