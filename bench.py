@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- PointSegment hot-path benchmark on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm  (one rank per GPU under torchrun)
+    python bench.py --impl reference [--steps K] [--warmup W]       the reference's CPU path on the host cores
+
+Workload (BASELINE.json configs[2]/[3]): PointSegment training step, synthetic BraTS-shaped clouds
+(4 MRI modality features, 180 000 points, K=16), batch 4 per GPU, weak scaling.  One step = GPU index pyramid
+(5x K=16 + 5x K=1 KNN) + forward + backward + (N>1) NCCL gradient all-reduce + Adam.
+`value`  : points/s with the batch resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same step through Trainer.train_step on pinned HOST buffers: H2D of xyz/features/labels and the
+           D2H read of the loss are inside the timed region.
+`roofline`: the dominant kernel of the step, timed live with CUDA events on its launch stream.
+`cpu_baseline` / --impl reference: nanoflann pyramid (the reference's own C++, oracle/_ref) + the PyTorch-CPU
+           restatement of the TF graph (TF 1.11 is not installable), fwd+bwd, all host threads, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 180000
+BATCH_PER_GPU = 4
+METRIC = "pointsegment_train_points_per_s"
+UNIT = "points/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tensor_burst=float(p["bf16_tflops"]),
+                    tensor_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (recipe in B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), power_w_max=max(power), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def algorithmic(name, tag):
+    """(bytes, flops, bound) per launch from SURVEY.md section 8(d) (fp32, unfused contract)."""
+    if tag is None:
+        return 0, 0, "hbm"
+    if name in ("pu_att_pooling_fwd",):
+        P, K, d = tag
+        return 4 * P * K * d + 4 * d * d + 4 * P * d, 2 * P * K * d * d, "tensor" if d >= 64 else "hbm"
+    if name in ("pu_att_pooling_bwd",):
+        P, K, d = tag  # reads x and g, writes d_act and dx_direct
+        return 3 * 4 * P * K * d + 4 * d * d + 4 * P * d, 2 * P * K * d * d, "tensor" if d >= 64 else "hbm"
+    if name == "pu_gather_rows_fwd":
+        R, n_src, d = tag
+        return 4 * R + 4 * n_src * d + 4 * R * d, 0, "hbm"
+    if name == "pu_segment_sum":
+        R, n_tgt, d = tag
+        return 4 * R + 4 * n_tgt * d + 4 * R * d, 0, "hbm"
+    return 0, 0, "hbm"
+
+
+def make_batch(rank, batch, n_points, kind="brats"):
+    import numpy as np
+    from point_unet_b200 import synthetic as syn
+    gen = syn.brats_cloud if kind == "brats" else syn.pancreas_cloud
+    clouds = [gen(n_points, 1000 * rank + i) for i in range(batch)]
+    return {k: np.stack([c[k] for c in clouds]) for k in ("xyz", "features", "labels")}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def reference_step_factory(n_sample, threads):
+    """The reference's CPU path for one cloud of n_sample points: tf_map with the reference's own nanoflann
+    wrapper (oracle/_ref; falls back to the C restatement when the .so is absent) + fwd+bwd of the PyTorch-CPU
+    restatement of the TF graph.  Returns (step_fn, kind, description)."""
+    import numpy as np
+    import torch
+    from oracle import knn as ok
+    from oracle import randla_ref as ref
+    from point_unet_b200 import synthetic as syn
+    from point_unet_b200.helper_tool import ConfigBraTS, DataProcessing as DP
+    from point_unet_b200.RandLANet import init_params
+
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+
+    class cfg(ConfigBraTS):
+        num_points = n_sample
+
+    kind = "reference" if ok.have_reference() else "port"
+    knn = ok.knn_reference if kind == "reference" else (lambda s, q, k: ok.knn_restated(s, q, k, tie_rule=0))
+    c = syn.brats_cloud(n_sample, 0)
+    params = {k: torch.from_numpy(v).requires_grad_("moving" not in k) for k, v in init_params(cfg, 7, 0).items()}
+    feats = torch.from_numpy(np.concatenate([c["xyz"], c["features"]], -1)[None])
+    labels = torch.from_numpy(c["labels"][None])
+    cw = DP.get_class_weights("BraTS20")
+    mask = torch.from_numpy(np.random.default_rng(0).random((1, n_sample, 1, 32)) < 0.5)
+
+    def step():
+        pyr = ref.tf_map(c["xyz"][None], cfg, knn)  # 5x K=16 + 5x K=1, B=1 => one thread, like the reference
+        inputs = dict(xyz=[torch.from_numpy(a) for a in pyr["xyz"]], neigh_idx=[torch.from_numpy(a) for a in pyr["neigh_idx"]],
+                      sub_idx=[torch.from_numpy(a) for a in pyr["sub_idx"]],
+                      interp_idx=[torch.from_numpy(a) for a in pyr["interp_idx"]], features=feats)
+        for p in params.values():
+            p.grad = None
+        logits = ref.inference(params, inputs, cfg, True, dropout_mask=mask)
+        loss = ref.get_loss(logits, labels, cw)
+        loss.backward()
+        return float(loss.detach())
+
+    desc = (f"1 BraTS-shaped cloud x {n_sample} points per step: nanoflann pyramid ({kind}) + torch-CPU fp32 restatement "
+            f"of the TF graph fwd+bwd (TF 1.11 not installable), {threads} threads")
+    return step, kind, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    n_sample = N_POINTS if total <= 4 else max(20000, N_POINTS // ((total + 3) // 4))
+    step, kind, desc = reference_step_factory(n_sample, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = n_sample / dt
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="PointSegment train step fwd+bwd, BraTS-shaped 180k-point clouds, K=16, batch 4/GPU",
+                            sample_points=n_sample),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=kind, sample=desc),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from point_unet_b200 import _lib, ops
+    from point_unet_b200.helper_tool import ConfigBraTS, knn_search_cuda
+    from point_unet_b200.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    class cfg(ConfigBraTS):
+        num_points = args.points
+
+    B, N = args.batch, args.points
+    host = make_batch(rank, B, N)
+    tr = Trainer(cfg, num_features=7, seed=0, device=dev, world_size=world)
+    x = torch.from_numpy(host["xyz"]).to(dev)
+    f = torch.from_numpy(host["features"]).to(dev)
+    l = torch.from_numpy(host["labels"]).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (>= 3); the last warm-up step also produces the per-kernel breakdown that picks the dominant kernel
+    names = set(_lib._OP_SIGS.keys())
+    for _ in range(max(args.warmup - 1, 2)):
+        tr.train_step_device(x, f, l)
+    with ops.KernelTimer(names) as kt:
+        tr.train_step_device(x, f, l)
+    breakdown = kt.summary()
+    top = max(breakdown.items(), key=lambda kv: kv[1][1])[0] if breakdown else "pu_att_pooling_fwd"
+    if top not in ("pu_att_pooling_fwd", "pu_att_pooling_bwd", "pu_gather_rows_fwd", "pu_segment_sum"):
+        # report the roofline on a kernel whose algorithmic bytes are defined in SURVEY 8(d)
+        cands = {k: v for k, v in breakdown.items() if k in ("pu_att_pooling_fwd", "pu_att_pooling_bwd",
+                                                             "pu_gather_rows_fwd", "pu_segment_sum")}
+        top_rf = max(cands.items(), key=lambda kv: kv[1][1])[0]
+    else:
+        top_rf = top
+
+    # ---- timed region: device-resident inputs
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ops.KernelTimer({top_rf}) as kt:
+        e0.record()
+        for _ in range(args.steps):
+            loss = tr.train_step_device(x, f, l)
+        e1.record()
+        barrier()
+        ktsum = kt.summary()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: public API on pinned host buffers (H2D + D2H inside the timed region)
+    pinned = tr.pin_batch(host["xyz"], host["features"], host["labels"])
+    for _ in range(2):
+        tr.train_step(pinned["xyz"], pinned["features"], pinned["labels"])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_val = tr.train_step(pinned["xyz"], pinned["features"], pinned["labels"])
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = sum(int(v.numel() * v.element_size()) for v in pinned.values())
+
+    if rank == 0:
+        # roofline of the dominant kernel (aggregate over its launches in the timed region)
+        n_l, t_ms, tags = ktsum[top_rf]
+        tot_b = tot_f = 0.0
+        bound = "hbm"
+        for tag, (cnt, tms) in tags.items():
+            b_, f_, bd = algorithmic(top_rf, tag)
+            tot_b += b_ * cnt
+            tot_f += f_ * cnt
+        # the bound of the launches that dominate the kernel's time
+        heavy = max(tags.items(), key=lambda kv: kv[1][1])[0]
+        bound = algorithmic(top_rf, heavy)[2]
+        if bound == "tensor":
+            achieved, peak, runit = tot_f / (t_ms * 1e-3) / 1e12, peaks["tensor_sustained"], "TFLOP/s"
+        else:
+            achieved, peak, runit = tot_b / (t_ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
+        roofline = dict(kernel=top_rf, bound=bound, achieved=achieved, peak=peak, unit=runit, frac=achieved / peak,
+                        traffic=None, launches_per_step=n_l / args.steps, ms_per_step=t_ms / args.steps,
+                        algorithmic_gb_per_step=tot_b / args.steps / 1e9, gflop_per_step=tot_f / args.steps / 1e9,
+                        hbm_gbs_equiv=tot_b / (t_ms * 1e-3) / 1e9, peak_source=peaks["source"],
+                        peak_kind="sustained (kernel timed inside a long step)" if bound == "tensor" else "copy")
+        bd = {k: dict(launches=v[0], ms=round(v[1], 3)) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][1])}
+
+        # KNN micro-bench (BASELINE.json configs[1]) on one 180k cloud, K=16 self-query
+        xk = x[:1].contiguous()
+        for _ in range(3):
+            knn_search_cuda(xk, xk, 16)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(10):
+            knn_search_cuda(xk, xk, 16)
+        k1.record()
+        torch.cuda.synchronize()
+        knn_ms = k0.elapsed_time(k1) / 10
+        knn = dict(queries_per_s=N / (knn_ms * 1e-3), ms=knn_ms, n=N, k=16, algorithmic_bytes=76 * N,
+                   hbm_frac=76 * N / (knn_ms * 1e-3) / 1e9 / peaks["hbm"], tie_rule="(distance, index)")
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_sample = args.cpu_sample
+            step, kind, desc = reference_step_factory(n_sample, threads)
+            step()
+            t0 = time.perf_counter()
+            step()
+            cdt = time.perf_counter() - t0
+            cpu = dict(value=n_sample / cdt, unit=UNIT, cores=threads, kind=kind, sample=desc, seconds=cdt)
+
+        pts = B * N * world
+        line = dict(metric=METRIC, value=pts / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="PointSegment train step (GPU index pyramid + fwd + bwd + Adam), BraTS-shaped "
+                                         "clouds, 4 modality features, K=16, d_out [16,64,128,256,512]",
+                                points_per_cloud=N, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
+                                l2_policy="working set per step >> 126 MB L2 (no flush needed)"),
+                    e2e=dict(value=pts / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=4),
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks, knn=knn,
+                    breakdown_ms_per_step=bd, loss=float(loss_val))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--cpu-sample", type=int, default=N_POINTS, help="points of the cpu_baseline sample cloud")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

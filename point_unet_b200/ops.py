@@ -67,6 +67,48 @@ def _L():
     return L
 
 
+class KernelTimer:
+    """CUDA-event timing of selected C-ABI entry points on the stream they are launched on (bench.py's roofline
+    leg).  ``with KernelTimer({"pu_att_pooling_fwd"}) as kt: step(); kt.summary()`` -> {name: (launches, ms)}."""
+    active = None
+
+    def __init__(self, names):
+        self.names, self.events = set(names), []
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, tag, e0, e1 in self.events:
+            n, ms, tags = out.get(name, (0, 0.0, {}))
+            dt = e0.elapsed_time(e1)
+            t = tags.get(tag, (0, 0.0))
+            tags[tag] = (t[0] + 1, t[1] + dt)
+            out[name] = (n + 1, ms + dt, tags)
+        return out
+
+
+def _call(name, *args, tag=None):
+    fn = getattr(_L(), name)
+    kt = KernelTimer.active
+    if kt is not None and name in kt.names:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = fn(*args)
+        e1.record()
+        kt.events.append((name, tag, e0, e1))
+    else:
+        st = fn(*args)
+    if st != 0:
+        _lib.check(st, name)
+
+
 def _stream(t: torch.Tensor):
     return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -122,8 +164,8 @@ class InverseIndex:
         self.perm = torch.empty(B * R, dtype=torch.int32, device=idx.device)
         nbytes = L.pu_inverse_workspace_bytes(B, R)
         ws = workspace(nbytes, idx.device, slot=1)
-        _lib.check(L.pu_build_inverse(idx.data_ptr(), R, B, n_src, self.offsets.data_ptr(), self.perm.data_ptr(),
-                                      ws.data_ptr(), ws.numel(), _stream(idx)), "pu_build_inverse")
+        _call("pu_build_inverse", idx.data_ptr(), R, B, n_src, self.offsets.data_ptr(), self.perm.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _stream(idx))
         self.n_targets = B * n_src
 
 
@@ -159,8 +201,8 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None =
         out = torch.empty(tuple(idx.shape) + (d,), dtype=torch.float32, device=src.device)
     o, Ro, do, ld_o = rows(out)
     assert o.data_ptr() == out.data_ptr() and do == d and Ro == B * Rpc, "gather_rows: bad output view"
-    _lib.check(_L().pu_gather_rows_fwd(s.data_ptr(), ld_s, n, idx.data_ptr(), Rpc, B, o.data_ptr(), ld_o, d, _stream(src)),
-               "pu_gather_rows_fwd")
+    _call("pu_gather_rows_fwd", s.data_ptr(), ld_s, n, idx.data_ptr(), Rpc, B, o.data_ptr(), ld_o, d, _stream(src),
+          tag=(B * Rpc, B * n, d))
     return out
 
 
@@ -172,8 +214,8 @@ def segment_sum(grad_out: torch.Tensor, inv: InverseIndex, d: int, out: torch.Te
         out = torch.empty((inv.n_targets, d), dtype=torch.float32, device=grad_out.device)
     o, Ro, do, ld_o = rows(out)
     assert o.data_ptr() == out.data_ptr() and Ro == inv.n_targets
-    _lib.check(_L().pu_segment_sum(g.data_ptr(), ld_g, inv.offsets.data_ptr(), inv.perm.data_ptr(), inv.n_targets,
-                                   o.data_ptr(), ld_o, d, int(accumulate), _stream(grad_out)), "pu_segment_sum")
+    _call("pu_segment_sum", g.data_ptr(), ld_g, inv.offsets.data_ptr(), inv.perm.data_ptr(), inv.n_targets,
+                                   o.data_ptr(), ld_o, d, int(accumulate), _stream(grad_out), tag=(R, inv.n_targets, d))
     return out
 
 
@@ -213,8 +255,7 @@ def relative_pos_encoding(xyz: torch.Tensor, neigh_idx: torch.Tensor) -> torch.T
     idx = _idx32(neigh_idx)
     B, N, K = idx.shape
     out = torch.empty((B, N, K, 10), dtype=torch.float32, device=xyz.device)
-    _lib.check(_L().pu_relative_pos_encoding_fwd(xyz.data_ptr(), idx.data_ptr(), B, N, K, out.data_ptr(), _stream(xyz)),
-               "pu_relative_pos_encoding_fwd")
+    _call("pu_relative_pos_encoding_fwd", xyz.data_ptr(), idx.data_ptr(), B, N, K, out.data_ptr(), _stream(xyz))
     return out
 
 
@@ -227,8 +268,8 @@ class _RandomSampleFn(torch.autograd.Function):
         f, _, d, ld_f = rows(feat)
         out = torch.empty((B, M, d), dtype=torch.float32, device=feat.device)
         ties = torch.empty((B * M, d), dtype=torch.uint8, device=feat.device)
-        _lib.check(_L().pu_random_sample_fwd(f.data_ptr(), ld_f, n, idx.data_ptr(), B, M, K, out.data_ptr(), d,
-                                             ties.data_ptr(), d, _stream(feat)), "pu_random_sample_fwd")
+        _call("pu_random_sample_fwd", f.data_ptr(), ld_f, n, idx.data_ptr(), B, M, K, out.data_ptr(), d,
+                                             ties.data_ptr(), d, _stream(feat))
         ctx.save_for_backward(f, out, ties)
         ctx.idx, ctx.dims = pool_idx, (B, n, M, K, d, ld_f)
         return out
@@ -240,9 +281,9 @@ class _RandomSampleFn(torch.autograd.Function):
         inv = inverse_of(ctx.idx, n)
         g, _, _, ld_g = rows(g_out)
         g_feat = torch.empty((B, n, d), dtype=torch.float32, device=f.device)
-        _lib.check(_L().pu_random_sample_bwd(f.data_ptr(), ld_f, out.data_ptr(), d, ties.data_ptr(), g.data_ptr(), ld_g,
+        _call("pu_random_sample_bwd", f.data_ptr(), ld_f, out.data_ptr(), d, ties.data_ptr(), g.data_ptr(), ld_g,
                                              inv.offsets.data_ptr(), inv.perm.data_ptr(), inv.n_targets, K,
-                                             g_feat.data_ptr(), d, d, _stream(f)), "pu_random_sample_bwd")
+                                             g_feat.data_ptr(), d, d, _stream(f))
         return g_feat, None
 
 
@@ -268,16 +309,16 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False):
         tiles = L.pu_linear_row_tiles(M, N)
         ssum = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
         ssq = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
-    _lib.check(L.pu_linear_fwd(xr.data_ptr(), ldx, w.data_ptr(), N, bias.data_ptr() if bias is not None else None,
+    _call("pu_linear_fwd", xr.data_ptr(), ldx, w.data_ptr(), N, bias.data_ptr() if bias is not None else None,
                                o.data_ptr(), ldo, M, K, N, int(accumulate),
                                ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None,
-                               _stream(x)), "pu_linear_fwd")
+                               _stream(x))
     if not want_stats:
         return out
     mean = torch.empty(N, dtype=torch.float32, device=x.device)
     var = torch.empty(N, dtype=torch.float32, device=x.device)
-    _lib.check(L.pu_stats_finalize(ssum.data_ptr(), ssq.data_ptr(), ssum.shape[0], N, M, mean.data_ptr(), var.data_ptr(),
-                                   _stream(x)), "pu_stats_finalize")
+    _call("pu_stats_finalize", ssum.data_ptr(), ssq.data_ptr(), ssum.shape[0], N, M, mean.data_ptr(), var.data_ptr(),
+                                   _stream(x))
     return out, mean, var
 
 
@@ -290,8 +331,8 @@ def wgrad_raw(x, dy, want_db=False):
     db = torch.empty(N, dtype=torch.float32, device=x.device) if want_db else None
     nbytes = L.pu_wgrad_workspace_bytes(M, K, N)
     ws = workspace(nbytes, x.device, slot=2)
-    _lib.check(L.pu_wgrad(xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
-                          db.data_ptr() if want_db else None, 0, ws.data_ptr(), ws.numel(), _stream(x)), "pu_wgrad")
+    _call("pu_wgrad", xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
+                          db.data_ptr() if want_db else None, 0, ws.data_ptr(), ws.numel(), _stream(x))
     return dw, db
 
 
@@ -338,11 +379,11 @@ def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shif
     if y2 is not None:
         y2r, R2, C2, ldy2 = rows(y2)
         assert R2 == R and C2 == C
-    _lib.check(_L().pu_bn_act_fwd(yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+    _call("pu_bn_act_fwd", yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
                                   y2r.data_ptr() if y2 is not None else None, ldy2 if y2 is not None else 0,
                                   scale2.data_ptr() if y2 is not None else None,
                                   shift2.data_ptr() if y2 is not None else None, float(slope), R, C, o.data_ptr(), ldo,
-                                  _stream(y)), "pu_bn_act_fwd")
+                                  _stream(y))
     return out
 
 
@@ -356,8 +397,8 @@ def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training):
     p1 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
     p2 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
     st = _stream(y)
-    _lib.check(L.pu_bn_bwd_reduce(dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
-                                  float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st), "pu_bn_bwd_reduce")
+    _call("pu_bn_bwd_reduce", dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+                                  float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st)
     sum_dz = p1.sum(0, dtype=torch.float64)
     sum_dzy = p2.sum(0, dtype=torch.float64)
     m64, i64, g64 = mean.double(), invstd.double(), gamma.double()
@@ -372,9 +413,8 @@ def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training):
         ka, kb, kc = g64 * i64, torch.zeros_like(g64), torch.zeros_like(g64)
     ka, kb, kc = ka.float().contiguous(), kb.float().contiguous(), kc.float().contiguous()
     dy = torch.empty(y.shape, dtype=torch.float32, device=y.device)
-    _lib.check(L.pu_bn_bwd_apply(dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(), float(slope),
-                                 ka.data_ptr(), kb.data_ptr(), kc.data_ptr(), R, C, dy.data_ptr(), C, st),
-               "pu_bn_bwd_apply")
+    _call("pu_bn_bwd_apply", dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(), float(slope),
+                                 ka.data_ptr(), kb.data_ptr(), kc.data_ptr(), R, C, dy.data_ptr(), C, st)
     return dy, dgamma, dbeta
 
 
@@ -411,8 +451,8 @@ class _BNActFn(torch.autograd.Function):
         dr, R, C, ldd = rows(dout)
         rr, _, _, ldr = rows(res)
         dz = torch.empty(res.shape, dtype=torch.float32, device=res.device)
-        _lib.check(_L().pu_act_bwd(dr.data_ptr(), ldd, rr.data_ptr(), ldr, float(ctx.slope), R, C, dz.data_ptr(), C,
-                                   _stream(res)), "pu_act_bwd")
+        _call("pu_act_bwd", dr.data_ptr(), ldd, rr.data_ptr(), ldr, float(ctx.slope), R, C, dz.data_ptr(), C,
+                                   _stream(res))
         dy, dg, db = _bn_bwd_raw(dz, y, scale, shift, 1.0, gamma, mean, invstd, ctx.training)
         dy2, dg2, db2 = _bn_bwd_raw(dz, y2, scale2, shift2, 1.0, gamma2, mean2, invstd2, ctx.training)
         return dy, None, None, dg, db, None, None, dy2, None, None, dg2, db2
@@ -436,8 +476,8 @@ class _AttPoolFn(torch.autograd.Function):
         B, N, K, d = feature_set.shape
         x, R, _, ldx = rows(feature_set)
         out = torch.empty((B, N, 1, d), dtype=torch.float32, device=feature_set.device)
-        _lib.check(_L().pu_att_pooling_fwd(x.data_ptr(), ldx, w.data_ptr(), B * N, K, d, out.data_ptr(), d, _stream(x)),
-                   "pu_att_pooling_fwd")
+        _call("pu_att_pooling_fwd", x.data_ptr(), ldx, w.data_ptr(), B * N, K, d, out.data_ptr(), d, _stream(x),
+              tag=(B * N, K, d))
         ctx.save_for_backward(x, w)
         ctx.dims = (B, N, K, d, ldx)
         return out
@@ -449,8 +489,8 @@ class _AttPoolFn(torch.autograd.Function):
         g, _, _, ldg = rows(g_agg)
         d_act = torch.empty((B * N * K, d), dtype=torch.float32, device=x.device)
         dx = torch.empty((B, N, K, d), dtype=torch.float32, device=x.device)
-        _lib.check(_L().pu_att_pooling_bwd(x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
-                                           d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x)), "pu_att_pooling_bwd")
+        _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
+                                           d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
         linear_raw(d_act, w.t().contiguous(), out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
         dw, _ = wgrad_raw(x, d_act)
         return dx, dw

@@ -1,0 +1,99 @@
+"""Training / inference steps of PointSegment on B200 -- the public API a user of the reference switches to.
+
+Reference flow replaced (PointSegment/RandLANet.py:156-206 ``Network.train`` + runPancreas.py:124-171 input
+pipeline): per step the reference runs ``tf_map`` (10 nanoflann KNN calls on the CPU), copies 24 tensors to the
+GPU, runs forward + TF autodiff + Adam, and fetches logits.  Here one process per GPU does all of it on the
+device: host batch -> pinned staging -> H2D -> GPU index pyramid (csrc/knn.cu) -> forward/backward on the
+hand-written kernels -> (N>1: NCCL all-reduce of the flat gradient buffer, gradients only) -> Adam.
+
+Data parallelism: batch-sharded, batch-norm statistics stay per replica, the loss is a
+local mean, so averaged gradients equal the global-batch mean gradient.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .RandLANet import Network, build_pyramid
+
+
+class Trainer:
+    def __init__(self, config, num_features=None, seed=0, device=None, lr=None, world_size=1):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.cfg = config
+        self.net = Network(config, num_features, seed=seed, device=self.device)
+        self.params = [t for _, t in self.net.named_variables()]
+        # one flat gradient buffer: every .grad is a view of it (a single all-reduce, no bucketing copies)
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        # tf.train.AdamOptimizer defaults (RandLANet.py:88): beta (0.9, 0.999), eps 1e-8
+        self.opt = torch.optim.Adam(self.params, lr=lr if lr is not None else config.learning_rate, betas=(0.9, 0.999),
+                                    eps=1e-8, fused=True)
+        self.world_size = world_size
+        self._pinned = {}
+        self._dev = {}
+
+    # -- host staging ----------------------------------------------------------------------------
+    def _stage(self, name, arr):
+        """numpy / CPU tensor -> pinned buffer -> device (async on the current stream)."""
+        t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr
+        if t.is_cuda:
+            return t
+        pin = self._pinned.get(name)
+        if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
+            pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned[name] = pin
+            self._dev[name] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        if t.data_ptr() != pin.data_ptr():
+            pin.copy_(t)
+        self._dev[name].copy_(pin, non_blocking=True)
+        return self._dev[name]
+
+    def pin_batch(self, xyz, features, labels):
+        """Pre-place a host batch in pinned memory (what a data-loader worker would hand over)."""
+        out = {}
+        for name, arr in (("xyz", xyz), ("features", features), ("labels", labels)):
+            t = torch.from_numpy(np.ascontiguousarray(arr))
+            out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        return out
+
+    # -- steps -----------------------------------------------------------------------------------
+    def train_step_device(self, xyz, features, labels, dropout_mask=None):
+        """One optimisation step on device-resident inputs: xyz [B,N,3] f32, features [B,N,F-3] f32, labels [B,N]."""
+        net = self.net
+        pyr = build_pyramid(xyz, self.cfg)                         # tf_map on the GPU
+        inputs = dict(pyr, features=torch.cat([xyz, features], dim=-1))  # runPancreas.py:125
+        self.flat_grad.zero_()
+        logits = net.inference(inputs, True, dropout_mask)
+        loss = net.get_loss(logits, labels)
+        loss.backward()
+        if self.world_size > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)  # gradients only, NCCL over NVLink
+        self.opt.step()
+        ops.clear_caches()
+        return loss.detach()
+
+    def train_step(self, xyz, features, labels):
+        """Public end-to-end step on HOST buffers (numpy or pinned CPU tensors); returns the loss as a float
+        (device -> host read)."""
+        x = self._stage("xyz", xyz)
+        f = self._stage("features", features)
+        l = self._stage("labels", labels)
+        return float(self.train_step_device(x, f, l).item())
+
+    @torch.no_grad()
+    def predict(self, xyz, features):
+        """Test-mode forward (moving BN statistics, no dropout) -> softmax probabilities [B,N,C] on the device
+        (testPancreas.py:133-134 ``prob_logits``)."""
+        x = self._stage("xyz", xyz)
+        f = self._stage("features", features)
+        pyr = build_pyramid(x, self.cfg)
+        logits = self.net.inference(dict(pyr, features=torch.cat([x, f], dim=-1)), False)
+        ops.clear_caches()
+        return torch.softmax(logits, dim=-1)
