@@ -119,6 +119,16 @@ PU_API int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long lon
 PU_API int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shift, const float *y2, int ldy2,
                          const float *scale2, const float *shift2, float slope, long long R, int C, float *out,
                          int ldo, pu_stream_t stream);
+/* Per-channel batch-norm coefficients, one launch each (tf.layers.batch_normalization, momentum 0.99, eps 1e-6):
+ *   forward : invstd = rsqrt(var+eps), scale = gamma*invstd, shift = beta - mean*scale, and (if moving_* given)
+ *             moving = momentum*moving + (1-momentum)*batch  (variance times `unbias`, n/(n-1) for TF's fused path);
+ *   backward: reduces the pu_bn_bwd_reduce partials and emits dgamma, dbeta and ka/kb/kc for pu_bn_bwd_apply. */
+PU_API int pu_bn_prepare(const float *mean, const float *var, const float *gamma, const float *beta, float eps, int C,
+                         float *invstd, float *scale, float *shift, float *moving_mean, float *moving_var,
+                         float momentum, float unbias, pu_stream_t stream);
+PU_API int pu_bn_bwd_coeffs(const float *part_dz, const float *part_dzy, int blocks, int C, const float *mean,
+                            const float *invstd, const float *gamma, long long rows, int training, float *dgamma,
+                            float *dbeta, float *ka, float *kb, float *kc, pu_stream_t stream);
 /* dz = dout * (out > 0 ? 1 : slope) */
 PU_API int pu_act_bwd(const float *dout, int ldd, const float *out, int ldo, float slope, long long R, int C,
                       float *dz, int ldz, pu_stream_t stream);

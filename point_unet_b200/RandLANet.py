@@ -168,18 +168,14 @@ class Network(torch.nn.Module):
 
     # -- layers (helper_tf_util.py) --------------------------------------------------------------
     def _bn_stats(self, scope, mean, var, count, is_training, fused_4d=True):
-        """Batch statistics in training (and the moving-average update, momentum 0.99, run with the step like
-        UPDATE_OPS at RandLANet.py:90,163); moving statistics at inference."""
+        """(mean, var, moving): batch statistics in training plus the moving-average buffers to update (momentum 0.99,
+        run with the step like UPDATE_OPS at RandLANet.py:90,163); moving statistics at inference."""
         mm, mv = self.stats[scope + "/bn/moving_mean"], self.stats[scope + "/bn/moving_variance"]
         if not is_training:
-            return mm, mv
-        if torch.is_grad_enabled():
-            with torch.no_grad():
-                # TF's fused kernel (4-D NHWC inputs) feeds the UNBIASED variance to the moving average
-                unbias = count / max(count - 1, 1) if fused_4d else 1.0
-                mm.mul_(ops.BN_MOMENTUM).add_(mean, alpha=1 - ops.BN_MOMENTUM)
-                mv.mul_(ops.BN_MOMENTUM).add_(var * unbias, alpha=1 - ops.BN_MOMENTUM)
-        return mean, var
+            return mm, mv, None
+        # TF's fused kernel (4-D NHWC inputs) feeds the UNBIASED variance to the moving average
+        unbias = count / max(count - 1, 1) if fused_4d else 1.0
+        return mean, var, ((mm, mv, unbias) if torch.is_grad_enabled() else None)
 
     def conv2d(self, x, scope, bn=True, is_training=True, activation=True, transpose=False, dense_names=False):
         """1x1 conv (+bias) [-> BN(0.99, 1e-6)] [-> LeakyReLU(0.2)]  (helper_tf_util.py:115-170 / :173-250)."""
@@ -198,9 +194,9 @@ class Network(torch.nn.Module):
         else:
             y = ops.linear(x, w, b)
             mean = var = None
-        mean, var = self._bn_stats(scope, mean, var, rows_n, is_training, fused_4d=not dense_names)
+        mean, var, moving = self._bn_stats(scope, mean, var, rows_n, is_training, fused_4d=not dense_names)
         return ops.bn_act(y, mean, var, self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta"),
-                          slope=ops.LEAKY_SLOPE if activation else 1.0, training=is_training)
+                          slope=ops.LEAKY_SLOPE if activation else 1.0, training=is_training, moving=moving)
 
     # -- LFA ops (RandLANet.py:337-401) ----------------------------------------------------------
     @staticmethod
@@ -246,11 +242,11 @@ class Network(torch.nn.Module):
                 y, mean, var = ops.linear(x, w, b, want_stats=True)
             else:
                 y, mean, var = ops.linear(x, w, b), None, None
-            mean, var = self._bn_stats(scope, mean, var, rows_n, is_training)
-            outs.append((y, mean, var, self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta")))
-        (y1, m1, v1, g1, b1), (y2, m2, v2, g2, b2) = outs
-        return ops.bn_act(y1, m1, v1, g1, b1, slope=ops.LEAKY_SLOPE, training=is_training,
-                          y2=y2, mean2=m2, var2=v2, gamma2=g2, beta2=b2)
+            mean, var, moving = self._bn_stats(scope, mean, var, rows_n, is_training)
+            outs.append((y, mean, var, self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta"), moving))
+        (y1, m1, v1, g1, b1, mv1), (y2, m2, v2, g2, b2, mv2) = outs
+        return ops.bn_act(y1, m1, v1, g1, b1, slope=ops.LEAKY_SLOPE, training=is_training, moving=mv1,
+                          y2=y2, mean2=m2, var2=v2, gamma2=g2, beta2=b2, moving2=mv2)
 
     def inference(self, inputs, is_training, dropout_mask=None):
         """RandLANet.py:110-152.  ``inputs``: dict(xyz, neigh_idx, sub_idx, interp_idx: lists of 5; features [B,N,F])."""

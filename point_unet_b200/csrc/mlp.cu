@@ -466,6 +466,151 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// narrow wgrad (K <= 16, N <= 32): HBM-bound.  Thread (row lane, y) owns rows r = lane, lane+RL, ... of the CTA's
+// chunk and the 4 output columns 4y..4y+3; it keeps a KP x 4 accumulator block in REGISTERS, so every x / dy
+// element is read once and costs one FMA -- no shared-memory traffic in the loop.  One block-level reduction per
+// CTA at the end, then the usual fixed-order reduction over CTAs.
+template <int KP>
+__global__ void __launch_bounds__(256) wgrad_narrow_kernel(const float *__restrict__ A, int lda,
+                                                           const float *__restrict__ G, int ldg, long long M, int K,
+                                                           int N, long long rows_per_chunk, float *__restrict__ part,
+                                                           float *__restrict__ db_part) {
+    __shared__ float s_red[8 * (KP + 1) * 8 * 4];  // [warp][(KP+1) rows of NY*4 columns]
+    int NY = 1;                               // column groups of 4, rounded up to a power of two (<= 8)
+    while (NY * 4 < N) NY <<= 1;
+    const int RL = 256 / NY;                  // row lanes per CTA
+    const int y = threadIdx.x % NY, rl = threadIdx.x / NY;
+    const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+    const long long r_end = min(M, r_begin + rows_per_chunk);
+    float acc[KP][4];
+#pragma unroll
+    for (int i = 0; i < KP; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool va4 = ((lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0) && ((K & 3) == 0);
+    const bool va2 = ((lda & 1) == 0) && ((((uintptr_t)A) & 7) == 0) && ((K & 1) == 0);
+    const bool vg4 = ((ldg & 3) == 0) && ((((uintptr_t)G) & 15) == 0) && (y * 4 + 3 < N);
+    {
+        for (long long r = r_begin + rl; r < r_end; r += RL) {
+            const float *a = A + (size_t)r * lda;
+            const float *g = G + (size_t)r * ldg + y * 4;
+            float av[KP], gv[4];
+            if (va4) {
+#pragma unroll
+                for (int i = 0; i < KP; i += 4) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < K) v = *reinterpret_cast<const float4 *>(a + i);
+                    av[i] = v.x; av[i + 1] = v.y; av[i + 2] = v.z; av[i + 3] = v.w;
+                }
+            } else if (va2) {
+#pragma unroll
+                for (int i = 0; i < KP; i += 2) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (i < K) v = *reinterpret_cast<const float2 *>(a + i);
+                    av[i] = v.x; av[i + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KP; ++i) av[i] = i < K ? a[i] : 0.f;
+            }
+            if (vg4) {
+                const float4 v = *reinterpret_cast<const float4 *>(g);
+                gv[0] = v.x; gv[1] = v.y; gv[2] = v.z; gv[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gv[j] = (y * 4 + j < N) ? g[j] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < KP; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dbacc[j] += gv[j];
+        }
+    }
+    // reduction over row lanes: butterfly over the lanes of a warp that share y, then 8 warps through shared memory
+    // (fixed order => deterministic)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (KP + 1) * NY * 4;  // floats per warp (acc rows + db row)
+    for (int o = NY; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < KP; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dbacc[j] += __shfl_xor_sync(0xffffffffu, dbacc[j], o);
+    }
+    if (lane < NY) {
+        float *o = s_red + (size_t)warp * per;
+#pragma unroll
+        for (int i = 0; i < KP; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[(i * NY + y) * 4 + j] = acc[i][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[(KP * NY + y) * 4 + j] = dbacc[j];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < per; e += 256) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_red[(size_t)w * per + e];
+        const int i = e / (NY * 4), col = e % (NY * 4);
+        if (col < N) {
+            if (i < K) part[(size_t)blockIdx.x * K * N + (size_t)i * N + col] = s;
+            else if (i == KP && db_part) db_part[(size_t)blockIdx.x * N + col] = s;
+        }
+    }
+}
+
+// per-channel batch-norm coefficients in one launch (replaces ~20 tiny elementwise launches per layer):
+//   forward : invstd, scale = gamma*invstd, shift = beta - mean*scale; optional moving-average update
+__global__ void bn_prepare_kernel(const float *__restrict__ mean, const float *__restrict__ var,
+                                  const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int C,
+                                  float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift,
+                                  float *__restrict__ moving_mean, float *__restrict__ moving_var, float momentum,
+                                  float unbias) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float is = rsqrtf(var[c] + eps);
+    const float sc = gamma[c] * is;
+    invstd[c] = is;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean[c] * sc;
+    if (moving_mean) {
+        moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * mean[c];
+        moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * var[c] * unbias;
+    }
+}
+//   backward: reduce the [blocks, C] partials (double), emit dgamma, dbeta and the apply coefficients ka, kb, kc
+__global__ void bn_bwd_coeffs_kernel(const float *__restrict__ part_dz, const float *__restrict__ part_dzy, int blocks,
+                                     int C, const float *__restrict__ mean, const float *__restrict__ invstd,
+                                     const float *__restrict__ gamma, double inv_rows, int training,
+                                     float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ ka,
+                                     float *__restrict__ kb, float *__restrict__ kc) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int t = lane; t < blocks; t += 32) { s += (double)part_dz[(size_t)t * C + warp]; q += (double)part_dzy[(size_t)t * C + warp]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+        const double m = mean[warp], is = invstd[warp], g = gamma[warp];
+        const double dzx = (q - m * s) * is;  // sum dz * xhat
+        dgamma[warp] = (float)dzx;
+        dbeta[warp] = (float)s;
+        if (training) {
+            const double a = g * is, c = -g * is * is * (dzx * inv_rows);
+            ka[warp] = (float)a;
+            kc[warp] = (float)c;
+            kb[warp] = (float)(-g * is * (s * inv_rows) - c * m);
+        } else {
+            ka[warp] = (float)(g * is); kb[warp] = 0.f; kc[warp] = 0.f;
+        }
+    }
+}
+
 static inline int ew_grid(long long total) {
     long long g = (total + 255) / 256;
     const long long cap = (long long)kNumSMs * 16;
@@ -548,7 +693,20 @@ int pu_att_pooling_bwd(const float *feature_set, int ldx, const float *w, const 
     return launch_gemm<EPI_ATT_BWD>(p, (cudaStream_t)stream);
 }
 
+static inline bool wgrad_is_narrow(int K, int N) { return K <= 16 && N <= 32; }
+
 static inline void wgrad_plan(long long M, int K, int N, int *chunks, long long *rows_per_chunk) {
+    if (wgrad_is_narrow(K, N)) {
+        long long want = (long long)kNumSMs * 8;
+        long long max_chunks = (M + 1023) / 1024;  // at least 1024 rows per CTA
+        if (want > max_chunks) want = max_chunks;
+        if (want < 1) want = 1;
+        long long rpc = (M + want - 1) / want;
+        *rows_per_chunk = rpc;
+        *chunks = (int)((M + rpc - 1) / rpc);
+        if (*chunks < 1) *chunks = 1;
+        return;
+    }
     const int tiles = ceil_div(K, WT) * ceil_div(N, WT);
     long long want = ((long long)kNumSMs * 8 + tiles - 1) / tiles;  // ~8 CTAs per SM in total
     long long max_chunks = (M + 255) / 256;                          // at least 256 rows per chunk
@@ -583,8 +741,15 @@ int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, in
     wgrad_plan(M, K, N, &chunks, &rpc);
     float *part = (float *)workspace;
     float *db_part = db ? part + (size_t)chunks * K * N : nullptr;
-    dim3 grid(ceil_div(K, WT), ceil_div(N, WT), chunks);
-    wgrad_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
+    if (wgrad_is_narrow(K, N)) {
+        if (K <= 8)
+            wgrad_narrow_kernel<8><<<chunks, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
+        else
+            wgrad_narrow_kernel<16><<<chunks, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
+    } else {
+        dim3 grid(ceil_div(K, WT), ceil_div(N, WT), chunks);
+        wgrad_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
+    }
     PU_LAUNCH_CHECK();
     reduce_chunks_kernel<<<ceil_div((long long)K * N, 256), 256, 0, st>>>(part, chunks, (long long)K * N, dw, accumulate);
     PU_LAUNCH_CHECK();
@@ -592,6 +757,29 @@ int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, in
         reduce_chunks_kernel<<<ceil_div(N, 256), 256, 0, st>>>(db_part, chunks, N, db, accumulate);
         PU_LAUNCH_CHECK();
     }
+    return PU_OK;
+}
+
+int pu_bn_prepare(const float *mean, const float *var, const float *gamma, const float *beta, float eps, int C,
+                  float *invstd, float *scale, float *shift, float *moving_mean, float *moving_var, float momentum,
+                  float unbias, pu_stream_t stream) {
+    if (!mean || !var || !gamma || !beta || !invstd || !scale || !shift || C < 1) return PU_ERR_INVALID_ARG;
+    if ((moving_mean == nullptr) != (moving_var == nullptr)) return PU_ERR_INVALID_ARG;
+    bn_prepare_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(mean, var, gamma, beta, eps, C, invstd, scale,
+                                                                         shift, moving_mean, moving_var, momentum, unbias);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_bn_bwd_coeffs(const float *part_dz, const float *part_dzy, int blocks, int C, const float *mean,
+                     const float *invstd, const float *gamma, long long rows, int training, float *dgamma, float *dbeta,
+                     float *ka, float *kb, float *kc, pu_stream_t stream) {
+    if (!part_dz || !part_dzy || !mean || !invstd || !gamma || !dgamma || !dbeta || !ka || !kb || !kc || blocks < 1 ||
+        C < 1 || rows < 1)
+        return PU_ERR_INVALID_ARG;
+    bn_bwd_coeffs_kernel<<<ceil_div((long long)C * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        part_dz, part_dzy, blocks, C, mean, invstd, gamma, 1.0 / (double)rows, training, dgamma, dbeta, ka, kb, kc);
+    PU_LAUNCH_CHECK();
     return PU_OK;
 }
 

@@ -43,6 +43,10 @@ _lib._OP_SIGS.update({
                          c_void_p],
     "pu_bn_bwd_apply": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                         c_ll, c_int, c_void_p, c_int, c_void_p],
+    "pu_bn_prepare": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                      c_void_p, c_float, c_float, c_void_p],
+    "pu_bn_bwd_coeffs": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_void_p],
     "pu_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p],
     "pu_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                            c_int, c_void_p],
@@ -399,19 +403,11 @@ def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training):
     st = _stream(y)
     _call("pu_bn_bwd_reduce", dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
                                   float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st)
-    sum_dz = p1.sum(0, dtype=torch.float64)
-    sum_dzy = p2.sum(0, dtype=torch.float64)
-    m64, i64, g64 = mean.double(), invstd.double(), gamma.double()
-    sum_dzxh = (sum_dzy - m64 * sum_dz) * i64          # sum dz * xhat
-    dgamma, dbeta = sum_dzxh.float(), sum_dz.float()
-    if training:
-        mdz, mdzx = sum_dz / R, sum_dzxh / R
-        ka = g64 * i64
-        kc = -g64 * i64 * i64 * mdzx
-        kb = -g64 * i64 * mdz - kc * m64
-    else:  # inference statistics are constants
-        ka, kb, kc = g64 * i64, torch.zeros_like(g64), torch.zeros_like(g64)
-    ka, kb, kc = ka.float().contiguous(), kb.float().contiguous(), kc.float().contiguous()
+    co = torch.empty((5, C), dtype=torch.float32, device=y.device)  # dgamma, dbeta, ka, kb, kc
+    dgamma, dbeta, ka, kb, kc = co[0], co[1], co[2], co[3], co[4]
+    _call("pu_bn_bwd_coeffs", p1.data_ptr(), p2.data_ptr(), blocks, C, mean.data_ptr(), invstd.data_ptr(),
+          gamma.data_ptr(), R, int(bool(training)), dgamma.data_ptr(), dbeta.data_ptr(), ka.data_ptr(), kb.data_ptr(),
+          kc.data_ptr(), st)
     dy = torch.empty(y.shape, dtype=torch.float32, device=y.device)
     _call("pu_bn_bwd_apply", dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(), float(slope),
                                  ka.data_ptr(), kb.data_ptr(), kc.data_ptr(), R, C, dy.data_ptr(), C, st)
@@ -422,15 +418,11 @@ class _BNActFn(torch.autograd.Function):
     """out = leaky_relu_slope(BN(y) [+ BN2(y2)]) with batch statistics given as (mean, var) of y (and y2)."""
 
     @staticmethod
-    def forward(ctx, y, mean, var, gamma, beta, slope, training, y2, mean2, var2, gamma2, beta2):
-        invstd = torch.rsqrt(var + BN_EPS)
-        scale = (gamma * invstd).contiguous()
-        shift = (beta - mean * scale).contiguous()
+    def forward(ctx, y, mean, var, gamma, beta, slope, training, moving, y2, mean2, var2, gamma2, beta2, moving2):
+        invstd, scale, shift = bn_prepare(mean, var, gamma, beta, moving if training else None)
         two = y2 is not None
         if two:
-            invstd2 = torch.rsqrt(var2 + BN_EPS)
-            scale2 = (gamma2 * invstd2).contiguous()
-            shift2 = (beta2 - mean2 * scale2).contiguous()
+            invstd2, scale2, shift2 = bn_prepare(mean2, var2, gamma2, beta2, moving2 if training else None)
             res = _bn_act_fwd_raw(y, scale, shift, slope, y2=y2, scale2=scale2, shift2=shift2)
             ctx.save_for_backward(y, scale, shift, gamma, mean, invstd, y2, scale2, shift2, gamma2, mean2, invstd2, res)
         else:
@@ -445,7 +437,7 @@ class _BNActFn(torch.autograd.Function):
         if not ctx.two:
             y, scale, shift, gamma, mean, invstd = ctx.saved_tensors
             dy, dg, db = _bn_bwd_raw(dout, y, scale, shift, ctx.slope, gamma, mean, invstd, ctx.training)
-            return (dy, None, None, dg, db, None, None) + none5
+            return (dy, None, None, dg, db, None, None, None) + none5 + (None,)
         y, scale, shift, gamma, mean, invstd, y2, scale2, shift2, gamma2, mean2, invstd2, res = ctx.saved_tensors
         # through the activation first (sign of the output), then each BN branch without activation
         dr, R, C, ldd = rows(dout)
@@ -455,15 +447,31 @@ class _BNActFn(torch.autograd.Function):
                                    _stream(res))
         dy, dg, db = _bn_bwd_raw(dz, y, scale, shift, 1.0, gamma, mean, invstd, ctx.training)
         dy2, dg2, db2 = _bn_bwd_raw(dz, y2, scale2, shift2, 1.0, gamma2, mean2, invstd2, ctx.training)
-        return dy, None, None, dg, db, None, None, dy2, None, None, dg2, db2
+        return dy, None, None, dg, db, None, None, None, dy2, None, None, dg2, db2, None
 
 
-def bn_act(y, mean, var, gamma, beta, slope=LEAKY_SLOPE, training=True,
-           y2=None, mean2=None, var2=None, gamma2=None, beta2=None):
+def bn_prepare(mean, var, gamma, beta, moving=None):
+    """invstd / scale / shift per channel in one launch; ``moving = (moving_mean, moving_var, unbias)`` also applies
+    the momentum-0.99 moving-average update in place (the reference runs it with the step, RandLANet.py:90,163)."""
+    C = mean.numel()
+    buf = torch.empty((3, C), dtype=torch.float32, device=mean.device)
+    mm = mv = None
+    unbias = 1.0
+    if moving is not None:
+        mm, mv, unbias = moving
+    _call("pu_bn_prepare", mean.data_ptr(), var.data_ptr(), gamma.data_ptr(), beta.data_ptr(), BN_EPS, C,
+          buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), mm.data_ptr() if mm is not None else None,
+          mv.data_ptr() if mv is not None else None, BN_MOMENTUM, float(unbias), _stream(mean))
+    return buf[0], buf[1], buf[2]
+
+
+def bn_act(y, mean, var, gamma, beta, slope=LEAKY_SLOPE, training=True, moving=None,
+           y2=None, mean2=None, var2=None, gamma2=None, beta2=None, moving2=None):
     """``leaky_relu_slope(BN(y) [+ BN2(y2)])`` with the given per-channel statistics (batch stats in training,
-    moving stats at inference); ``slope=1`` means no activation (helper_tf_util.py:166-169)."""
+    moving stats at inference); ``slope=1`` means no activation (helper_tf_util.py:166-169).  ``moving`` =
+    ``(moving_mean, moving_var, unbias)`` is updated in place in training mode."""
     _need_cuda(y)
-    return _BNActFn.apply(y, mean, var, gamma, beta, slope, training, y2, mean2, var2, gamma2, beta2)
+    return _BNActFn.apply(y, mean, var, gamma, beta, slope, training, moving, y2, mean2, var2, gamma2, beta2, moving2)
 
 
 # ---------------------------------------------------------------------------------------------
