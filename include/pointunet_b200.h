@@ -98,6 +98,16 @@ PU_API int pu_random_sample_bwd(const float *feat, int ld_f, const float *out, i
                                 const float *g_out, int ld_g, const int32_t *offsets, const int32_t *perm,
                                 long long n_targets, int K, float *g_feat, int ld_gf, int d, pu_stream_t stream);
 
+/* ref: point2prod  PointSegment/testPancreas.py:71-85, testBraTS.py:83-101 (test-mode fusion of per-point
+ *   probabilities into a dense volume).  probs [n,C] f32, xyz_origin int32 [*,3] = (x,y,z) voxel coordinates,
+ *   point_idx (optional int32 [n]: row of xyz_origin for point i -- the BraTS `test_probs[p_idx] = probs` step,
+ *   testBraTS.py:226-231) -> volume f32 [Z,Y,X,C], i.e. `volume[z][x][y] = prob[i]` followed by
+ *   np.moveaxis(volume, 1, 2); untouched voxels are 0; if several points hit one voxel the last one wins, as in
+ *   the reference's sequential loop.  Out-of-range coordinates are skipped. */
+PU_API size_t pu_point2prod_workspace_bytes(int Z, int X, int Y);
+PU_API int pu_point2prod(const float *probs, const int32_t *xyz_origin, const int32_t *point_idx, int n, int C, int Z,
+                         int X, int Y, float *volume, void *workspace, size_t workspace_bytes, pu_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Shared MLP = 1x1 convolution over channels-last rows.
  * ref: helper_tf_util.conv2d  PointSegment/helper_tf_util.py:115-170 ; conv2d_transpose :173-250 ;

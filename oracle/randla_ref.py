@@ -25,6 +25,7 @@ What follows what (paths relative to /root/reference/PointSegment):
                           in training, moving statistics at inference
   dropout                 helper_tf_util.py:553-574   (keep 0.5, inverted scaling; the mask is INJECTED)
   tf_map (index pyramid)  runPancreas.py:124-145
+  point2prod              testPancreas.py:71-85, testBraTS.py:83-101 (+ the p_idx expansion testBraTS.py:226-231)
 """
 from __future__ import annotations
 
@@ -200,3 +201,19 @@ def tf_map(xyz, cfg, knn):
         out["interp_idx"].append(up_i)
         xyz = np.ascontiguousarray(sub_points)
     return out
+
+
+def point2prod(list_point_prod, list_xyz, volume_shape, point_idx=None):
+    """testPancreas.py:71-85: the per-point Python loop, verbatim semantics (later points overwrite earlier ones),
+    followed by np.moveaxis(volume, 1, 2).  ``point_idx`` restates testBraTS.py:226-231 (``test_probs[p_idx] = probs``
+    into a zero array over all brain points, then the loop over ALL of them)."""
+    list_point_prod = np.asarray(list_point_prod)
+    list_xyz = np.asarray(list_xyz)
+    if point_idx is not None:
+        test_probs = np.zeros((list_xyz.shape[0], list_point_prod.shape[1]), dtype=np.float32)
+        test_probs[np.asarray(point_idx)] = list_point_prod
+        list_point_prod = test_probs
+    volume = np.zeros(volume_shape)
+    for i in range(len(list_point_prod)):
+        volume[list_xyz[i][2]][list_xyz[i][0]][list_xyz[i][1]] = list_point_prod[i]
+    return np.moveaxis(volume, 1, 2)

@@ -204,6 +204,34 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// point2prod (PointSegment/testPancreas.py:71-85, testBraTS.py:83-101): scatter per-point class probabilities into
+// a dense volume.  The reference loops `volume[z][x][y] = prob[i]` on the host and then moves axis 1 <-> 2; here the
+// result is written directly in the final [Z, Y, X, C] layout.  Sequential semantics (the LAST point writing a voxel
+// wins) are kept deterministically: pass 1 records the highest point index per voxel, pass 2 lets only that point write.
+__global__ void __launch_bounds__(256) p2v_owner_kernel(const int32_t *__restrict__ xyz_origin,
+                                                        const int32_t *__restrict__ point_idx, int n, int Z, int X, int Y,
+                                                        int32_t *__restrict__ owner) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t *o = xyz_origin + (size_t)(point_idx ? point_idx[i] : i) * 3;
+    const int x = o[0], y = o[1], z = o[2];
+    if ((unsigned)x >= (unsigned)X || (unsigned)y >= (unsigned)Y || (unsigned)z >= (unsigned)Z) return;
+    atomicMax(&owner[((size_t)z * Y + y) * X + x], i);
+}
+__global__ void __launch_bounds__(256) p2v_write_kernel(const float *__restrict__ probs, const int32_t *__restrict__ xyz_origin,
+                                                        const int32_t *__restrict__ point_idx, int n, int C, int Z, int X,
+                                                        int Y, const int32_t *__restrict__ owner, float *__restrict__ vol) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t *o = xyz_origin + (size_t)(point_idx ? point_idx[i] : i) * 3;
+    const int x = o[0], y = o[1], z = o[2];
+    if ((unsigned)x >= (unsigned)X || (unsigned)y >= (unsigned)Y || (unsigned)z >= (unsigned)Z) return;
+    const size_t v = ((size_t)z * Y + y) * X + x;
+    if (owner[v] != i) return;
+    for (int c = 0; c < C; ++c) vol[v * C + c] = probs[(size_t)i * C + c];
+}
+
 static inline int grid_for(long long total, int block = 256) {
     long long g = (total + block - 1) / block;
     const long long cap = (long long)kNumSMs * 32;  // grid-stride loops; cap at 32 CTAs per SM
@@ -336,6 +364,28 @@ int pu_random_sample_bwd(const float *feat, int ld_f, const float *out, int ld_o
         maxpool_bwd_kernel<1><<<grid_for(n_targets * d), 256, 0, st>>>(feat, ld_f, out, ld_o, ties, g_out, ld_g, offsets,
                                                                      perm, n_targets, K, g_feat, ld_gf, d);
     }
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+size_t pu_point2prod_workspace_bytes(int Z, int X, int Y) {
+    if (Z <= 0 || X <= 0 || Y <= 0) return 0;
+    return (size_t)Z * X * Y * sizeof(int32_t);
+}
+
+int pu_point2prod(const float *probs, const int32_t *xyz_origin, const int32_t *point_idx, int n, int C, int Z, int X,
+                  int Y, float *volume, void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    if (!probs || !xyz_origin || !volume || n < 0 || C < 1 || Z < 1 || X < 1 || Y < 1) return PU_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < pu_point2prod_workspace_bytes(Z, X, Y)) return PU_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nvox = (size_t)Z * X * Y;
+    PU_CUDA_TRY(cudaMemsetAsync(workspace, 0xFF, nvox * sizeof(int32_t), st));  // owner = -1
+    PU_CUDA_TRY(cudaMemsetAsync(volume, 0, nvox * C * sizeof(float), st));      // np.zeros(volume_shape)
+    if (n == 0) return PU_OK;
+    p2v_owner_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyz_origin, point_idx, n, Z, X, Y, (int32_t *)workspace);
+    PU_LAUNCH_CHECK();
+    p2v_write_kernel<<<ceil_div(n, 256), 256, 0, st>>>(probs, xyz_origin, point_idx, n, C, Z, X, Y,
+                                                       (const int32_t *)workspace, volume);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

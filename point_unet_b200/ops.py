@@ -47,6 +47,8 @@ _lib._OP_SIGS.update({
                       c_void_p, c_float, c_float, c_void_p],
     "pu_bn_bwd_coeffs": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p],
+    "pu_point2prod": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                      c_void_p],
     "pu_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p],
     "pu_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                            c_int, c_void_p],
@@ -65,6 +67,8 @@ def _L():
         L.pu_inverse_workspace_bytes.argtypes = [c_int, c_ll]
         L.pu_wgrad_workspace_bytes.restype = c_size_t
         L.pu_wgrad_workspace_bytes.argtypes = [c_ll, c_int, c_int]
+        L.pu_point2prod_workspace_bytes.restype = c_size_t
+        L.pu_point2prod_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.pu_linear_row_tiles.argtypes = [c_ll, c_int]
         L.pu_bn_bwd_reduce_blocks.argtypes = [c_ll, c_int]
         L._pu_extra_declared = True
@@ -508,3 +512,22 @@ def att_pool(feature_set: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """Fused FC + softmax over K + weighted sum: ``[B,N,K,d]`` x ``[d,d]`` -> ``[B,N,1,d]``."""
     _need_cuda(feature_set, w)
     return _AttPoolFn.apply(feature_set, w)
+
+
+# ---------------------------------------------------------------------------------------------
+def point2prod(probs: torch.Tensor, xyz_origin: torch.Tensor, volume_shape, point_idx: torch.Tensor | None = None):
+    """testPancreas.py:71-85 / testBraTS.py:83-101 on the device: ``probs [n,C]`` scattered through integer voxel
+    coordinates ``xyz_origin [*,3] = (x,y,z)`` into a dense fp32 volume.  ``volume_shape = (Z, X, Y, C)`` is the shape
+    the reference allocates; the result has the reference's final layout ``[Z, Y, X, C]`` (after its
+    ``np.moveaxis(volume, 1, 2)``).  ``point_idx`` maps point i to its row of ``xyz_origin`` (BraTS)."""
+    _need_cuda(probs, xyz_origin)
+    Z, X, Y, C = (int(v) for v in volume_shape)
+    probs = probs.contiguous().float()
+    assert probs.dim() == 2 and probs.shape[1] == C
+    xo = xyz_origin.to(torch.int32).contiguous()
+    pi = point_idx.to(torch.int32).contiguous() if point_idx is not None else None
+    vol = torch.empty((Z, Y, X, C), dtype=torch.float32, device=probs.device)
+    ws = workspace(_L().pu_point2prod_workspace_bytes(Z, X, Y), probs.device, slot=3)
+    _call("pu_point2prod", probs.data_ptr(), xo.data_ptr(), pi.data_ptr() if pi is not None else None, probs.shape[0], C,
+          Z, X, Y, vol.data_ptr(), ws.data_ptr(), ws.numel(), _stream(probs))
+    return vol

@@ -16,6 +16,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from .parallel import FlatGradBucket
 from .RandLANet import Network, build_pyramid
 
 
@@ -26,12 +27,8 @@ class Trainer:
         self.net = Network(config, num_features, seed=seed, device=self.device)
         self.params = [t for _, t in self.net.named_variables()]
         # one flat gradient buffer: every .grad is a view of it (a single all-reduce, no bucketing copies)
-        total = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.bucket = FlatGradBucket(self.params, self.device)
+        self.flat_grad = self.bucket.flat
         # tf.train.AdamOptimizer defaults (RandLANet.py:88): beta (0.9, 0.999), eps 1e-8
         self.opt = torch.optim.Adam(self.params, lr=lr if lr is not None else config.learning_rate, betas=(0.9, 0.999),
                                     eps=1e-8, fused=True)
@@ -74,7 +71,7 @@ class Trainer:
         loss = net.get_loss(logits, labels)
         loss.backward()
         if self.world_size > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)  # gradients only, NCCL over NVLink
+            self.bucket.all_reduce_mean()                          # gradients only, NCCL over NVLink
         self.opt.step()
         ops.clear_caches()
         return loss.detach()
@@ -97,3 +94,20 @@ class Trainer:
         logits = self.net.inference(dict(pyr, features=torch.cat([x, f], dim=-1)), False)
         ops.clear_caches()
         return torch.softmax(logits, dim=-1)
+
+    @torch.no_grad()
+    def predict_to_volume(self, xyz, features, xyz_origin, volume_shape, point_idx=None):
+        """Test-mode fusion (testPancreas.py:141-202 / testBraTS.py:155-232) for ONE cloud per batch row: softmax
+        probabilities scattered through the saved integer voxel coordinates into dense ``[Z,Y,X,C]`` volumes.
+        ``xyz_origin`` is ``[B, n, 3]`` (or a list), ``volume_shape = (Z, X, Y, C)`` as the reference allocates it."""
+        probs = self.predict(xyz, features)
+        vols = []
+        for b in range(probs.shape[0]):
+            xo = xyz_origin[b]
+            xo = torch.as_tensor(np.ascontiguousarray(xo)).to(self.device) if not torch.is_tensor(xo) else xo.to(self.device)
+            pi = None
+            if point_idx is not None:
+                pi = point_idx[b]
+                pi = torch.as_tensor(np.ascontiguousarray(pi)).to(self.device) if not torch.is_tensor(pi) else pi.to(self.device)
+            vols.append(ops.point2prod(probs[b], xo, volume_shape, pi))
+        return vols
