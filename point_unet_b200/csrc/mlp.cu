@@ -120,9 +120,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
 
     const int gn = n0 + tx * TN;
     if constexpr (EPI == EPI_STORE) {
-        float cs[TN], cq[TN];
+        float cs[TN];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+        for (int j = 0; j < TN; ++j) cs[j] = 0.f;
+        float (&vals)[TM][TN] = acc;  // the stored values overwrite the accumulators in place
         float bj[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) bj[j] = (p.bias && gn + j < p.N) ? p.bias[gn + j] : 0.f;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
             const long long gm = m0 + ty * TM + i;
             if (gm >= p.M) continue;
             float *c = p.C + (size_t)gm * p.ldc + gn;
-            float v[TN];
+            float (&v)[TN] = vals[i];
 #pragma unroll
             for (int j = 0; j < TN; ++j) v[j] = acc[i][j] + bj[j];
             if (vecC) {
@@ -150,21 +151,44 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
                     }
             }
 #pragma unroll
-            for (int j = 0; j < TN; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
+            for (int j = 0; j < TN; ++j) cs[j] += v[j];
         }
         if (p.stat_sum) {  // per-CTA column partials (fixed order => deterministic)
-            float *red = &As[0][0];  // TY x BN x 2 floats <= BK*LDA_S
-            static_assert(TY * BN * 2 <= BK * LDA_S, "reduction scratch");
+            // Robust batch statistics: each tile emits (sum, M2) with M2 = sum (v - tile_mean)^2 computed from the
+            // values still in registers; pu_stats_finalize merges tiles with Chan's parallel-variance formula in
+            // double.  (E[y^2] - E[y]^2 loses ~|mean|/sigma digits; this form does not.)
+            float *red = &As[0][0];  // TY x BN floats <= BK*LDA_S
+            static_assert(TY * BN <= BK * LDA_S, "reduction scratch");
+            __shared__ float s_mean[BN];
+            const long long rows_here = min((long long)BM, p.M - m0);
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                red[(ty * BN + tx * TN + j) * 2 + 0] = cs[j];
-                red[(ty * BN + tx * TN + j) * 2 + 1] = cq[j];
+            for (int j = 0; j < TN; ++j) red[ty * BN + tx * TN + j] = cs[j];
+            __syncthreads();
+            if (tid < BN) {
+                float s = 0.f;
+                for (int r = 0; r < TY; ++r) s += red[r * BN + tid];
+                s_mean[tid] = s / (float)rows_here;
+                if (n0 + tid < p.N) p.stat_sum[(size_t)blockIdx.x * p.N + n0 + tid] = s;
             }
             __syncthreads();
+            float m2[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) m2[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                if (m0 + ty * TM + i >= p.M) continue;
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    const float dlt = vals[i][j] - s_mean[tx * TN + j];
+                    m2[j] = fmaf(dlt, dlt, m2[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TN; ++j) red[ty * BN + tx * TN + j] = m2[j];
+            __syncthreads();
             if (tid < BN && n0 + tid < p.N) {
-                float s = 0.f, q = 0.f;
-                for (int r = 0; r < TY; ++r) { s += red[(r * BN + tid) * 2]; q += red[(r * BN + tid) * 2 + 1]; }
-                p.stat_sum[(size_t)blockIdx.x * p.N + n0 + tid] = s;
+                float q = 0.f;
+                for (int r = 0; r < TY; ++r) q += red[r * BN + tid];
                 p.stat_sq[(size_t)blockIdx.x * p.N + n0 + tid] = q;
             }
         }
@@ -338,26 +362,42 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float *__restr
     out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
-// mean/var (biased) per channel from per-tile partials, in double
-__global__ void __launch_bounds__(256) stats_finalize_kernel(const float *__restrict__ psum, const float *__restrict__ psq,
-                                                             int tiles, int C, double inv_count,
+// mean/var (biased) per channel from per-tile (sum, M2) partials: Chan et al. parallel merge, in double.
+// var = [ sum_t M2_t + sum_t n_t (mean_t - mean)^2 ] / n
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float *__restrict__ psum, const float *__restrict__ pm2,
+                                                             int tiles, int C, long long count, int rows_per_tile,
                                                              float *__restrict__ mean, float *__restrict__ var) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int t = lane; t < tiles; t += 32) { s += (double)psum[(size_t)t * C + warp]; q += (double)psq[(size_t)t * C + warp]; }
+    double s = 0.0;
+    for (int t = lane; t < tiles; t += 32) s += (double)psum[(size_t)t * C + warp];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double m = s / (double)count;
+    double q = 0.0;
+    for (int t = lane; t < tiles; t += 32) {
+        const long long r0 = (long long)t * rows_per_tile;
+        const double nt = (double)min((long long)rows_per_tile, count - r0);
+        const double mt = (double)psum[(size_t)t * C + warp] / nt;
+        q += (double)pm2[(size_t)t * C + warp] + nt * (mt - m) * (mt - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     if (lane == 0) {
-        const double m = s * inv_count;
-        double v = q * inv_count - m * m;
         mean[warp] = (float)m;
-        var[warp] = (float)(v > 0.0 ? v : 0.0);
+        var[warp] = (float)(q / (double)count);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // elementwise: out = lrelu_slope(y*scale[c] + shift[c] (+ y2*scale2[c] + shift2[c])) ; mask = optional dropout scale
+// NOTE on "shift": all batch-norm kernels below evaluate z = (y - mean[c]) * scale[c] + beta[c] (centered form, no
+// cancellation between y*scale and mean*scale); `shift` is a [2,C] array: row 0 = mean, row 1 = beta.
+__device__ __forceinline__ float4 bn_z(const float4 v, const float4 mu, const float4 sc, const float4 be) {
+    return make_float4(fmaf(v.x - mu.x, sc.x, be.x), fmaf(v.y - mu.y, sc.y, be.y), fmaf(v.z - mu.z, sc.z, be.z),
+                       fmaf(v.w - mu.w, sc.w, be.w));
+}
+
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict__ y, int ld_y, const float *__restrict__ scale,
                                                          const float *__restrict__ shift, const float *__restrict__ y2,
                                                          int ld_y2, const float *__restrict__ scale2,
@@ -370,13 +410,16 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict
         const long long r = t / cq;
         const int c = (int)(t - r * cq) * 4;
         const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
-        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), sh = *reinterpret_cast<const float4 *>(shift + c);
-        float z[4] = {fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)};
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), mu = *reinterpret_cast<const float4 *>(shift + c),
+                     be = *reinterpret_cast<const float4 *>(shift + C + c);
+        const float4 z1 = bn_z(v, mu, sc, be);
+        float z[4] = {z1.x, z1.y, z1.z, z1.w};
         if (y2) {
             const float4 w = *reinterpret_cast<const float4 *>(y2 + (size_t)r * ld_y2 + c);
-            const float4 s2 = *reinterpret_cast<const float4 *>(scale2 + c), h2 = *reinterpret_cast<const float4 *>(shift2 + c);
-            z[0] += fmaf(w.x, s2.x, h2.x); z[1] += fmaf(w.y, s2.y, h2.y);
-            z[2] += fmaf(w.z, s2.z, h2.z); z[3] += fmaf(w.w, s2.w, h2.w);
+            const float4 s2 = *reinterpret_cast<const float4 *>(scale2 + c), m2 = *reinterpret_cast<const float4 *>(shift2 + c),
+                         b2 = *reinterpret_cast<const float4 *>(shift2 + C + c);
+            const float4 z2 = bn_z(w, m2, s2, b2);
+            z[0] += z2.x; z[1] += z2.y; z[2] += z2.z; z[3] += z2.w;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * slope;
@@ -415,13 +458,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restr
     const int my_c = (threadIdx.x % cq) * 4, my_r = threadIdx.x / cq;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
     if (my_r < rpb) {
-        const float4 sc = *reinterpret_cast<const float4 *>(scale + my_c), sh = *reinterpret_cast<const float4 *>(shift + my_c);
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + my_c), mu = *reinterpret_cast<const float4 *>(shift + my_c),
+                     be = *reinterpret_cast<const float4 *>(shift + C + my_c);
         for (long long r = (long long)blockIdx.x * rpb + my_r; r < R; r += (long long)gridDim.x * rpb) {
             const float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + my_c);
             const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + my_c);
-            const float gz[4] = {fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : g.x * slope, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : g.y * slope,
-                                 fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : g.z * slope, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : g.w * slope};
-            const float yv[4] = {v.x, v.y, v.z, v.w};
+            const float4 z = bn_z(v, mu, sc, be);
+            const float gz[4] = {z.x > 0.f ? g.x : g.x * slope, z.y > 0.f ? g.y : g.y * slope,
+                                 z.z > 0.f ? g.z : g.z * slope, z.w > 0.f ? g.w : g.w * slope};
+            const float yv[4] = {v.x - mu.x, v.y - mu.y, v.z - mu.z, v.w - mu.w};  // centered: sum dz*(y-mean)
 #pragma unroll
             for (int j = 0; j < 4; ++j) { s[j] += gz[j]; q[j] = fmaf(gz[j], yv[j], q[j]); }
         }
@@ -455,14 +500,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restri
         const int c = (int)(t - r * cq) * 4;
         const float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + c);
         const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
-        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), sh = *reinterpret_cast<const float4 *>(shift + c);
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), mu = *reinterpret_cast<const float4 *>(shift + c),
+                     be = *reinterpret_cast<const float4 *>(shift + C + c);
         const float4 a = *reinterpret_cast<const float4 *>(ka + c), b = *reinterpret_cast<const float4 *>(kb + c),
                      cc = *reinterpret_cast<const float4 *>(kc + c);
-        const float gz[4] = {fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : g.x * slope, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : g.y * slope,
-                             fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : g.z * slope, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : g.w * slope};
+        const float4 z = bn_z(v, mu, sc, be);
+        const float gz[4] = {z.x > 0.f ? g.x : g.x * slope, z.y > 0.f ? g.y : g.y * slope,
+                             z.z > 0.f ? g.z : g.z * slope, z.w > 0.f ? g.w : g.w * slope};
+        // dy = ka*dz + kb + kc*(y - mean)
         *reinterpret_cast<float4 *>(dy + (size_t)r * ld_dy + c) =
-            make_float4(fmaf(a.x, gz[0], fmaf(cc.x, v.x, b.x)), fmaf(a.y, gz[1], fmaf(cc.y, v.y, b.y)),
-                        fmaf(a.z, gz[2], fmaf(cc.z, v.z, b.z)), fmaf(a.w, gz[3], fmaf(cc.w, v.w, b.w)));
+            make_float4(fmaf(a.x, gz[0], fmaf(cc.x, v.x - mu.x, b.x)), fmaf(a.y, gz[1], fmaf(cc.y, v.y - mu.y, b.y)),
+                        fmaf(a.z, gz[2], fmaf(cc.z, v.z - mu.z, b.z)), fmaf(a.w, gz[3], fmaf(cc.w, v.w - mu.w, b.w)));
     }
 }
 
@@ -577,7 +625,8 @@ __global__ void bn_prepare_kernel(const float *__restrict__ mean, const float *_
     const float sc = gamma[c] * is;
     invstd[c] = is;
     scale[c] = sc;
-    shift[c] = beta[c] - mean[c] * sc;
+    shift[c] = mean[c];       // row 0: mean
+    shift[C + c] = beta[c];   // row 1: beta   (z = (y - mean) * scale + beta)
     if (moving_mean) {
         moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * mean[c];
         moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * var[c] * unbias;
@@ -596,15 +645,15 @@ __global__ void bn_bwd_coeffs_kernel(const float *__restrict__ part_dz, const fl
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
     if (lane == 0) {
-        const double m = mean[warp], is = invstd[warp], g = gamma[warp];
-        const double dzx = (q - m * s) * is;  // sum dz * xhat
+        const double is = invstd[warp], g = gamma[warp];
+        const double dzx = q * is;  // sum dz * xhat   (q = sum dz * (y - mean), already centered)
         dgamma[warp] = (float)dzx;
         dbeta[warp] = (float)s;
         if (training) {
             const double a = g * is, c = -g * is * is * (dzx * inv_rows);
             ka[warp] = (float)a;
             kc[warp] = (float)c;
-            kb[warp] = (float)(-g * is * (s * inv_rows) - c * m);
+            kb[warp] = (float)(-g * is * (s * inv_rows));  // applied as ka*dz + kb + kc*(y - mean)
         } else {
             ka[warp] = (float)(g * is); kb[warp] = 0.f; kc[warp] = 0.f;
         }
@@ -655,8 +704,10 @@ int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float 
 int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int C, long long count, float *mean,
                       float *var, pu_stream_t stream) {
     if (!stat_sum || !stat_sq || !mean || !var || tiles < 1 || C < 1 || count < 1) return PU_ERR_INVALID_ARG;
+    const int rows_per_tile = C <= 16 ? 256 : 128;  // must match launch_gemm's tile choice
+    if ((long long)tiles != (count + rows_per_tile - 1) / rows_per_tile) return PU_ERR_INVALID_ARG;
     stats_finalize_kernel<<<ceil_div((long long)C * 32, 256), 256, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
-                                                                                          1.0 / (double)count, mean, var);
+                                                                                          count, rows_per_tile, mean, var);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

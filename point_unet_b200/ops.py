@@ -458,7 +458,7 @@ def bn_prepare(mean, var, gamma, beta, moving=None):
     """invstd / scale / shift per channel in one launch; ``moving = (moving_mean, moving_var, unbias)`` also applies
     the momentum-0.99 moving-average update in place (the reference runs it with the step, RandLANet.py:90,163)."""
     C = mean.numel()
-    buf = torch.empty((3, C), dtype=torch.float32, device=mean.device)
+    buf = torch.empty((4, C), dtype=torch.float32, device=mean.device)  # invstd, scale, [mean; beta]
     mm = mv = None
     unbias = 1.0
     if moving is not None:
@@ -466,7 +466,7 @@ def bn_prepare(mean, var, gamma, beta, moving=None):
     _call("pu_bn_prepare", mean.data_ptr(), var.data_ptr(), gamma.data_ptr(), beta.data_ptr(), BN_EPS, C,
           buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), mm.data_ptr() if mm is not None else None,
           mv.data_ptr() if mv is not None else None, BN_MOMENTUM, float(unbias), _stream(mean))
-    return buf[0], buf[1], buf[2]
+    return buf[0], buf[1], buf[2:4]
 
 
 def bn_act(y, mean, var, gamma, beta, slope=LEAKY_SLOPE, training=True, moving=None,
