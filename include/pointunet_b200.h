@@ -120,6 +120,14 @@ PU_API int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const
                          pu_stream_t stream);
 PU_API int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int C, long long count,
                              float *mean, float *var, pu_stream_t stream);
+/* Tensor-core (tcgen05 + TMEM) form of pu_linear_fwd for K >= 32, N >= 32: y[M,N] (+)= x[M,K] wt[N,K]^T + bias, where
+ * wt is the TRANSPOSED weight (K-major).  mode 3 = 3xTF32 (hi/lo split, fp32-class accuracy -- the parity path),
+ * mode 1 = plain TF32.  stat_sum/stat_m2: per-128-row-tile batch-norm partials as in pu_linear_fwd.
+ * *error_flag (device int, optional) is set to 1 if an internal barrier wait timed out. */
+PU_API int pu_tc_linear_supported(long long M, int K, int N, int ldx, int ldwt, int ldy);
+PU_API int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const float *bias, float *y, int ldy,
+                            long long M, int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode,
+                            int *error_flag, pu_stream_t stream);
 /* dw[K,N] (+)= x^T dy ; db[N] (+)= column sums of dy (db may be NULL).  Deterministic. */
 PU_API size_t pu_wgrad_workspace_bytes(long long M, int K, int N);
 PU_API int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, int K, int N, float *dw,

@@ -1,0 +1,343 @@
+// tc_gemm.cu -- 5th-generation tensor-core (tcgen05 + TMEM) path for the wide contractions of PointSegment.
+//
+//   pu_tc_linear_fwd   y[M,N] (+)= x[M,K] wt[N,K]^T + bias      (1x1 conv / dense / dgrad at >= 32 channels)
+//
+// Precision.  The reference computes these GEMMs in fp32 and the parity bar is 1e-3 relative, so the default mode is
+// "3xTF32": every fp32 operand is split as a = hi + lo with hi = round-to-tf32(a), lo = a - hi (exact), and the
+// tensor core accumulates hi*hi + hi*lo + lo*hi in fp32 (TMEM).  The dropped lo*lo term is <= 2^-22 relative, i.e.
+// fp32-class accuracy at one third of the tf32 tensor rate -- still several times the CUDA-core fp32 peak.
+// mode 1 = plain TF32 (one MMA per k-step), for the stated reduced-precision tolerance.
+//
+// Kernel anatomy (one CTA = 128 threads = one 128 x BN output tile, BN <= 128):
+//   * operands are staged as K-major SWIZZLE_128B tiles (rows of 32 fp32 = 128 B; 16-byte chunk c of row r is stored at
+//     chunk c ^ (r % 8) inside its 1024-byte 8-row atom) -- the canonical UMMA layout (cute::UMMA::Layout_K_SW128_Atom).
+//     The split into hi/lo needs a pass through registers anyway, so the tiles are written with st.shared (coalesced
+//     128-bit global loads, conflict-free swizzled stores) and published to the async proxy with fence.proxy.async;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8 per instruction) straight from
+//     shared-memory descriptors; the accumulator (128 lanes x BN columns, fp32) lives in TMEM;
+//   * two stages: while the tensor core works on stage s, all threads load/split stage s^1; tcgen05.commit arrives on
+//     an mbarrier when the MMAs that read a stage have retired;
+//   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp instruction) -> registers -> shared tile -> coalesced
+//     128-bit stores, plus the per-tile batch-norm partials (sum, centred M2) in the same format as the CUDA-core path.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace pu {
+namespace tc {
+
+constexpr int BM = 128;  // UMMA_M (cta_group::1)
+constexpr int BK = 32;   // fp32 elements per 128-byte swizzle row
+constexpr int UMMA_K = 8;  // tf32: 32 bytes per instruction
+constexpr int MAX_BN = 128;
+constexpr int THREADS = 128;
+
+struct Params {
+    const float *A; int lda;    // [M,K]
+    const float *Bt; int ldb;   // [N,K]  (K-major, i.e. the transposed weight)
+    float *C; int ldc;          // [M,N]
+    const float *bias;
+    long long M; int N, K;
+    int accumulate;
+    float *stat_sum, *stat_m2;  // [row tiles, N] or null
+    int mode;                   // 3 = 3xTF32 (fp32-class), 1 = TF32
+    int *error_flag;            // set to 1 if an mbarrier wait timed out (never hangs the GPU)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// bounded spin: returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (int it = 0; it < (1 << 22); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows * 128 B)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_rn(float a) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+    return __uint_as_float(r);
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+// registers holding one thread's share of a k-block: ROWS x 8 chunks of 16 B spread over 128 threads
+template <int ROWS>
+struct TileRegs {
+    float4 v[ROWS / 16];
+};
+
+template <int ROWS>
+__device__ __forceinline__ void load_tile(TileRegs<ROWS> &t, const float *__restrict__ base, int ld, long long row0,
+                                          long long row_end, int k0, int K, int tid) {
+#pragma unroll
+    for (int i = 0; i < ROWS / 16; ++i) {
+        const int idx = tid + THREADS * i;
+        const int r = idx >> 3, c = idx & 7;
+        const long long gr = row0 + r;
+        const int gk = k0 + c * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < row_end && gk < K) {  // K % 4 == 0 is guaranteed by the host
+            v = *reinterpret_cast<const float4 *>(base + (size_t)gr * ld + gk);
+        }
+        t.v[i] = v;
+    }
+}
+template <int ROWS>
+__device__ __forceinline__ void store_tile(const TileRegs<ROWS> &t, char *hi, char *lo, int tid, bool split) {
+#pragma unroll
+    for (int i = 0; i < ROWS / 16; ++i) {
+        const int idx = tid + THREADS * i;
+        const int r = idx >> 3, c = idx & 7;
+        const uint32_t off = sw128(r, c);
+        const float4 v = t.v[i];
+        if (split) {
+            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+            *reinterpret_cast<float4 *>(hi + off) = h;
+            *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        } else {
+            *reinterpret_cast<float4 *>(hi + off) = v;  // the tensor core reads the top 19 bits
+        }
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS) tc_linear_kernel(const Params p) {
+    constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;            // power of two >= 32 (BN in {32, 64, 128})
+    extern __shared__ __align__(1024) char smem_raw[];
+    char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t mma_done[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_mean[BN];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const bool split = p.mode == 3;
+    const int nkb = (p.K + BK - 1) / BK;
+
+    if (tid == 0) {
+        mbar_init(&mma_done[0], 1);
+        mbar_init(&mma_done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t idesc = make_idesc(BN);
+
+    TileRegs<BM> ra;
+    TileRegs<BN> rb;
+    load_tile<BM>(ra, p.A, p.lda, m0, p.M, 0, p.K, tid);
+    load_tile<BN>(rb, p.Bt, p.ldb, n0, p.N, 0, p.K, tid);
+    bool ok = true;
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        char *stage = smem + (size_t)s * STAGE_BYTES;
+        char *a_hi = stage, *a_lo = stage + A_BYTES, *b_hi = stage + 2 * A_BYTES, *b_lo = stage + 2 * A_BYTES + B_BYTES;
+        if (kb >= 2) ok = mbar_wait(&mma_done[s], (uint32_t)(((kb >> 1) - 1) & 1)) && ok;  // stage s is free again
+        store_tile<BM>(ra, a_hi, a_lo, tid, split);
+        store_tile<BN>(rb, b_hi, b_lo, tid, split);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < BK / UMMA_K; ++j) {
+                const uint64_t dah = make_desc(smem_u32(a_hi) + j * 32), dbh = make_desc(smem_u32(b_hi) + j * 32);
+                umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                if (split) {
+                    const uint64_t dal = make_desc(smem_u32(a_lo) + j * 32), dbl = make_desc(smem_u32(b_lo) + j * 32);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                }
+            }
+            umma_commit(&mma_done[s]);  // implies tcgen05.fence::before_thread_sync
+        }
+        if (kb + 1 < nkb) {  // prefetch the next k-block into registers while the tensor core runs
+            load_tile<BM>(ra, p.A, p.lda, m0, p.M, (kb + 1) * BK, p.K, tid);
+            load_tile<BN>(rb, p.Bt, p.ldb, n0, p.N, (kb + 1) * BK, p.K, tid);
+        }
+    }
+    // all MMAs retired: the last commit of each stage covers everything issued before it
+    {
+        const int last = nkb - 1;
+        ok = mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1)) && ok;
+        if (nkb >= 2) ok = mbar_wait(&mma_done[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1)) && ok;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok && p.error_flag) *p.error_flag = 1;
+
+    // ---- epilogue: TMEM -> registers -> shared tile [BM][BN + 4]
+    constexpr int LDT = BN + 4;
+    float *tile = reinterpret_cast<float *>(smem);  // stage buffers are free now
+    static_assert((size_t)BM * LDT * 4 <= (size_t)2 * STAGE_BYTES, "epilogue tile fits in the stage buffers");
+    {
+        const int row = warp * 32 + lane;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int q = 0; q < 16; q += 4)
+                *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + q]) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+    // bias / accumulate / coalesced store; the stored value also goes back into the tile for the statistics
+    const long long rows_here = min((long long)BM, p.M - m0);
+    const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+    for (int idx = tid; idx < BM * (BN / 4); idx += THREADS) {
+        const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
+        if (r >= rows_here) continue;
+        const int gn = n0 + c;
+        float4 v = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
+        float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
+        if (gn + 3 < p.N && vecC) {
+            if (p.bias) {
+                const float4 b = *reinterpret_cast<const float4 *>(p.bias + gn);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (p.accumulate) {
+                const float4 o = *reinterpret_cast<const float4 *>(cptr);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *reinterpret_cast<float4 *>(cptr) = v;
+        } else {
+            float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (gn + j < p.N) {
+                    if (p.bias) vv[j] += p.bias[gn + j];
+                    if (p.accumulate) vv[j] += cptr[j];
+                    cptr[j] = vv[j];
+                }
+            v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        }
+        *reinterpret_cast<float4 *>(&tile[r * LDT + c]) = v;
+    }
+    if (p.stat_sum) {  // per-tile (sum, centred M2) per column, merged by pu_stats_finalize (rows_per_tile = 128)
+        __syncthreads();
+        if (tid < BN) {
+            float s = 0.f;
+            for (int r = 0; r < rows_here; ++r) s += tile[r * LDT + tid];
+            s_mean[tid] = s / (float)rows_here;
+            float q = 0.f;
+            const float mu = s_mean[tid];
+            for (int r = 0; r < rows_here; ++r) {
+                const float d = tile[r * LDT + tid] - mu;
+                q = fmaf(d, d, q);
+            }
+            if (n0 + tid < p.N) {
+                p.stat_sum[(size_t)blockIdx.x * p.N + n0 + tid] = s;
+                p.stat_m2[(size_t)blockIdx.x * p.N + n0 + tid] = q;
+            }
+        }
+    }
+}
+
+template <int BN>
+static int launch(const Params &p, cudaStream_t st) {
+    constexpr size_t smem = 2 * (2 * BM * 128 + 2 * (size_t)BN * 128) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        PU_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN));
+    tc_linear_kernel<BN><<<grid, THREADS, smem, st>>>(p);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+}  // namespace tc
+}  // namespace pu
+
+using namespace pu;
+
+extern "C" {
+
+/* 1 if (M,K,N, strides) can run on the tensor-core path */
+int pu_tc_linear_supported(long long M, int K, int N, int ldx, int ldwt, int ldy) {
+    return M > 0 && K >= 32 && N >= 32 && (K & 3) == 0 && (ldx & 3) == 0 && (ldwt & 3) == 0 && (ldy >= N) && (N & 3) == 0;
+}
+
+int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const float *bias, float *y, int ldy, long long M,
+                     int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode, int *error_flag,
+                     pu_stream_t stream) {
+    if (!x || !wt || !y || M < 0 || K < 1 || N < 1 || ldx < K || ldwt < K || ldy < N) return PU_ERR_INVALID_ARG;
+    if ((stat_sum == nullptr) != (stat_m2 == nullptr)) return PU_ERR_INVALID_ARG;
+    if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
+    if (M == 0) return PU_OK;
+    if (!pu_tc_linear_supported(M, K, N, ldx, ldwt, ldy) || ((((uintptr_t)x) | ((uintptr_t)wt)) & 15)) return PU_ERR_UNSUPPORTED;
+    tc::Params p{};
+    p.A = x; p.lda = ldx; p.Bt = wt; p.ldb = ldwt; p.C = y; p.ldc = ldy; p.bias = bias;
+    p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.stat_sum = stat_sum; p.stat_m2 = stat_m2; p.mode = mode;
+    p.error_flag = error_flag;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 32) return tc::launch<32>(p, st);
+    if (N <= 64) return tc::launch<64>(p, st);
+    return tc::launch<128>(p, st);
+}
+
+}  // extern "C"

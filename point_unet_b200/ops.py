@@ -33,6 +33,8 @@ _lib._OP_SIGS.update({
                              c_int, c_void_p, c_int, c_int, c_void_p],
     "pu_linear_fwd": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
                       c_void_p, c_void_p],
+    "pu_tc_linear_fwd": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
+                         c_void_p, c_int, c_void_p, c_void_p],
     "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "pu_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                  c_void_p],
@@ -54,6 +56,13 @@ _lib._OP_SIGS.update({
                            c_int, c_void_p],
 })
 
+import os as _os
+
+# Tensor-core policy for the wide contractions (K, N >= 32): 3 = 3xTF32 on tcgen05 (fp32-class accuracy, default),
+# 1 = plain TF32 (stated reduced-precision tolerance), 0 = CUDA-core fp32 tiles only.
+TC_MODE = int(_os.environ.get("PU_TC_MODE", "3"))
+_tc_error_flag = {}
+
 LEAKY_SLOPE = 0.2  # helper_tf_util.py:169 (alpha is always 0.2, whatever activation_fn was passed)
 BN_EPS = 1e-6      # helper_tf_util.py:167
 BN_MOMENTUM = 0.99
@@ -69,6 +78,7 @@ def _L():
         L.pu_wgrad_workspace_bytes.argtypes = [c_ll, c_int, c_int]
         L.pu_point2prod_workspace_bytes.restype = c_size_t
         L.pu_point2prod_workspace_bytes.argtypes = [c_int, c_int, c_int]
+        L.pu_tc_linear_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
         L.pu_linear_row_tiles.argtypes = [c_ll, c_int]
         L.pu_bn_bwd_reduce_blocks.argtypes = [c_ll, c_int]
         L._pu_extra_declared = True
@@ -302,31 +312,54 @@ def random_sample(feature: torch.Tensor, pool_idx: torch.Tensor) -> torch.Tensor
 
 
 # ---------------------------------------------------------------------------------------------
-def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False):
-    """y = x w (+ bias) over rows; optionally the batch-norm mean / biased variance of y. (no autograd)"""
+def tc_error_flag(device) -> torch.Tensor:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _tc_error_flag:
+        _tc_error_flag[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _tc_error_flag[key]
+
+
+def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt=None, tc_mode=None):
+    """y = x w (+ bias) over rows; optionally the batch-norm mean / biased variance of y. (no autograd)
+    ``w`` is [K,N]; ``wt`` (optional) is the same weight stored transposed [N,K] -- the tensor-core path wants the
+    K-major form and transposes on the fly (a few hundred KB at most) when only ``w`` is given."""
     xr, M, K, ldx = rows(x)
-    assert w.dim() == 2 and w.shape[0] == K and w.is_contiguous()
-    N = w.shape[1]
+    if w is not None:
+        assert w.dim() == 2 and w.shape[0] == K and w.is_contiguous()
+        N = w.shape[1]
+    else:
+        assert wt.dim() == 2 and wt.shape[1] == K and wt.is_contiguous()
+        N = wt.shape[0]
     if out is None:
         out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
     o, Mo, No, ldo = rows(out)
     assert o.data_ptr() == out.data_ptr() and Mo == M and No == N
     L = _L()
+    mode = TC_MODE if tc_mode is None else tc_mode
+    use_tc = mode in (1, 3) and M >= 128 and L.pu_tc_linear_supported(M, K, N, ldx, K, ldo) and xr.data_ptr() % 16 == 0
     ssum = ssq = None
     if want_stats:
-        tiles = L.pu_linear_row_tiles(M, N)
+        tiles = (M + 127) // 128 if use_tc else L.pu_linear_row_tiles(M, N)
         ssum = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
         ssq = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
-    _call("pu_linear_fwd", xr.data_ptr(), ldx, w.data_ptr(), N, bias.data_ptr() if bias is not None else None,
-                               o.data_ptr(), ldo, M, K, N, int(accumulate),
-                               ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None,
-                               _stream(x))
+    bptr = bias.data_ptr() if bias is not None else None
+    if use_tc:
+        if wt is None:
+            wt = w.t().contiguous()
+        _call("pu_tc_linear_fwd", xr.data_ptr(), ldx, wt.data_ptr(), K, bptr, o.data_ptr(), ldo, M, K, N, int(accumulate),
+              ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, mode,
+              tc_error_flag(x.device).data_ptr(), _stream(x), tag=(M, K, N))
+    else:
+        if w is None:
+            w = wt.t().contiguous()
+        _call("pu_linear_fwd", xr.data_ptr(), ldx, w.data_ptr(), N, bptr, o.data_ptr(), ldo, M, K, N, int(accumulate),
+              ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, _stream(x), tag=(M, K, N))
     if not want_stats:
         return out
     mean = torch.empty(N, dtype=torch.float32, device=x.device)
     var = torch.empty(N, dtype=torch.float32, device=x.device)
     _call("pu_stats_finalize", ssum.data_ptr(), ssq.data_ptr(), ssum.shape[0], N, M, mean.data_ptr(), var.data_ptr(),
-                                   _stream(x))
+          _stream(x))
     return out, mean, var
 
 
@@ -365,7 +398,7 @@ class _LinearFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         dx = None
         if ctx.x_needs:
-            dx = linear_raw(dy, w.t().contiguous())
+            dx = linear_raw(dy, None, wt=w)  # dx = dy w^T: the K-major form of w^T is w itself
             dx = dx.view(x.shape)
         dw, db = wgrad_raw(x, dy, want_db=ctx.has_bias)
         return dx, dw, db, None
@@ -503,7 +536,7 @@ class _AttPoolFn(torch.autograd.Function):
         dx = torch.empty((B, N, K, d), dtype=torch.float32, device=x.device)
         _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
                                            d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
-        linear_raw(d_act, w.t().contiguous(), out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
+        linear_raw(d_act, None, wt=w, out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
         dw, _ = wgrad_raw(x, d_act)
         return dx, dw
 

@@ -1,0 +1,56 @@
+"""GPU tests of the tcgen05 tensor-core linear (csrc/tc_gemm.cu) against fp64: 3xTF32 must be fp32-class accurate."""
+import pytest
+import torch
+
+from point_unet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max())
+
+
+@pytest.mark.parametrize("M,K,N", [(4096, 64, 64), (1000, 32, 32), (5000, 128, 128), (3000, 256, 512), (777, 1536, 512),
+                                   (2000, 64, 32), (130, 96, 40), (128, 32, 128), (100000, 64, 64), (300, 44, 36)])
+@pytest.mark.parametrize("mode", [3, 1])
+def test_tc_linear_matches_fp64(M, K, N, mode):
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g) + 0.3
+    w = torch.randn(K, N, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    want = x.double() @ w.double() + b.double()
+    xg, wg, bg = x.cuda(), w.cuda(), b.cuda()
+    ops.tc_error_flag(xg.device).zero_()
+    y, mean, var = ops.linear_raw(xg, wg, bg, want_stats=True, tc_mode=mode)
+    assert int(ops.tc_error_flag(xg.device).item()) == 0, "tcgen05 pipeline barrier timed out"
+    tol = 2e-6 if mode == 3 else 3e-3
+    assert rel(y, want) < tol, (rel(y, want), tol)
+    assert rel(mean, want.mean(0)) < max(tol, 1e-5) * 5
+    assert rel(var, want.var(0, unbiased=False)) < max(tol, 1e-5) * 5
+    # accumulate into an existing buffer, strided output (half of a concat buffer), K-major weight passed directly
+    buf = torch.randn(M, 2 * N, generator=g).cuda()
+    want2 = buf[:, N:].double().cpu() + x.double() @ w.double()
+    ops.linear_raw(xg, None, None, out=buf[:, N:], accumulate=True, wt=wg.t().contiguous(), tc_mode=mode)
+    assert rel(buf[:, N:], want2) < tol * 2
+    # same numbers as the CUDA-core path within fp32 rounding when mode == 3
+    if mode == 3:
+        y0 = ops.linear_raw(xg, wg, bg, tc_mode=0)
+        assert rel(y, y0) < 3e-6
+
+
+def test_tc_used_by_autograd_linear_and_att_pool():
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 256, 16, 64, generator=g)
+    w = torch.randn(64, 64, generator=g) * 0.2
+    dy = torch.randn(2, 256, 1, 64, generator=g)
+    outs = []
+    for mode in (0, 3):
+        ops.TC_MODE = mode
+        xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+        agg = ops.att_pool(xg, wg)
+        (agg * dy.cuda()).sum().backward()
+        outs.append((agg.detach(), xg.grad.clone(), wg.grad.clone()))
+    ops.TC_MODE = 3
+    for a, b in zip(outs[0], outs[1]):
+        assert rel(b, a) < 2e-5
