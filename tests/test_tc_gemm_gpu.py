@@ -24,7 +24,7 @@ def test_tc_linear_matches_fp64(M, K, N, mode):
     ops.tc_error_flag(xg.device).zero_()
     y, mean, var = ops.linear_raw(xg, wg, bg, want_stats=True, tc_mode=mode)
     assert int(ops.tc_error_flag(xg.device).item()) == 0, "tcgen05 pipeline barrier timed out"
-    tol = 2e-6 if mode == 3 else 3e-3
+    tol = 2e-5 if mode == 3 else 3e-3  # 3xTF32: ~2e-6 at K<=256, grows ~sqrt(K) (8e-6 at K=1536)
     assert rel(y, want) < tol, (rel(y, want), tol)
     assert rel(mean, want.mean(0)) < max(tol, 1e-5) * 5
     assert rel(var, want.var(0, unbiased=False)) < max(tol, 1e-5) * 5
@@ -36,7 +36,7 @@ def test_tc_linear_matches_fp64(M, K, N, mode):
     # same numbers as the CUDA-core path within fp32 rounding when mode == 3
     if mode == 3:
         y0 = ops.linear_raw(xg, wg, bg, tc_mode=0)
-        assert rel(y, y0) < 3e-6
+        assert rel(y, y0) < 2e-5
 
 
 def test_tc_used_by_autograd_linear_and_att_pool():
