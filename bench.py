@@ -99,10 +99,10 @@ def algorithmic(name, tag):
     """(bytes, flops, bound) per launch from SURVEY.md section 8(d) (fp32, unfused contract)."""
     if tag is None:
         return 0, 0, "hbm"
-    if name in ("pu_att_pooling_fwd",):
+    if name in ("pu_att_pooling_fwd", "pu_tc_att_pooling_fwd"):
         P, K, d = tag
         return 4 * P * K * d + 4 * d * d + 4 * P * d, 2 * P * K * d * d, "tensor" if d >= 64 else "hbm"
-    if name in ("pu_att_pooling_bwd",):
+    if name in ("pu_att_pooling_bwd", "pu_tc_att_pooling_bwd"):
         P, K, d = tag  # reads x and g, writes d_act and dx_direct
         return 3 * 4 * P * K * d + 4 * d * d + 4 * P * d, 2 * P * K * d * d, "tensor" if d >= 64 else "hbm"
     if name == "pu_gather_rows_fwd":
@@ -236,10 +236,11 @@ def run_ours(args):
         tr.train_step_device(x, f, l)
     breakdown = kt.summary()
     top = max(breakdown.items(), key=lambda kv: kv[1][1])[0] if breakdown else "pu_att_pooling_fwd"
-    if top not in ("pu_att_pooling_fwd", "pu_att_pooling_bwd", "pu_gather_rows_fwd", "pu_segment_sum"):
+    RF = ("pu_att_pooling_fwd", "pu_att_pooling_bwd", "pu_tc_att_pooling_fwd", "pu_tc_att_pooling_bwd",
+          "pu_gather_rows_fwd", "pu_segment_sum")
+    if top not in RF:
         # report the roofline on a kernel whose algorithmic bytes are defined in SURVEY 8(d)
-        cands = {k: v for k, v in breakdown.items() if k in ("pu_att_pooling_fwd", "pu_att_pooling_bwd",
-                                                             "pu_gather_rows_fwd", "pu_segment_sum")}
+        cands = {k: v for k, v in breakdown.items() if k in RF}
         top_rf = max(cands.items(), key=lambda kv: kv[1][1])[0]
     else:
         top_rf = top

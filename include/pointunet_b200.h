@@ -128,6 +128,14 @@ PU_API int pu_tc_linear_supported(long long M, int K, int N, int ldx, int ldwt, 
 PU_API int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const float *bias, float *y, int ldy,
                             long long M, int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode,
                             int *error_flag, pu_stream_t stream);
+/* Tensor-core forms of pu_att_pooling_fwd / _bwd (channel width d >= 32, K = 16): same contract, but `wt` is the
+ * TRANSPOSED FC kernel [d_out, d_in] (K-major); the softmax-over-K epilogue runs out of TMEM. */
+PU_API int pu_tc_att_supported(int K, int d, int ldx);
+PU_API int pu_tc_att_pooling_fwd(const float *feature_set, int ldx, const float *wt, long long P, int K, int d,
+                                 float *f_agg, int ldo, int mode, int *error_flag, pu_stream_t stream);
+PU_API int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, const float *g_agg, int ldg,
+                                 long long P, int K, int d, float *d_act, int ldda, float *dx_direct, int lddx,
+                                 int mode, int *error_flag, pu_stream_t stream);
 /* dw[K,N] (+)= x^T dy ; db[N] (+)= column sums of dy (db may be NULL).  Deterministic. */
 PU_API size_t pu_wgrad_workspace_bytes(long long M, int K, int N);
 PU_API int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, int K, int N, float *dw,

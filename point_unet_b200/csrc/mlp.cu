@@ -363,34 +363,40 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float *__restr
 }
 
 // mean/var (biased) per channel from per-tile (sum, M2) partials: Chan et al. parallel merge, in double.
-// var = [ sum_t M2_t + sum_t n_t (mean_t - mean)^2 ] / n
+//   var = [ sum_t M2_t + sum_t n_t mean_t^2 - n mean^2 ] / n      (the subtraction is done in double)
+// One CTA per channel, 256 threads stride over the tiles, fixed-order block reduction.
 __global__ void __launch_bounds__(256) stats_finalize_kernel(const float *__restrict__ psum, const float *__restrict__ pm2,
                                                              int tiles, int C, long long count, int rows_per_tile,
                                                              float *__restrict__ mean, float *__restrict__ var) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= C) return;
-    double s = 0.0;
-    for (int t = lane; t < tiles; t += 32) s += (double)psum[(size_t)t * C + warp];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const double m = s / (double)count;
-    double q = 0.0;
-    for (int t = lane; t < tiles; t += 32) {
+    __shared__ double red[3][256];
+    const int c = blockIdx.x;
+    double s = 0.0, q = 0.0, r = 0.0;
+    for (int t = threadIdx.x; t < tiles; t += 256) {
         const long long r0 = (long long)t * rows_per_tile;
         const double nt = (double)min((long long)rows_per_tile, count - r0);
-        const double mt = (double)psum[(size_t)t * C + warp] / nt;
-        q += (double)pm2[(size_t)t * C + warp] + nt * (mt - m) * (mt - m);
+        const double st = (double)psum[(size_t)t * C + c];
+        s += st;
+        q += (double)pm2[(size_t)t * C + c];
+        r += st * st / nt;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (lane == 0) {
-        mean[warp] = (float)m;
-        var[warp] = (float)(q / (double)count);
+    red[0][threadIdx.x] = s; red[1][threadIdx.x] = q; red[2][threadIdx.x] = r;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + o];
+            red[1][threadIdx.x] += red[1][threadIdx.x + o];
+            red[2][threadIdx.x] += red[2][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double n = (double)count, m = red[0][0] / n;
+        const double v = (red[1][0] + red[2][0] - n * m * m) / n;
+        mean[c] = (float)m;
+        var[c] = (float)(v > 0.0 ? v : 0.0);
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// elementwise: out = lrelu_slope(y*scale[c] + shift[c] (+ y2*scale2[c] + shift2[c])) ; mask = optional dropout scale
 // NOTE on "shift": all batch-norm kernels below evaluate z = (y - mean[c]) * scale[c] + beta[c] (centered form, no
 // cancellation between y*scale and mean*scale); `shift` is a [2,C] array: row 0 = mean, row 1 = beta.
 __device__ __forceinline__ float4 bn_z(const float4 v, const float4 mu, const float4 sc, const float4 be) {
@@ -706,7 +712,7 @@ int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, in
     if (!stat_sum || !stat_sq || !mean || !var || tiles < 1 || C < 1 || count < 1) return PU_ERR_INVALID_ARG;
     const int rows_per_tile = C <= 16 ? 256 : 128;  // must match launch_gemm's tile choice
     if ((long long)tiles != (count + rows_per_tile - 1) / rows_per_tile) return PU_ERR_INVALID_ARG;
-    stats_finalize_kernel<<<ceil_div((long long)C * 32, 256), 256, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
+    stats_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
                                                                                           count, rows_per_tile, mean, var);
     PU_LAUNCH_CHECK();
     return PU_OK;

@@ -310,6 +310,313 @@ static int launch(const Params &p, cudaStream_t st) {
     return PU_OK;
 }
 
+
+// =============================================================================================================
+// v2: persistent, warp-specialised kernel.  grid = a multiple of the SM count; every CTA walks 128-row tiles.
+//   warps 0-3  producers: global -> registers (prefetched one k-block ahead) -> hi/lo split -> swizzled smem ring;
+//              thread 0 additionally issues the MMAs of the stage it just helped to fill (one elected issuer)
+//   warps 4-7  epilogue: wait for the tile's accumulator (TMEM, double-buffered), tcgen05.ld, release the buffer,
+//              then finish the tile (bias/accumulate/statistics, or the att_pooling softmax) while the tensor core
+//              already works on the next tile
+//   the weight operand (<= 96 KB as hi+lo tf32 pairs) is split once and stays resident in shared memory.
+// Three epilogues share the pipeline:
+//   EPI_STORE    y (+)= x wt^T + bias, optional per-tile batch-norm partials           (pu_tc_linear_fwd)
+//   EPI_ATT_FWD  f_agg[p,c] = sum_k x[p,k,c] softmax_k(x w)[c]                          (pu_att_pooling_fwd, K = 16)
+//   EPI_ATT_BWD  d_act = s (g x - sum_k g x s),  dx_direct = g s                        (pu_att_pooling_bwd)
+enum { EPI_STORE = 0, EPI_ATT_FWD = 1, EPI_ATT_BWD = 2 };
+constexpr int STAGES = 3;
+constexpr int P_THREADS = 128;  // producer threads == epilogue threads
+
+struct Params2 {
+    Params g;                  // the GEMM proper (A = x rows, Bt = weight in K-major form, C, bias, stats, mode)
+    const float *X; int ldx;   // att: feature_set rows (same memory as A)
+    const float *G; int ldg;   // att bwd: upstream gradient [M/16, N]
+    float *OUT; int ldo;       // att fwd: f_agg [M/16, N];  att bwd: dx_direct [M, N]
+    long long ntiles;
+};
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
+    const Params &p = q.g;
+    constexpr int A_BYTES = BM * 128;                 // one 128 x 32 fp32 tile
+    constexpr int A_STAGE = 2 * A_BYTES;              // hi + lo
+    constexpr int B_KB = 2 * BN * 128;                // hi + lo of one k-block of the weight
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (BN in {32,64,128})
+    constexpr int LDT = BN + 4;
+    extern __shared__ __align__(1024) char smem_raw[];
+    char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t stage_free[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ int s_err;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = (p.K + BK - 1) / BK;
+    const int n0 = blockIdx.y * BN;
+    const bool split = p.mode == 3;
+    char *a_ring = smem;
+    char *b_res = smem + STAGES * A_STAGE;
+    float *tile = reinterpret_cast<float *>(b_res + (size_t)nkb * B_KB);  // epilogue staging [BM][LDT]
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) mbar_init(&stage_free[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P_THREADS); }
+        s_err = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // resident weight: all 256 threads load + split every k-block once
+    for (int kb = 0; kb < nkb; ++kb) {
+        char *b_hi = b_res + (size_t)kb * B_KB, *b_lo = b_hi + BN * 128;
+        for (int idx = tid; idx < BN * 8; idx += 256) {
+            const int r = idx >> 3, c = idx & 7;
+            const int gn = n0 + r, gk = kb * BK + c * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gn < p.N && gk < p.K) v = *reinterpret_cast<const float4 *>(p.Bt + (size_t)gn * p.ldb + gk);
+            const uint32_t off = sw128(r, c);
+            if (split) {
+                const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                *reinterpret_cast<float4 *>(b_hi + off) = h;
+                *reinterpret_cast<float4 *>(b_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            } else {
+                *reinterpret_cast<float4 *>(b_hi + off) = v;
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp < 4) {
+        // ======================= producers (+ elected MMA issuer) =======================
+        const uint32_t idesc = make_idesc(BN);
+        long long tile_i = blockIdx.x;
+        int kb = 0;
+        bool have = tile_i < q.ntiles;
+        TileRegs<BM> ra;
+        if (have) load_tile<BM>(ra, p.A, p.lda, tile_i * BM, p.M, 0, p.K, tid);
+        int it = 0, tile_count = 0;
+        bool ok = true;
+        while (have) {
+            const int s = it % STAGES, u = it / STAGES;
+            char *a_hi = a_ring + (size_t)s * A_STAGE, *a_lo = a_hi + A_BYTES;
+            if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;
+            store_tile<BM>(ra, a_hi, a_lo, tid, split);
+            const int cur_kb = kb;
+            kb++;
+            if (kb == nkb) { kb = 0; tile_i += gridDim.x; }
+            const bool have_next = tile_i < q.ntiles;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_sync_named(1, P_THREADS);
+            if (have_next) load_tile<BM>(ra, p.A, p.lda, tile_i * BM, p.M, kb * BK, p.K, tid);  // prefetch
+            if (tid == 0) {
+                const int buf = tile_count & 1, v = tile_count >> 1;
+                if (cur_kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[buf], (uint32_t)((v - 1) & 1)) && ok;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                const char *b_hi = b_res + (size_t)cur_kb * B_KB, *b_lo = b_hi + BN * 128;
+#pragma unroll
+                for (int j = 0; j < BK / UMMA_K; ++j) {
+                    const uint64_t dah = make_desc(smem_u32(a_hi) + j * 32), dbh = make_desc(smem_u32(b_hi) + j * 32);
+                    umma_tf32(d_tmem, dah, dbh, idesc, (cur_kb > 0 || j > 0) ? 1u : 0u);
+                    if (split) {
+                        const uint64_t dal = make_desc(smem_u32(a_lo) + j * 32), dbl = make_desc(smem_u32(b_lo) + j * 32);
+                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+                    }
+                }
+                umma_commit(&stage_free[s]);
+                if (cur_kb == nkb - 1) umma_commit(&acc_full[buf]);
+            }
+            if (cur_kb == nkb - 1) tile_count++;
+            it++;
+            have = have_next;
+        }
+        if (!ok) s_err = 1;
+    } else {
+        // ======================= epilogue warps =======================
+        const int etid = tid - P_THREADS, ewarp = warp - 4;
+        int tile_count = 0;
+        bool ok = true;
+        for (long long tile_i = blockIdx.x; tile_i < q.ntiles; tile_i += gridDim.x, ++tile_count) {
+            const int buf = tile_count & 1, v = tile_count >> 1;
+            const long long m0 = tile_i * BM;
+            const long long rows_here = min((long long)BM, p.M - m0);
+            ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {   // TMEM -> registers -> staging tile
+                const int row = ewarp * 32 + lane;
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    float vals[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(buf * BN + c0), vals);
+#pragma unroll
+                    for (int qd = 0; qd < 16; qd += 4)
+                        *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
+                            make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
+            bar_sync_named(2, P_THREADS);
+
+            if constexpr (EPI == EPI_STORE) {
+                const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+                for (int idx = etid; idx < BM * (BN / 4); idx += P_THREADS) {
+                    const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
+                    if (r >= rows_here) continue;
+                    const int gn = n0 + c;
+                    float4 val = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
+                    float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
+                    if (gn + 3 < p.N && vecC) {
+                        if (p.bias) {
+                            const float4 b = *reinterpret_cast<const float4 *>(p.bias + gn);
+                            val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
+                        }
+                        if (p.accumulate) {
+                            const float4 o = *reinterpret_cast<const float4 *>(cptr);
+                            val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                        }
+                        *reinterpret_cast<float4 *>(cptr) = val;
+                    } else {
+                        float vv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (gn + j < p.N) {
+                                if (p.bias) vv[j] += p.bias[gn + j];
+                                if (p.accumulate) vv[j] += cptr[j];
+                                cptr[j] = vv[j];
+                            }
+                        val = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    }
+                    *reinterpret_cast<float4 *>(&tile[r * LDT + c]) = val;
+                }
+                if (p.stat_sum) {
+                    bar_sync_named(2, P_THREADS);
+                    for (int c = etid; c < BN; c += P_THREADS) {
+                        float s = 0.f;
+                        for (int r = 0; r < rows_here; ++r) s += tile[r * LDT + c];
+                        const float mu = s / (float)rows_here;
+                        float m2 = 0.f;
+                        for (int r = 0; r < rows_here; ++r) {
+                            const float d = tile[r * LDT + c] - mu;
+                            m2 = fmaf(d, d, m2);
+                        }
+                        if (n0 + c < p.N) {
+                            p.stat_sum[(size_t)tile_i * p.N + n0 + c] = s;
+                            p.stat_m2[(size_t)tile_i * p.N + n0 + c] = m2;
+                        }
+                    }
+                }
+            } else {
+                // one (point, channel) pair per thread step: the 16 neighbour rows of a point sit 16 apart in `tile`
+                const long long pt0 = m0 / 16;
+                const int npts = (int)(rows_here / 16);
+                for (int pair = etid; pair < (BM / 16) * BN; pair += P_THREADS) {
+                    const int pl = pair / BN, c = pair % BN;
+                    const int gn = n0 + c;
+                    if (pl >= npts || gn >= p.N) continue;
+                    float a[16], x[16];
+                    float mx = -FLT_MAX;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        a[k] = tile[(pl * 16 + k) * LDT + c];
+                        mx = fmaxf(mx, a[k]);
+                        x[k] = q.X[(size_t)(m0 + pl * 16 + k) * q.ldx + gn];
+                    }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) { a[k] = __expf(a[k] - mx); sum += a[k]; }
+                    const float inv = 1.f / sum;
+                    if constexpr (EPI == EPI_ATT_FWD) {
+                        float num = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) num = fmaf(x[k], a[k], num);
+                        q.OUT[(size_t)(pt0 + pl) * q.ldo + gn] = num * inv;
+                    } else {
+                        const float g = q.G[(size_t)(pt0 + pl) * q.ldg + gn];
+                        float dot = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * x[k], a[k], dot); }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const size_t row = (size_t)(m0 + pl * 16 + k);
+                            p.C[row * p.ldc + gn] = a[k] * (g * x[k] - dot);   // d_act
+                            q.OUT[row * q.ldo + gn] = g * a[k];                 // dx_direct
+                        }
+                    }
+                }
+            }
+            bar_sync_named(2, P_THREADS);  // staging tile is reused by the next tile
+        }
+        if (!ok) s_err = 1;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+    if (tid == 0 && s_err && p.error_flag) *p.error_flag = 1;
+}
+
+template <int BN>
+static size_t persist_smem_bytes(int K) {
+    const int nkb = (K + BK - 1) / BK;
+    return (size_t)STAGES * 2 * BM * 128 + (size_t)nkb * 2 * BN * 128 + (size_t)BM * (BN + 4) * 4 + 1024;
+}
+constexpr size_t kMaxDynSmem = 227 * 1024 - 2048;
+
+template <int BN, int EPI>
+static int launch_persist(const Params2 &q, cudaStream_t st) {
+    const size_t smem = persist_smem_bytes<BN>(q.g.K);
+    static size_t configured = 0;
+    if (configured < smem) {
+        PU_CUDA_TRY(cudaFuncSetAttribute(tc_persist_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        configured = kMaxDynSmem;
+    }
+    const int ny = ceil_div(q.g.N, BN);
+    long long gx = kNumSMs / ny;  // ~one CTA per SM in total (227 KB-class shared memory); each walks its row tiles
+    if (gx < 1) gx = 1;
+    if (gx > q.ntiles) gx = q.ntiles;
+    dim3 grid((unsigned)gx, ny);
+    tc_persist_kernel<BN, EPI><<<grid, 256, smem, st>>>(q);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+// picks the N tile so that the resident weight fits; returns 0 if the shape needs the streaming (v1) kernel
+static int persist_bn(int K, int N) {
+    if (N <= 32 && persist_smem_bytes<32>(K) <= kMaxDynSmem) return 32;
+    if (N <= 64 && persist_smem_bytes<64>(K) <= kMaxDynSmem) return 64;
+    if (N > 64 && persist_smem_bytes<128>(K) <= kMaxDynSmem) return 128;
+    if (persist_smem_bytes<64>(K) <= kMaxDynSmem) return 64;
+    if (persist_smem_bytes<32>(K) <= kMaxDynSmem) return 32;
+    return 0;
+}
+
+template <int EPI>
+static int dispatch_persist(const Params2 &q, cudaStream_t st) {
+    switch (persist_bn(q.g.K, q.g.N)) {
+        case 32: return launch_persist<32, EPI>(q, st);
+        case 64: return launch_persist<64, EPI>(q, st);
+        case 128: return launch_persist<128, EPI>(q, st);
+    }
+    return PU_ERR_UNSUPPORTED;
+}
+
 }  // namespace tc
 }  // namespace pu
 
@@ -335,9 +642,50 @@ int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const f
     p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.stat_sum = stat_sum; p.stat_m2 = stat_m2; p.mode = mode;
     p.error_flag = error_flag;
     cudaStream_t st = (cudaStream_t)stream;
+    if (tc::persist_bn(K, N) != 0) {
+        tc::Params2 q{};
+        q.g = p;
+        q.ntiles = (M + tc::BM - 1) / tc::BM;
+        return tc::dispatch_persist<tc::EPI_STORE>(q, st);
+    }
     if (N <= 32) return tc::launch<32>(p, st);
     if (N <= 64) return tc::launch<64>(p, st);
     return tc::launch<128>(p, st);
+}
+
+/* 1 if the fused att_pooling kernels can run on the tensor-core path for channel width d */
+int pu_tc_att_supported(int K, int d, int ldx) {
+    return K == 16 && d >= 32 && (d & 3) == 0 && (ldx & 3) == 0 && tc::persist_bn(d, d) != 0;
+}
+
+int pu_tc_att_pooling_fwd(const float *feature_set, int ldx, const float *wt, long long P, int K, int d, float *f_agg,
+                          int ldo, int mode, int *error_flag, pu_stream_t stream) {
+    if (!feature_set || !wt || !f_agg || P < 0 || ldx < d || ldo < d) return PU_ERR_INVALID_ARG;
+    if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
+    if (!pu_tc_att_supported(K, d, ldx) || (((uintptr_t)feature_set | (uintptr_t)wt) & 15)) return PU_ERR_UNSUPPORTED;
+    if (P == 0) return PU_OK;
+    tc::Params2 q{};
+    q.g.A = feature_set; q.g.lda = ldx; q.g.Bt = wt; q.g.ldb = d; q.g.M = P * K; q.g.N = d; q.g.K = d; q.g.mode = mode;
+    q.g.error_flag = error_flag;
+    q.X = feature_set; q.ldx = ldx; q.OUT = f_agg; q.ldo = ldo;
+    q.ntiles = (q.g.M + tc::BM - 1) / tc::BM;
+    return tc::dispatch_persist<tc::EPI_ATT_FWD>(q, (cudaStream_t)stream);
+}
+
+int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, const float *g_agg, int ldg, long long P,
+                          int K, int d, float *d_act, int ldda, float *dx_direct, int lddx, int mode, int *error_flag,
+                          pu_stream_t stream) {
+    if (!feature_set || !wt || !g_agg || !d_act || !dx_direct || P < 0 || ldx < d || ldg < d || ldda < d || lddx < d)
+        return PU_ERR_INVALID_ARG;
+    if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
+    if (!pu_tc_att_supported(K, d, ldx) || (((uintptr_t)feature_set | (uintptr_t)wt) & 15)) return PU_ERR_UNSUPPORTED;
+    if (P == 0) return PU_OK;
+    tc::Params2 q{};
+    q.g.A = feature_set; q.g.lda = ldx; q.g.Bt = wt; q.g.ldb = d; q.g.M = P * K; q.g.N = d; q.g.K = d; q.g.mode = mode;
+    q.g.C = d_act; q.g.ldc = ldda; q.g.error_flag = error_flag;
+    q.X = feature_set; q.ldx = ldx; q.G = g_agg; q.ldg = ldg; q.OUT = dx_direct; q.ldo = lddx;
+    q.ntiles = (q.g.M + tc::BM - 1) / tc::BM;
+    return tc::dispatch_persist<tc::EPI_ATT_BWD>(q, (cudaStream_t)stream);
 }
 
 }  // extern "C"

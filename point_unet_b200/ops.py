@@ -35,6 +35,9 @@ _lib._OP_SIGS.update({
                       c_void_p, c_void_p],
     "pu_tc_linear_fwd": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
                          c_void_p, c_int, c_void_p, c_void_p],
+    "pu_tc_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "pu_tc_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
+                              c_int, c_int, c_void_p, c_void_p],
     "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "pu_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                  c_void_p],
@@ -79,6 +82,7 @@ def _L():
         L.pu_point2prod_workspace_bytes.restype = c_size_t
         L.pu_point2prod_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.pu_tc_linear_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
+        L.pu_tc_att_supported.argtypes = [c_int, c_int, c_int]
         L.pu_linear_row_tiles.argtypes = [c_ll, c_int]
         L.pu_bn_bwd_reduce_blocks.argtypes = [c_ll, c_int]
         L._pu_extra_declared = True
@@ -521,21 +525,32 @@ class _AttPoolFn(torch.autograd.Function):
         B, N, K, d = feature_set.shape
         x, R, _, ldx = rows(feature_set)
         out = torch.empty((B, N, 1, d), dtype=torch.float32, device=feature_set.device)
-        _call("pu_att_pooling_fwd", x.data_ptr(), ldx, w.data_ptr(), B * N, K, d, out.data_ptr(), d, _stream(x),
-              tag=(B * N, K, d))
-        ctx.save_for_backward(x, w)
-        ctx.dims = (B, N, K, d, ldx)
+        use_tc = TC_MODE in (1, 3) and B * N * K >= 128 and x.data_ptr() % 16 == 0 and _L().pu_tc_att_supported(K, d, ldx)
+        wt = w.t().contiguous() if use_tc else None
+        if use_tc:
+            _call("pu_tc_att_pooling_fwd", x.data_ptr(), ldx, wt.data_ptr(), B * N, K, d, out.data_ptr(), d, TC_MODE,
+                  tc_error_flag(x.device).data_ptr(), _stream(x), tag=(B * N, K, d))
+        else:
+            _call("pu_att_pooling_fwd", x.data_ptr(), ldx, w.data_ptr(), B * N, K, d, out.data_ptr(), d, _stream(x),
+                  tag=(B * N, K, d))
+        ctx.save_for_backward(x, w, wt if use_tc else w)
+        ctx.dims = (B, N, K, d, ldx, use_tc)
         return out
 
     @staticmethod
     def backward(ctx, g_agg):
-        x, w = ctx.saved_tensors
-        B, N, K, d, ldx = ctx.dims
+        x, w, wt = ctx.saved_tensors
+        B, N, K, d, ldx, use_tc = ctx.dims
         g, _, _, ldg = rows(g_agg)
         d_act = torch.empty((B * N * K, d), dtype=torch.float32, device=x.device)
         dx = torch.empty((B, N, K, d), dtype=torch.float32, device=x.device)
-        _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
-                                           d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
+        if use_tc:
+            _call("pu_tc_att_pooling_bwd", x.data_ptr(), ldx, wt.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
+                  d_act.data_ptr(), d, dx.data_ptr(), d, TC_MODE, tc_error_flag(x.device).data_ptr(), _stream(x),
+                  tag=(B * N, K, d))
+        else:
+            _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
+                  d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
         linear_raw(d_act, None, wt=w, out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
         dw, _ = wgrad_raw(x, d_act)
         return dx, dw
