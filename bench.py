@@ -210,6 +210,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PU_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
@@ -343,7 +344,8 @@ def run_ours(args):
                              d2h_bytes_per_step=4),
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks, knn=knn,
                     breakdown_ms_per_step=bd, loss=float(loss_val))
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -324,10 +324,60 @@ static int launch(const Params &p, cudaStream_t st) {
 //   EPI_ATT_FWD  f_agg[p,c] = sum_k x[p,k,c] softmax_k(x w)[c]                          (pu_att_pooling_fwd, K = 16)
 //   EPI_ATT_BWD  d_act = s (g x - sum_k g x s),  dx_direct = g s                        (pu_att_pooling_bwd)
 enum { EPI_STORE = 0, EPI_ATT_FWD = 1, EPI_ATT_BWD = 2 };
-constexpr int STAGES = 3;
-constexpr int P_THREADS = 128;  // producer threads == epilogue threads
+constexpr int STAGES = 2;        // operand (hi/lo) stages consumed by the tensor core
+constexpr int MAX_RAW = 6;       // raw fp32 ring filled by cp.async (no registers held while the bytes are in flight)
+constexpr int P_THREADS = 128;   // producer threads == epilogue threads
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
+    const uint32_t d = smem_u32(smem_dst);
+    const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // wait until at most `pending` groups are in flight
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    }
+}
+// raw ring slot: [128 rows][8 chunks of 16 B], chunk (r,c) at (r*8 + c)*16 -- each thread later reads back exactly
+// the chunks it copied itself, so cp.async.wait_group alone orders the hand-over (no CTA barrier)
+__device__ __forceinline__ void raw_issue(char *slot, const float *__restrict__ base, int ld, long long row0, long long row_end,
+                                          int k0, int K, int tid) {
+#pragma unroll
+    for (int i = 0; i < BM / 16; ++i) {
+        const int idx = tid + P_THREADS * i;
+        const int r = idx >> 3, c = idx & 7;
+        const long long gr = row0 + r;
+        const int gk = k0 + c * 4;
+        const bool valid = gr < row_end && gk < K;
+        const float *src = valid ? base + (size_t)gr * ld + gk : base;
+        cp_async16(slot + (size_t)idx * 16, src, valid);
+    }
+}
+__device__ __forceinline__ void raw_convert(const char *slot, char *hi, char *lo, int tid, bool split) {
+#pragma unroll
+    for (int i = 0; i < BM / 16; ++i) {
+        const int idx = tid + P_THREADS * i;
+        const int r = idx >> 3, c = idx & 7;
+        const float4 v = *reinterpret_cast<const float4 *>(slot + (size_t)idx * 16);
+        const uint32_t off = sw128(r, c);
+        if (split) {
+            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+            *reinterpret_cast<float4 *>(hi + off) = h;
+            *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        } else {
+            *reinterpret_cast<float4 *>(hi + off) = v;
+        }
+    }
+}
 
 struct Params2 {
+    int raw_depth;             // cp.async raw-ring depth D (k-blocks of 16 KB in flight per CTA = D - 1)
     Params g;                  // the GEMM proper (A = x rows, Bt = weight in K-major form, C, bias, stats, mode)
     const float *X; int ldx;   // att: feature_set rows (same memory as A)
     const float *G; int ldg;   // att bwd: upstream gradient [M/16, N]
@@ -360,8 +410,10 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
     const int nkb = (p.K + BK - 1) / BK;
     const int n0 = blockIdx.y * BN;
     const bool split = p.mode == 3;
+    const int D = q.raw_depth;
     char *a_ring = smem;
-    char *b_res = smem + STAGES * A_STAGE;
+    char *raw_ring = smem + STAGES * A_STAGE;
+    char *b_res = raw_ring + (size_t)D * A_BYTES;
     float *tile = reinterpret_cast<float *>(b_res + (size_t)nkb * B_KB);  // epilogue staging [BM][LDT]
 
     if (tid == 0) {
@@ -403,25 +455,29 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
     if (warp < 4) {
         // ======================= producers (+ elected MMA issuer) =======================
         const uint32_t idesc = make_idesc(BN);
-        long long tile_i = blockIdx.x;
-        int kb = 0;
-        bool have = tile_i < q.ntiles;
-        TileRegs<BM> ra;
-        if (have) load_tile<BM>(ra, p.A, p.lda, tile_i * BM, p.M, 0, p.K, tid);
-        int it = 0, tile_count = 0;
+        // work items = (tile, k-block) pairs in order; `issue_*` runs D-1 items ahead of `cur_*`
+        long long cur_tile = blockIdx.x, iss_tile = blockIdx.x;
+        int cur_kb = 0, iss_kb = 0;
+        int it = 0, tile_count = 0, issued = 0;
         bool ok = true;
-        while (have) {
+        auto issue_one = [&]() {
+            if (iss_tile < q.ntiles) {
+                raw_issue(raw_ring + (size_t)(issued % D) * A_BYTES, p.A, p.lda, iss_tile * BM, p.M, iss_kb * BK, p.K, tid);
+                if (++iss_kb == nkb) { iss_kb = 0; iss_tile += gridDim.x; }
+            }
+            cp_async_commit();  // always commit (possibly empty) so the group arithmetic stays uniform
+            ++issued;
+        };
+        for (int i = 0; i < D - 1; ++i) issue_one();
+        while (cur_tile < q.ntiles) {
+            issue_one();                 // keep D-1 k-blocks in flight behind the one we are about to convert
+            cp_async_wait_dyn(D - 1);    // the oldest outstanding group (= item `it`) has landed
             const int s = it % STAGES, u = it / STAGES;
             char *a_hi = a_ring + (size_t)s * A_STAGE, *a_lo = a_hi + A_BYTES;
             if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;
-            store_tile<BM>(ra, a_hi, a_lo, tid, split);
-            const int cur_kb = kb;
-            kb++;
-            if (kb == nkb) { kb = 0; tile_i += gridDim.x; }
-            const bool have_next = tile_i < q.ntiles;
+            raw_convert(raw_ring + (size_t)(it % D) * A_BYTES, a_hi, a_lo, tid, split);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_sync_named(1, P_THREADS);
-            if (have_next) load_tile<BM>(ra, p.A, p.lda, tile_i * BM, p.M, kb * BK, p.K, tid);  // prefetch
             if (tid == 0) {
                 const int buf = tile_count & 1, v = tile_count >> 1;
                 if (cur_kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[buf], (uint32_t)((v - 1) & 1)) && ok;
@@ -441,10 +497,10 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
                 umma_commit(&stage_free[s]);
                 if (cur_kb == nkb - 1) umma_commit(&acc_full[buf]);
             }
-            if (cur_kb == nkb - 1) tile_count++;
+            if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
             it++;
-            have = have_next;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (!ok) s_err = 1;
     } else {
         // ======================= epilogue warps =======================
@@ -573,15 +629,25 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
 }
 
 template <int BN>
-static size_t persist_smem_bytes(int K) {
+static size_t persist_fixed_bytes(int K) {  // everything except the raw ring
     const int nkb = (K + BK - 1) / BK;
     return (size_t)STAGES * 2 * BM * 128 + (size_t)nkb * 2 * BN * 128 + (size_t)BM * (BN + 4) * 4 + 1024;
 }
 constexpr size_t kMaxDynSmem = 227 * 1024 - 2048;
+template <int BN>
+static int persist_raw_depth(int K) {  // 0 => does not fit
+    const size_t fixed = persist_fixed_bytes<BN>(K);
+    if (fixed + 2 * (size_t)BM * 128 > kMaxDynSmem) return 0;
+    long long d = (long long)((kMaxDynSmem - fixed) / ((size_t)BM * 128));
+    return (int)(d > MAX_RAW ? MAX_RAW : d);
+}
 
 template <int BN, int EPI>
 static int launch_persist(const Params2 &q, cudaStream_t st) {
-    const size_t smem = persist_smem_bytes<BN>(q.g.K);
+    Params2 qq = q;
+    qq.raw_depth = persist_raw_depth<BN>(q.g.K);
+    if (qq.raw_depth < 2) return PU_ERR_UNSUPPORTED;
+    const size_t smem = persist_fixed_bytes<BN>(q.g.K) + (size_t)qq.raw_depth * BM * 128;
     static size_t configured = 0;
     if (configured < smem) {
         PU_CUDA_TRY(cudaFuncSetAttribute(tc_persist_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
@@ -592,18 +658,18 @@ static int launch_persist(const Params2 &q, cudaStream_t st) {
     if (gx < 1) gx = 1;
     if (gx > q.ntiles) gx = q.ntiles;
     dim3 grid((unsigned)gx, ny);
-    tc_persist_kernel<BN, EPI><<<grid, 256, smem, st>>>(q);
+    tc_persist_kernel<BN, EPI><<<grid, 256, smem, st>>>(qq);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
 
 // picks the N tile so that the resident weight fits; returns 0 if the shape needs the streaming (v1) kernel
 static int persist_bn(int K, int N) {
-    if (N <= 32 && persist_smem_bytes<32>(K) <= kMaxDynSmem) return 32;
-    if (N <= 64 && persist_smem_bytes<64>(K) <= kMaxDynSmem) return 64;
-    if (N > 64 && persist_smem_bytes<128>(K) <= kMaxDynSmem) return 128;
-    if (persist_smem_bytes<64>(K) <= kMaxDynSmem) return 64;
-    if (persist_smem_bytes<32>(K) <= kMaxDynSmem) return 32;
+    if (N <= 32 && persist_raw_depth<32>(K) >= 3) return 32;
+    if (N <= 64 && persist_raw_depth<64>(K) >= 3) return 64;
+    if (N > 64 && persist_raw_depth<128>(K) >= 3) return 128;
+    if (persist_raw_depth<64>(K) >= 2) return 64;
+    if (persist_raw_depth<32>(K) >= 2) return 32;
     return 0;
 }
 
