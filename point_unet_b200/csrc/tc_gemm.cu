@@ -326,7 +326,7 @@ static int launch(const Params &p, cudaStream_t st) {
 enum { EPI_STORE = 0, EPI_ATT_FWD = 1, EPI_ATT_BWD = 2 };
 constexpr int STAGES = 2;        // operand (hi/lo) stages consumed by the tensor core
 constexpr int MAX_RAW = 6;       // raw fp32 ring filled by cp.async (no registers held while the bytes are in flight)
-constexpr int P_THREADS = 128;   // producer threads == epilogue threads
+constexpr int P_THREADS = 256;   // 8 producer warps + 8 epilogue warps: the kernel is issue-latency bound with fewer
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
     const uint32_t d = smem_u32(smem_dst);
@@ -349,7 +349,7 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // wait until 
 __device__ __forceinline__ void raw_issue(char *slot, const float *__restrict__ base, int ld, long long row0, long long row_end,
                                           int k0, int K, int tid) {
 #pragma unroll
-    for (int i = 0; i < BM / 16; ++i) {
+    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
         const int idx = tid + P_THREADS * i;
         const int r = idx >> 3, c = idx & 7;
         const long long gr = row0 + r;
@@ -361,7 +361,7 @@ __device__ __forceinline__ void raw_issue(char *slot, const float *__restrict__ 
 }
 __device__ __forceinline__ void raw_convert(const char *slot, char *hi, char *lo, int tid, bool split) {
 #pragma unroll
-    for (int i = 0; i < BM / 16; ++i) {
+    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
         const int idx = tid + P_THREADS * i;
         const int r = idx >> 3, c = idx & 7;
         const float4 v = *reinterpret_cast<const float4 *>(slot + (size_t)idx * 16);
@@ -393,7 +393,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
+__global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Params2 q) {
     const Params &p = q.g;
     constexpr int A_BYTES = BM * 128;                 // one 128 x 32 fp32 tile
     constexpr int A_STAGE = 2 * A_BYTES;              // hi + lo
@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
     __shared__ uint64_t stage_free[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
+    __shared__ float s_red[2 * 4 * P_THREADS];  // statistics partials: [row lane][BN][2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = (p.K + BK - 1) / BK;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
     // resident weight: all 256 threads load + split every k-block once
     for (int kb = 0; kb < nkb; ++kb) {
         char *b_hi = b_res + (size_t)kb * B_KB, *b_lo = b_hi + BN * 128;
-        for (int idx = tid; idx < BN * 8; idx += 256) {
+        for (int idx = tid; idx < BN * 8; idx += 2 * P_THREADS) {
             const int r = idx >> 3, c = idx & 7;
             const int gn = n0 + r, gk = kb * BK + c * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp < 4) {
+    if (warp < P_THREADS / 32) {
         // ======================= producers (+ elected MMA issuer) =======================
         const uint32_t idesc = make_idesc(BN);
         // work items = (tile, k-block) pairs in order; `issue_*` runs D-1 items ahead of `cur_*`
@@ -504,7 +505,8 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
         if (!ok) s_err = 1;
     } else {
         // ======================= epilogue warps =======================
-        const int etid = tid - P_THREADS, ewarp = warp - 4;
+        const int etid = tid - P_THREADS, ewarp = warp - P_THREADS / 32;
+        const int quarter = ewarp & 3, chalf = ewarp >> 2;  // TMEM lane quarter (= warp id % 4) and column half
         int tile_count = 0;
         bool ok = true;
         for (long long tile_i = blockIdx.x; tile_i < q.ntiles; tile_i += gridDim.x, ++tile_count) {
@@ -513,12 +515,13 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
             const long long rows_here = min((long long)BM, p.M - m0);
             ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            {   // TMEM -> registers -> staging tile
-                const int row = ewarp * 32 + lane;
+            {   // TMEM -> registers -> staging tile: warp (quarter, chalf) moves 32 rows x BN/2 columns
+                const int row = quarter * 32 + lane;
 #pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                for (int cc = 0; cc < BN / 2; cc += 16) {
+                    const int c0 = chalf * (BN / 2) + cc;
                     float vals[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(buf * BN + c0), vals);
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), vals);
 #pragma unroll
                     for (int qd = 0; qd < 16; qd += 4)
                         *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
@@ -531,17 +534,26 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
 
             if constexpr (EPI == EPI_STORE) {
                 const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-                for (int idx = etid; idx < BM * (BN / 4); idx += P_THREADS) {
-                    const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
-                    if (r >= rows_here) continue;
-                    const int gn = n0 + c;
+                // thread -> fixed group of 4 columns (P_THREADS % (BN/4) == 0), rows strided: the batch-norm partials
+                // accumulate in registers during the copy-out.  Shifted single pass: sums of (v - sh) and (v - sh)^2
+                // with sh = the tile's first stored row, so M2 = S2 - S1^2/n loses nothing to cancellation.
+                constexpr int CG = BN / 4, RLANES = P_THREADS / CG;
+                const int cg = etid % CG, rl = etid / CG, c = cg * 4, gn = n0 + c;
+                float sh[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) {
+                    bias4.x = gn + 0 < p.N ? p.bias[gn + 0] : 0.f; bias4.y = gn + 1 < p.N ? p.bias[gn + 1] : 0.f;
+                    bias4.z = gn + 2 < p.N ? p.bias[gn + 2] : 0.f; bias4.w = gn + 3 < p.N ? p.bias[gn + 3] : 0.f;
+                }
+                if (p.stat_sum) {  // shift = stored value of row 0 (recomputed identically by every thread of the group)
+                    const float4 t0 = *reinterpret_cast<float4 *>(&tile[c]);
+                    sh[0] = t0.x + bias4.x; sh[1] = t0.y + bias4.y; sh[2] = t0.z + bias4.z; sh[3] = t0.w + bias4.w;
+                }
+                for (int r = rl; r < rows_here; r += RLANES) {
                     float4 val = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
+                    val.x += bias4.x; val.y += bias4.y; val.z += bias4.z; val.w += bias4.w;
                     float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
                     if (gn + 3 < p.N && vecC) {
-                        if (p.bias) {
-                            const float4 b = *reinterpret_cast<const float4 *>(p.bias + gn);
-                            val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
-                        }
                         if (p.accumulate) {
                             const float4 o = *reinterpret_cast<const float4 *>(cptr);
                             val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
@@ -552,29 +564,30 @@ __global__ void __launch_bounds__(256, 1) tc_persist_kernel(const Params2 q) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (gn + j < p.N) {
-                                if (p.bias) vv[j] += p.bias[gn + j];
                                 if (p.accumulate) vv[j] += cptr[j];
                                 cptr[j] = vv[j];
                             }
                         val = make_float4(vv[0], vv[1], vv[2], vv[3]);
                     }
-                    *reinterpret_cast<float4 *>(&tile[r * LDT + c]) = val;
+                    const float dv[4] = {val.x - sh[0], val.y - sh[1], val.z - sh[2], val.w - sh[3]};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], dv[j], s2[j]); }
                 }
                 if (p.stat_sum) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s_red[(rl * BN + c + j) * 2 + 0] = s1[j];
+                        s_red[(rl * BN + c + j) * 2 + 1] = s2[j];
+                    }
                     bar_sync_named(2, P_THREADS);
-                    for (int c = etid; c < BN; c += P_THREADS) {
-                        float s = 0.f;
-                        for (int r = 0; r < rows_here; ++r) s += tile[r * LDT + c];
-                        const float mu = s / (float)rows_here;
-                        float m2 = 0.f;
-                        for (int r = 0; r < rows_here; ++r) {
-                            const float d = tile[r * LDT + c] - mu;
-                            m2 = fmaf(d, d, m2);
-                        }
-                        if (n0 + c < p.N) {
-                            p.stat_sum[(size_t)tile_i * p.N + n0 + c] = s;
-                            p.stat_m2[(size_t)tile_i * p.N + n0 + c] = m2;
-                        }
+                    if (etid < BN && n0 + etid < p.N) {
+                        float a = 0.f, b = 0.f;
+                        for (int l = 0; l < RLANES; ++l) { a += s_red[(l * BN + etid) * 2]; b += s_red[(l * BN + etid) * 2 + 1]; }
+                        // shift of column etid: recompute exactly as above
+                        const float shc = tile[etid] + (p.bias ? p.bias[n0 + etid] : 0.f);  // same shift as above
+                        const float n = (float)rows_here;
+                        p.stat_sum[(size_t)tile_i * p.N + n0 + etid] = fmaf(n, shc, a);
+                        p.stat_m2[(size_t)tile_i * p.N + n0 + etid] = fmaxf(b - a * a / n, 0.f);
                     }
                 }
             } else {
@@ -633,7 +646,7 @@ static size_t persist_fixed_bytes(int K) {  // everything except the raw ring
     const int nkb = (K + BK - 1) / BK;
     return (size_t)STAGES * 2 * BM * 128 + (size_t)nkb * 2 * BN * 128 + (size_t)BM * (BN + 4) * 4 + 1024;
 }
-constexpr size_t kMaxDynSmem = 227 * 1024 - 2048;
+constexpr size_t kMaxDynSmem = 227 * 1024 - 10 * 1024;  // dynamic budget: 227 KB minus the kernel's static shared memory (~9 KB)
 template <int BN>
 static int persist_raw_depth(int K) {  // 0 => does not fit
     const size_t fixed = persist_fixed_bytes<BN>(K);
@@ -658,7 +671,7 @@ static int launch_persist(const Params2 &q, cudaStream_t st) {
     if (gx < 1) gx = 1;
     if (gx > q.ntiles) gx = q.ntiles;
     dim3 grid((unsigned)gx, ny);
-    tc_persist_kernel<BN, EPI><<<grid, 256, smem, st>>>(qq);
+    tc_persist_kernel<BN, EPI><<<grid, 2 * tc::P_THREADS, smem, st>>>(qq);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
