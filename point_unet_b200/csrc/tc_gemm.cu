@@ -513,6 +513,25 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
             const int buf = tile_count & 1, v = tile_count >> 1;
             const long long m0 = tile_i * BM;
             const long long rows_here = min((long long)BM, p.M - m0);
+            // att epilogues: fetch this thread's x (and g) values BEFORE waiting for the accumulator -- they do not depend
+            // on the MMA, so their L2 latency hides behind the tensor-core work of this tile
+            constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * BN + P_THREADS - 1) / P_THREADS;
+            float xv[PAIRS][16];
+            float gv[PAIRS];
+            if constexpr (EPI != EPI_STORE) {
+                const int npts = (int)(rows_here / 16);
+#pragma unroll
+                for (int pp = 0; pp < PAIRS; ++pp) {
+                    const int pair = etid + pp * P_THREADS;
+                    const int pl = pair / BN, c = pair % BN;
+                    const bool pv = pair < (BM / 16) * BN && pl < npts && n0 + c < p.N;
+                    const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + n0 + c;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
+                    gv[pp] = 0.f;
+                    if constexpr (EPI == EPI_ATT_BWD) gv[pp] = pv ? q.G[(size_t)(m0 / 16 + pl) * q.ldg + n0 + c] : 0.f;
+                }
+            }
             ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {   // TMEM -> registers -> staging tile: warp (quarter, chalf) moves 32 rows x BN/2 columns
@@ -591,20 +610,21 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
                     }
                 }
             } else {
-                // one (point, channel) pair per thread step: the 16 neighbour rows of a point sit 16 apart in `tile`
+                // one (point, channel) pair per thread step: the 16 neighbour rows of a point are consecutive rows of `tile`
                 const long long pt0 = m0 / 16;
                 const int npts = (int)(rows_here / 16);
-                for (int pair = etid; pair < (BM / 16) * BN; pair += P_THREADS) {
+#pragma unroll
+                for (int pp = 0; pp < PAIRS; ++pp) {
+                    const int pair = etid + pp * P_THREADS;
                     const int pl = pair / BN, c = pair % BN;
                     const int gn = n0 + c;
-                    if (pl >= npts || gn >= p.N) continue;
-                    float a[16], x[16];
+                    if (pair >= (BM / 16) * BN || pl >= npts || gn >= p.N) continue;
+                    float a[16];
                     float mx = -FLT_MAX;
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         a[k] = tile[(pl * 16 + k) * LDT + c];
                         mx = fmaxf(mx, a[k]);
-                        x[k] = q.X[(size_t)(m0 + pl * 16 + k) * q.ldx + gn];
                     }
                     float sum = 0.f;
 #pragma unroll
@@ -613,18 +633,19 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
                     if constexpr (EPI == EPI_ATT_FWD) {
                         float num = 0.f;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) num = fmaf(x[k], a[k], num);
+                        for (int k = 0; k < 16; ++k) num = fmaf(xv[pp][k], a[k], num);
                         q.OUT[(size_t)(pt0 + pl) * q.ldo + gn] = num * inv;
                     } else {
-                        const float g = q.G[(size_t)(pt0 + pl) * q.ldg + gn];
+                        const float g = gv[pp];
                         float dot = 0.f;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * x[k], a[k], dot); }
+                        for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * xv[pp][k], a[k], dot); }
+                        float *cp = p.C + (size_t)(m0 + pl * 16) * p.ldc + gn;
+                        float *op = q.OUT + (size_t)(m0 + pl * 16) * q.ldo + gn;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
-                            const size_t row = (size_t)(m0 + pl * 16 + k);
-                            p.C[row * p.ldc + gn] = a[k] * (g * x[k] - dot);   // d_act
-                            q.OUT[row * q.ldo + gn] = g * a[k];                 // dx_direct
+                            cp[(size_t)k * p.ldc] = a[k] * (g * xv[pp][k] - dot);   // d_act
+                            op[(size_t)k * q.ldo] = g * a[k];                       // dx_direct
                         }
                     }
                 }
@@ -686,9 +707,16 @@ static int persist_bn(int K, int N) {
     return 0;
 }
 
+static int persist_bn_att(int d) {  // att epilogues keep (points x channels)/threads small: BN <= 64
+    if (d <= 32 && persist_raw_depth<32>(d) >= 3) return 32;
+    if (persist_raw_depth<64>(d) >= 2) return 64;
+    if (persist_raw_depth<32>(d) >= 2) return 32;
+    return 0;
+}
+
 template <int EPI>
 static int dispatch_persist(const Params2 &q, cudaStream_t st) {
-    switch (persist_bn(q.g.K, q.g.N)) {
+    switch (EPI == EPI_STORE ? persist_bn(q.g.K, q.g.N) : persist_bn_att(q.g.K)) {
         case 32: return launch_persist<32, EPI>(q, st);
         case 64: return launch_persist<64, EPI>(q, st);
         case 128: return launch_persist<128, EPI>(q, st);
@@ -734,7 +762,7 @@ int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const f
 
 /* 1 if the fused att_pooling kernels can run on the tensor-core path for channel width d */
 int pu_tc_att_supported(int K, int d, int ldx) {
-    return K == 16 && d >= 32 && (d & 3) == 0 && (ldx & 3) == 0 && tc::persist_bn(d, d) != 0;
+    return K == 16 && d >= 32 && (d & 3) == 0 && (ldx & 3) == 0 && tc::persist_bn_att(d) != 0;
 }
 
 int pu_tc_att_pooling_fwd(const float *feature_set, int ldx, const float *wt, long long P, int K, int d, float *f_agg,
