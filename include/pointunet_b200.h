@@ -136,6 +136,13 @@ PU_API int pu_tc_att_pooling_fwd(const float *feature_set, int ldx, const float 
 PU_API int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, const float *g_agg, int ldg,
                                  long long P, int K, int d, float *d_act, int ldda, float *dx_direct, int lddx,
                                  int mode, int *error_flag, pu_stream_t stream);
+/* Tensor-core weight gradient (tcgen05, MN-major operands, all rows of a CTA accumulated in TMEM): same contract as
+ * pu_wgrad for Kin, N >= 32 and M >= 4096; db is produced through a ones row and needs Kin % 128 != 0. */
+PU_API int pu_tc_wgrad_supported(long long M, int Kin, int N, int ldx, int lddy, int want_db);
+PU_API size_t pu_tc_wgrad_workspace_bytes(long long M, int Kin, int N);
+PU_API int pu_tc_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, int Kin, int N, float *dw,
+                       float *db, int accumulate, int mode, void *workspace, size_t workspace_bytes, int *error_flag,
+                       pu_stream_t stream);
 /* dw[K,N] (+)= x^T dy ; db[N] (+)= column sums of dy (db may be NULL).  Deterministic. */
 PU_API size_t pu_wgrad_workspace_bytes(long long M, int K, int N);
 PU_API int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, int K, int N, float *dw,

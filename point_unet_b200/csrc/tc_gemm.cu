@@ -724,6 +724,250 @@ static int dispatch_persist(const Params2 &q, cudaStream_t st) {
     return PU_ERR_UNSUPPORTED;
 }
 
+
+// =============================================================================================================
+// Tensor-core weight gradient:  dW[Kin, N] = sum_r X[r, Kin]^T dY[r, N]   (+ db = column sums of dY via a ones row)
+// The reduction runs over ROWS, so both operands are "MN-major" for the MMA (element (m, k) of A is X[k][m]: m
+// contiguous).  A 32-row x 32-column slab of a row-major matrix stored as 32 rows of 128 B with the usual 16-byte
+// chunk XOR (row % 8) is exactly the canonical MN-major SWIZZLE_128B atom stack, so the producers reuse the same
+// stores; only the descriptors (LBO = slab stride, SBO = 8-row group stride) and the major bits of the instruction
+// descriptor differ.  Each CTA owns a contiguous chunk of rows and one (128 x BN) block of dW, accumulates ALL its rows
+// in TMEM and writes one partial at the end; pu_tc_wgrad then reduces the partials in fixed order (deterministic).
+struct WParams {
+    const float *X; int ldx;   // [M, Kin]
+    const float *G; int ldg;   // [M, N]
+    long long M; int Kin, N;
+    long long rows_per_cta;
+    float *part;               // [gridDim.x][Kin][N]
+    float *db_part;            // [gridDim.x][N] or null (needs Kin % 128 != 0 for the free ones row)
+    int mode;
+    int raw_depth;
+    int *error_flag;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t slab_bytes) {
+    // MN-major SWIZZLE_128B: LBO = byte stride between 32-element MN slabs, SBO = byte stride between 8-row k groups
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {  // as make_idesc, a_major = b_major = 1 (MN-major)
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+constexpr int WG_THREADS = 256;
+constexpr int WG_ROWS = 32;  // rows (= MMA k) per pipeline step: 4 instructions of K = 8
+
+// copies a [32 rows x COLS] block of a row-major matrix (columns col0.., zero beyond ncols / row_end) into a raw slot
+template <int COLS>
+__device__ __forceinline__ void wg_raw_issue(char *slot, const float *__restrict__ base, int ld, long long row0, long long row_end,
+                                             int col0, int ncols, int tid) {
+    constexpr int CHUNKS = WG_ROWS * COLS / 4;  // 16-byte chunks
+#pragma unroll
+    for (int i = 0; i < (CHUNKS + WG_THREADS - 1) / WG_THREADS; ++i) {
+        const int idx = tid + WG_THREADS * i;
+        if (idx < CHUNKS) {
+            const int r = idx / (COLS / 4), c4 = (idx % (COLS / 4)) * 4;
+            const long long gr = row0 + r;
+            const bool valid = gr < row_end && col0 + c4 < ncols;  // ncols % 4 == 0 (host)
+            const float *src = valid ? base + (size_t)gr * ld + col0 + c4 : base;
+            cp_async16(slot + (size_t)idx * 16, src, valid);
+        }
+    }
+}
+// raw [32][COLS] -> operand image: slab s = 32 columns, each slab 32 rows x 128 B swizzled; optional ones row at column
+// `ones_col` (the bias-gradient trick) for valid rows
+template <int COLS>
+__device__ __forceinline__ void wg_convert(const char *slot, char *hi, char *lo, int tid, bool split, int ones_col,
+                                           long long row0, long long row_end) {
+    constexpr int CHUNKS = WG_ROWS * COLS / 4;
+#pragma unroll
+    for (int i = 0; i < (CHUNKS + WG_THREADS - 1) / WG_THREADS; ++i) {
+        const int idx = tid + WG_THREADS * i;
+        if (idx < CHUNKS) {
+            const int r = idx / (COLS / 4), c4 = (idx % (COLS / 4)) * 4;
+            float4 v = *reinterpret_cast<const float4 *>(slot + (size_t)idx * 16);
+            if (ones_col >= c4 && ones_col < c4 + 4 && row0 + r < row_end) {
+                const float one = 1.f;
+                if (ones_col == c4) v.x = one; else if (ones_col == c4 + 1) v.y = one; else if (ones_col == c4 + 2) v.z = one; else v.w = one;
+            }
+            const uint32_t off = (uint32_t)((c4 >> 5) * (WG_ROWS * 128)) + sw128(r, (c4 & 31) >> 2);
+            if (split) {
+                const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                *reinterpret_cast<float4 *>(hi + off) = h;
+                *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            } else {
+                *reinterpret_cast<float4 *>(hi + off) = v;
+            }
+        }
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w) {
+    constexpr int A_BYTES = WG_ROWS * BM * 4;   // 16 KB: 4 slabs of 32 rows x 128 B
+    constexpr int B_BYTES = WG_ROWS * BN * 4;
+    constexpr int STAGE = 2 * (A_BYTES + B_BYTES);  // hi + lo of both operands
+    constexpr int RAW = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ __align__(1024) char smem_raw[];
+    char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t stage_free[2], all_done;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k0 = blockIdx.y * BM;   // first Kin column (= MMA M index) of this CTA's block
+    const int n0 = blockIdx.z * BN;
+    const bool split = w.mode == 3;
+    const int D = w.raw_depth;
+    char *op_ring = smem;                       // 2 operand stages
+    char *raw_ring = smem + 2 * STAGE;          // D raw slots
+    const long long r_begin = (long long)blockIdx.x * w.rows_per_cta;
+    const long long r_end = min(w.M, r_begin + w.rows_per_cta);
+    const int nsteps = r_end > r_begin ? (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS) : 0;
+    // ones row: first padded M index of the last Kin block, if any
+    const int ones_col = (w.db_part && blockIdx.y == gridDim.y - 1 && (w.Kin % BM) != 0) ? (w.Kin - k0) : -1;
+
+    if (tid == 0) {
+        mbar_init(&stage_free[0], 1); mbar_init(&stage_free[1], 1); mbar_init(&all_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t idesc = make_idesc_mn(BN);
+
+    bool ok = true;
+    int issued = 0;
+    auto issue_one = [&]() {
+        if (issued < nsteps) {
+            char *slot = raw_ring + (size_t)(issued % D) * RAW;
+            const long long row0 = r_begin + (long long)issued * WG_ROWS;
+            wg_raw_issue<BM>(slot, w.X, w.ldx, row0, r_end, k0, w.Kin, tid);
+            wg_raw_issue<BN>(slot + A_BYTES, w.G, w.ldg, row0, r_end, n0, w.N, tid);
+        }
+        cp_async_commit();
+        ++issued;
+    };
+    for (int i = 0; i < D - 1; ++i) issue_one();
+    for (int it = 0; it < nsteps; ++it) {
+        issue_one();
+        cp_async_wait_dyn(D - 1);
+        const int s = it & 1, u = it >> 1;
+        char *a_hi = op_ring + (size_t)s * STAGE, *a_lo = a_hi + A_BYTES, *b_hi = a_lo + A_BYTES, *b_lo = b_hi + B_BYTES;
+        if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;
+        const char *slot = raw_ring + (size_t)(it % D) * RAW;
+        const long long row0 = r_begin + (long long)it * WG_ROWS;
+        wg_convert<BM>(slot, a_hi, a_lo, tid, split, ones_col, row0, r_end);
+        wg_convert<BN>(slot + A_BYTES, b_hi, b_lo, tid, split, -1, row0, r_end);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < WG_ROWS / UMMA_K; ++j) {  // 8 rows = one 1024-byte k group per slab
+                const uint64_t dah = make_desc_mn(smem_u32(a_hi) + j * 1024, WG_ROWS * 128);
+                const uint64_t dbh = make_desc_mn(smem_u32(b_hi) + j * 1024, WG_ROWS * 128);
+                umma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                if (split) {
+                    const uint64_t dal = make_desc_mn(smem_u32(a_lo) + j * 1024, WG_ROWS * 128);
+                    const uint64_t dbl = make_desc_mn(smem_u32(b_lo) + j * 1024, WG_ROWS * 128);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                }
+            }
+            umma_commit(&stage_free[s]);
+            if (it == nsteps - 1) umma_commit(&all_done);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (nsteps > 0) ok = mbar_wait(&all_done, 0u) && ok;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: TMEM lane = Kin index (k0 + lane), column = N index; warps 0-3 and 4-7 split the columns
+    {
+        const int quarter = warp & 3, chalf = warp >> 2;
+        const int m = quarter * 32 + lane;      // row of the dW block
+        const int gk = k0 + m;
+        float *prow = w.part + ((size_t)blockIdx.x * w.Kin + gk) * w.N + n0;
+#pragma unroll
+        for (int cc = 0; cc < BN / 2; cc += 16) {
+            const int c0 = chalf * (BN / 2) + cc;
+            float vals[16];
+            if (nsteps > 0) tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, vals);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vals[i] = 0.f;
+            }
+            if (gk < w.Kin) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n0 + c0 + i < w.N) prow[c0 + i] = vals[i];
+            } else if (m == ones_col && w.db_part) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n0 + c0 + i < w.N) w.db_part[(size_t)blockIdx.x * w.N + n0 + c0 + i] = vals[i];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+    if (tid == 0 && !ok && w.error_flag) *w.error_flag = 1;
+}
+
+struct WgPlan { int bn, gx, gy, gz, depth; long long rows_per_cta; size_t smem; };
+static WgPlan wgrad_plan_tc(long long M, int Kin, int N) {
+    WgPlan pl{};
+    pl.bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    pl.gy = ceil_div(Kin, BM);
+    pl.gz = ceil_div(N, pl.bn);
+    long long gx = kNumSMs / (pl.gy * pl.gz);
+    if (gx < 1) gx = 1;
+    const long long max_gx = (M + 4 * WG_ROWS - 1) / (4 * WG_ROWS);  // at least 128 rows per CTA
+    if (gx > max_gx) gx = max_gx;
+    if (gx < 1) gx = 1;
+    long long rpc = (M + gx - 1) / gx;
+    rpc = (rpc + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+    pl.rows_per_cta = rpc;
+    pl.gx = (int)((M + rpc - 1) / rpc);
+    const size_t stage = 2 * ((size_t)WG_ROWS * BM * 4 + (size_t)WG_ROWS * pl.bn * 4);
+    const size_t raw = (size_t)WG_ROWS * BM * 4 + (size_t)WG_ROWS * pl.bn * 4;
+    long long d = (long long)((kMaxDynSmem - 2 * stage - 1024) / raw);
+    pl.depth = (int)(d > MAX_RAW ? MAX_RAW : d);
+    pl.smem = 2 * stage + (size_t)pl.depth * raw + 1024;
+    return pl;
+}
+
+template <int BN>
+static int launch_wgrad(const WParams &w, const WgPlan &pl, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        PU_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        configured = true;
+    }
+    dim3 grid(pl.gx, pl.gy, pl.gz);
+    tc_wgrad_kernel<BN><<<grid, WG_THREADS, pl.smem, st>>>(w);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order)
+__global__ void __launch_bounds__(256) tc_reduce_parts_kernel(const float *__restrict__ part, int chunks, long long n,
+                                                              float *__restrict__ out, int accumulate) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += (double)part[(size_t)c * n + i];
+    out[i] = accumulate ? out[i] + (float)s : (float)s;
+}
+
 }  // namespace tc
 }  // namespace pu
 
@@ -793,6 +1037,48 @@ int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, co
     q.X = feature_set; q.ldx = ldx; q.G = g_agg; q.ldg = ldg; q.OUT = dx_direct; q.ldo = lddx;
     q.ntiles = (q.g.M + tc::BM - 1) / tc::BM;
     return tc::dispatch_persist<tc::EPI_ATT_BWD>(q, (cudaStream_t)stream);
+}
+
+/* Tensor-core weight gradient: dw[Kin,N] (+)= x^T dy, db[N] (+)= column sums of dy (db only when Kin % 128 != 0).
+ * Supported when Kin >= 32 or N > 32, all of Kin, N, ldx, lddy multiples of 4. */
+int pu_tc_wgrad_supported(long long M, int Kin, int N, int ldx, int lddy, int want_db) {
+    if (M < 4096 || (Kin & 3) || (N & 3) || (ldx & 3) || (lddy & 3) || N < 32 || Kin < 32) return 0;
+    if (want_db && (Kin % tc::BM) == 0) return 0;
+    return 1;
+}
+
+size_t pu_tc_wgrad_workspace_bytes(long long M, int Kin, int N) {
+    const tc::WgPlan pl = tc::wgrad_plan_tc(M, Kin, N);
+    return ((size_t)pl.gx * Kin * N + (size_t)pl.gx * N) * sizeof(float) + 256;
+}
+
+int pu_tc_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, int Kin, int N, float *dw, float *db,
+                int accumulate, int mode, void *workspace, size_t workspace_bytes, int *error_flag, pu_stream_t stream) {
+    if (!x || !dy || !dw || M < 1 || Kin < 1 || N < 1 || ldx < Kin || lddy < N) return PU_ERR_INVALID_ARG;
+    if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
+    if (!pu_tc_wgrad_supported(M, Kin, N, ldx, lddy, db != nullptr) || ((((uintptr_t)x) | ((uintptr_t)dy)) & 15))
+        return PU_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < pu_tc_wgrad_workspace_bytes(M, Kin, N)) return PU_ERR_WORKSPACE;
+    const tc::WgPlan pl = tc::wgrad_plan_tc(M, Kin, N);
+    if (pl.depth < 2) return PU_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::WParams w{};
+    w.X = x; w.ldx = ldx; w.G = dy; w.ldg = lddy; w.M = M; w.Kin = Kin; w.N = N; w.rows_per_cta = pl.rows_per_cta;
+    w.part = (float *)workspace;
+    w.db_part = db ? w.part + (size_t)pl.gx * Kin * N : nullptr;
+    w.mode = mode; w.raw_depth = pl.depth; w.error_flag = error_flag;
+    int rc;
+    if (pl.bn == 32) rc = tc::launch_wgrad<32>(w, pl, st);
+    else if (pl.bn == 64) rc = tc::launch_wgrad<64>(w, pl, st);
+    else rc = tc::launch_wgrad<128>(w, pl, st);
+    if (rc != PU_OK) return rc;
+    tc::tc_reduce_parts_kernel<<<ceil_div((long long)Kin * N, 256), 256, 0, st>>>(w.part, pl.gx, (long long)Kin * N, dw, accumulate);
+    PU_LAUNCH_CHECK();
+    if (db) {
+        tc::tc_reduce_parts_kernel<<<ceil_div(N, 256), 256, 0, st>>>(w.db_part, pl.gx, N, db, accumulate);
+        PU_LAUNCH_CHECK();
+    }
+    return PU_OK;
 }
 
 }  // extern "C"

@@ -38,6 +38,8 @@ _lib._OP_SIGS.update({
     "pu_tc_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "pu_tc_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p, c_void_p],
+    "pu_tc_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
+                    c_void_p, c_void_p],
     "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "pu_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                  c_void_p],
@@ -83,6 +85,9 @@ def _L():
         L.pu_point2prod_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.pu_tc_linear_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
         L.pu_tc_att_supported.argtypes = [c_int, c_int, c_int]
+        L.pu_tc_wgrad_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
+        L.pu_tc_wgrad_workspace_bytes.restype = c_size_t
+        L.pu_tc_wgrad_workspace_bytes.argtypes = [c_ll, c_int, c_int]
         L.pu_linear_row_tiles.argtypes = [c_ll, c_int]
         L.pu_bn_bwd_reduce_blocks.argtypes = [c_ll, c_int]
         L._pu_extra_declared = True
@@ -367,17 +372,26 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
     return out, mean, var
 
 
-def wgrad_raw(x, dy, want_db=False):
+def wgrad_raw(x, dy, want_db=False, tc_mode=None):
+    """dw = x^T dy (and db = column sums of dy): tensor cores for wide shapes, CUDA cores otherwise (no autograd)."""
     xr, M, K, ldx = rows(x)
     gr, Mg, N, ldg = rows(dy)
     assert M == Mg
     L = _L()
     dw = torch.empty((K, N), dtype=torch.float32, device=x.device)
     db = torch.empty(N, dtype=torch.float32, device=x.device) if want_db else None
+    mode = TC_MODE if tc_mode is None else tc_mode
+    if mode in (1, 3) and xr.data_ptr() % 16 == 0 and gr.data_ptr() % 16 == 0 and \
+            L.pu_tc_wgrad_supported(M, K, N, ldx, ldg, int(want_db)):
+        ws = workspace(L.pu_tc_wgrad_workspace_bytes(M, K, N), x.device, slot=2)
+        _call("pu_tc_wgrad", xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
+              db.data_ptr() if want_db else None, 0, mode, ws.data_ptr(), ws.numel(), tc_error_flag(x.device).data_ptr(),
+              _stream(x), tag=(M, K, N))
+        return dw, db
     nbytes = L.pu_wgrad_workspace_bytes(M, K, N)
     ws = workspace(nbytes, x.device, slot=2)
     _call("pu_wgrad", xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
-                          db.data_ptr() if want_db else None, 0, ws.data_ptr(), ws.numel(), _stream(x))
+          db.data_ptr() if want_db else None, 0, ws.data_ptr(), ws.numel(), _stream(x), tag=(M, K, N))
     return dw, db
 
 

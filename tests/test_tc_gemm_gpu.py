@@ -54,3 +54,29 @@ def test_tc_used_by_autograd_linear_and_att_pool():
     ops.TC_MODE = 3
     for a, b in zip(outs[0], outs[1]):
         assert rel(b, a) < 2e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(8192, 64, 64), (50000, 32, 32), (20000, 128, 128), (9000, 256, 512), (5000, 1536, 512),
+                                   (100000, 64, 32), (4100, 96, 40), (300000, 32, 64), (6000, 160, 32)])
+@pytest.mark.parametrize("mode", [3, 1])
+def test_tc_wgrad_matches_fp64(M, K, N, mode):
+    g = torch.Generator().manual_seed(M + K + N + 1)
+    x = torch.randn(M, K, generator=g) + 0.2
+    dy = torch.randn(M, N, generator=g)
+    want = x.double().t() @ dy.double()
+    want_db = dy.double().sum(0)
+    xg, dg = x.cuda(), dy.cuda()
+    ops.tc_error_flag(xg.device).zero_()
+    with_db = (K % 128) != 0
+    dw, db = ops.wgrad_raw(xg, dg, want_db=with_db, tc_mode=mode)
+    assert int(ops.tc_error_flag(xg.device).item()) == 0, "tcgen05 pipeline barrier timed out"
+    tol = 2e-5 if mode == 3 else 5e-3
+    assert rel(dw, want) < tol, (rel(dw, want), tol)
+    if with_db:
+        assert rel(db, want_db) < tol
+    dw0, _ = ops.wgrad_raw(xg, dg, tc_mode=0)
+    assert rel(dw, dw0) < (3e-5 if mode == 3 else 5e-3)
+    # strided operands (halves of wider buffers) and bit-determinism
+    wide = torch.zeros(M, 2 * K, device="cuda"); wide[:, K:] = xg
+    dw2, _ = ops.wgrad_raw(wide[:, K:], dg, tc_mode=mode)
+    assert torch.equal(dw2, dw)
