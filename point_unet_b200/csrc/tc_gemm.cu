@@ -728,10 +728,10 @@ static int dispatch_persist(const Params2 &q, cudaStream_t st) {
 // =============================================================================================================
 // Tensor-core weight gradient:  dW[Kin, N] = sum_r X[r, Kin]^T dY[r, N]   (+ db = column sums of dY via a ones row)
 // The reduction runs over ROWS, so both operands are "MN-major" for the MMA (element (m, k) of A is X[k][m]: m
-// contiguous).  A 32-row x 32-column slab of a row-major matrix stored as 32 rows of 128 B with the usual 16-byte
-// chunk XOR (row % 8) is exactly the canonical MN-major SWIZZLE_128B atom stack, so the producers reuse the same
-// stores; only the descriptors (LBO = slab stride, SBO = 8-row group stride) and the major bits of the instruction
-// descriptor differ.  Each CTA owns a contiguous chunk of rows and one (128 x BN) block of dW, accumulates ALL its rows
+// contiguous).  For 32-bit operands the only MN-major shared-memory layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom): a 32-column slab of a row-major matrix is stored as rows
+// of 128 B, and inside every 512-byte group of 4 rows the 32-BYTE chunk index is XOR-ed with (row % 4)
+// (Swizzle<2,5,2>).  Descriptors: layout type 1, LBO = slab stride, SBO = stride between 4-row groups (512 B).  Each CTA owns a contiguous chunk of rows and one (128 x BN) block of dW, accumulates ALL its rows
 // in TMEM and writes one partial at the end; pu_tc_wgrad then reduces the partials in fixed order (deterministic).
 struct WParams {
     const float *X; int ldx;   // [M, Kin]
@@ -746,9 +746,13 @@ struct WParams {
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t slab_bytes) {
-    // MN-major SWIZZLE_128B: LBO = byte stride between 32-element MN slabs, SBO = byte stride between 8-row k groups
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    // MN-major SWIZZLE_128B_BASE32B: LBO = byte stride between 32-element MN slabs, SBO = byte stride between 4-row k groups
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset inside a slab of the 16-byte piece holding columns cin..cin+3 (cin % 4 == 0, < 32) of k-row r
+__device__ __forceinline__ uint32_t sw128_32b(int r, int cin) {
+    return (uint32_t)((r >> 2) * 512 + (r & 3) * 128 + ((((cin >> 3) ^ (r & 3)) & 3) << 5) + ((cin >> 2) & 1) * 16);
 }
 __device__ __forceinline__ uint32_t make_idesc_mn(int n) {  // as make_idesc, a_major = b_major = 1 (MN-major)
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -790,7 +794,7 @@ __device__ __forceinline__ void wg_convert(const char *slot, char *hi, char *lo,
                 const float one = 1.f;
                 if (ones_col == c4) v.x = one; else if (ones_col == c4 + 1) v.y = one; else if (ones_col == c4 + 2) v.z = one; else v.w = one;
             }
-            const uint32_t off = (uint32_t)((c4 >> 5) * (WG_ROWS * 128)) + sw128(r, (c4 & 31) >> 2);
+            const uint32_t off = (uint32_t)((c4 >> 5) * (WG_ROWS * 128)) + sw128_32b(r, c4 & 31);
             if (split) {
                 const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
                 *reinterpret_cast<float4 *>(hi + off) = h;
@@ -870,7 +874,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < WG_ROWS / UMMA_K; ++j) {  // 8 rows = one 1024-byte k group per slab
+            for (int j = 0; j < WG_ROWS / UMMA_K; ++j) {  // 8 rows = two 512-byte k groups per slab
                 const uint64_t dah = make_desc_mn(smem_u32(a_hi) + j * 1024, WG_ROWS * 128);
                 const uint64_t dbh = make_desc_mn(smem_u32(b_hi) + j * 1024, WG_ROWS * 128);
                 umma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
