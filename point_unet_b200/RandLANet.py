@@ -190,7 +190,7 @@ class Network(torch.nn.Module):
             return ops.linear(x, w, b)
         rows_n = x.numel() // x.shape[-1]
         if is_training:
-            y, mean, var = ops.linear(x, w, b, want_stats=True)
+            y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True)
         else:
             y = ops.linear(x, w, b)
             mean = var = None
@@ -239,7 +239,7 @@ class Network(torch.nn.Module):
             w, b = self.v(scope + "/weights"), self.v(scope + "/biases")
             rows_n = x.numel() // x.shape[-1]
             if is_training:
-                y, mean, var = ops.linear(x, w, b, want_stats=True)
+                y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True)
             else:
                 y, mean, var = ops.linear(x, w, b), None, None
             mean, var, moving = self._bn_stats(scope, mean, var, rows_n, is_training)

@@ -193,9 +193,19 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
             }
         }
     } else {
-        // rows ty*8 .. ty*8+7 are one half of point (m0/16 + ty/2); the other half lives in lane ^ 16
-        static_assert(BM == 128 && TM == 8 && TX == 16, "att epilogue layout");
-        const long long pt = m0 / 16 + ty / 2;
+        // A point = 16 consecutive rows.  <128,64,8,4>: a thread holds 8 of them, the other half lives in lane ^ 16.
+        // <256,16,4,4>: a thread holds 4, the other three quarters live in lanes ^4, ^8, ^12 (ty = lane >> 2).
+        static_assert((BM == 128 && TM == 8 && TX == 16) || (BM == 256 && TM == 4 && TX == 4), "att epilogue layout");
+        auto point_reduce_max = [](float v) {
+            if constexpr (TM == 8) return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+            else { v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4)); return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8)); }
+        };
+        auto point_reduce_sum = [](float v) {
+            if constexpr (TM == 8) return v + __shfl_xor_sync(0xffffffffu, v, 16);
+            else { v += __shfl_xor_sync(0xffffffffu, v, 4); return v + __shfl_xor_sync(0xffffffffu, v, 8); }
+        };
+        const long long pt = m0 / 16 + (ty * TM) / 16;
+        const bool writer = ((ty * TM) & 15) == 0;
         const bool pt_ok = (m0 + ty * TM) < p.M && gn < p.N;
         float cmax[TN], csum[TN];
 #pragma unroll
@@ -203,14 +213,14 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
             float m = acc[0][j];
 #pragma unroll
             for (int i = 1; i < TM; ++i) m = fmaxf(m, acc[i][j]);
-            cmax[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            cmax[j] = point_reduce_max(m);
         }
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < TM; ++i) { acc[i][j] = __expf(acc[i][j] - cmax[j]); s += acc[i][j]; }
-            csum[j] = s + __shfl_xor_sync(0xffffffffu, s, 16);
+            csum[j] = point_reduce_sum(s);
         }
         float x[TM][TN];
 #pragma unroll
@@ -226,9 +236,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
                 float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < TM; ++i) s = fmaf(x[i][j], acc[i][j], s);
-                num[j] = s + __shfl_xor_sync(0xffffffffu, s, 16);
+                num[j] = point_reduce_sum(s);
             }
-            if (pt_ok && (ty & 1) == 0)
+            if (pt_ok && writer)
                 *reinterpret_cast<float4 *>(p.OUT + (size_t)pt * p.ldo + gn) =
                     make_float4(num[0] / csum[0], num[1] / csum[1], num[2] / csum[2], num[3] / csum[3]);
         } else {  // EPI_ATT_BWD
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
                     acc[i][j] *= inv;                      // s_k  (softmax score)
                     s = fmaf(g[j] * x[i][j], acc[i][j], s);  // sum_k ds_k s_k,  ds_k = g x_k
                 }
-                dot[j] = s + __shfl_xor_sync(0xffffffffu, s, 16);
+                dot[j] = point_reduce_sum(s);
             }
             if (pt_ok) {
 #pragma unroll
@@ -674,9 +684,9 @@ static inline int ew_grid(long long total) {
 
 template <int EPI>
 static int launch_gemm(const GemmParams &p, cudaStream_t st) {
-    if (EPI == EPI_STORE && p.N <= 16) {
+    if (p.N <= 16) {
         dim3 grid(ceil_div(p.M, 256), ceil_div(p.N, 16));
-        gemm_kernel<256, 16, 4, 4, EPI_STORE><<<grid, 256, 0, st>>>(p);
+        gemm_kernel<256, 16, 4, 4, EPI><<<grid, 256, 0, st>>>(p);
     } else {
         dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, 64));
         gemm_kernel<128, 64, 8, 4, EPI><<<grid, 256, 0, st>>>(p);

@@ -399,9 +399,10 @@ class _LinearFn(torch.autograd.Function):
     """y = x w + b with batch statistics of y as non-differentiable side outputs."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, want_stats):
+    def forward(ctx, x, w, bias, want_stats, zero_bias_grad):
         w = w.contiguous()
         res = linear_raw(x, w, bias, want_stats=want_stats)
+        ctx.zero_bias_grad = zero_bias_grad
         y, mean, var = res if want_stats else (res, None, None)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
@@ -418,15 +419,23 @@ class _LinearFn(torch.autograd.Function):
         if ctx.x_needs:
             dx = linear_raw(dy, None, wt=w)  # dx = dy w^T: the K-major form of w^T is w itself
             dx = dx.view(x.shape)
-        dw, db = wgrad_raw(x, dy, want_db=ctx.has_bias)
-        return dx, dw, db, None
+        if ctx.has_bias and ctx.zero_bias_grad:
+            # a bias that feeds a training-mode batch norm has an identically zero gradient (the BN backward makes every
+            # column of dy sum to zero); return the exact value instead of accumulating rounding noise
+            dw, _ = wgrad_raw(x, dy, want_db=False)
+            db = torch.zeros(dy.shape[-1], dtype=torch.float32, device=dy.device)
+        else:
+            dw, db = wgrad_raw(x, dy, want_db=ctx.has_bias)
+        return dx, dw, db, None, None
 
 
-def linear(x, w, bias=None, want_stats=False):
+def linear(x, w, bias=None, want_stats=False, zero_bias_grad=False):
     """``y = x w + b`` over the last axis (1x1 conv / dense); with ``want_stats`` also returns the batch mean and
-    biased variance of ``y`` per channel (non-differentiable side outputs consumed by :func:`bn_act`)."""
+    biased variance of ``y`` per channel (non-differentiable side outputs consumed by :func:`bn_act`).
+    ``zero_bias_grad``: the caller asserts that ``y`` goes straight into a training-mode batch norm, whose backward
+    makes the bias gradient identically zero."""
     _need_cuda(x, w)
-    return _LinearFn.apply(x, w, bias, want_stats)
+    return _LinearFn.apply(x, w, bias, want_stats, zero_bias_grad)
 
 
 def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shift2=None):
