@@ -21,6 +21,35 @@ namespace lfa {
 
 // ---------------------------------------------------------------------------------------------
 // out[b, r, 0:d] = src[b, idx[b, r], 0:d]        r in [0, R)   (R = M*K rows per cloud)
+// 128-bit path: grid (x, B); a thread owns ONE 16-byte column chunk (fixed for its lifetime: no div/mod in the loop) and
+// walks rows with 4 independent (index -> row -> streaming store) chains in flight.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) gather_rows_v4_kernel(const float *__restrict__ src, int ld_src, int n_src,
+                                                             const int32_t *__restrict__ idx, int R,
+                                                             float *__restrict__ dst, int ld_dst, int cpr) {
+    const int b = blockIdx.y;
+    const int c = (threadIdx.x % cpr) * 4, rl = threadIdx.x / cpr, rpb = 256 / cpr;
+    if (rl >= rpb) return;
+    const float *sb = src + (size_t)b * n_src * ld_src + c;
+    const int32_t *ib = idx + (size_t)b * R;
+    float *db = dst + (size_t)b * R * ld_dst + c;
+    const int step = gridDim.x * rpb;
+    int r = blockIdx.x * rpb + rl;
+    for (; r + (UNROLL - 1) * step < R; r += UNROLL * step) {
+        int j[UNROLL];
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) j[u] = ib[r + u * step];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = *reinterpret_cast<const float4 *>(sb + (size_t)j[u] * ld_src);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) st_stream_f4(reinterpret_cast<float4 *>(db + (size_t)(r + u * step) * ld_dst), v[u]);
+    }
+    for (; r < R; r += step)
+        st_stream_f4(reinterpret_cast<float4 *>(db + (size_t)r * ld_dst),
+                     *reinterpret_cast<const float4 *>(sb + (size_t)ib[r] * ld_src));
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ src, int ld_src, int n_src,
                                                           const int32_t *__restrict__ idx, long long R, int B,
@@ -45,6 +74,40 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
 
 // grad_src[b, j, 0:d] = sum over e in [off[b*n+j], off[b*n+j+1]) of grad_out[perm[e], 0:d]
 // (perm holds GLOBAL row numbers b*R + r, ascending inside a segment => fixed summation order)
+// 128-bit path: a thread owns one 16-byte column chunk; the segment is walked 4 edges at a time (4 independent
+// perm -> row loads in flight), added in the fixed ascending order.
+__global__ void __launch_bounds__(256) segment_sum_v4_kernel(const float *__restrict__ grad_out, int ld_go,
+                                                             const int32_t *__restrict__ off,
+                                                             const int32_t *__restrict__ perm, long long n_targets,
+                                                             float *__restrict__ grad_src, int ld_gs, int cpr,
+                                                             int accumulate) {
+    const int c = (threadIdx.x % cpr) * 4, rl = threadIdx.x / cpr, rpb = 256 / cpr;
+    if (rl >= rpb) return;
+    const float *g = grad_out + c;
+    for (long long j = (long long)blockIdx.x * rpb + rl; j < n_targets; j += (long long)gridDim.x * rpb) {
+        const int e0 = off[j], e1 = off[j + 1];
+        float *o = grad_src + (size_t)j * ld_gs + c;
+        float4 acc = accumulate ? *reinterpret_cast<float4 *>(o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = e0;
+        for (; e + 4 <= e1; e += 4) {
+            const int p0 = perm[e], p1 = perm[e + 1], p2 = perm[e + 2], p3 = perm[e + 3];
+            const float4 a = ld_stream_f4(reinterpret_cast<const float4 *>(g + (size_t)p0 * ld_go));
+            const float4 b = ld_stream_f4(reinterpret_cast<const float4 *>(g + (size_t)p1 * ld_go));
+            const float4 cc = ld_stream_f4(reinterpret_cast<const float4 *>(g + (size_t)p2 * ld_go));
+            const float4 dd = ld_stream_f4(reinterpret_cast<const float4 *>(g + (size_t)p3 * ld_go));
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            acc.x += cc.x; acc.y += cc.y; acc.z += cc.z; acc.w += cc.w;
+            acc.x += dd.x; acc.y += dd.y; acc.z += dd.z; acc.w += dd.w;
+        }
+        for (; e < e1; ++e) {
+            const float4 a = ld_stream_f4(reinterpret_cast<const float4 *>(g + (size_t)perm[e] * ld_go));
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+        *reinterpret_cast<float4 *>(o) = acc;
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) segment_sum_kernel(const float *__restrict__ grad_out, int ld_go,
                                                           const int32_t *__restrict__ off,
@@ -59,18 +122,9 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float *__restric
         const int c = (int)(t - j * cpr) * VEC;
         const int e0 = off[j], e1 = off[j + 1];
         float *o = grad_src + (size_t)j * ld_gs + c;
-        if (VEC == 4) {
-            float4 acc = accumulate ? *reinterpret_cast<float4 *>(o) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int e = e0; e < e1; ++e) {
-                const float4 g = ld_stream_f4(reinterpret_cast<const float4 *>(grad_out + (size_t)perm[e] * ld_go + c));
-                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-            }
-            *reinterpret_cast<float4 *>(o) = acc;
-        } else {
-            float acc = accumulate ? *o : 0.f;
-            for (int e = e0; e < e1; ++e) acc += grad_out[(size_t)perm[e] * ld_go + c];
-            *o = acc;
-        }
+        float acc = accumulate ? *o : 0.f;
+        for (int e = e0; e < e1; ++e) acc += grad_out[(size_t)perm[e] * ld_go + c];
+        *o = acc;
     }
 }
 
@@ -255,9 +309,14 @@ int pu_gather_rows_fwd(const float *src, int ld_src, int n_src, const int32_t *i
         return PU_ERR_INVALID_ARG;
     if (B == 0 || rows_per_cloud == 0) return PU_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((d & 3) == 0 && vec4_ok(src, ld_src) && vec4_ok(dst, ld_dst)) {
-        gather_rows_kernel<4><<<grid_for((long long)B * rows_per_cloud * (d / 4)), 256, 0, st>>>(
-            src, ld_src, n_src, idx, rows_per_cloud, B, dst, ld_dst, d);
+    if ((d & 3) == 0 && d <= 1024 && rows_per_cloud < (1ll << 31) && vec4_ok(src, ld_src) && vec4_ok(dst, ld_dst)) {
+        const int cpr = d / 4, rpb = 256 / cpr;
+        long long gx = (rows_per_cloud + (long long)rpb * 4 - 1) / ((long long)rpb * 4);  // ~4 rows per thread
+        const long long cap = (long long)kNumSMs * 16 / (B > 0 ? B : 1) + 1;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        dim3 grid((unsigned)gx, B);
+        gather_rows_v4_kernel<4><<<grid, 256, 0, st>>>(src, ld_src, n_src, idx, (int)rows_per_cloud, dst, ld_dst, cpr);
     } else {
         gather_rows_kernel<1><<<grid_for((long long)B * rows_per_cloud * d), 256, 0, st>>>(
             src, ld_src, n_src, idx, rows_per_cloud, B, dst, ld_dst, d);
@@ -272,9 +331,14 @@ int pu_segment_sum(const float *grad_out, int ld_go, const int32_t *offsets, con
         return PU_ERR_INVALID_ARG;
     if (n_targets == 0) return PU_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((d & 3) == 0 && vec4_ok(grad_out, ld_go) && vec4_ok(grad_src, ld_gs)) {
-        segment_sum_kernel<4><<<grid_for(n_targets * (d / 4)), 256, 0, st>>>(grad_out, ld_go, offsets, perm, n_targets,
-                                                                          grad_src, ld_gs, d, accumulate);
+    if ((d & 3) == 0 && d <= 1024 && vec4_ok(grad_out, ld_go) && vec4_ok(grad_src, ld_gs)) {
+        const int cpr = d / 4, rpb = 256 / cpr;
+        long long gx = (n_targets + rpb - 1) / rpb;
+        const long long cap = (long long)kNumSMs * 16;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        segment_sum_v4_kernel<<<(unsigned)gx, 256, 0, st>>>(grad_out, ld_go, offsets, perm, n_targets, grad_src, ld_gs, cpr,
+                                                           accumulate);
     } else {
         segment_sum_kernel<1><<<grid_for(n_targets * d), 256, 0, st>>>(grad_out, ld_go, offsets, perm, n_targets,
                                                                     grad_src, ld_gs, d, accumulate);
