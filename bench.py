@@ -111,7 +111,22 @@ def algorithmic(name, tag):
     if name == "pu_segment_sum":
         R, n_tgt, d = tag
         return 4 * R + 4 * n_tgt * d + 4 * R * d, 0, "hbm"
+    if name in ("pu_tc_linear_fwd", "pu_linear_fwd", "pu_tc_wgrad", "pu_wgrad"):
+        # 1x1 conv / dgrad / wgrad over M rows: read x [M,K] and y or dy [M,N] once (weights are negligible);
+        # 2*K*N/(4*(K+N)) flop per byte stays below the B200 ridge (~212 flop/B) for every layer => HBM-bound
+        M, K, N = tag
+        return 4 * M * (K + N), 2 * M * K * N, "hbm"
     return 0, 0, "hbm"
+
+
+def load_traffic():
+    """Measured DRAM bytes per launch of each C-ABI entry (ncu dram__bytes_read+write), written by
+    tools/summarize_launches.py into profiles/; null if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 def make_batch(rank, batch, n_points, kind="brats"):
@@ -238,7 +253,7 @@ def run_ours(args):
     breakdown = kt.summary()
     top = max(breakdown.items(), key=lambda kv: kv[1][1])[0] if breakdown else "pu_att_pooling_fwd"
     RF = ("pu_att_pooling_fwd", "pu_att_pooling_bwd", "pu_tc_att_pooling_fwd", "pu_tc_att_pooling_bwd",
-          "pu_gather_rows_fwd", "pu_segment_sum")
+          "pu_gather_rows_fwd", "pu_segment_sum", "pu_tc_linear_fwd", "pu_linear_fwd", "pu_tc_wgrad", "pu_wgrad")
     if top not in RF:
         # report the roofline on a kernel whose algorithmic bytes are defined in SURVEY 8(d)
         cands = {k: v for k, v in breakdown.items() if k in RF}
@@ -300,8 +315,9 @@ def run_ours(args):
             achieved, peak, runit = tot_f / (t_ms * 1e-3) / 1e12, peaks["tensor_sustained"], "TFLOP/s"
         else:
             achieved, peak, runit = tot_b / (t_ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
+        traffic = load_traffic().get(top_rf)
         roofline = dict(kernel=top_rf, bound=bound, achieved=achieved, peak=peak, unit=runit, frac=achieved / peak,
-                        traffic=None, launches_per_step=n_l / args.steps, ms_per_step=t_ms / args.steps,
+                        traffic=traffic, launches_per_step=n_l / args.steps, ms_per_step=t_ms / args.steps,
                         algorithmic_gb_per_step=tot_b / args.steps / 1e9, gflop_per_step=tot_f / args.steps / 1e9,
                         hbm_gbs_equiv=tot_b / (t_ms * 1e-3) / 1e9, peak_source=peaks["source"],
                         peak_kind="sustained (kernel timed inside a long step)" if bound == "tensor" else "copy")

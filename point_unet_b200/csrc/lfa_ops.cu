@@ -286,6 +286,89 @@ __global__ void __launch_bounds__(256) p2v_write_kernel(const float *__restrict_
     for (int c = 0; c < C; ++c) vol[v * C + c] = probs[(size_t)i * C + c];
 }
 
+// 128-bit max-pool forward for K = 16: a thread owns one 16-byte column chunk of one output point, loads the 16
+// neighbour ids as four int4 and keeps all 16 row loads in flight before reducing.
+__global__ void __launch_bounds__(256) maxpool_fwd_v4_kernel(const float *__restrict__ feat, int ld_f, int n_src,
+                                                             const int32_t *__restrict__ idx, int M,
+                                                             float *__restrict__ out, int ld_o,
+                                                             unsigned char *__restrict__ ties, int d, int cpr) {
+    constexpr int K = 16;
+    const int b = blockIdx.y;
+    const int c = (threadIdx.x % cpr) * 4, rl = threadIdx.x / cpr, rpb = 256 / cpr;
+    if (rl >= rpb) return;
+    const float *fb = feat + (size_t)b * n_src * ld_f + c;
+    for (int m = blockIdx.x * rpb + rl; m < M; m += gridDim.x * rpb) {
+        const size_t gm = (size_t)b * M + m;
+        const int4 *ip = reinterpret_cast<const int4 *>(idx + gm * K);
+        int j[K];
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q) {
+            const int4 t = ip[q];
+            j[4 * q] = t.x; j[4 * q + 1] = t.y; j[4 * q + 2] = t.z; j[4 * q + 3] = t.w;
+        }
+        float4 v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = *reinterpret_cast<const float4 *>(fb + (size_t)j[k] * ld_f);
+        float4 best = v[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            best.x = fmaxf(best.x, v[k].x); best.y = fmaxf(best.y, v[k].y);
+            best.z = fmaxf(best.z, v[k].z); best.w = fmaxf(best.w, v[k].w);
+        }
+        st_stream_f4(reinterpret_cast<float4 *>(out + gm * ld_o + c), best);
+        if (ties) {
+            int cx = 0, cy = 0, cz = 0, cw = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                cx += v[k].x == best.x; cy += v[k].y == best.y; cz += v[k].z == best.z; cw += v[k].w == best.w;
+            }
+            *reinterpret_cast<uchar4 *>(ties + gm * d + c) = make_uchar4((unsigned char)cx, (unsigned char)cy, (unsigned char)cz, (unsigned char)cw);
+        }
+    }
+}
+
+// 128-bit max-pool backward: fixed column chunk per thread, the (short) inverse list walked two edges at a time
+__global__ void __launch_bounds__(256) maxpool_bwd_v4_kernel(const float *__restrict__ feat, int ld_f,
+                                                             const float *__restrict__ out, int ld_o,
+                                                             const unsigned char *__restrict__ ties,
+                                                             const float *__restrict__ g_out, int ld_g,
+                                                             const int32_t *__restrict__ off,
+                                                             const int32_t *__restrict__ perm, long long n_targets,
+                                                             int K, float *__restrict__ g_feat, int ld_gf, int d, int cpr) {
+    const int c = (threadIdx.x % cpr) * 4, rl = threadIdx.x / cpr, rpb = 256 / cpr;
+    if (rl >= rpb) return;
+    for (long long j = (long long)blockIdx.x * rpb + rl; j < n_targets; j += (long long)gridDim.x * rpb) {
+        const float4 x = *reinterpret_cast<const float4 *>(feat + (size_t)j * ld_f + c);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int e0 = off[j], e1 = off[j + 1];
+        int e = e0;
+        auto add = [&](const float4 &o, const float4 &g, const uchar4 &t) {
+            if (x.x == o.x) acc.x += g.x / (float)t.x;
+            if (x.y == o.y) acc.y += g.y / (float)t.y;
+            if (x.z == o.z) acc.z += g.z / (float)t.z;
+            if (x.w == o.w) acc.w += g.w / (float)t.w;
+        };
+        for (; e + 2 <= e1; e += 2) {
+            const long long m0 = perm[e] / K, m1 = perm[e + 1] / K;
+            const float4 o0 = *reinterpret_cast<const float4 *>(out + (size_t)m0 * ld_o + c);
+            const float4 o1 = *reinterpret_cast<const float4 *>(out + (size_t)m1 * ld_o + c);
+            const float4 g0 = *reinterpret_cast<const float4 *>(g_out + (size_t)m0 * ld_g + c);
+            const float4 g1 = *reinterpret_cast<const float4 *>(g_out + (size_t)m1 * ld_g + c);
+            const uchar4 t0 = *reinterpret_cast<const uchar4 *>(ties + (size_t)m0 * d + c);
+            const uchar4 t1 = *reinterpret_cast<const uchar4 *>(ties + (size_t)m1 * d + c);
+            add(o0, g0, t0);
+            add(o1, g1, t1);
+        }
+        for (; e < e1; ++e) {
+            const long long m0 = perm[e] / K;
+            add(*reinterpret_cast<const float4 *>(out + (size_t)m0 * ld_o + c),
+                *reinterpret_cast<const float4 *>(g_out + (size_t)m0 * ld_g + c),
+                *reinterpret_cast<const uchar4 *>(ties + (size_t)m0 * d + c));
+        }
+        st_stream_f4(reinterpret_cast<float4 *>(g_feat + (size_t)j * ld_gf + c), acc);
+    }
+}
+
 static inline int grid_for(long long total, int block = 256) {
     long long g = (total + block - 1) / block;
     const long long cap = (long long)kNumSMs * 32;  // grid-stride loops; cap at 32 CTAs per SM
@@ -403,7 +486,15 @@ int pu_random_sample_fwd(const float *feat, int ld_f, int n_src, const int32_t *
         return PU_ERR_INVALID_ARG;
     if (B == 0 || M == 0) return PU_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((d & 3) == 0 && vec4_ok(feat, ld_f) && vec4_ok(out, ld_o)) {
+    if (K == 16 && (d & 3) == 0 && d <= 1024 && vec4_ok(feat, ld_f) && vec4_ok(out, ld_o) &&
+        ((((uintptr_t)pool_idx) & 15) == 0) && (!ties || ((((uintptr_t)ties) & 3) == 0))) {
+        const int cpr = d / 4, rpb = 256 / cpr;
+        long long gx = ((long long)M + rpb - 1) / rpb;
+        const long long cap = (long long)kNumSMs * 16 / (B > 0 ? B : 1) + 1;
+        if (gx > cap) gx = cap;
+        dim3 grid((unsigned)gx, B);
+        maxpool_fwd_v4_kernel<<<grid, 256, 0, st>>>(feat, ld_f, n_src, pool_idx, M, out, ld_o, ties, d, cpr);
+    } else if ((d & 3) == 0 && vec4_ok(feat, ld_f) && vec4_ok(out, ld_o)) {
         maxpool_fwd_kernel<4><<<grid_for((long long)B * M * (d / 4)), 256, 0, st>>>(feat, ld_f, n_src, pool_idx, M, K, B,
                                                                                   out, ld_o, ties, d);
     } else {
@@ -421,7 +512,16 @@ int pu_random_sample_bwd(const float *feat, int ld_f, const float *out, int ld_o
         return PU_ERR_INVALID_ARG;
     if (n_targets == 0) return PU_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((d & 3) == 0) {
+    if ((d & 3) == 0 && d <= 1024 && vec4_ok(feat, ld_f) && vec4_ok(out, ld_o) && vec4_ok(g_out, ld_g) &&
+        vec4_ok(g_feat, ld_gf) && ((((uintptr_t)ties) & 3) == 0)) {
+        const int cpr = d / 4, rpb = 256 / cpr;
+        long long gx = (n_targets + rpb - 1) / rpb;
+        const long long cap = (long long)kNumSMs * 16;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        maxpool_bwd_v4_kernel<<<(unsigned)gx, 256, 0, st>>>(feat, ld_f, out, ld_o, ties, g_out, ld_g, offsets, perm, n_targets,
+                                                           K, g_feat, ld_gf, d, cpr);
+    } else if ((d & 3) == 0) {
         maxpool_bwd_kernel<4><<<grid_for(n_targets * (d / 4)), 256, 0, st>>>(feat, ld_f, out, ld_o, ties, g_out, ld_g,
                                                                            offsets, perm, n_targets, K, g_feat, ld_gf, d);
     } else {

@@ -1,0 +1,40 @@
+"""Turns an ncu launch list (CSV with gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum per launch)
+into profiles/<tag>_launch_summary.txt and profiles/r1_kernel_traffic.json.   python tools/summarize_launches.py <csv> <tag>"""
+import collections, csv, json, os, re, sys
+src, tag = sys.argv[1], sys.argv[2]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lines = [l for l in open(src) if not l.startswith("==")]
+launch = collections.OrderedDict()
+MUL = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+for row in csv.DictReader(lines):
+    d = launch.setdefault(row["ID"], dict(name=row["Kernel Name"], grid=row["Grid Size"], us=0.0, rd=0.0, wr=0.0))
+    v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]; m = row["Metric Name"]
+    if m == "gpu__time_duration.sum": d["us"] = v / 1e3 if u == "ns" else (v if u == "us" else v * 1e3)
+    elif m.startswith("dram__bytes_read"): d["rd"] = v * MUL[u]
+    elif m.startswith("dram__bytes_write"): d["wr"] = v * MUL[u]
+def short(n): return re.sub(r"void |pu::|\(.*", "", n)[:64]
+agg = collections.OrderedDict()
+for d in launch.values():
+    a = agg.setdefault(short(d["name"]), dict(n=0, us=0.0, bytes=0.0)); a["n"] += 1; a["us"] += d["us"]; a["bytes"] += d["rd"] + d["wr"]
+tot = sum(d["us"] for d in launch.values())
+out = [f"# ncu launch list of ONE training step (batch 4 x 180k BraTS-shaped clouds), {len(launch)} launches, {tot/1e3:.2f} ms of kernel time",
+       "# (cold-cache, serialised durations: compare SHARES, not absolutes)", f"{'share':>6} {'ms':>8} {'n':>5} {'GB/s(dram)':>10}  kernel"]
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+    out.append(f"{100*a['us']/tot:6.2f} {a['us']/1e3:8.3f} {a['n']:5d} {a['bytes']/max(a['us'],1e-9)/1e3:10.0f}  {k}")
+out.append("\n# 25 longest individual launches")
+for d in sorted(launch.values(), key=lambda d: -d["us"])[:25]:
+    out.append(f"{d['us']:9.1f} us  {(d['rd']+d['wr'])/d['us']/1e3:7.0f} GB/s  rd {d['rd']/1e6:8.1f} MB  wr {d['wr']/1e6:8.1f} MB  {short(d['name'])} {d['grid']}")
+os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+open(os.path.join(ROOT, "profiles", f"{tag}_launch_summary.txt"), "w").write("\n".join(out) + "\n")
+# per C-ABI entry traffic (bytes per launch), mapping kernel names to the entry points bench.py times
+ENTRY = {"tc::tc_persist_kernel<64, 0>": "pu_tc_linear_fwd", "tc::tc_persist_kernel<32, 0>": "pu_tc_linear_fwd", "tc::tc_persist_kernel<128, 0>": "pu_tc_linear_fwd",
+         "tc::tc_linear_kernel": "pu_tc_linear_fwd", "tc::tc_persist_kernel<64, 1>": "pu_tc_att_pooling_fwd", "tc::tc_persist_kernel<32, 1>": "pu_tc_att_pooling_fwd",
+         "tc::tc_persist_kernel<64, 2>": "pu_tc_att_pooling_bwd", "tc::tc_persist_kernel<32, 2>": "pu_tc_att_pooling_bwd", "tc::tc_wgrad_kernel": "pu_tc_wgrad",
+         "lfa::gather_rows": "pu_gather_rows_fwd", "lfa::segment_sum": "pu_segment_sum", "mlp::wgrad": "pu_wgrad"}
+tr = collections.defaultdict(lambda: [0, 0.0])
+for k, a in agg.items():
+    for pat, entry in ENTRY.items():
+        if k.startswith(pat):
+            tr[entry][0] += a["n"]; tr[entry][1] += a["bytes"]
+json.dump({e: v[1] / v[0] for e, v in tr.items() if v[0]}, open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json"), "w"), indent=1)
+print("\n".join(out[:30]))
