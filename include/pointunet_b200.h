@@ -125,17 +125,20 @@ PU_API int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int ti
  * mode 1 = plain TF32.  stat_sum/stat_m2: per-128-row-tile batch-norm partials as in pu_linear_fwd.
  * *error_flag (device int, optional) is set to 1 if an internal barrier wait timed out. */
 PU_API int pu_tc_linear_supported(long long M, int K, int N, int ldx, int ldwt, int ldy);
+PU_API size_t pu_tc_workspace_bytes(int K, int N); /* scratch for the packed weight image (streamed-weight kernels) */
 PU_API int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const float *bias, float *y, int ldy,
                             long long M, int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode,
-                            int *error_flag, pu_stream_t stream);
+                            int *error_flag, void *workspace, size_t workspace_bytes, pu_stream_t stream);
 /* Tensor-core forms of pu_att_pooling_fwd / _bwd (channel width d >= 32, K = 16): same contract, but `wt` is the
  * TRANSPOSED FC kernel [d_out, d_in] (K-major); the softmax-over-K epilogue runs out of TMEM. */
 PU_API int pu_tc_att_supported(int K, int d, int ldx);
 PU_API int pu_tc_att_pooling_fwd(const float *feature_set, int ldx, const float *wt, long long P, int K, int d,
-                                 float *f_agg, int ldo, int mode, int *error_flag, pu_stream_t stream);
+                                 float *f_agg, int ldo, int mode, int *error_flag, void *workspace,
+                                 size_t workspace_bytes, pu_stream_t stream);
 PU_API int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, const float *g_agg, int ldg,
                                  long long P, int K, int d, float *d_act, int ldda, float *dx_direct, int lddx,
-                                 int mode, int *error_flag, pu_stream_t stream);
+                                 int mode, int *error_flag, void *workspace, size_t workspace_bytes,
+                                 pu_stream_t stream);
 /* Tensor-core weight gradient (tcgen05, MN-major operands, all rows of a CTA accumulated in TMEM): same contract as
  * pu_wgrad for Kin, N >= 32 and M >= 4096; db is produced through a ones row and needs Kin % 128 != 0. */
 PU_API int pu_tc_wgrad_supported(long long M, int Kin, int N, int ldx, int lddy, int want_db);

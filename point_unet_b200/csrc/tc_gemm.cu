@@ -378,6 +378,7 @@ __device__ __forceinline__ void raw_convert(const char *slot, char *hi, char *lo
 
 struct Params2 {
     int raw_depth;             // cp.async raw-ring depth D (k-blocks of 16 KB in flight per CTA = D - 1)
+    const char *Bp;            // streamed variant: packed hi/lo swizzled weight image (tc_pack_weight_kernel)
     Params g;                  // the GEMM proper (A = x rows, Bt = weight in K-major form, C, bias, stats, mode)
     const float *X; int ldx;   // att: feature_set rows (same memory as A)
     const float *G; int ldg;   // att bwd: upstream gradient [M/16, N]
@@ -392,20 +393,56 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int EPI>
+// ---- streamed weight operand: pre-split / pre-swizzled image in global memory, fetched with 1-D bulk copies (TMA engine)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// packed image: [n slab][k block][hi: BN rows x 128 B swizzled | lo: same]; one thread per 16-byte chunk
+__global__ void __launch_bounds__(256) tc_pack_weight_kernel(const float *__restrict__ Bt, int ldb, int N, int K, int BN, int nkb,
+                                                             int nslabs, int split, char *__restrict__ out) {
+    const long long total = (long long)nslabs * nkb * BN * 8;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t & 7);
+        const int r = (int)((t >> 3) % BN);
+        const long long sk = (t >> 3) / BN;  // slab * nkb + kb
+        const int kb = (int)(sk % nkb), slab = (int)(sk / nkb);
+        const int gn = slab * BN + r, gk = kb * BK + c * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gn < N && gk < K) v = *reinterpret_cast<const float4 *>(Bt + (size_t)gn * ldb + gk);
+        char *base = out + (size_t)sk * (2 * BN * 128);
+        const uint32_t off = sw128(r, c);
+        if (split) {
+            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+            *reinterpret_cast<float4 *>(base + off) = h;
+            *reinterpret_cast<float4 *>(base + BN * 128 + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        } else {
+            *reinterpret_cast<float4 *>(base + off) = v;
+            *reinterpret_cast<float4 *>(base + BN * 128 + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+template <int BN, int EPI, bool STREAM>
 __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Params2 q) {
     const Params &p = q.g;
     constexpr int A_BYTES = BM * 128;                 // one 128 x 32 fp32 tile
     constexpr int A_STAGE = 2 * A_BYTES;              // hi + lo
     constexpr int B_KB = 2 * BN * 128;                // hi + lo of one k-block of the weight
     constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (BN in {32,64,128})
-    constexpr int LDT = BN + 4;
+    constexpr int EC = BN > 64 ? 64 : BN;             // epilogue works on EC columns at a time (staging tile fits smem)
+    constexpr int NPASS = BN / EC;
+    constexpr int LDT = EC + 4;
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t stage_free[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint64_t stage_free[STAGES], b_full[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
-    __shared__ float s_red[2 * 4 * P_THREADS];  // statistics partials: [row lane][BN][2]
+    __shared__ float s_red[2 * 4 * P_THREADS];  // statistics partials: [row lane][EC][2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = (p.K + BK - 1) / BK;
@@ -414,11 +451,12 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
     const int D = q.raw_depth;
     char *a_ring = smem;
     char *raw_ring = smem + STAGES * A_STAGE;
-    char *b_res = raw_ring + (size_t)D * A_BYTES;
-    float *tile = reinterpret_cast<float *>(b_res + (size_t)nkb * B_KB);  // epilogue staging [BM][LDT]
+    char *b_res = raw_ring + (size_t)D * A_BYTES;     // resident: nkb k-blocks; streamed: STAGES k-blocks
+    float *tile = reinterpret_cast<float *>(b_res + (size_t)(STREAM ? STAGES : nkb) * B_KB);  // epilogue staging [BM][LDT]
+    const char *b_packed = STREAM ? q.Bp + (size_t)blockIdx.y * nkb * B_KB : nullptr;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) mbar_init(&stage_free[i], 1);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&b_full[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P_THREADS); }
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -429,21 +467,23 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // resident weight: all 256 threads load + split every k-block once
-    for (int kb = 0; kb < nkb; ++kb) {
-        char *b_hi = b_res + (size_t)kb * B_KB, *b_lo = b_hi + BN * 128;
-        for (int idx = tid; idx < BN * 8; idx += 2 * P_THREADS) {
-            const int r = idx >> 3, c = idx & 7;
-            const int gn = n0 + r, gk = kb * BK + c * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gn < p.N && gk < p.K) v = *reinterpret_cast<const float4 *>(p.Bt + (size_t)gn * p.ldb + gk);
-            const uint32_t off = sw128(r, c);
-            if (split) {
-                const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                *reinterpret_cast<float4 *>(b_hi + off) = h;
-                *reinterpret_cast<float4 *>(b_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            } else {
-                *reinterpret_cast<float4 *>(b_hi + off) = v;
+    if constexpr (!STREAM) {
+        // resident weight: all threads load + split every k-block once
+        for (int kb = 0; kb < nkb; ++kb) {
+            char *b_hi = b_res + (size_t)kb * B_KB, *b_lo = b_hi + BN * 128;
+            for (int idx = tid; idx < BN * 8; idx += 2 * P_THREADS) {
+                const int r = idx >> 3, c = idx & 7;
+                const int gn = n0 + r, gk = kb * BK + c * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gn < p.N && gk < p.K) v = *reinterpret_cast<const float4 *>(p.Bt + (size_t)gn * p.ldb + gk);
+                const uint32_t off = sw128(r, c);
+                if (split) {
+                    const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                    *reinterpret_cast<float4 *>(b_hi + off) = h;
+                    *reinterpret_cast<float4 *>(b_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                } else {
+                    *reinterpret_cast<float4 *>(b_hi + off) = v;
+                }
             }
         }
     }
@@ -469,6 +509,12 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
             cp_async_commit();  // always commit (possibly empty) so the group arithmetic stays uniform
             ++issued;
         };
+        if constexpr (STREAM) {
+            if (tid == 0 && cur_tile < q.ntiles) {  // weight k-block of item 0
+                mbar_expect_tx(&b_full[0], (uint32_t)B_KB);
+                bulk_g2s(b_res, b_packed, (uint32_t)B_KB, &b_full[0]);
+            }
+        }
         for (int i = 0; i < D - 1; ++i) issue_one();
         while (cur_tile < q.ntiles) {
             issue_one();                 // keep D-1 k-blocks in flight behind the one we are about to convert
@@ -479,12 +525,15 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
             raw_convert(raw_ring + (size_t)(it % D) * A_BYTES, a_hi, a_lo, tid, split);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_sync_named(1, P_THREADS);
+            const bool last_kb = cur_kb == nkb - 1;
             if (tid == 0) {
                 const int buf = tile_count & 1, v = tile_count >> 1;
                 if (cur_kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[buf], (uint32_t)((v - 1) & 1)) && ok;
+                const char *b_hi = STREAM ? b_res + (size_t)s * B_KB : b_res + (size_t)cur_kb * B_KB;
+                const char *b_lo = b_hi + BN * 128;
+                if constexpr (STREAM) ok = mbar_wait(&b_full[s], (uint32_t)(u & 1)) && ok;  // this k-block of the weight landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-                const char *b_hi = b_res + (size_t)cur_kb * B_KB, *b_lo = b_hi + BN * 128;
 #pragma unroll
                 for (int j = 0; j < BK / UMMA_K; ++j) {
                     const uint64_t dah = make_desc(smem_u32(a_hi) + j * 32), dbh = make_desc(smem_u32(b_hi) + j * 32);
@@ -496,7 +545,17 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
                     }
                 }
                 umma_commit(&stage_free[s]);
-                if (cur_kb == nkb - 1) umma_commit(&acc_full[buf]);
+                if (last_kb) umma_commit(&acc_full[buf]);
+                if constexpr (STREAM) {  // fetch the weight k-block of the NEXT item into the other stage
+                    const int nkb_next = last_kb ? 0 : cur_kb + 1;
+                    const long long ntile = last_kb ? cur_tile + gridDim.x : cur_tile;
+                    if (ntile < q.ntiles) {
+                        const int s1 = (it + 1) % STAGES, u1 = (it + 1) / STAGES;
+                        if (u1 >= 1) ok = mbar_wait(&stage_free[s1], (uint32_t)((u1 - 1) & 1)) && ok;  // its previous reader retired
+                        mbar_expect_tx(&b_full[s1], (uint32_t)B_KB);
+                        bulk_g2s(b_res + (size_t)s1 * B_KB, b_packed + (size_t)nkb_next * B_KB, (uint32_t)B_KB, &b_full[s1]);
+                    }
+                }
             }
             if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
             it++;
@@ -513,144 +572,151 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
             const int buf = tile_count & 1, v = tile_count >> 1;
             const long long m0 = tile_i * BM;
             const long long rows_here = min((long long)BM, p.M - m0);
-            // att epilogues: fetch this thread's x (and g) values BEFORE waiting for the accumulator -- they do not depend
-            // on the MMA, so their L2 latency hides behind the tensor-core work of this tile
-            constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * BN + P_THREADS - 1) / P_THREADS;
+            constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * EC + P_THREADS - 1) / P_THREADS;
             float xv[PAIRS][16];
             float gv[PAIRS];
-            if constexpr (EPI != EPI_STORE) {
-                const int npts = (int)(rows_here / 16);
+#pragma unroll 1
+            for (int pass = 0; pass < NPASS; ++pass) {
+                const int nb = n0 + pass * EC;  // first global column of this pass
+                // att epilogues: fetch this thread's x (and g) values BEFORE waiting for the accumulator -- they do not
+                // depend on the MMA, so (for the first pass) their L2 latency hides behind the tensor-core work
+                if constexpr (EPI != EPI_STORE) {
+                    const int npts = (int)(rows_here / 16);
 #pragma unroll
-                for (int pp = 0; pp < PAIRS; ++pp) {
-                    const int pair = etid + pp * P_THREADS;
-                    const int pl = pair / BN, c = pair % BN;
-                    const bool pv = pair < (BM / 16) * BN && pl < npts && n0 + c < p.N;
-                    const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + n0 + c;
+                    for (int pp = 0; pp < PAIRS; ++pp) {
+                        const int pair = etid + pp * P_THREADS;
+                        const int pl = pair / EC, c = pair % EC;
+                        const bool pv = pair < (BM / 16) * EC && pl < npts && nb + c < p.N;
+                        const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + nb + c;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
-                    gv[pp] = 0.f;
-                    if constexpr (EPI == EPI_ATT_BWD) gv[pp] = pv ? q.G[(size_t)(m0 / 16 + pl) * q.ldg + n0 + c] : 0.f;
+                        for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
+                        gv[pp] = 0.f;
+                        if constexpr (EPI == EPI_ATT_BWD) gv[pp] = pv ? q.G[(size_t)(m0 / 16 + pl) * q.ldg + nb + c] : 0.f;
+                    }
                 }
-            }
-            ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            {   // TMEM -> registers -> staging tile: warp (quarter, chalf) moves 32 rows x BN/2 columns
-                const int row = quarter * 32 + lane;
-#pragma unroll
-                for (int cc = 0; cc < BN / 2; cc += 16) {
-                    const int c0 = chalf * (BN / 2) + cc;
-                    float vals[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), vals);
-#pragma unroll
-                    for (int qd = 0; qd < 16; qd += 4)
-                        *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
-                            make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
+                if (pass == 0) {
+                    ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
-            bar_sync_named(2, P_THREADS);
+                {   // TMEM -> registers -> staging tile: warp (quarter, chalf) moves 32 rows x EC/2 columns
+                    const int row = quarter * 32 + lane;
+#pragma unroll
+                    for (int cc = 0; cc < EC / 2; cc += 16) {
+                        const int c0 = chalf * (EC / 2) + cc;
+                        float vals[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + pass * EC + c0), vals);
+#pragma unroll
+                        for (int qd = 0; qd < 16; qd += 4)
+                            *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
+                                make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
+                    }
+                }
+                if (pass == NPASS - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
+                }
+                bar_sync_named(2, P_THREADS);
 
-            if constexpr (EPI == EPI_STORE) {
-                const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-                // thread -> fixed group of 4 columns (P_THREADS % (BN/4) == 0), rows strided: the batch-norm partials
-                // accumulate in registers during the copy-out.  Shifted single pass: sums of (v - sh) and (v - sh)^2
-                // with sh = the tile's first stored row, so M2 = S2 - S1^2/n loses nothing to cancellation.
-                constexpr int CG = BN / 4, RLANES = P_THREADS / CG;
-                const int cg = etid % CG, rl = etid / CG, c = cg * 4, gn = n0 + c;
-                float sh[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias) {
-                    bias4.x = gn + 0 < p.N ? p.bias[gn + 0] : 0.f; bias4.y = gn + 1 < p.N ? p.bias[gn + 1] : 0.f;
-                    bias4.z = gn + 2 < p.N ? p.bias[gn + 2] : 0.f; bias4.w = gn + 3 < p.N ? p.bias[gn + 3] : 0.f;
-                }
-                if (p.stat_sum) {  // shift = stored value of row 0 (recomputed identically by every thread of the group)
-                    const float4 t0 = *reinterpret_cast<float4 *>(&tile[c]);
-                    sh[0] = t0.x + bias4.x; sh[1] = t0.y + bias4.y; sh[2] = t0.z + bias4.z; sh[3] = t0.w + bias4.w;
-                }
-                for (int r = rl; r < rows_here; r += RLANES) {
-                    float4 val = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
-                    val.x += bias4.x; val.y += bias4.y; val.z += bias4.z; val.w += bias4.w;
-                    float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
-                    if (gn + 3 < p.N && vecC) {
-                        if (p.accumulate) {
-                            const float4 o = *reinterpret_cast<const float4 *>(cptr);
-                            val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
-                        }
-                        *reinterpret_cast<float4 *>(cptr) = val;
-                    } else {
-                        float vv[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (gn + j < p.N) {
-                                if (p.accumulate) vv[j] += cptr[j];
-                                cptr[j] = vv[j];
+                if constexpr (EPI == EPI_STORE) {
+                    const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+                    // thread -> fixed group of 4 columns (P_THREADS % (EC/4) == 0), rows strided: the batch-norm partials
+                    // accumulate in registers during the copy-out.  Shifted single pass: sums of (v - sh) and (v - sh)^2
+                    // with sh = the tile's first stored row, so M2 = S2 - S1^2/n loses nothing to cancellation.
+                    constexpr int CG = EC / 4, RLANES = P_THREADS / CG;
+                    const int cg = etid % CG, rl = etid / CG, c = cg * 4, gn = nb + c;
+                    float sh[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) {
+                        bias4.x = gn + 0 < p.N ? p.bias[gn + 0] : 0.f; bias4.y = gn + 1 < p.N ? p.bias[gn + 1] : 0.f;
+                        bias4.z = gn + 2 < p.N ? p.bias[gn + 2] : 0.f; bias4.w = gn + 3 < p.N ? p.bias[gn + 3] : 0.f;
+                    }
+                    if (p.stat_sum) {  // shift = stored value of row 0 (recomputed identically by every thread of the group)
+                        const float4 t0 = *reinterpret_cast<float4 *>(&tile[c]);
+                        sh[0] = t0.x + bias4.x; sh[1] = t0.y + bias4.y; sh[2] = t0.z + bias4.z; sh[3] = t0.w + bias4.w;
+                    }
+                    for (int r = rl; r < rows_here; r += RLANES) {
+                        float4 val = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
+                        val.x += bias4.x; val.y += bias4.y; val.z += bias4.z; val.w += bias4.w;
+                        float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
+                        if (gn + 3 < p.N && vecC) {
+                            if (p.accumulate) {
+                                const float4 o = *reinterpret_cast<const float4 *>(cptr);
+                                val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
                             }
-                        val = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                            *reinterpret_cast<float4 *>(cptr) = val;
+                        } else {
+                            float vv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (gn + j < p.N) {
+                                    if (p.accumulate) vv[j] += cptr[j];
+                                    cptr[j] = vv[j];
+                                }
+                            val = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                        }
+                        const float dv[4] = {val.x - sh[0], val.y - sh[1], val.z - sh[2], val.w - sh[3]};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], dv[j], s2[j]); }
                     }
-                    const float dv[4] = {val.x - sh[0], val.y - sh[1], val.z - sh[2], val.w - sh[3]};
+                    if (p.stat_sum) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], dv[j], s2[j]); }
-                }
-                if (p.stat_sum) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        s_red[(rl * BN + c + j) * 2 + 0] = s1[j];
-                        s_red[(rl * BN + c + j) * 2 + 1] = s2[j];
+                        for (int j = 0; j < 4; ++j) {
+                            s_red[(rl * EC + c + j) * 2 + 0] = s1[j];
+                            s_red[(rl * EC + c + j) * 2 + 1] = s2[j];
+                        }
+                        bar_sync_named(2, P_THREADS);
+                        if (etid < EC && nb + etid < p.N) {
+                            float a = 0.f, b = 0.f;
+                            for (int l = 0; l < RLANES; ++l) { a += s_red[(l * EC + etid) * 2]; b += s_red[(l * EC + etid) * 2 + 1]; }
+                            const float shc = tile[etid] + (p.bias ? p.bias[nb + etid] : 0.f);  // same shift as above
+                            const float n = (float)rows_here;
+                            p.stat_sum[(size_t)tile_i * p.N + nb + etid] = fmaf(n, shc, a);
+                            p.stat_m2[(size_t)tile_i * p.N + nb + etid] = fmaxf(b - a * a / n, 0.f);
+                        }
                     }
-                    bar_sync_named(2, P_THREADS);
-                    if (etid < BN && n0 + etid < p.N) {
-                        float a = 0.f, b = 0.f;
-                        for (int l = 0; l < RLANES; ++l) { a += s_red[(l * BN + etid) * 2]; b += s_red[(l * BN + etid) * 2 + 1]; }
-                        // shift of column etid: recompute exactly as above
-                        const float shc = tile[etid] + (p.bias ? p.bias[n0 + etid] : 0.f);  // same shift as above
-                        const float n = (float)rows_here;
-                        p.stat_sum[(size_t)tile_i * p.N + n0 + etid] = fmaf(n, shc, a);
-                        p.stat_m2[(size_t)tile_i * p.N + n0 + etid] = fmaxf(b - a * a / n, 0.f);
-                    }
-                }
-            } else {
-                // one (point, channel) pair per thread step: the 16 neighbour rows of a point are consecutive rows of `tile`
-                const long long pt0 = m0 / 16;
-                const int npts = (int)(rows_here / 16);
+                } else {
+                    // one (point, channel) pair per thread step: the 16 neighbour rows of a point are consecutive rows of `tile`
+                    const long long pt0 = m0 / 16;
+                    const int npts = (int)(rows_here / 16);
 #pragma unroll
-                for (int pp = 0; pp < PAIRS; ++pp) {
-                    const int pair = etid + pp * P_THREADS;
-                    const int pl = pair / BN, c = pair % BN;
-                    const int gn = n0 + c;
-                    if (pair >= (BM / 16) * BN || pl >= npts || gn >= p.N) continue;
-                    float a[16];
-                    float mx = -FLT_MAX;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        a[k] = tile[(pl * 16 + k) * LDT + c];
-                        mx = fmaxf(mx, a[k]);
-                    }
-                    float sum = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) { a[k] = __expf(a[k] - mx); sum += a[k]; }
-                    const float inv = 1.f / sum;
-                    if constexpr (EPI == EPI_ATT_FWD) {
-                        float num = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) num = fmaf(xv[pp][k], a[k], num);
-                        q.OUT[(size_t)(pt0 + pl) * q.ldo + gn] = num * inv;
-                    } else {
-                        const float g = gv[pp];
-                        float dot = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * xv[pp][k], a[k], dot); }
-                        float *cp = p.C + (size_t)(m0 + pl * 16) * p.ldc + gn;
-                        float *op = q.OUT + (size_t)(m0 + pl * 16) * q.ldo + gn;
+                    for (int pp = 0; pp < PAIRS; ++pp) {
+                        const int pair = etid + pp * P_THREADS;
+                        const int pl = pair / EC, c = pair % EC;
+                        const int gn = nb + c;
+                        if (pair >= (BM / 16) * EC || pl >= npts || gn >= p.N) continue;
+                        float a[16];
+                        float mx = -FLT_MAX;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
-                            cp[(size_t)k * p.ldc] = a[k] * (g * xv[pp][k] - dot);   // d_act
-                            op[(size_t)k * q.ldo] = g * a[k];                       // dx_direct
+                            a[k] = tile[(pl * 16 + k) * LDT + c];
+                            mx = fmaxf(mx, a[k]);
+                        }
+                        float sum = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) { a[k] = __expf(a[k] - mx); sum += a[k]; }
+                        const float inv = 1.f / sum;
+                        if constexpr (EPI == EPI_ATT_FWD) {
+                            float num = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) num = fmaf(xv[pp][k], a[k], num);
+                            q.OUT[(size_t)(pt0 + pl) * q.ldo + gn] = num * inv;
+                        } else {
+                            const float g = gv[pp];
+                            float dot = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * xv[pp][k], a[k], dot); }
+                            float *cp = p.C + (size_t)(m0 + pl * 16) * p.ldc + gn;
+                            float *op = q.OUT + (size_t)(m0 + pl * 16) * q.ldo + gn;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                cp[(size_t)k * p.ldc] = a[k] * (g * xv[pp][k] - dot);   // d_act
+                                op[(size_t)k * q.ldo] = g * a[k];                       // dx_direct
+                            }
                         }
                     }
                 }
+                bar_sync_named(2, P_THREADS);  // staging tile is reused by the next pass / tile
             }
-            bar_sync_named(2, P_THREADS);  // staging tile is reused by the next tile
         }
         if (!ok) s_err = 1;
     }
@@ -662,64 +728,97 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
     if (tid == 0 && s_err && p.error_flag) *p.error_flag = 1;
 }
 
-template <int BN>
+constexpr size_t kMaxDynSmem = 227 * 1024 - 10 * 1024;  // dynamic budget: 227 KB minus the kernel's static shared memory (~9 KB)
+template <int BN, bool STREAM>
 static size_t persist_fixed_bytes(int K) {  // everything except the raw ring
     const int nkb = (K + BK - 1) / BK;
-    return (size_t)STAGES * 2 * BM * 128 + (size_t)nkb * 2 * BN * 128 + (size_t)BM * (BN + 4) * 4 + 1024;
+    const int ec = BN > 64 ? 64 : BN;
+    return (size_t)STAGES * 2 * BM * 128 + (size_t)(STREAM ? STAGES : nkb) * 2 * BN * 128 + (size_t)BM * (ec + 4) * 4 + 1024;
 }
-constexpr size_t kMaxDynSmem = 227 * 1024 - 10 * 1024;  // dynamic budget: 227 KB minus the kernel's static shared memory (~9 KB)
-template <int BN>
+template <int BN, bool STREAM>
 static int persist_raw_depth(int K) {  // 0 => does not fit
-    const size_t fixed = persist_fixed_bytes<BN>(K);
+    const size_t fixed = persist_fixed_bytes<BN, STREAM>(K);
     if (fixed + 2 * (size_t)BM * 128 > kMaxDynSmem) return 0;
     long long d = (long long)((kMaxDynSmem - fixed) / ((size_t)BM * 128));
     return (int)(d > MAX_RAW ? MAX_RAW : d);
 }
 
-template <int BN, int EPI>
-static int launch_persist(const Params2 &q, cudaStream_t st) {
+static inline size_t packed_weight_bytes(int K, int N, int bn) {
+    const int nkb = (K + BK - 1) / BK, nslabs = (N + bn - 1) / bn;
+    return (size_t)nslabs * nkb * 2 * bn * 128;
+}
+
+template <int BN, int EPI, bool STREAM>
+static int launch_persist(const Params2 &q, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     Params2 qq = q;
-    qq.raw_depth = persist_raw_depth<BN>(q.g.K);
+    qq.raw_depth = persist_raw_depth<BN, STREAM>(q.g.K);
     if (qq.raw_depth < 2) return PU_ERR_UNSUPPORTED;
-    const size_t smem = persist_fixed_bytes<BN>(q.g.K) + (size_t)qq.raw_depth * BM * 128;
-    static size_t configured = 0;
-    if (configured < smem) {
-        PU_CUDA_TRY(cudaFuncSetAttribute(tc_persist_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        configured = kMaxDynSmem;
+    const size_t smem = persist_fixed_bytes<BN, STREAM>(q.g.K) + (size_t)qq.raw_depth * BM * 128;
+    static bool configured = false;
+    if (!configured) {
+        PU_CUDA_TRY(cudaFuncSetAttribute(tc_persist_kernel<BN, EPI, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        configured = true;
     }
     const int ny = ceil_div(q.g.N, BN);
+    if (STREAM) {
+        const size_t need = packed_weight_bytes(q.g.K, q.g.N, BN);
+        if (!workspace || workspace_bytes < need || (((uintptr_t)workspace) & 15)) return PU_ERR_WORKSPACE;
+        const int nkb = (q.g.K + BK - 1) / BK;
+        const long long chunks = (long long)ny * nkb * BN * 8;
+        tc_pack_weight_kernel<<<(unsigned)((chunks + 255) / 256 > 4096 ? 4096 : (chunks + 255) / 256), 256, 0, st>>>(
+            q.g.Bt, q.g.ldb, q.g.N, q.g.K, BN, nkb, ny, q.g.mode == 3 ? 1 : 0, (char *)workspace);
+        PU_LAUNCH_CHECK();
+        qq.Bp = (const char *)workspace;
+    }
     long long gx = kNumSMs / ny;  // ~one CTA per SM in total (227 KB-class shared memory); each walks its row tiles
     if (gx < 1) gx = 1;
     if (gx > q.ntiles) gx = q.ntiles;
     dim3 grid((unsigned)gx, ny);
-    tc_persist_kernel<BN, EPI><<<grid, 2 * tc::P_THREADS, smem, st>>>(qq);
+    tc_persist_kernel<BN, EPI, STREAM><<<grid, 2 * tc::P_THREADS, smem, st>>>(qq);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
 
-// picks the N tile so that the resident weight fits; returns 0 if the shape needs the streaming (v1) kernel
-static int persist_bn(int K, int N) {
-    if (N <= 32 && persist_raw_depth<32>(K) >= 3) return 32;
-    if (N <= 64 && persist_raw_depth<64>(K) >= 3) return 64;
-    if (N > 64 && persist_raw_depth<128>(K) >= 3) return 128;
-    if (persist_raw_depth<64>(K) >= 2) return 64;
-    if (persist_raw_depth<32>(K) >= 2) return 32;
-    return 0;
+// Shape policy.  Resident weights (no packing pass) when the whole [K x BN] hi/lo pair fits beside a >= 3-deep raw ring
+// with BN covering N in at most two slabs; otherwise the streamed-weight variant with the widest tile (BN = 128).
+struct Choice { int bn; bool stream; };
+static Choice choose_linear(int K, int N) {
+    if (N <= 32 && persist_raw_depth<32, false>(K) >= 3) return {32, false};
+    if (N <= 64 && persist_raw_depth<64, false>(K) >= 3) return {64, false};
+    if (N > 64 && persist_raw_depth<128, false>(K) >= 3) return {128, false};
+    if (N > 64 && N <= 128 && persist_raw_depth<64, false>(K) >= 3) return {64, false};
+    if (N <= 32) return {32, true};
+    if (N <= 64) return {64, true};
+    return {128, true};
 }
-
-static int persist_bn_att(int d) {  // att epilogues keep (points x channels)/threads small: BN <= 64
-    if (d <= 32 && persist_raw_depth<32>(d) >= 3) return 32;
-    if (persist_raw_depth<64>(d) >= 2) return 64;
-    if (persist_raw_depth<32>(d) >= 2) return 32;
-    return 0;
+static Choice choose_att(int d) {
+    if (d <= 32 && persist_raw_depth<32, false>(d) >= 3) return {32, false};
+    if (d <= 64 && persist_raw_depth<64, false>(d) >= 3) return {64, false};
+    return {128, true};
+}
+static size_t tc_workspace_bytes(int K, int N) {
+    size_t m = packed_weight_bytes(K, N, 128);
+    const size_t a = packed_weight_bytes(K, N, 64), b = packed_weight_bytes(K, N, 32);
+    if (a > m) m = a;
+    if (b > m) m = b;
+    return m + 256;
 }
 
 template <int EPI>
-static int dispatch_persist(const Params2 &q, cudaStream_t st) {
-    switch (EPI == EPI_STORE ? persist_bn(q.g.K, q.g.N) : persist_bn_att(q.g.K)) {
-        case 32: return launch_persist<32, EPI>(q, st);
-        case 64: return launch_persist<64, EPI>(q, st);
-        case 128: return launch_persist<128, EPI>(q, st);
+static int dispatch_persist(const Params2 &q, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const Choice ch = EPI == EPI_STORE ? choose_linear(q.g.K, q.g.N) : choose_att(q.g.K);
+    if (!ch.stream) {
+        switch (ch.bn) {
+            case 32: return launch_persist<32, EPI, false>(q, workspace, workspace_bytes, st);
+            case 64: return launch_persist<64, EPI, false>(q, workspace, workspace_bytes, st);
+            case 128: return launch_persist<128, EPI, false>(q, workspace, workspace_bytes, st);
+        }
+    } else {
+        switch (ch.bn) {
+            case 32: return launch_persist<32, EPI, true>(q, workspace, workspace_bytes, st);
+            case 64: return launch_persist<64, EPI, true>(q, workspace, workspace_bytes, st);
+            case 128: return launch_persist<128, EPI, true>(q, workspace, workspace_bytes, st);
+        }
     }
     return PU_ERR_UNSUPPORTED;
 }
@@ -984,37 +1083,30 @@ int pu_tc_linear_supported(long long M, int K, int N, int ldx, int ldwt, int ldy
     return M > 0 && K >= 32 && N >= 32 && (K & 3) == 0 && (ldx & 3) == 0 && (ldwt & 3) == 0 && (ldy >= N) && (N & 3) == 0;
 }
 
+/* scratch for the packed (pre-split, pre-swizzled) weight image of the streamed-weight kernels */
+size_t pu_tc_workspace_bytes(int K, int N) { return tc::tc_workspace_bytes(K, N); }
+
 int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const float *bias, float *y, int ldy, long long M,
                      int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode, int *error_flag,
-                     pu_stream_t stream) {
+                     void *workspace, size_t workspace_bytes, pu_stream_t stream) {
     if (!x || !wt || !y || M < 0 || K < 1 || N < 1 || ldx < K || ldwt < K || ldy < N) return PU_ERR_INVALID_ARG;
     if ((stat_sum == nullptr) != (stat_m2 == nullptr)) return PU_ERR_INVALID_ARG;
     if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
     if (M == 0) return PU_OK;
     if (!pu_tc_linear_supported(M, K, N, ldx, ldwt, ldy) || ((((uintptr_t)x) | ((uintptr_t)wt)) & 15)) return PU_ERR_UNSUPPORTED;
-    tc::Params p{};
-    p.A = x; p.lda = ldx; p.Bt = wt; p.ldb = ldwt; p.C = y; p.ldc = ldy; p.bias = bias;
-    p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.stat_sum = stat_sum; p.stat_m2 = stat_m2; p.mode = mode;
-    p.error_flag = error_flag;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (tc::persist_bn(K, N) != 0) {
-        tc::Params2 q{};
-        q.g = p;
-        q.ntiles = (M + tc::BM - 1) / tc::BM;
-        return tc::dispatch_persist<tc::EPI_STORE>(q, st);
-    }
-    if (N <= 32) return tc::launch<32>(p, st);
-    if (N <= 64) return tc::launch<64>(p, st);
-    return tc::launch<128>(p, st);
+    tc::Params2 q{};
+    q.g.A = x; q.g.lda = ldx; q.g.Bt = wt; q.g.ldb = ldwt; q.g.C = y; q.g.ldc = ldy; q.g.bias = bias;
+    q.g.M = M; q.g.N = N; q.g.K = K; q.g.accumulate = accumulate; q.g.stat_sum = stat_sum; q.g.stat_m2 = stat_m2; q.g.mode = mode;
+    q.g.error_flag = error_flag;
+    q.ntiles = (M + tc::BM - 1) / tc::BM;
+    return tc::dispatch_persist<tc::EPI_STORE>(q, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 /* 1 if the fused att_pooling kernels can run on the tensor-core path for channel width d */
-int pu_tc_att_supported(int K, int d, int ldx) {
-    return K == 16 && d >= 32 && (d & 3) == 0 && (ldx & 3) == 0 && tc::persist_bn_att(d) != 0;
-}
+int pu_tc_att_supported(int K, int d, int ldx) { return K == 16 && d >= 32 && (d & 3) == 0 && (ldx & 3) == 0; }
 
 int pu_tc_att_pooling_fwd(const float *feature_set, int ldx, const float *wt, long long P, int K, int d, float *f_agg,
-                          int ldo, int mode, int *error_flag, pu_stream_t stream) {
+                          int ldo, int mode, int *error_flag, void *workspace, size_t workspace_bytes, pu_stream_t stream) {
     if (!feature_set || !wt || !f_agg || P < 0 || ldx < d || ldo < d) return PU_ERR_INVALID_ARG;
     if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
     if (!pu_tc_att_supported(K, d, ldx) || (((uintptr_t)feature_set | (uintptr_t)wt) & 15)) return PU_ERR_UNSUPPORTED;
@@ -1024,12 +1116,12 @@ int pu_tc_att_pooling_fwd(const float *feature_set, int ldx, const float *wt, lo
     q.g.error_flag = error_flag;
     q.X = feature_set; q.ldx = ldx; q.OUT = f_agg; q.ldo = ldo;
     q.ntiles = (q.g.M + tc::BM - 1) / tc::BM;
-    return tc::dispatch_persist<tc::EPI_ATT_FWD>(q, (cudaStream_t)stream);
+    return tc::dispatch_persist<tc::EPI_ATT_FWD>(q, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, const float *g_agg, int ldg, long long P,
                           int K, int d, float *d_act, int ldda, float *dx_direct, int lddx, int mode, int *error_flag,
-                          pu_stream_t stream) {
+                          void *workspace, size_t workspace_bytes, pu_stream_t stream) {
     if (!feature_set || !wt || !g_agg || !d_act || !dx_direct || P < 0 || ldx < d || ldg < d || ldda < d || lddx < d)
         return PU_ERR_INVALID_ARG;
     if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
@@ -1040,7 +1132,7 @@ int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, co
     q.g.C = d_act; q.g.ldc = ldda; q.g.error_flag = error_flag;
     q.X = feature_set; q.ldx = ldx; q.G = g_agg; q.ldg = ldg; q.OUT = dx_direct; q.ldo = lddx;
     q.ntiles = (q.g.M + tc::BM - 1) / tc::BM;
-    return tc::dispatch_persist<tc::EPI_ATT_BWD>(q, (cudaStream_t)stream);
+    return tc::dispatch_persist<tc::EPI_ATT_BWD>(q, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 /* Tensor-core weight gradient: dw[Kin,N] (+)= x^T dy, db[N] (+)= column sums of dy (db only when Kin % 128 != 0).

@@ -34,10 +34,11 @@ _lib._OP_SIGS.update({
     "pu_linear_fwd": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
                       c_void_p, c_void_p],
     "pu_tc_linear_fwd": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
-                         c_void_p, c_int, c_void_p, c_void_p],
-    "pu_tc_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
+                         c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    "pu_tc_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                              c_size_t, c_void_p],
     "pu_tc_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
-                              c_int, c_int, c_void_p, c_void_p],
+                              c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     "pu_tc_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
                     c_void_p, c_void_p],
     "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
@@ -85,6 +86,8 @@ def _L():
         L.pu_point2prod_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.pu_tc_linear_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
         L.pu_tc_att_supported.argtypes = [c_int, c_int, c_int]
+        L.pu_tc_workspace_bytes.restype = c_size_t
+        L.pu_tc_workspace_bytes.argtypes = [c_int, c_int]
         L.pu_tc_wgrad_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
         L.pu_tc_wgrad_workspace_bytes.restype = c_size_t
         L.pu_tc_wgrad_workspace_bytes.argtypes = [c_ll, c_int, c_int]
@@ -355,9 +358,10 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
     if use_tc:
         if wt is None:
             wt = w.t().contiguous()
+        tws = workspace(L.pu_tc_workspace_bytes(K, N), x.device, slot=4)
         _call("pu_tc_linear_fwd", xr.data_ptr(), ldx, wt.data_ptr(), K, bptr, o.data_ptr(), ldo, M, K, N, int(accumulate),
               ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, mode,
-              tc_error_flag(x.device).data_ptr(), _stream(x), tag=(M, K, N))
+              tc_error_flag(x.device).data_ptr(), tws.data_ptr(), tws.numel(), _stream(x), tag=(M, K, N))
     else:
         if w is None:
             w = wt.t().contiguous()
@@ -551,8 +555,9 @@ class _AttPoolFn(torch.autograd.Function):
         use_tc = TC_MODE in (1, 3) and B * N * K >= 128 and x.data_ptr() % 16 == 0 and _L().pu_tc_att_supported(K, d, ldx)
         wt = w.t().contiguous() if use_tc else None
         if use_tc:
+            tws = workspace(_L().pu_tc_workspace_bytes(d, d), x.device, slot=4)
             _call("pu_tc_att_pooling_fwd", x.data_ptr(), ldx, wt.data_ptr(), B * N, K, d, out.data_ptr(), d, TC_MODE,
-                  tc_error_flag(x.device).data_ptr(), _stream(x), tag=(B * N, K, d))
+                  tc_error_flag(x.device).data_ptr(), tws.data_ptr(), tws.numel(), _stream(x), tag=(B * N, K, d))
         else:
             _call("pu_att_pooling_fwd", x.data_ptr(), ldx, w.data_ptr(), B * N, K, d, out.data_ptr(), d, _stream(x),
                   tag=(B * N, K, d))
@@ -568,9 +573,10 @@ class _AttPoolFn(torch.autograd.Function):
         d_act = torch.empty((B * N * K, d), dtype=torch.float32, device=x.device)
         dx = torch.empty((B, N, K, d), dtype=torch.float32, device=x.device)
         if use_tc:
+            tws = workspace(_L().pu_tc_workspace_bytes(d, d), x.device, slot=4)
             _call("pu_tc_att_pooling_bwd", x.data_ptr(), ldx, wt.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
-                  d_act.data_ptr(), d, dx.data_ptr(), d, TC_MODE, tc_error_flag(x.device).data_ptr(), _stream(x),
-                  tag=(B * N, K, d))
+                  d_act.data_ptr(), d, dx.data_ptr(), d, TC_MODE, tc_error_flag(x.device).data_ptr(), tws.data_ptr(),
+                  tws.numel(), _stream(x), tag=(B * N, K, d))
         else:
             _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
                   d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
