@@ -427,8 +427,10 @@ __global__ void __launch_bounds__(256) tc_pack_weight_kernel(const float *__rest
     }
 }
 
+constexpr int PERSIST_THREADS = 2 * P_THREADS + 32;  // 8 producer warps, 8 epilogue warps, 1 MMA-issuer warp
+
 template <int BN, int EPI, bool STREAM>
-__global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Params2 q) {
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Params2 q) {
     const Params &p = q.g;
     constexpr int A_BYTES = BM * 128;                 // one 128 x 32 fp32 tile
     constexpr int A_STAGE = 2 * A_BYTES;              // hi + lo
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
     constexpr int LDT = EC + 4;
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t stage_free[STAGES], b_full[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint64_t stage_free[STAGES], stage_ready[STAGES], b_full[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
     __shared__ float s_red[2 * 4 * P_THREADS];  // statistics partials: [row lane][EC][2]
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
     const char *b_packed = STREAM ? q.Bp + (size_t)blockIdx.y * nkb * B_KB : nullptr;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&b_full[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS); mbar_init(&b_full[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P_THREADS); }
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
         // resident weight: all threads load + split every k-block once
         for (int kb = 0; kb < nkb; ++kb) {
             char *b_hi = b_res + (size_t)kb * B_KB, *b_lo = b_hi + BN * 128;
-            for (int idx = tid; idx < BN * 8; idx += 2 * P_THREADS) {
+            for (int idx = tid; idx < BN * 8; idx += PERSIST_THREADS) {
                 const int r = idx >> 3, c = idx & 7;
                 const int gn = n0 + r, gk = kb * BK + c * 4;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -494,12 +496,11 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp < P_THREADS / 32) {
-        // ======================= producers (+ elected MMA issuer) =======================
-        const uint32_t idesc = make_idesc(BN);
+        // ======================= producers =======================
         // work items = (tile, k-block) pairs in order; `issue_*` runs D-1 items ahead of `cur_*`
         long long cur_tile = blockIdx.x, iss_tile = blockIdx.x;
         int cur_kb = 0, iss_kb = 0;
-        int it = 0, tile_count = 0, issued = 0;
+        int it = 0, issued = 0;
         bool ok = true;
         auto issue_one = [&]() {
             if (iss_tile < q.ntiles) {
@@ -509,26 +510,41 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
             cp_async_commit();  // always commit (possibly empty) so the group arithmetic stays uniform
             ++issued;
         };
-        if constexpr (STREAM) {
-            if (tid == 0 && cur_tile < q.ntiles) {  // weight k-block of item 0
-                mbar_expect_tx(&b_full[0], (uint32_t)B_KB);
-                bulk_g2s(b_res, b_packed, (uint32_t)B_KB, &b_full[0]);
-            }
-        }
         for (int i = 0; i < D - 1; ++i) issue_one();
         while (cur_tile < q.ntiles) {
             issue_one();                 // keep D-1 k-blocks in flight behind the one we are about to convert
             cp_async_wait_dyn(D - 1);    // the oldest outstanding group (= item `it`) has landed
             const int s = it % STAGES, u = it / STAGES;
             char *a_hi = a_ring + (size_t)s * A_STAGE, *a_lo = a_hi + A_BYTES;
-            if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;
+            if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;  // MMAs that read stage s retired
             raw_convert(raw_ring + (size_t)(it % D) * A_BYTES, a_hi, a_lo, tid, split);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bar_sync_named(1, P_THREADS);
-            const bool last_kb = cur_kb == nkb - 1;
-            if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(&stage_ready[s]);                                 // hand the stage to the issuer; do not wait for it
+            if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; }
+            it++;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!ok) s_err = 1;
+    } else if (warp == 2 * P_THREADS / 32) {
+        // ======================= MMA issuer (one elected lane of its own warp) =======================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN);
+            long long cur_tile = blockIdx.x;
+            int cur_kb = 0, it = 0, tile_count = 0;
+            bool ok = true;
+            if constexpr (STREAM) {
+                if (cur_tile < q.ntiles) {  // weight k-block of item 0
+                    mbar_expect_tx(&b_full[0], (uint32_t)B_KB);
+                    bulk_g2s(b_res, b_packed, (uint32_t)B_KB, &b_full[0]);
+                }
+            }
+            while (cur_tile < q.ntiles) {
+                const int s = it % STAGES, u = it / STAGES;
+                const char *a_hi = a_ring + (size_t)s * A_STAGE, *a_lo = a_hi + A_BYTES;
+                const bool last_kb = cur_kb == nkb - 1;
                 const int buf = tile_count & 1, v = tile_count >> 1;
                 if (cur_kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[buf], (uint32_t)((v - 1) & 1)) && ok;
+                ok = mbar_wait(&stage_ready[s], (uint32_t)(u & 1)) && ok;           // all 256 producers filled stage s
                 const char *b_hi = STREAM ? b_res + (size_t)s * B_KB : b_res + (size_t)cur_kb * B_KB;
                 const char *b_lo = b_hi + BN * 128;
                 if constexpr (STREAM) ok = mbar_wait(&b_full[s], (uint32_t)(u & 1)) && ok;  // this k-block of the weight landed
@@ -556,12 +572,11 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
                         bulk_g2s(b_res + (size_t)s1 * B_KB, b_packed + (size_t)nkb_next * B_KB, (uint32_t)B_KB, &b_full[s1]);
                     }
                 }
+                if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
+                it++;
             }
-            if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
-            it++;
+            if (!ok) s_err = 1;
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (!ok) s_err = 1;
     } else {
         // ======================= epilogue warps =======================
         const int etid = tid - P_THREADS, ewarp = warp - P_THREADS / 32;
@@ -634,15 +649,26 @@ __global__ void __launch_bounds__(2 * P_THREADS, 1) tc_persist_kernel(const Para
                         const float4 t0 = *reinterpret_cast<float4 *>(&tile[c]);
                         sh[0] = t0.x + bias4.x; sh[1] = t0.y + bias4.y; sh[2] = t0.z + bias4.z; sh[3] = t0.w + bias4.w;
                     }
-                    for (int r = rl; r < rows_here; r += RLANES) {
+                    constexpr int RPT = BM / RLANES;  // rows per thread (8 for EC = 64, 4 for EC = 32)
+                    const bool fast = gn + 3 < p.N && vecC;
+                    float4 old[RPT];
+                    if (p.accumulate && fast) {  // all loads of C first: RPT independent requests in flight, not a serial chain
+#pragma unroll
+                        for (int i = 0; i < RPT; ++i) {
+                            const int r = rl + i * RLANES;
+                            old[i] = r < rows_here ? *reinterpret_cast<const float4 *>(p.C + (size_t)(m0 + r) * p.ldc + gn)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {
+                        const int r = rl + i * RLANES;
+                        if (r >= rows_here) continue;
                         float4 val = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
                         val.x += bias4.x; val.y += bias4.y; val.z += bias4.z; val.w += bias4.w;
                         float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
-                        if (gn + 3 < p.N && vecC) {
-                            if (p.accumulate) {
-                                const float4 o = *reinterpret_cast<const float4 *>(cptr);
-                                val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
-                            }
+                        if (fast) {
+                            if (p.accumulate) { val.x += old[i].x; val.y += old[i].y; val.z += old[i].z; val.w += old[i].w; }
                             *reinterpret_cast<float4 *>(cptr) = val;
                         } else {
                             float vv[4] = {val.x, val.y, val.z, val.w};
@@ -774,7 +800,7 @@ static int launch_persist(const Params2 &q, void *workspace, size_t workspace_by
     if (gx < 1) gx = 1;
     if (gx > q.ntiles) gx = q.ntiles;
     dim3 grid((unsigned)gx, ny);
-    tc_persist_kernel<BN, EPI, STREAM><<<grid, 2 * tc::P_THREADS, smem, st>>>(qq);
+    tc_persist_kernel<BN, EPI, STREAM><<<grid, PERSIST_THREADS, smem, st>>>(qq);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
