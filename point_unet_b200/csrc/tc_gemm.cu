@@ -883,7 +883,8 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int n) {  // as make_idesc, a_
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-constexpr int WG_THREADS = 256;
+constexpr int WG_THREADS = 512;          // 16 producer warps
+constexpr int WG_TOTAL = WG_THREADS + 32;  // + 1 MMA-issuer warp
 constexpr int WG_ROWS = 32;  // rows (= MMA k) per pipeline step: 4 instructions of K = 8
 
 // copies a [32 rows x COLS] block of a row-major matrix (columns col0.., zero beyond ncols / row_end) into a raw slot
@@ -932,7 +933,7 @@ __device__ __forceinline__ void wg_convert(const char *slot, char *hi, char *lo,
 }
 
 template <int BN>
-__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w) {
+__global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) {
     constexpr int A_BYTES = WG_ROWS * BM * 4;   // 16 KB: 4 slabs of 32 rows x 128 B
     constexpr int B_BYTES = WG_ROWS * BN * 4;
     constexpr int STAGE = 2 * (A_BYTES + B_BYTES);  // hi + lo of both operands
@@ -940,8 +941,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t stage_free[2], all_done;
+    __shared__ uint64_t stage_free[2], stage_ready[2], all_done;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int s_err;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k0 = blockIdx.y * BM;   // first Kin column (= MMA M index) of this CTA's block
@@ -958,6 +960,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w
 
     if (tid == 0) {
         mbar_init(&stage_free[0], 1); mbar_init(&stage_free[1], 1); mbar_init(&all_done, 1);
+        mbar_init(&stage_ready[0], WG_THREADS); mbar_init(&stage_ready[1], WG_THREADS);
+        s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -972,31 +976,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w
     const uint32_t idesc = make_idesc_mn(BN);
 
     bool ok = true;
-    int issued = 0;
-    auto issue_one = [&]() {
-        if (issued < nsteps) {
-            char *slot = raw_ring + (size_t)(issued % D) * RAW;
-            const long long row0 = r_begin + (long long)issued * WG_ROWS;
-            wg_raw_issue<BM>(slot, w.X, w.ldx, row0, r_end, k0, w.Kin, tid);
-            wg_raw_issue<BN>(slot + A_BYTES, w.G, w.ldg, row0, r_end, n0, w.N, tid);
+    if (warp < WG_THREADS / 32) {
+        // ======================= producers =======================
+        int issued = 0;
+        auto issue_one = [&]() {
+            if (issued < nsteps) {
+                char *slot = raw_ring + (size_t)(issued % D) * RAW;
+                const long long row0 = r_begin + (long long)issued * WG_ROWS;
+                wg_raw_issue<BM>(slot, w.X, w.ldx, row0, r_end, k0, w.Kin, tid);
+                wg_raw_issue<BN>(slot + A_BYTES, w.G, w.ldg, row0, r_end, n0, w.N, tid);
+            }
+            cp_async_commit();
+            ++issued;
+        };
+        for (int i = 0; i < D - 1; ++i) issue_one();
+        for (int it = 0; it < nsteps; ++it) {
+            issue_one();
+            cp_async_wait_dyn(D - 1);
+            const int s = it & 1, u = it >> 1;
+            char *a_hi = op_ring + (size_t)s * STAGE, *a_lo = a_hi + A_BYTES, *b_hi = a_lo + A_BYTES, *b_lo = b_hi + B_BYTES;
+            if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;
+            const char *slot = raw_ring + (size_t)(it % D) * RAW;
+            const long long row0 = r_begin + (long long)it * WG_ROWS;
+            wg_convert<BM>(slot, a_hi, a_lo, tid, split, ones_col, row0, r_end);
+            wg_convert<BN>(slot + A_BYTES, b_hi, b_lo, tid, split, -1, row0, r_end);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&stage_ready[s]);
         }
-        cp_async_commit();
-        ++issued;
-    };
-    for (int i = 0; i < D - 1; ++i) issue_one();
-    for (int it = 0; it < nsteps; ++it) {
-        issue_one();
-        cp_async_wait_dyn(D - 1);
-        const int s = it & 1, u = it >> 1;
-        char *a_hi = op_ring + (size_t)s * STAGE, *a_lo = a_hi + A_BYTES, *b_hi = a_lo + A_BYTES, *b_lo = b_hi + B_BYTES;
-        if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;
-        const char *slot = raw_ring + (size_t)(it % D) * RAW;
-        const long long row0 = r_begin + (long long)it * WG_ROWS;
-        wg_convert<BM>(slot, a_hi, a_lo, tid, split, ones_col, row0, r_end);
-        wg_convert<BN>(slot + A_BYTES, b_hi, b_lo, tid, split, -1, row0, r_end);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (lane == 0) {
+        // ======================= MMA issuer =======================
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it & 1, u = it >> 1;
+            const char *a_hi = op_ring + (size_t)s * STAGE, *a_lo = a_hi + A_BYTES, *b_hi = a_lo + A_BYTES, *b_lo = b_hi + B_BYTES;
+            ok = mbar_wait(&stage_ready[s], (uint32_t)(u & 1)) && ok;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < WG_ROWS / UMMA_K; ++j) {  // 8 rows = two 512-byte k groups per slab
@@ -1014,11 +1027,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w
             if (it == nsteps - 1) umma_commit(&all_done);
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (nsteps > 0) ok = mbar_wait(&all_done, 0u) && ok;
+    if (warp < 8 && nsteps > 0) ok = mbar_wait(&all_done, 0u) && ok;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok) s_err = 1;
     // epilogue: TMEM lane = Kin index (k0 + lane), column = N index; warps 0-3 and 4-7 split the columns
-    {
+    if (warp < 8) {
         const int quarter = warp & 3, chalf = warp >> 2;
         const int m = quarter * 32 + lane;      // row of the dW block
         const int gk = k0 + m;
@@ -1048,7 +1061,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WParams w
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
-    if (tid == 0 && !ok && w.error_flag) *w.error_flag = 1;
+    if (tid == 0 && s_err && w.error_flag) *w.error_flag = 1;
 }
 
 struct WgPlan { int bn, gx, gy, gz, depth; long long rows_per_cta; size_t smem; };
@@ -1082,7 +1095,7 @@ static int launch_wgrad(const WParams &w, const WgPlan &pl, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(pl.gx, pl.gy, pl.gz);
-    tc_wgrad_kernel<BN><<<grid, WG_THREADS, pl.smem, st>>>(w);
+    tc_wgrad_kernel<BN><<<grid, WG_TOTAL, pl.smem, st>>>(w);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
