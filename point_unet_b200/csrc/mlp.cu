@@ -362,14 +362,18 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A,
     }
 }
 
-// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order)
+// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order): one warp per output element, lanes stride over the
+// chunks, xor-tree combine -- the order depends only on (chunks), never on scheduling
 __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float *__restrict__ part, int chunks, long long n,
                                                             float *__restrict__ out, int accumulate) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= n) return;
     double s = 0.0;
-    for (int c = 0; c < chunks; ++c) s += (double)part[(size_t)c * n + i];
-    out[i] = accumulate ? out[i] + (float)s : (float)s;
+    for (int c = lane; c < chunks; c += 32) s += (double)part[(size_t)c * n + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
 // mean/var (biased) per channel from per-tile (sum, M2) partials: Chan et al. parallel merge, in double.
@@ -818,10 +822,10 @@ int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, in
         wgrad_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
     }
     PU_LAUNCH_CHECK();
-    reduce_chunks_kernel<<<ceil_div((long long)K * N, 256), 256, 0, st>>>(part, chunks, (long long)K * N, dw, accumulate);
+    reduce_chunks_kernel<<<ceil_div((long long)K * N * 32, 256), 256, 0, st>>>(part, chunks, (long long)K * N, dw, accumulate);
     PU_LAUNCH_CHECK();
     if (db) {
-        reduce_chunks_kernel<<<ceil_div(N, 256), 256, 0, st>>>(db_part, chunks, N, db, accumulate);
+        reduce_chunks_kernel<<<ceil_div((long long)N * 32, 256), 256, 0, st>>>(db_part, chunks, N, db, accumulate);
         PU_LAUNCH_CHECK();
     }
     return PU_OK;

@@ -1100,13 +1100,19 @@ static int launch_wgrad(const WParams &w, const WgPlan &pl, cudaStream_t st) {
     return PU_OK;
 }
 
-// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order)
+// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order; the partial count is <= 148 so a thread per element)
 __global__ void __launch_bounds__(256) tc_reduce_parts_kernel(const float *__restrict__ part, int chunks, long long n,
                                                               float *__restrict__ out, int accumulate) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s = 0.0;
-    for (int c = 0; c < chunks; ++c) s += (double)part[(size_t)c * n + i];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = 0;
+    for (; c + 4 <= chunks; c += 4) {  // 4 independent loads in flight
+        s0 += (double)part[(size_t)c * n + i]; s1 += (double)part[(size_t)(c + 1) * n + i];
+        s2 += (double)part[(size_t)(c + 2) * n + i]; s3 += (double)part[(size_t)(c + 3) * n + i];
+    }
+    for (; c < chunks; ++c) s0 += (double)part[(size_t)c * n + i];
+    const double s = (s0 + s1) + (s2 + s3);
     out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
