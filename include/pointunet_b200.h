@@ -154,7 +154,9 @@ PU_API int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long lon
  * the two-input form is the residual sum of dilated_res_block (RandLANet.py:317-321). */
 PU_API int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shift, const float *y2, int ldy2,
                          const float *scale2, const float *shift2, float slope, long long R, int C, float *out,
-                         int ldo, pu_stream_t stream);
+                         int ldo, float *out2, int ldo2, pu_stream_t stream);
+/* (`shift` is a [2,C] array: row 0 = mean, row 1 = beta -- z = (y - mean)*scale + beta.  `out2` optionally receives a
+ *  second copy of the result, e.g. the right half of an LFA concat buffer, RandLANet.py:328,333.) */
 /* Per-channel batch-norm coefficients, one launch each (tf.layers.batch_normalization, momentum 0.99, eps 1e-6):
  *   forward : invstd = rsqrt(var+eps), scale = gamma*invstd, shift = beta - mean*scale, and (if moving_* given)
  *             moving = momentum*moving + (1-momentum)*batch  (variance times `unbias`, n/(n-1) for TF's fused path);
@@ -171,12 +173,13 @@ PU_API int pu_act_bwd(const float *dout, int ldd, const float *out, int ldo, flo
 /* batch-norm backward: pass 1 reduces sum(dz) and sum(dz*y) per channel into [pu_bn_bwd_reduce_blocks, C]
  * partials (dz = dout * lrelu'(y*scale+shift)); pass 2 applies dy = ka*dz + kb + kc*y. */
 PU_API int pu_bn_bwd_reduce_blocks(long long R, int C);
-PU_API int pu_bn_bwd_reduce(const float *dout, int ldd, const float *y, int ldy, const float *scale,
-                            const float *shift, float slope, long long R, int C, float *part_dz, float *part_dzy,
-                            pu_stream_t stream);
-PU_API int pu_bn_bwd_apply(const float *dout, int ldd, const float *y, int ldy, const float *scale, const float *shift,
-                           float slope, const float *ka, const float *kb, const float *kc, long long R, int C,
-                           float *dy, int lddy, pu_stream_t stream);
+/* dout2 (optional) is a second upstream gradient added on the fly: dz = (dout + dout2) * lrelu'(...) */
+PU_API int pu_bn_bwd_reduce(const float *dout, int ldd, const float *dout2, int ldd2, const float *y, int ldy,
+                            const float *scale, const float *shift, float slope, long long R, int C, float *part_dz,
+                            float *part_dzy, pu_stream_t stream);
+PU_API int pu_bn_bwd_apply(const float *dout, int ldd, const float *dout2, int ldd2, const float *y, int ldy,
+                           const float *scale, const float *shift, float slope, const float *ka, const float *kb,
+                           const float *kc, long long R, int C, float *dy, int lddy, pu_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * ref: Network.att_pooling  RandLANet.py:388-401 (up to f_agg; the trailing conv2d is pu_linear_fwd)

@@ -219,15 +219,26 @@ class Network(torch.nn.Module):
         f_agg = ops.att_pool(feature_set, self.v(name + "fc/kernel"))
         return self.conv2d(f_agg, name + "mlp", True, is_training, True)
 
+    def _linear_stats(self, x, scope, is_training):
+        """1x1 conv + batch statistics, without the BN/activation (fused into the consumer)."""
+        w, b = self.v(scope + "/weights"), self.v(scope + "/biases")
+        rows_n = x.numel() // x.shape[-1]
+        if is_training:
+            y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True)
+        else:
+            y, mean, var = ops.linear(x, w, b), None, None
+        mean, var, moving = self._bn_stats(scope, mean, var, rows_n, is_training)
+        return y, mean, var, self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta"), moving
+
     def building_block(self, xyz, feature, neigh_idx, d_out, name, is_training):
+        """RandLANet.py:323-335.  Same dataflow; the two tf.concat's are produced in place by ops.lfa_concat (gather into
+        the left half, BN + LeakyReLU of the position MLP into the right half)."""
         f_xyz = self.relative_pos_encoding(xyz, neigh_idx)
-        f_xyz = self.conv2d(f_xyz, name + "mlp1", True, is_training)
-        f_neighbours = self.gather_neighbour(feature.squeeze(2), neigh_idx)
-        f_concat = torch.cat([f_neighbours, f_xyz], dim=-1)
+        y, m, v, g, b, mv = self._linear_stats(f_xyz, name + "mlp1", is_training)
+        f_concat, f_xyz = ops.lfa_concat(feature.squeeze(2), neigh_idx, y, m, v, g, b, is_training, mv, need_fxyz=True)
         f_pc_agg = self.att_pooling(f_concat, d_out // 2, name + "att_pooling_1", is_training)
-        f_xyz = self.conv2d(f_xyz, name + "mlp2", True, is_training)
-        f_neighbours = self.gather_neighbour(f_pc_agg.squeeze(2), neigh_idx)
-        f_concat = torch.cat([f_neighbours, f_xyz], dim=-1)
+        y, m, v, g, b, mv = self._linear_stats(f_xyz, name + "mlp2", is_training)
+        f_concat, _ = ops.lfa_concat(f_pc_agg.squeeze(2), neigh_idx, y, m, v, g, b, is_training, mv, need_fxyz=False)
         return self.att_pooling(f_concat, d_out, name + "att_pooling_2", is_training)
 
     def dilated_res_block(self, feature, xyz, neigh_idx, d_out, name, is_training):

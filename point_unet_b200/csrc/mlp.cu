@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict
                                                          const float *__restrict__ shift, const float *__restrict__ y2,
                                                          int ld_y2, const float *__restrict__ scale2,
                                                          const float *__restrict__ shift2, float slope, long long R, int C,
-                                                         float *__restrict__ out, int ld_o) {
+                                                         float *__restrict__ out, int ld_o, float *__restrict__ out2, int ld_o2) {
     const int cq = C >> 2;
     const long long total = R * cq;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * slope;
         *reinterpret_cast<float4 *>(out + (size_t)r * ld_o + c) = make_float4(z[0], z[1], z[2], z[3]);
+        if (out2) *reinterpret_cast<float4 *>(out2 + (size_t)r * ld_o2 + c) = make_float4(z[0], z[1], z[2], z[3]);
     }
 }
 
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float *__restrict__ 
 // BN backward, pass 1: per-channel partials of  sum(dz)  and  sum(dz * y)  with dz = dout * lrelu'(y*scale+shift).
 // grid = fixed number of CTAs; each CTA strides over rows; thread owns one float4 column group.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restrict__ dout, int ld_d,
+                                                            const float *__restrict__ dout2, int ld_d2,
                                                             const float *__restrict__ y, int ld_y,
                                                             const float *__restrict__ scale, const float *__restrict__ shift,
                                                             float slope, long long R, int C, float *__restrict__ part_dz,
@@ -481,7 +483,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restr
         const float4 sc = *reinterpret_cast<const float4 *>(scale + my_c), mu = *reinterpret_cast<const float4 *>(shift + my_c),
                      be = *reinterpret_cast<const float4 *>(shift + C + my_c);
         for (long long r = (long long)blockIdx.x * rpb + my_r; r < R; r += (long long)gridDim.x * rpb) {
-            const float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + my_c);
+            float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + my_c);
+            if (dout2) {
+                const float4 g2 = *reinterpret_cast<const float4 *>(dout2 + (size_t)r * ld_d2 + my_c);
+                g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+            }
             const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + my_c);
             const float4 z = bn_z(v, mu, sc, be);
             const float gz[4] = {z.x > 0.f ? g.x : g.x * slope, z.y > 0.f ? g.y : g.y * slope,
@@ -506,7 +512,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restr
 }
 
 // BN backward, pass 2: dy = ka[c]*dz + kb[c] + kc[c]*y
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restrict__ dout, int ld_d, const float *__restrict__ y,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restrict__ dout, int ld_d,
+                                                           const float *__restrict__ dout2, int ld_d2,
+                                                           const float *__restrict__ y,
                                                            int ld_y, const float *__restrict__ scale,
                                                            const float *__restrict__ shift, float slope,
                                                            const float *__restrict__ ka, const float *__restrict__ kb,
@@ -518,7 +526,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restri
          t += (long long)gridDim.x * blockDim.x) {
         const long long r = t / cq;
         const int c = (int)(t - r * cq) * 4;
-        const float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + c);
+        float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + c);
+        if (dout2) {
+            const float4 g2 = *reinterpret_cast<const float4 *>(dout2 + (size_t)r * ld_d2 + c);
+            g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+        }
         const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
         const float4 sc = *reinterpret_cast<const float4 *>(scale + c), mu = *reinterpret_cast<const float4 *>(shift + c),
                      be = *reinterpret_cast<const float4 *>(shift + C + c);
@@ -856,13 +868,14 @@ int pu_bn_bwd_coeffs(const float *part_dz, const float *part_dzy, int blocks, in
 
 int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shift, const float *y2, int ldy2,
                   const float *scale2, const float *shift2, float slope, long long R, int C, float *out, int ldo,
-                  pu_stream_t stream) {
+                  float *out2, int ldo2, pu_stream_t stream) {
     if (!y || !scale || !shift || !out || R < 0 || C < 4 || (C & 3) || ((ldy | ldo) & 3) || ldy < C || ldo < C)
         return PU_ERR_INVALID_ARG;
     if (y2 && (!scale2 || !shift2 || (ldy2 & 3) || ldy2 < C)) return PU_ERR_INVALID_ARG;
+    if (out2 && ((ldo2 & 3) || ldo2 < C || (((uintptr_t)out2) & 15))) return PU_ERR_INVALID_ARG;
     if (R == 0) return PU_OK;
     bn_act_fwd_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, scale, shift, y2, ldy2, scale2, shift2,
-                                                                            slope, R, C, out, ldo);
+                                                                            slope, R, C, out, ldo, out2, ldo2);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
@@ -883,8 +896,9 @@ int pu_bn_bwd_reduce_blocks(long long R, int C) {
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
-int pu_bn_bwd_reduce(const float *dout, int ldd, const float *y, int ldy, const float *scale, const float *shift,
-                     float slope, long long R, int C, float *part_dz, float *part_dzy, pu_stream_t stream) {
+int pu_bn_bwd_reduce(const float *dout, int ldd, const float *dout2, int ldd2, const float *y, int ldy, const float *scale,
+                     const float *shift, float slope, long long R, int C, float *part_dz, float *part_dzy,
+                     pu_stream_t stream) {
     if (!dout || !y || !scale || !shift || !part_dz || !part_dzy || R < 1 || C < 4 || (C & 3) || C > 1024 * 4 ||
         ((ldd | ldy) & 3))
         return PU_ERR_INVALID_ARG;
@@ -893,21 +907,23 @@ int pu_bn_bwd_reduce(const float *dout, int ldd, const float *y, int ldy, const 
     const int rpb = 256 / cq;
     const size_t smem = (size_t)rpb * C * 2 * sizeof(float);
     if (smem > 48 * 1024) return PU_ERR_UNSUPPORTED;
-    bn_bwd_reduce_kernel<<<pu_bn_bwd_reduce_blocks(R, C), 256, smem, (cudaStream_t)stream>>>(dout, ldd, y, ldy, scale, shift,
-                                                                                            slope, R, C, part_dz, part_dzy);
+    if (dout2 && ((ldd2 & 3) || (((uintptr_t)dout2) & 15))) return PU_ERR_INVALID_ARG;
+    bn_bwd_reduce_kernel<<<pu_bn_bwd_reduce_blocks(R, C), 256, smem, (cudaStream_t)stream>>>(dout, ldd, dout2, ldd2, y, ldy, scale,
+                                                                                            shift, slope, R, C, part_dz, part_dzy);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
 
-int pu_bn_bwd_apply(const float *dout, int ldd, const float *y, int ldy, const float *scale, const float *shift,
-                    float slope, const float *ka, const float *kb, const float *kc, long long R, int C, float *dy,
-                    int lddy, pu_stream_t stream) {
+int pu_bn_bwd_apply(const float *dout, int ldd, const float *dout2, int ldd2, const float *y, int ldy, const float *scale,
+                    const float *shift, float slope, const float *ka, const float *kb, const float *kc, long long R, int C,
+                    float *dy, int lddy, pu_stream_t stream) {
     if (!dout || !y || !scale || !shift || !ka || !kb || !kc || !dy || R < 0 || C < 4 || (C & 3) ||
         ((ldd | ldy | lddy) & 3))
         return PU_ERR_INVALID_ARG;
     if (R == 0) return PU_OK;
-    bn_bwd_apply_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dout, ldd, y, ldy, scale, shift, slope, ka, kb,
-                                                                              kc, R, C, dy, lddy);
+    if (dout2 && ((ldd2 & 3) || (((uintptr_t)dout2) & 15))) return PU_ERR_INVALID_ARG;
+    bn_bwd_apply_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dout, ldd, dout2, ldd2, y, ldy, scale, shift, slope,
+                                                                              ka, kb, kc, R, C, dy, lddy);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

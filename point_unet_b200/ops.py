@@ -45,12 +45,12 @@ _lib._OP_SIGS.update({
     "pu_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                  c_void_p],
     "pu_bn_act_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_int,
-                      c_void_p, c_int, c_void_p],
+                      c_void_p, c_int, c_void_p, c_int, c_void_p],
     "pu_act_bwd": [c_void_p, c_int, c_void_p, c_int, c_float, c_ll, c_int, c_void_p, c_int, c_void_p],
-    "pu_bn_bwd_reduce": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_int, c_void_p, c_void_p,
-                         c_void_p],
-    "pu_bn_bwd_apply": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
-                        c_ll, c_int, c_void_p, c_int, c_void_p],
+    "pu_bn_bwd_reduce": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_int, c_void_p,
+                         c_void_p, c_void_p],
+    "pu_bn_bwd_apply": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                        c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p],
     "pu_bn_prepare": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                       c_void_p, c_float, c_float, c_void_p],
     "pu_bn_bwd_coeffs": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p,
@@ -442,7 +442,7 @@ def linear(x, w, bias=None, want_stats=False, zero_bias_grad=False):
     return _LinearFn.apply(x, w, bias, want_stats, zero_bias_grad)
 
 
-def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shift2=None):
+def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shift2=None, out2=None):
     yr, R, C, ldy = rows(y)
     if out is None:
         out = torch.empty(y.shape, dtype=torch.float32, device=y.device)
@@ -451,34 +451,43 @@ def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shif
     if y2 is not None:
         y2r, R2, C2, ldy2 = rows(y2)
         assert R2 == R and C2 == C
+    ldo2 = 0
+    if out2 is not None:
+        o2, R2o, C2o, ldo2 = rows(out2)
+        assert o2.data_ptr() == out2.data_ptr() and R2o == R and C2o == C
     _call("pu_bn_act_fwd", yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
-                                  y2r.data_ptr() if y2 is not None else None, ldy2 if y2 is not None else 0,
-                                  scale2.data_ptr() if y2 is not None else None,
-                                  shift2.data_ptr() if y2 is not None else None, float(slope), R, C, o.data_ptr(), ldo,
-                                  _stream(y))
+          y2r.data_ptr() if y2 is not None else None, ldy2 if y2 is not None else 0,
+          scale2.data_ptr() if y2 is not None else None, shift2.data_ptr() if y2 is not None else None, float(slope), R, C,
+          o.data_ptr(), ldo, out2.data_ptr() if out2 is not None else None, ldo2, _stream(y))
     return out
 
 
-def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training):
-    """Gradient of out = lrelu(BN(y)) wrt y, gamma, beta given dout (= dz when slope == 1)."""
+def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training, dz2=None):
+    """Gradient of out = lrelu(BN(y)) wrt y, gamma, beta given dout = dz (+ dz2, a second upstream gradient summed on
+    the fly inside the kernels)."""
     dzr, R, C, ldd = rows(dz)
     yr, Ry, Cy, ldy = rows(y)
     assert R == Ry and C == Cy
+    d2ptr, ldd2 = None, 0
+    if dz2 is not None:
+        d2r, R2, C2, ldd2 = rows(dz2)
+        assert R2 == R and C2 == C
+        d2ptr = d2r.data_ptr()
     L = _L()
     blocks = L.pu_bn_bwd_reduce_blocks(R, C)
     p1 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
     p2 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
     st = _stream(y)
-    _call("pu_bn_bwd_reduce", dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
-                                  float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st)
+    _call("pu_bn_bwd_reduce", dzr.data_ptr(), ldd, d2ptr, ldd2, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+          float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st)
     co = torch.empty((5, C), dtype=torch.float32, device=y.device)  # dgamma, dbeta, ka, kb, kc
     dgamma, dbeta, ka, kb, kc = co[0], co[1], co[2], co[3], co[4]
     _call("pu_bn_bwd_coeffs", p1.data_ptr(), p2.data_ptr(), blocks, C, mean.data_ptr(), invstd.data_ptr(),
           gamma.data_ptr(), R, int(bool(training)), dgamma.data_ptr(), dbeta.data_ptr(), ka.data_ptr(), kb.data_ptr(),
           kc.data_ptr(), st)
     dy = torch.empty(y.shape, dtype=torch.float32, device=y.device)
-    _call("pu_bn_bwd_apply", dzr.data_ptr(), ldd, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(), float(slope),
-                                 ka.data_ptr(), kb.data_ptr(), kc.data_ptr(), R, C, dy.data_ptr(), C, st)
+    _call("pu_bn_bwd_apply", dzr.data_ptr(), ldd, d2ptr, ldd2, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+          float(slope), ka.data_ptr(), kb.data_ptr(), kc.data_ptr(), R, C, dy.data_ptr(), C, st)
     return dy, dgamma, dbeta
 
 
@@ -540,6 +549,49 @@ def bn_act(y, mean, var, gamma, beta, slope=LEAKY_SLOPE, training=True, moving=N
     ``(moving_mean, moving_var, unbias)`` is updated in place in training mode."""
     _need_cuda(y)
     return _BNActFn.apply(y, mean, var, gamma, beta, slope, training, moving, y2, mean2, var2, gamma2, beta2, moving2)
+
+
+class _LFAConcatFn(torch.autograd.Function):
+    """``concat([gather_neighbour(f_pc, idx), lrelu(BN(y))], -1)`` of building_block (RandLANet.py:326-328, 331-333)
+    without a concat copy: the gather writes the left half of the buffer, the BN/activation kernel writes its result
+    into the right half (and, if ``need_fxyz``, also into a tensor of its own for the following ``mlp2``)."""
+
+    @staticmethod
+    def forward(ctx, f_pc, idx, y, mean, var, gamma, beta, training, moving, need_fxyz):
+        B, N, K, h = y.shape
+        invstd, scale, shift = bn_prepare(mean, var, gamma, beta, moving if training else None)
+        buf = torch.empty((B, N, K, 2 * h), dtype=torch.float32, device=y.device)
+        gather_rows(f_pc, idx, out=buf[..., :h])
+        if need_fxyz:
+            f_xyz = _bn_act_fwd_raw(y, scale, shift, LEAKY_SLOPE, out2=buf[..., h:])
+        else:
+            f_xyz = None
+            _bn_act_fwd_raw(y, scale, shift, LEAKY_SLOPE, out=buf[..., h:])
+        ctx.save_for_backward(y, scale, shift, gamma, mean, invstd)
+        ctx.idx, ctx.dims, ctx.training, ctx.need_fxyz = idx, (B, N, K, h, f_pc.shape[1]), training, need_fxyz
+        if need_fxyz:
+            return buf, f_xyz
+        return buf
+
+    @staticmethod
+    def backward(ctx, d_buf, d_fxyz=None):
+        y, scale, shift, gamma, mean, invstd = ctx.saved_tensors
+        B, N, K, h, n_src = ctx.dims
+        if d_buf is None:
+            d_buf = torch.zeros((B, N, K, 2 * h), dtype=torch.float32, device=y.device)
+        inv = inverse_of(ctx.idx, n_src)
+        d_fpc = segment_sum(d_buf[..., :h], inv, h).view(B, n_src, h)
+        dy, dg, db = _bn_bwd_raw(d_buf[..., h:], y, scale, shift, LEAKY_SLOPE, gamma, mean, invstd, ctx.training,
+                                 dz2=d_fxyz if ctx.need_fxyz else None)
+        return d_fpc, None, dy, None, None, dg, db, None, None, None
+
+
+def lfa_concat(f_pc, idx, y, mean, var, gamma, beta, training=True, moving=None, need_fxyz=True):
+    """Fused ``concat([gather_neighbour(f_pc, idx), leaky_relu(BN(y))])``; returns ``(concat, f_xyz)`` (f_xyz is None
+    when ``need_fxyz`` is False)."""
+    _need_cuda(f_pc, idx, y)
+    res = _LFAConcatFn.apply(f_pc, idx, y, mean, var, gamma, beta, training, moving, need_fxyz)
+    return res if need_fxyz else (res, None)
 
 
 # ---------------------------------------------------------------------------------------------
