@@ -112,14 +112,16 @@ PU_API int pu_point2prod(const float *probs, const int32_t *xyz_origin, const in
  * Shared MLP = 1x1 convolution over channels-last rows.
  * ref: helper_tf_util.conv2d  PointSegment/helper_tf_util.py:115-170 ; conv2d_transpose :173-250 ;
  *      tf.layers.dense RandLANet.py:114.   y[M,N] (+)= x[M,K] w[K,N] + bias.
- *   stat_sum/stat_sq (optional, [pu_linear_row_tiles(M,N), N]) receive per-tile column sums of y and y^2;
+ *   stat_sum/stat_sq (optional, [pu_linear_row_tiles(M,K,N), N]) receive per-tile (sum, centred M2) of every column of y
+ *   (tiles of pu_linear_rows_per_tile(M,K,N) rows; 128 rows for the tensor-core path);
  *   pu_stats_finalize turns them into the batch-norm mean and BIASED variance (training mode, :166). */
-PU_API int pu_linear_row_tiles(long long M, int N);
+PU_API int pu_linear_rows_per_tile(long long M, int K, int N);
+PU_API int pu_linear_row_tiles(long long M, int K, int N);
 PU_API int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float *bias, float *y, int ldy,
                          long long M, int K, int N, int accumulate, float *stat_sum, float *stat_sq,
                          pu_stream_t stream);
-PU_API int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int C, long long count,
-                             float *mean, float *var, pu_stream_t stream);
+PU_API int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int rows_per_tile, int C,
+                             long long count, float *mean, float *var, pu_stream_t stream);
 /* Tensor-core (tcgen05 + TMEM) form of pu_linear_fwd for K >= 32, N >= 32: y[M,N] (+)= x[M,K] wt[N,K]^T + bias, where
  * wt is the TRANSPOSED weight (K-major).  mode 3 = 3xTF32 (hi/lo split, fp32-class accuracy -- the parity path),
  * mode 1 = plain TF32.  stat_sum/stat_m2: per-128-row-tile batch-norm partials as in pu_linear_fwd.

@@ -278,6 +278,121 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// narrow linear (K <= 16, N <= 16): HBM-bound.  Thread (row lane, y) owns the 4 output columns 4y..4y+3 with the K x 4
+// weight slice in REGISTERS and walks the rows of its CTA's chunk: one vector load of the x row, 4K FMAs, one 128-bit
+// store.  Each CTA covers exactly NARROW_ROWS consecutive rows (= one statistics tile); batch-norm partials (sum, centred
+// M2, shifted by the tile's first output row) are reduced per CTA in fixed order.
+constexpr int NARROW_ROWS = 2048;
+template <int KP>
+__global__ void __launch_bounds__(256) linear_narrow_kernel(const GemmParams p) {
+    __shared__ float s_red[8 * 4 * 4 * 2];  // [warp][NY*4 columns][2]
+    int NY = 1;
+    while (NY * 4 < p.N) NY <<= 1;           // column groups of 4 (power of two <= 4)
+    const int RL = 256 / NY;
+    const int y = threadIdx.x % NY, rl = threadIdx.x / NY;
+    const int c0 = y * 4;
+    const long long r_begin = (long long)blockIdx.x * NARROW_ROWS;
+    const long long r_end = min(p.M, r_begin + NARROW_ROWS);
+    float w[KP][4];
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[k][j] = (k < p.K && c0 + j < p.N) ? p.B[(size_t)k * p.ldb + c0 + j] : 0.f;
+    float bj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bj[j] = (p.bias && c0 + j < p.N) ? p.bias[c0 + j] : 0.f;
+    const bool va4 = ((p.lda & 3) == 0) && ((((uintptr_t)p.A) & 15) == 0) && ((p.K & 3) == 0);
+    const bool va2 = ((p.lda & 1) == 0) && ((((uintptr_t)p.A) & 7) == 0) && ((p.K & 1) == 0);
+    const bool vc4 = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0) && (c0 + 3 < p.N);
+    auto load_row = [&](long long r, float (&xv)[KP]) {
+        const float *a = p.A + (size_t)r * p.lda;
+        if (va4) {
+#pragma unroll
+            for (int i = 0; i < KP; i += 4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < p.K) v = *reinterpret_cast<const float4 *>(a + i);
+                xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+            }
+        } else if (va2) {
+#pragma unroll
+            for (int i = 0; i < KP; i += 2) {
+                float2 v = make_float2(0.f, 0.f);
+                if (i < p.K) v = *reinterpret_cast<const float2 *>(a + i);
+                xv[i] = v.x; xv[i + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < KP; ++i) xv[i] = i < p.K ? a[i] : 0.f;
+        }
+    };
+    auto dot_row = [&](const float (&xv)[KP], float (&o)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = bj[j];
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaf(xv[k], w[k][j], o[j]);
+    };
+    float sh[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.stat_sum && r_begin < r_end) {  // shift = output of the tile's first row (every thread of a column group agrees)
+        float xv[KP];
+        load_row(r_begin, xv);
+        dot_row(xv, sh);
+    }
+    for (long long r = r_begin + rl; r < r_end; r += RL) {
+        float xv[KP], o[4];
+        load_row(r, xv);
+        dot_row(xv, o);
+        float *c = p.C + (size_t)r * p.ldc + c0;
+        if (vc4) {
+            if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4 *>(c);
+                o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+            }
+            *reinterpret_cast<float4 *>(c) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < p.N) {
+                    if (p.accumulate) o[j] += c[j];
+                    c[j] = o[j];
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float d = o[j] - sh[j]; s1[j] += d; s2[j] = fmaf(d, d, s2[j]); }
+    }
+    if (p.stat_sum) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int o = NY; o < 32; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+            }
+        }
+        if (lane < NY) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s_red[((warp * 16) + y * 4 + j) * 2 + 0] = s1[j];
+                s_red[((warp * 16) + y * 4 + j) * 2 + 1] = s2[j];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < NY * 4 && threadIdx.x < p.N) {
+            float a = 0.f, b = 0.f;
+            for (int wv = 0; wv < 8; ++wv) { a += s_red[(wv * 16 + threadIdx.x) * 2]; b += s_red[(wv * 16 + threadIdx.x) * 2 + 1]; }
+            // the shift of column threadIdx.x lives in the thread with y = threadIdx.x / 4: recompute it here
+            float shc = p.bias ? p.bias[threadIdx.x] : 0.f;
+            const float *a0 = p.A + (size_t)r_begin * p.lda;
+            for (int k = 0; k < p.K; ++k) shc = fmaf(a0[k], p.B[(size_t)k * p.ldb + threadIdx.x], shc);
+            const float n = (float)(r_end - r_begin);
+            p.stat_sum[(size_t)blockIdx.x * p.N + threadIdx.x] = fmaf(n, shc, a);
+            p.stat_sq[(size_t)blockIdx.x * p.N + threadIdx.x] = fmaxf(b - a * a / n, 0.f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // wgrad: dW[K,N] = sum_r A[r,K]^T G[r,N]  (+ db[N] = sum_r G[r,N]); grid (k tiles, n tiles, row chunks);
 // each CTA writes its partial tile to part[chunk][K][N]; pu_wgrad then reduces over chunks in a fixed order.
 constexpr int WT = 64, WR = 16;
@@ -698,9 +813,15 @@ static inline int ew_grid(long long total) {
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
+static inline bool linear_is_narrow(long long M, int K, int N) { return K <= 16 && N <= 16 && M >= 4 * NARROW_ROWS; }
+
 template <int EPI>
 static int launch_gemm(const GemmParams &p, cudaStream_t st) {
-    if (p.N <= 16) {
+    if (EPI == EPI_STORE && linear_is_narrow(p.M, p.K, p.N)) {
+        const int grid = ceil_div(p.M, NARROW_ROWS);
+        if (p.K <= 8) linear_narrow_kernel<8><<<grid, 256, 0, st>>>(p);
+        else linear_narrow_kernel<16><<<grid, 256, 0, st>>>(p);
+    } else if (p.N <= 16) {
         dim3 grid(ceil_div(p.M, 256), ceil_div(p.N, 16));
         gemm_kernel<256, 16, 4, 4, EPI><<<grid, 256, 0, st>>>(p);
     } else {
@@ -719,7 +840,12 @@ using namespace pu::mlp;
 
 extern "C" {
 
-int pu_linear_row_tiles(long long M, int N) { return N <= 16 ? ceil_div(M, 256) : ceil_div(M, 128); }
+/* statistics tiling of pu_linear_fwd for a given shape: rows per tile (the kernel choice decides it) and tile count */
+int pu_linear_rows_per_tile(long long M, int K, int N) {
+    if (linear_is_narrow(M, K, N)) return NARROW_ROWS;
+    return N <= 16 ? 256 : 128;
+}
+int pu_linear_row_tiles(long long M, int K, int N) { return ceil_div(M, pu_linear_rows_per_tile(M, K, N)); }
 
 int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float *bias, float *y, int ldy, long long M,
                   int K, int N, int accumulate, float *stat_sum, float *stat_sq, pu_stream_t stream) {
@@ -733,10 +859,9 @@ int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float 
     return launch_gemm<EPI_STORE>(p, (cudaStream_t)stream);
 }
 
-int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int C, long long count, float *mean,
-                      float *var, pu_stream_t stream) {
-    if (!stat_sum || !stat_sq || !mean || !var || tiles < 1 || C < 1 || count < 1) return PU_ERR_INVALID_ARG;
-    const int rows_per_tile = C <= 16 ? 256 : 128;  // must match launch_gemm's tile choice
+int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int rows_per_tile, int C, long long count,
+                      float *mean, float *var, pu_stream_t stream) {
+    if (!stat_sum || !stat_sq || !mean || !var || tiles < 1 || C < 1 || count < 1 || rows_per_tile < 1) return PU_ERR_INVALID_ARG;
     if ((long long)tiles != (count + rows_per_tile - 1) / rows_per_tile) return PU_ERR_INVALID_ARG;
     stats_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
                                                                                           count, rows_per_tile, mean, var);

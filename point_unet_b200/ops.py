@@ -41,7 +41,7 @@ _lib._OP_SIGS.update({
                               c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     "pu_tc_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
                     c_void_p, c_void_p],
-    "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
+    "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "pu_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                  c_void_p],
     "pu_bn_act_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_int,
@@ -91,7 +91,8 @@ def _L():
         L.pu_tc_wgrad_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
         L.pu_tc_wgrad_workspace_bytes.restype = c_size_t
         L.pu_tc_wgrad_workspace_bytes.argtypes = [c_ll, c_int, c_int]
-        L.pu_linear_row_tiles.argtypes = [c_ll, c_int]
+        L.pu_linear_row_tiles.argtypes = [c_ll, c_int, c_int]
+        L.pu_linear_rows_per_tile.argtypes = [c_ll, c_int, c_int]
         L.pu_bn_bwd_reduce_blocks.argtypes = [c_ll, c_int]
         L._pu_extra_declared = True
     return L
@@ -351,7 +352,8 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
     use_tc = mode in (1, 3) and M >= 128 and L.pu_tc_linear_supported(M, K, N, ldx, K, ldo) and xr.data_ptr() % 16 == 0
     ssum = ssq = None
     if want_stats:
-        tiles = (M + 127) // 128 if use_tc else L.pu_linear_row_tiles(M, N)
+        rpt = 128 if use_tc else L.pu_linear_rows_per_tile(M, K, N)
+        tiles = (M + rpt - 1) // rpt
         ssum = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
         ssq = torch.empty((tiles, N), dtype=torch.float32, device=x.device)
     bptr = bias.data_ptr() if bias is not None else None
@@ -371,7 +373,7 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
         return out
     mean = torch.empty(N, dtype=torch.float32, device=x.device)
     var = torch.empty(N, dtype=torch.float32, device=x.device)
-    _call("pu_stats_finalize", ssum.data_ptr(), ssq.data_ptr(), ssum.shape[0], N, M, mean.data_ptr(), var.data_ptr(),
+    _call("pu_stats_finalize", ssum.data_ptr(), ssq.data_ptr(), ssum.shape[0], rpt, N, M, mean.data_ptr(), var.data_ptr(),
           _stream(x))
     return out, mean, var
 
