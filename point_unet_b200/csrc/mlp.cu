@@ -278,26 +278,27 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// narrow linear (K <= 16, N <= 16): HBM-bound.  Thread (row lane, y) owns the 4 output columns 4y..4y+3 with the K x 4
+// narrow linear (K <= 16, N <= 32): HBM-bound.  Thread (row lane, y) owns the 4 output columns 4y..4y+3 with the K x 4
 // weight slice in REGISTERS and walks the rows of its CTA's chunk: one vector load of the x row, 4K FMAs, one 128-bit
 // store.  Each CTA covers exactly NARROW_ROWS consecutive rows (= one statistics tile); batch-norm partials (sum, centred
 // M2, shifted by the tile's first output row) are reduced per CTA in fixed order.
 constexpr int NARROW_ROWS = 2048;
 template <int KP>
-__global__ void __launch_bounds__(256) linear_narrow_kernel(const GemmParams p) {
-    __shared__ float s_red[8 * 4 * 4 * 2];  // [warp][NY*4 columns][2]
+__global__ void __launch_bounds__(256, 3) linear_narrow_kernel(const GemmParams p) {
+    __shared__ float s_red[8 * 32 * 2];            // [warp][NY*4 columns][2]
+    __shared__ __align__(16) float s_w[KP * 32];   // weight [k][32 columns], zero padded (broadcast reads)
     int NY = 1;
-    while (NY * 4 < p.N) NY <<= 1;           // column groups of 4 (power of two <= 4)
+    while (NY * 4 < p.N) NY <<= 1;           // column groups of 4 (power of two <= 8)
     const int RL = 256 / NY;
     const int y = threadIdx.x % NY, rl = threadIdx.x / NY;
     const int c0 = y * 4;
     const long long r_begin = (long long)blockIdx.x * NARROW_ROWS;
     const long long r_end = min(p.M, r_begin + NARROW_ROWS);
-    float w[KP][4];
-#pragma unroll
-    for (int k = 0; k < KP; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[k][j] = (k < p.K && c0 + j < p.N) ? p.B[(size_t)k * p.ldb + c0 + j] : 0.f;
+    for (int i = threadIdx.x; i < KP * 32; i += 256) {
+        const int k = i >> 5, c = i & 31;
+        s_w[i] = (k < p.K && c < p.N) ? p.B[(size_t)k * p.ldb + c] : 0.f;
+    }
+    __syncthreads();
     float bj[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bj[j] = (p.bias && c0 + j < p.N) ? p.bias[c0 + j] : 0.f;
@@ -329,9 +330,11 @@ __global__ void __launch_bounds__(256) linear_narrow_kernel(const GemmParams p) 
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = bj[j];
 #pragma unroll
-        for (int k = 0; k < KP; ++k)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = fmaf(xv[k], w[k][j], o[j]);
+        for (int k = 0; k < KP; ++k) {
+            const float4 wk = *reinterpret_cast<const float4 *>(&s_w[k * 32 + c0]);
+            o[0] = fmaf(xv[k], wk.x, o[0]); o[1] = fmaf(xv[k], wk.y, o[1]);
+            o[2] = fmaf(xv[k], wk.z, o[2]); o[3] = fmaf(xv[k], wk.w, o[3]);
+        }
     };
     float sh[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (p.stat_sum && r_begin < r_end) {  // shift = output of the tile's first row (every thread of a column group agrees)
@@ -339,16 +342,10 @@ __global__ void __launch_bounds__(256) linear_narrow_kernel(const GemmParams p) 
         load_row(r_begin, xv);
         dot_row(xv, sh);
     }
-    for (long long r = r_begin + rl; r < r_end; r += RL) {
-        float xv[KP], o[4];
-        load_row(r, xv);
-        dot_row(xv, o);
+    auto finish_row = [&](long long r, float (&o)[4], const float4 &old) {
         float *c = p.C + (size_t)r * p.ldc + c0;
         if (vc4) {
-            if (p.accumulate) {
-                const float4 old = *reinterpret_cast<const float4 *>(c);
-                o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
-            }
+            if (p.accumulate) { o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w; }
             *reinterpret_cast<float4 *>(c) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
@@ -360,6 +357,29 @@ __global__ void __launch_bounds__(256) linear_narrow_kernel(const GemmParams p) 
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float d = o[j] - sh[j]; s1[j] += d; s2[j] = fmaf(d, d, s2[j]); }
+    };
+    long long r = r_begin + rl;
+    for (; r + RL < r_end; r += 2 * RL) {  // two rows per trip: both x rows (and old C values) are in flight together
+        float xa[KP], xb[KP], oa[4], ob[4];
+        load_row(r, xa);
+        load_row(r + RL, xb);
+        float4 olda = make_float4(0.f, 0.f, 0.f, 0.f), oldb = olda;
+        if (p.accumulate && vc4) {
+            olda = *reinterpret_cast<const float4 *>(p.C + (size_t)r * p.ldc + c0);
+            oldb = *reinterpret_cast<const float4 *>(p.C + (size_t)(r + RL) * p.ldc + c0);
+        }
+        dot_row(xa, oa);
+        dot_row(xb, ob);
+        finish_row(r, oa, olda);
+        finish_row(r + RL, ob, oldb);
+    }
+    for (; r < r_end; r += RL) {
+        float xa[KP], oa[4];
+        load_row(r, xa);
+        float4 olda = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.accumulate && vc4) olda = *reinterpret_cast<const float4 *>(p.C + (size_t)r * p.ldc + c0);
+        dot_row(xa, oa);
+        finish_row(r, oa, olda);
     }
     if (p.stat_sum) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,14 +393,14 @@ __global__ void __launch_bounds__(256) linear_narrow_kernel(const GemmParams p) 
         if (lane < NY) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                s_red[((warp * 16) + y * 4 + j) * 2 + 0] = s1[j];
-                s_red[((warp * 16) + y * 4 + j) * 2 + 1] = s2[j];
+                s_red[((warp * 32) + y * 4 + j) * 2 + 0] = s1[j];
+                s_red[((warp * 32) + y * 4 + j) * 2 + 1] = s2[j];
             }
         }
         __syncthreads();
         if (threadIdx.x < NY * 4 && threadIdx.x < p.N) {
             float a = 0.f, b = 0.f;
-            for (int wv = 0; wv < 8; ++wv) { a += s_red[(wv * 16 + threadIdx.x) * 2]; b += s_red[(wv * 16 + threadIdx.x) * 2 + 1]; }
+            for (int wv = 0; wv < 8; ++wv) { a += s_red[(wv * 32 + threadIdx.x) * 2]; b += s_red[(wv * 32 + threadIdx.x) * 2 + 1]; }
             // the shift of column threadIdx.x lives in the thread with y = threadIdx.x / 4: recompute it here
             float shc = p.bias ? p.bias[threadIdx.x] : 0.f;
             const float *a0 = p.A + (size_t)r_begin * p.lda;
@@ -813,7 +833,7 @@ static inline int ew_grid(long long total) {
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
-static inline bool linear_is_narrow(long long M, int K, int N) { return K <= 16 && N <= 16 && M >= 4 * NARROW_ROWS; }
+static inline bool linear_is_narrow(long long M, int K, int N) { return K <= 16 && N <= 32 && M >= 4 * NARROW_ROWS; }
 
 template <int EPI>
 static int launch_gemm(const GemmParams &p, cudaStream_t st) {
