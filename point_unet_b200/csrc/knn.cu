@@ -356,9 +356,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
         home = min(pos, N1 - 1) / BS;
     }
     home = min(home, NB - 1);
-    // seed: the warp's own position in the support's Morton order (fills every lane's list: 32 candidates >= K)
-    const int seed_lo = home, seed_hi = home;
+    const int seed_lo = max(home - 1, 0), seed_hi = min(home + 1, NB - 1);
     S.sweep_bucket(sp_cloud, N1, home, tile, lane);
+    for (int t = seed_lo; t <= seed_hi; ++t)
+        if (t != home) S.sweep_bucket(sp_cloud, N1, t, tile, lane);
 
     // warp search radius^2 = max over lanes of the current K-th distance (+inf while a lane is not full)
     auto warp_radius = [&]() -> float {
@@ -367,9 +368,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
     };
     float R2 = warp_radius();
 
-    // ---- walk super-buckets: chunks of 32 outward from the home chunk; inside a chunk, and inside every super-bucket,
-    // always take the NEAREST remaining box first (warp-box distance, picked with redux.min) so the K-th distances
-    // tighten as early as possible and later boxes are pruned
+    // ---- walk super-buckets, nearest chunk first (outward from the home chunk)
     const int nchunks = (NSB + 31) >> 5;
     const int home_chunk = (home / SBS) >> 5;
     for (int step = 0; step < 2 * nchunks; ++step) {  // step 0: home; 2k-1: home+k; 2k: home-k
@@ -386,12 +385,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
         unsigned m = __ballot_sync(0xffffffffu, hit);
         S.n_tests += 1;
         while (m) {
-            // nearest remaining super-bucket of this chunk
-            const unsigned skey = ((m >> lane) & 1u) ? __float_as_uint(sd2) : 0xFFFFFFFFu;
-            const unsigned smin = __reduce_min_sync(0xffffffffu, skey);
-            const int bit = __ffs(__ballot_sync(0xffffffffu, skey == smin)) - 1;
-            m &= ~(1u << bit);
-            if (__uint_as_float(smin) > R2) break;  // all remaining ones are farther still
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const float sd2b = __shfl_sync(0xffffffffu, sd2, bit);
+            if (sd2b > R2) continue;  // radius shrank since the ballot
             const int sbi = chunk * 32 + bit;
             const int t0 = sbi * SBS;
             const int tn = min(SBS, NB - t0);
@@ -413,13 +410,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
             }
             unsigned need = __reduce_or_sync(0xffffffffu, want);
             S.n_tests += tn;
-            // ordering key of bucket `lane`: its distance to the warp's query box
-            const float wd = lane < tn ? box_box_dist2(qlo, qhi, s_blo[wib][lane], s_bhi[wib][lane]) : FLT_MAX;
             while (need) {
-                const unsigned bkey = ((need >> lane) & 1u) ? __float_as_uint(wd) : 0xFFFFFFFFu;
-                const unsigned bmin = __reduce_min_sync(0xffffffffu, bkey);
-                const int j = __ffs(__ballot_sync(0xffffffffu, bkey == bmin)) - 1;
-                need &= ~(1u << j);
+                const int j = __ffs(need) - 1;
+                need &= need - 1;
                 const int t = t0 + j;
                 if (t >= seed_lo && t <= seed_hi) continue;  // already swept
                 // re-test against the lanes' current K-th distances (they shrink as buckets are swept)
