@@ -114,8 +114,9 @@ def algorithmic(name, tag):
     if name in ("pu_tc_linear_fwd", "pu_linear_fwd", "pu_tc_wgrad", "pu_wgrad"):
         # 1x1 conv / dgrad / wgrad over M rows: read x [M,K] and y or dy [M,N] once (weights are negligible);
         # 2*K*N/(4*(K+N)) flop per byte stays below the B200 ridge (~212 flop/B) for every layer => HBM-bound
-        M, K, N = tag
-        return 4 * M * (K + N), 2 * M * K * N, "hbm"
+        M, K, N = tag[:3]
+        acc = tag[3] if len(tag) > 3 else 0   # accumulate launches also read the previous output (dx = dx_direct + ...)
+        return 4 * M * (K + N * (1 + acc)), 2 * M * K * N, "hbm"
     return 0, 0, "hbm"
 
 

@@ -363,12 +363,13 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
         tws = workspace(L.pu_tc_workspace_bytes(K, N), x.device, slot=4)
         _call("pu_tc_linear_fwd", xr.data_ptr(), ldx, wt.data_ptr(), K, bptr, o.data_ptr(), ldo, M, K, N, int(accumulate),
               ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, mode,
-              tc_error_flag(x.device).data_ptr(), tws.data_ptr(), tws.numel(), _stream(x), tag=(M, K, N))
+              tc_error_flag(x.device).data_ptr(), tws.data_ptr(), tws.numel(), _stream(x), tag=(M, K, N, int(accumulate)))
     else:
         if w is None:
             w = wt.t().contiguous()
         _call("pu_linear_fwd", xr.data_ptr(), ldx, w.data_ptr(), N, bptr, o.data_ptr(), ldo, M, K, N, int(accumulate),
-              ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, _stream(x), tag=(M, K, N))
+              ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, _stream(x),
+              tag=(M, K, N, int(accumulate)))
     if not want_stats:
         return out
     mean = torch.empty(N, dtype=torch.float32, device=x.device)
