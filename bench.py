@@ -316,7 +316,7 @@ def run_ours(args):
             achieved, peak, runit = tot_f / (t_ms * 1e-3) / 1e12, peaks["tensor_sustained"], "TFLOP/s"
         else:
             achieved, peak, runit = tot_b / (t_ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
-        traffic = load_traffic().get(top_rf)
+        traffic = (load_traffic().get(top_rf) or {}).get("dram_bytes_per_launch")
         roofline = dict(kernel=top_rf, bound=bound, achieved=achieved, peak=peak, unit=runit, frac=achieved / peak,
                         traffic=traffic, launches_per_step=n_l / args.steps, ms_per_step=t_ms / args.steps,
                         algorithmic_gb_per_step=tot_b / args.steps / 1e9, gflop_per_step=tot_f / args.steps / 1e9,

@@ -1,6 +1,8 @@
 // tc_gemm.cu -- 5th-generation tensor-core (tcgen05 + TMEM) path for the wide contractions of PointSegment.
 //
-//   pu_tc_linear_fwd   y[M,N] (+)= x[M,K] wt[N,K]^T + bias      (1x1 conv / dense / dgrad at >= 32 channels)
+//   pu_tc_linear_fwd        y[M,N] (+)= x[M,K] wt[N,K]^T + bias   (1x1 conv / dense / dgrad at >= 32 channels)
+//   pu_tc_att_pooling_fwd/_bwd   fused FC + softmax over K + weighted sum and its gradient
+//   pu_tc_wgrad             dW = x^T dy
 //
 // Precision.  The reference computes these GEMMs in fp32 and the parity bar is 1e-3 relative, so the default mode is
 // "3xTF32": every fp32 operand is split as a = hi + lo with hi = round-to-tf32(a), lo = a - hi (exact), and the
@@ -8,17 +10,11 @@
 // fp32-class accuracy at one third of the tf32 tensor rate -- still several times the CUDA-core fp32 peak.
 // mode 1 = plain TF32 (one MMA per k-step), for the stated reduced-precision tolerance.
 //
-// Kernel anatomy (one CTA = 128 threads = one 128 x BN output tile, BN <= 128):
-//   * operands are staged as K-major SWIZZLE_128B tiles (rows of 32 fp32 = 128 B; 16-byte chunk c of row r is stored at
-//     chunk c ^ (r % 8) inside its 1024-byte 8-row atom) -- the canonical UMMA layout (cute::UMMA::Layout_K_SW128_Atom).
-//     The split into hi/lo needs a pass through registers anyway, so the tiles are written with st.shared (coalesced
-//     128-bit global loads, conflict-free swizzled stores) and published to the async proxy with fence.proxy.async;
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8 per instruction) straight from
-//     shared-memory descriptors; the accumulator (128 lanes x BN columns, fp32) lives in TMEM;
-//   * two stages: while the tensor core works on stage s, all threads load/split stage s^1; tcgen05.commit arrives on
-//     an mbarrier when the MMAs that read a stage have retired;
-//   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp instruction) -> registers -> shared tile -> coalesced
-//     128-bit stores, plus the per-tile batch-norm partials (sum, centred M2) in the same format as the CUDA-core path.
+// Operand layout shared by all kernels: K-major SWIZZLE_128B tiles (rows of 32 fp32 = 128 B; 16-byte chunk c of row r is
+// stored at chunk c ^ (r % 8) inside its 1024-byte 8-row atom) -- the canonical UMMA layout (cute::UMMA::Layout_K_SW128_Atom).
+// The hi/lo split needs a pass through registers anyway, so the tiles are written with st.shared (coalesced loads,
+// conflict-free swizzled stores) and published to the async proxy with fence.proxy.async; accumulators live in TMEM and
+// come back through tcgen05.ld (32 lanes x 16 columns per warp instruction).  Kernel anatomy: see tc_persist_kernel.
 #include <float.h>
 
 #include "common.cuh"
@@ -29,8 +25,6 @@ namespace tc {
 constexpr int BM = 128;  // UMMA_M (cta_group::1)
 constexpr int BK = 32;   // fp32 elements per 128-byte swizzle row
 constexpr int UMMA_K = 8;  // tf32: 32 bytes per instruction
-constexpr int MAX_BN = 128;
-constexpr int THREADS = 128;
 
 struct Params {
     const float *A; int lda;    // [M,K]
@@ -108,211 +102,8 @@ __device__ __forceinline__ float tf32_rn(float a) {
 // byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
-// registers holding one thread's share of a k-block: ROWS x 8 chunks of 16 B spread over 128 threads
-template <int ROWS>
-struct TileRegs {
-    float4 v[ROWS / 16];
-};
-
-template <int ROWS>
-__device__ __forceinline__ void load_tile(TileRegs<ROWS> &t, const float *__restrict__ base, int ld, long long row0,
-                                          long long row_end, int k0, int K, int tid) {
-#pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
-        const int idx = tid + THREADS * i;
-        const int r = idx >> 3, c = idx & 7;
-        const long long gr = row0 + r;
-        const int gk = k0 + c * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < row_end && gk < K) {  // K % 4 == 0 is guaranteed by the host
-            v = *reinterpret_cast<const float4 *>(base + (size_t)gr * ld + gk);
-        }
-        t.v[i] = v;
-    }
-}
-template <int ROWS>
-__device__ __forceinline__ void store_tile(const TileRegs<ROWS> &t, char *hi, char *lo, int tid, bool split) {
-#pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
-        const int idx = tid + THREADS * i;
-        const int r = idx >> 3, c = idx & 7;
-        const uint32_t off = sw128(r, c);
-        const float4 v = t.v[i];
-        if (split) {
-            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-            *reinterpret_cast<float4 *>(hi + off) = h;
-            *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        } else {
-            *reinterpret_cast<float4 *>(hi + off) = v;  // the tensor core reads the top 19 bits
-        }
-    }
-}
-
-template <int BN>
-__global__ void __launch_bounds__(THREADS) tc_linear_kernel(const Params p) {
-    constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
-    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands
-    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;            // power of two >= 32 (BN in {32, 64, 128})
-    extern __shared__ __align__(1024) char smem_raw[];
-    char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t mma_done[2];
-    __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_mean[BN];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long m0 = (long long)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;
-    const bool split = p.mode == 3;
-    const int nkb = (p.K + BK - 1) / BK;
-
-    if (tid == 0) {
-        mbar_init(&mma_done[0], 1);
-        mbar_init(&mma_done[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                     "r"((uint32_t)TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_slot;
-    const uint32_t idesc = make_idesc(BN);
-
-    TileRegs<BM> ra;
-    TileRegs<BN> rb;
-    load_tile<BM>(ra, p.A, p.lda, m0, p.M, 0, p.K, tid);
-    load_tile<BN>(rb, p.Bt, p.ldb, n0, p.N, 0, p.K, tid);
-    bool ok = true;
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
-        char *stage = smem + (size_t)s * STAGE_BYTES;
-        char *a_hi = stage, *a_lo = stage + A_BYTES, *b_hi = stage + 2 * A_BYTES, *b_lo = stage + 2 * A_BYTES + B_BYTES;
-        if (kb >= 2) ok = mbar_wait(&mma_done[s], (uint32_t)(((kb >> 1) - 1) & 1)) && ok;  // stage s is free again
-        store_tile<BM>(ra, a_hi, a_lo, tid, split);
-        store_tile<BN>(rb, b_hi, b_lo, tid, split);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < BK / UMMA_K; ++j) {
-                const uint64_t dah = make_desc(smem_u32(a_hi) + j * 32), dbh = make_desc(smem_u32(b_hi) + j * 32);
-                umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                if (split) {
-                    const uint64_t dal = make_desc(smem_u32(a_lo) + j * 32), dbl = make_desc(smem_u32(b_lo) + j * 32);
-                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-                }
-            }
-            umma_commit(&mma_done[s]);  // implies tcgen05.fence::before_thread_sync
-        }
-        if (kb + 1 < nkb) {  // prefetch the next k-block into registers while the tensor core runs
-            load_tile<BM>(ra, p.A, p.lda, m0, p.M, (kb + 1) * BK, p.K, tid);
-            load_tile<BN>(rb, p.Bt, p.ldb, n0, p.N, (kb + 1) * BK, p.K, tid);
-        }
-    }
-    // all MMAs retired: the last commit of each stage covers everything issued before it
-    {
-        const int last = nkb - 1;
-        ok = mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1)) && ok;
-        if (nkb >= 2) ok = mbar_wait(&mma_done[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1)) && ok;
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (!ok && p.error_flag) *p.error_flag = 1;
-
-    // ---- epilogue: TMEM -> registers -> shared tile [BM][BN + 4]
-    constexpr int LDT = BN + 4;
-    float *tile = reinterpret_cast<float *>(smem);  // stage buffers are free now
-    static_assert((size_t)BM * LDT * 4 <= (size_t)2 * STAGE_BYTES, "epilogue tile fits in the stage buffers");
-    {
-        const int row = warp * 32 + lane;
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-            for (int q = 0; q < 16; q += 4)
-                *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + q]) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
-    }
-    // bias / accumulate / coalesced store; the stored value also goes back into the tile for the statistics
-    const long long rows_here = min((long long)BM, p.M - m0);
-    const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-    for (int idx = tid; idx < BM * (BN / 4); idx += THREADS) {
-        const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
-        if (r >= rows_here) continue;
-        const int gn = n0 + c;
-        float4 v = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
-        float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
-        if (gn + 3 < p.N && vecC) {
-            if (p.bias) {
-                const float4 b = *reinterpret_cast<const float4 *>(p.bias + gn);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            }
-            if (p.accumulate) {
-                const float4 o = *reinterpret_cast<const float4 *>(cptr);
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            *reinterpret_cast<float4 *>(cptr) = v;
-        } else {
-            float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (gn + j < p.N) {
-                    if (p.bias) vv[j] += p.bias[gn + j];
-                    if (p.accumulate) vv[j] += cptr[j];
-                    cptr[j] = vv[j];
-                }
-            v = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        }
-        *reinterpret_cast<float4 *>(&tile[r * LDT + c]) = v;
-    }
-    if (p.stat_sum) {  // per-tile (sum, centred M2) per column, merged by pu_stats_finalize (rows_per_tile = 128)
-        __syncthreads();
-        if (tid < BN) {
-            float s = 0.f;
-            for (int r = 0; r < rows_here; ++r) s += tile[r * LDT + tid];
-            s_mean[tid] = s / (float)rows_here;
-            float q = 0.f;
-            const float mu = s_mean[tid];
-            for (int r = 0; r < rows_here; ++r) {
-                const float d = tile[r * LDT + tid] - mu;
-                q = fmaf(d, d, q);
-            }
-            if (n0 + tid < p.N) {
-                p.stat_sum[(size_t)blockIdx.x * p.N + n0 + tid] = s;
-                p.stat_m2[(size_t)blockIdx.x * p.N + n0 + tid] = q;
-            }
-        }
-    }
-}
-
-template <int BN>
-static int launch(const Params &p, cudaStream_t st) {
-    constexpr size_t smem = 2 * (2 * BM * 128 + 2 * (size_t)BN * 128) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        PU_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN));
-    tc_linear_kernel<BN><<<grid, THREADS, smem, st>>>(p);
-    PU_LAUNCH_CHECK();
-    return PU_OK;
-}
-
-
 // =============================================================================================================
-// v2: persistent, warp-specialised kernel.  grid = a multiple of the SM count; every CTA walks 128-row tiles.
+// persistent, warp-specialised kernel.  grid = a multiple of the SM count; every CTA walks 128-row tiles.
 //   warps 0-3  producers: global -> registers (prefetched one k-block ahead) -> hi/lo split -> swizzled smem ring;
 //              thread 0 additionally issues the MMAs of the stage it just helped to fill (one elected issuer)
 //   warps 4-7  epilogue: wait for the tile's accumulator (TMEM, double-buffered), tcgen05.ld, release the buffer,

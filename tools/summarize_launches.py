@@ -27,14 +27,18 @@ for d in sorted(launch.values(), key=lambda d: -d["us"])[:25]:
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 open(os.path.join(ROOT, "profiles", f"{tag}_launch_summary.txt"), "w").write("\n".join(out) + "\n")
 # per C-ABI entry traffic (bytes per launch), mapping kernel names to the entry points bench.py times
-ENTRY = {"tc::tc_persist_kernel<64, 0>": "pu_tc_linear_fwd", "tc::tc_persist_kernel<32, 0>": "pu_tc_linear_fwd", "tc::tc_persist_kernel<128, 0>": "pu_tc_linear_fwd",
-         "tc::tc_linear_kernel": "pu_tc_linear_fwd", "tc::tc_persist_kernel<64, 1>": "pu_tc_att_pooling_fwd", "tc::tc_persist_kernel<32, 1>": "pu_tc_att_pooling_fwd",
-         "tc::tc_persist_kernel<64, 2>": "pu_tc_att_pooling_bwd", "tc::tc_persist_kernel<32, 2>": "pu_tc_att_pooling_bwd", "tc::tc_wgrad_kernel": "pu_tc_wgrad",
-         "lfa::gather_rows": "pu_gather_rows_fwd", "lfa::segment_sum": "pu_segment_sum", "mlp::wgrad": "pu_wgrad"}
-tr = collections.defaultdict(lambda: [0, 0.0])
+ENTRY = [(r"tc::tc_persist_kernel<\d+, 0,", "pu_tc_linear_fwd"), (r"tc::tc_linear_kernel", "pu_tc_linear_fwd"),
+         (r"tc::tc_persist_kernel<\d+, 1,", "pu_tc_att_pooling_fwd"), (r"tc::tc_persist_kernel<\d+, 2,", "pu_tc_att_pooling_bwd"),
+         (r"tc::tc_wgrad_kernel", "pu_tc_wgrad"), (r"lfa::gather_rows", "pu_gather_rows_fwd"), (r"lfa::segment_sum", "pu_segment_sum"),
+         (r"mlp::wgrad", "pu_wgrad"), (r"mlp::linear_narrow|mlp::gemm_kernel<\d+, \d+, \d+, \d+, 0>", "pu_linear_fwd"),
+         (r"knn::knn_search_kernel", "pu_knn_batch")]
+tr = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for k, a in agg.items():
-    for pat, entry in ENTRY.items():
-        if k.startswith(pat):
-            tr[entry][0] += a["n"]; tr[entry][1] += a["bytes"]
-json.dump({e: v[1] / v[0] for e, v in tr.items() if v[0]}, open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json"), "w"), indent=1)
+    for pat, entry in ENTRY:
+        if re.match(pat, k):
+            tr[entry][0] += a["n"]; tr[entry][1] += a["bytes"]; tr[entry][2] += a["us"]
+            break
+json.dump({e: dict(dram_bytes_per_launch=v[1] / v[0], launches_per_step=v[0], ncu_ms_per_step=v[2] / 1e3,
+                   dram_gbs_under_ncu=v[1] / max(v[2], 1e-9) / 1e3) for e, v in tr.items() if v[0]},
+          open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json"), "w"), indent=1)
 print("\n".join(out[:30]))
