@@ -226,7 +226,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PU_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout (one JSON line)
+        # keep NCCL's version banner / logger off stdout (rank 0 prints exactly one JSON line there)
+        if "PU_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["PU_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
