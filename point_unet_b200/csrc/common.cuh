@@ -54,4 +54,39 @@ __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
                  : "memory");
 }
 
+// out[i] (+)= sum_c part[c][i], double accumulation in an order that depends only on (chunks, E): thread (e, g) of a CTA owns
+// element blockIdx.x*E + e and the chunks g, g+G, ... (G = 256/E) with four independent loads in flight; the G group sums
+// are combined by a shared-memory tree.  Loads are coalesced over e (E*4 bytes per group and chunk).
+template <int E>
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const float *__restrict__ part, int chunks, long long n,
+                                                           float *__restrict__ out, int accumulate) {
+    constexpr int G = 256 / E;
+    __shared__ double red[G][E];
+    const int e = threadIdx.x % E, g = threadIdx.x / E;
+    const long long i = (long long)blockIdx.x * E + e;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (i < n) {
+        int c = g;
+        for (; c + 3 * G < chunks; c += 4 * G) {
+            const float a = part[(size_t)c * n + i], b = part[(size_t)(c + G) * n + i], d = part[(size_t)(c + 2 * G) * n + i],
+                        f = part[(size_t)(c + 3 * G) * n + i];
+            s0 += (double)a; s1 += (double)b; s2 += (double)d; s3 += (double)f;
+        }
+        for (; c < chunks; c += G) s0 += (double)part[(size_t)c * n + i];
+    }
+    red[g][e] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        if (g < o) red[g][e] += red[g + o][e];
+        __syncthreads();
+    }
+    if (g == 0 && i < n) out[i] = accumulate ? out[i] + (float)red[0][e] : (float)red[0][e];
+}
+// launch helper: narrow CTAs (8 elements x 32 chunk groups) for small outputs, wide ones (32 x 8) otherwise
+inline void launch_reduce_parts(const float *part, int chunks, long long n, float *out, int accumulate, cudaStream_t st) {
+    if (n <= 8192) reduce_parts_kernel<8><<<ceil_div(n, 8), 256, 0, st>>>(part, chunks, n, out, accumulate);
+    else reduce_parts_kernel<32><<<ceil_div(n, 32), 256, 0, st>>>(part, chunks, n, out, accumulate);
+}
+
 }  // namespace pu

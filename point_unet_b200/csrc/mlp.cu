@@ -497,20 +497,6 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A,
     }
 }
 
-// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order): one warp per output element, lanes stride over the
-// chunks, xor-tree combine -- the order depends only on (chunks), never on scheduling
-__global__ void __launch_bounds__(256) reduce_chunks_kernel(const float *__restrict__ part, int chunks, long long n,
-                                                            float *__restrict__ out, int accumulate) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= n) return;
-    double s = 0.0;
-    for (int c = lane; c < chunks; c += 32) s += (double)part[(size_t)c * n + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[i] = accumulate ? out[i] + (float)s : (float)s;
-}
-
 // mean/var (biased) per channel from per-tile (sum, M2) partials: Chan et al. parallel merge, in double.
 //   var = [ sum_t M2_t + sum_t n_t mean_t^2 - n mean^2 ] / n      (the subtraction is done in double)
 // One CTA per channel, 256 threads stride over the tiles, fixed-order block reduction.
@@ -520,7 +506,24 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float *__rest
     __shared__ double red[3][256];
     const int c = blockIdx.x;
     double s = 0.0, q = 0.0, r = 0.0;
-    for (int t = threadIdx.x; t < tiles; t += 256) {
+    int t = threadIdx.x;
+    for (; t + 768 < tiles; t += 1024) {  // four tiles per trip: eight independent loads in flight per thread
+        float st[4], mt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            st[j] = psum[(size_t)(t + 256 * j) * C + c];
+            mt[j] = pm2[(size_t)(t + 256 * j) * C + c];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long r0 = (long long)(t + 256 * j) * rows_per_tile;
+            const double nt = (double)min((long long)rows_per_tile, count - r0);
+            s += (double)st[j];
+            q += (double)mt[j];
+            r += (double)st[j] * (double)st[j] / nt;
+        }
+    }
+    for (; t < tiles; t += 256) {
         const long long r0 = (long long)t * rows_per_tile;
         const double nt = (double)min((long long)rows_per_tile, count - r0);
         const double st = (double)psum[(size_t)t * C + c];
@@ -808,7 +811,15 @@ __global__ void bn_bwd_coeffs_kernel(const float *__restrict__ part_dz, const fl
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= C) return;
     double s = 0.0, q = 0.0;
-    for (int t = lane; t < blocks; t += 32) { s += (double)part_dz[(size_t)t * C + warp]; q += (double)part_dzy[(size_t)t * C + warp]; }
+    int t = lane;
+    for (; t + 96 < blocks; t += 128) {  // eight independent loads in flight per lane
+        float a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[j] = part_dz[(size_t)(t + 32 * j) * C + warp]; b[j] = part_dzy[(size_t)(t + 32 * j) * C + warp]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s += (double)a[j]; q += (double)b[j]; }
+    }
+    for (; t < blocks; t += 32) { s += (double)part_dz[(size_t)t * C + warp]; q += (double)part_dzy[(size_t)t * C + warp]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
     if (lane == 0) {
@@ -979,10 +990,10 @@ int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, in
         wgrad_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
     }
     PU_LAUNCH_CHECK();
-    reduce_chunks_kernel<<<ceil_div((long long)K * N * 32, 256), 256, 0, st>>>(part, chunks, (long long)K * N, dw, accumulate);
+    launch_reduce_parts(part, chunks, (long long)K * N, dw, accumulate, st);
     PU_LAUNCH_CHECK();
     if (db) {
-        reduce_chunks_kernel<<<ceil_div((long long)N * 32, 256), 256, 0, st>>>(db_part, chunks, N, db, accumulate);
+        launch_reduce_parts(db_part, chunks, N, db, accumulate, st);
         PU_LAUNCH_CHECK();
     }
     return PU_OK;

@@ -93,11 +93,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float tf32_rn(float a) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
-    return __uint_as_float(r);
-}
+// round-to-nearest (ties away from zero) to 10 mantissa bits == cvt.rna.tf32.f32 for finite values and infinities, in two
+// integer instructions (ptxas expands the cvt into four); a NaN stays a NaN through the lo = a - hi term
+__device__ __forceinline__ float tf32_rn(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u); }
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
@@ -150,19 +148,26 @@ __device__ __forceinline__ void raw_issue(char *slot, const float *__restrict__ 
         cp_async16(slot + (size_t)idx * 16, src, valid);
     }
 }
-__device__ __forceinline__ void raw_convert(const char *slot, char *hi, char *lo, int tid, bool split) {
+// thread `tid` owns chunk c = tid & 7 of the rows (tid >> 3) + 32 i, i = 0..3: all four share (row & 7), so both the raw
+// offset and the swizzled offset advance by 4096 bytes per i -- no per-chunk address arithmetic in the loop
+__device__ __forceinline__ void raw_issue_full(char *slot_thr, const float *__restrict__ src, size_t row_step) {
 #pragma unroll
     for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
-        const int idx = tid + P_THREADS * i;
-        const int r = idx >> 3, c = idx & 7;
-        const float4 v = *reinterpret_cast<const float4 *>(slot + (size_t)idx * 16);
-        const uint32_t off = sw128(r, c);
+        const uint32_t d = smem_u32(slot_thr + i * 4096);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i * row_step) : "memory");
+    }
+}
+__device__ __forceinline__ void raw_convert(const char *slot_thr, char *hi_thr, bool split) {
+    constexpr int A_BYTES = BM * 128;
+#pragma unroll
+    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
+        const float4 v = *reinterpret_cast<const float4 *>(slot_thr + i * 4096);
         if (split) {
             const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-            *reinterpret_cast<float4 *>(hi + off) = h;
-            *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            *reinterpret_cast<float4 *>(hi_thr + i * 4096) = h;
+            *reinterpret_cast<float4 *>(hi_thr + A_BYTES + i * 4096) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
         } else {
-            *reinterpret_cast<float4 *>(hi + off) = v;
+            *reinterpret_cast<float4 *>(hi_thr + i * 4096) = v;
         }
     }
 }
@@ -231,7 +236,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     constexpr int NPASS = BN / EC;
     constexpr int LDT = EC + 4;
     extern __shared__ __align__(1024) char smem_raw[];
-    char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSET (not by an integer round trip): the pointer stays in the shared address space, so the
+    // compiler emits LDS/STS with 32-bit addresses instead of generic LD/ST
+    char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t stage_free[STAGES], stage_ready[STAGES], b_full[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
@@ -291,27 +298,37 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
         // work items = (tile, k-block) pairs in order; `issue_*` runs D-1 items ahead of `cur_*`
         long long cur_tile = blockIdx.x, iss_tile = blockIdx.x;
         int cur_kb = 0, iss_kb = 0;
-        int it = 0, issued = 0;
+        int it = 0, iss_slot = 0, cur_slot = 0;  // ring slots advance with a compare, not a modulo by the runtime depth
         bool ok = true;
+        const int pr = tid >> 3, pc = tid & 7;
+        const uint32_t thr_raw = (uint32_t)tid * 16u, thr_sw = sw128(pr, pc);
+        const size_t row_step = (size_t)32 * p.lda;
+        const bool k_full = (p.K % BK) == 0;
         auto issue_one = [&]() {
             if (iss_tile < q.ntiles) {
-                raw_issue(raw_ring + (size_t)(issued % D) * A_BYTES, p.A, p.lda, iss_tile * BM, p.M, iss_kb * BK, p.K, tid);
+                char *slot = raw_ring + (size_t)iss_slot * A_BYTES;
+                const long long row0 = iss_tile * BM;
+                if (k_full && row0 + BM <= p.M)
+                    raw_issue_full(slot + thr_raw, p.A + (size_t)(row0 + pr) * p.lda + iss_kb * BK + pc * 4, row_step);
+                else
+                    raw_issue(slot, p.A, p.lda, row0, p.M, iss_kb * BK, p.K, tid);
                 if (++iss_kb == nkb) { iss_kb = 0; iss_tile += gridDim.x; }
             }
             cp_async_commit();  // always commit (possibly empty) so the group arithmetic stays uniform
-            ++issued;
+            if (++iss_slot == D) iss_slot = 0;
         };
         for (int i = 0; i < D - 1; ++i) issue_one();
         while (cur_tile < q.ntiles) {
             issue_one();                 // keep D-1 k-blocks in flight behind the one we are about to convert
             cp_async_wait_dyn(D - 1);    // the oldest outstanding group (= item `it`) has landed
             const int s = it % STAGES, u = it / STAGES;
-            char *a_hi = a_ring + (size_t)s * A_STAGE, *a_lo = a_hi + A_BYTES;
+            char *a_hi = a_ring + (size_t)s * A_STAGE;
             if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;  // MMAs that read stage s retired
-            raw_convert(raw_ring + (size_t)(it % D) * A_BYTES, a_hi, a_lo, tid, split);
+            raw_convert(raw_ring + (size_t)cur_slot * A_BYTES + thr_raw, a_hi + thr_sw, split);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
             mbar_arrive(&stage_ready[s]);                                 // hand the stage to the issuer; do not wait for it
             if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; }
+            if (++cur_slot == D) cur_slot = 0;
             it++;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -731,7 +748,7 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
     constexpr int RAW = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ __align__(1024) char smem_raw[];
-    char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // aligned by offset: stays a shared pointer
     __shared__ uint64_t stage_free[2], stage_ready[2], all_done;
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
@@ -760,6 +777,9 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
                      "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // the operand stages start as zeros: the padding columns (Kin - k0 < 128, N - n0 < BN) are never written again
+    for (int i = tid; i < 2 * STAGE / 16; i += WG_TOTAL) reinterpret_cast<float4 *>(op_ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -767,8 +787,8 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
     const uint32_t idesc = make_idesc_mn(BN);
 
     bool ok = true;
-    if (warp < WG_THREADS / 32) {
-        // ======================= producers =======================
+    if (warp < WG_THREADS / 32 && ones_col >= 0) {
+        // ======================= producers, generic path (the CTA that also carries the ones row for db) =======================
         int issued = 0;
         auto issue_one = [&]() {
             if (issued < nsteps) {
@@ -793,6 +813,83 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
             wg_convert<BN>(slot + A_BYTES, b_hi, b_lo, tid, split, -1, row0, r_end);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&stage_ready[s]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp < WG_THREADS / 32) {
+        // ======================= producers =======================
+        // Only the REAL columns are moved: chunk idx < nA belongs to X (row idx / cprA), the rest to dY.  Every thread
+        // keeps its (<= MAXC) chunks in a small register table built once -- source pointer at the CTA's first row,
+        // operand-image offset -- so a pipeline step costs one pointer add, one cp.async, one LDS and two STS per chunk.
+        constexpr int MAXC = (WG_ROWS * (BM + BN) / 4 + WG_THREADS - 1) / WG_THREADS;
+        const int colsA = min(w.Kin - k0, BM), colsB = min(w.N - n0, BN);
+        const int cprA = colsA >> 2, cprB = colsB >> 2, nA = WG_ROWS * cprA, nT = nA + WG_ROWS * cprB;
+        const float *c_src[MAXC];
+        size_t c_step[MAXC];
+        uint32_t c_op[MAXC], c_lo[MAXC];
+        int c_row[MAXC];
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int idx = tid + WG_THREADS * i;
+            c_src[i] = w.X; c_step[i] = 0; c_op[i] = 0; c_lo[i] = 0; c_row[i] = 0;
+            if (idx < nA) {
+                const int r = idx / cprA, c4 = (idx - r * cprA) * 4;
+                c_src[i] = w.X + (size_t)(r_begin + r) * w.ldx + k0 + c4;
+                c_step[i] = (size_t)WG_ROWS * w.ldx;
+                c_op[i] = (uint32_t)((c4 >> 5) * (WG_ROWS * 128)) + sw128_32b(r, c4 & 31);
+                c_lo[i] = A_BYTES; c_row[i] = r;
+            } else if (idx < nT) {
+                const int j = idx - nA, r = j / cprB, c4 = (j - r * cprB) * 4;
+                c_src[i] = w.G + (size_t)(r_begin + r) * w.ldg + n0 + c4;
+                c_step[i] = (size_t)WG_ROWS * w.ldg;
+                c_op[i] = (uint32_t)(2 * A_BYTES + (c4 >> 5) * (WG_ROWS * 128)) + sw128_32b(r, c4 & 31);
+                c_lo[i] = B_BYTES; c_row[i] = r;
+            }
+        }
+        const uint32_t thr_raw = (uint32_t)tid * 16u;
+        int issued = 0, iss_slot = 0, cur_slot = 0;
+        auto issue_one = [&]() {
+            if (issued < nsteps) {
+                const uint32_t slot = smem_u32(raw_ring + (size_t)iss_slot * RAW) + thr_raw;
+                const int rows_left = (int)min((long long)WG_ROWS, r_end - (r_begin + (long long)issued * WG_ROWS));
+#pragma unroll
+                for (int i = 0; i < MAXC; ++i) {
+                    if (tid + WG_THREADS * i < nT) {
+                        const int sz = c_row[i] < rows_left ? 16 : 0;  // rows past the CTA's chunk are zero-filled
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + i * (WG_THREADS * 16)),
+                                     "l"(sz ? c_src[i] : w.X), "r"(sz) : "memory");
+                        c_src[i] += c_step[i];
+                    }
+                }
+            }
+            cp_async_commit();
+            ++issued;
+            if (++iss_slot == D) iss_slot = 0;
+        };
+        for (int i = 0; i < D - 1; ++i) issue_one();
+        for (int it = 0; it < nsteps; ++it) {
+            issue_one();
+            cp_async_wait_dyn(D - 1);
+            const int s = it & 1, u = it >> 1;
+            char *st_base = op_ring + (size_t)s * STAGE;
+            if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;
+            const char *slot = raw_ring + (size_t)cur_slot * RAW + thr_raw;
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                if (tid + WG_THREADS * i < nT) {
+                    const float4 v = *reinterpret_cast<const float4 *>(slot + i * (WG_THREADS * 16));
+                    char *dst = st_base + c_op[i];
+                    if (split) {
+                        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                        *reinterpret_cast<float4 *>(dst) = h;
+                        *reinterpret_cast<float4 *>(dst + c_lo[i]) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    } else {
+                        *reinterpret_cast<float4 *>(dst) = v;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&stage_ready[s]);
+            if (++cur_slot == D) cur_slot = 0;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (lane == 0) {
@@ -889,22 +986,6 @@ static int launch_wgrad(const WParams &w, const WgPlan &pl, cudaStream_t st) {
     tc_wgrad_kernel<BN><<<grid, WG_TOTAL, pl.smem, st>>>(w);
     PU_LAUNCH_CHECK();
     return PU_OK;
-}
-
-// out[i] (+)= sum_c part[c][i]   (double accumulation, fixed order; the partial count is <= 148 so a thread per element)
-__global__ void __launch_bounds__(256) tc_reduce_parts_kernel(const float *__restrict__ part, int chunks, long long n,
-                                                              float *__restrict__ out, int accumulate) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int c = 0;
-    for (; c + 4 <= chunks; c += 4) {  // 4 independent loads in flight
-        s0 += (double)part[(size_t)c * n + i]; s1 += (double)part[(size_t)(c + 1) * n + i];
-        s2 += (double)part[(size_t)(c + 2) * n + i]; s3 += (double)part[(size_t)(c + 3) * n + i];
-    }
-    for (; c < chunks; ++c) s0 += (double)part[(size_t)c * n + i];
-    const double s = (s0 + s1) + (s2 + s3);
-    out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
 }  // namespace tc
@@ -1004,10 +1085,10 @@ int pu_tc_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M,
     else if (pl.bn == 64) rc = tc::launch_wgrad<64>(w, pl, st);
     else rc = tc::launch_wgrad<128>(w, pl, st);
     if (rc != PU_OK) return rc;
-    tc::tc_reduce_parts_kernel<<<ceil_div((long long)Kin * N, 256), 256, 0, st>>>(w.part, pl.gx, (long long)Kin * N, dw, accumulate);
+    launch_reduce_parts(w.part, pl.gx, (long long)Kin * N, dw, accumulate, st);
     PU_LAUNCH_CHECK();
     if (db) {
-        tc::tc_reduce_parts_kernel<<<ceil_div(N, 256), 256, 0, st>>>(w.db_part, pl.gx, N, db, accumulate);
+        launch_reduce_parts(w.db_part, pl.gx, N, db, accumulate, st);
         PU_LAUNCH_CHECK();
     }
     return PU_OK;
