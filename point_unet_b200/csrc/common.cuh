@@ -54,6 +54,18 @@ __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
                  : "memory");
 }
 
+// 2^x and 1/x on the SFU, one instruction each (arguments of the softmax are <= 0, results in (0, 1]; the denominators >= 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // out[i] (+)= sum_c part[c][i], double accumulation in an order that depends only on (chunks, E): thread (e, g) of a CTA owns
 // element blockIdx.x*E + e and the chunks g, g+G, ... (G = 256/E) with four independent loads in flight; the G group sums
 // are combined by a shared-memory tree.  Loads are coalesced over e (E*4 bytes per group and chunk).

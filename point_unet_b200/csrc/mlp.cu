@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
         for (int j = 0; j < TN; ++j) {
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < TM; ++i) { acc[i][j] = __expf(acc[i][j] - cmax[j]); s += acc[i][j]; }
+            for (int i = 0; i < TM; ++i) { acc[i][j] = ex2_approx(fmaf(acc[i][j], 1.4426950408889634f, -cmax[j] * 1.4426950408889634f)); s += acc[i][j]; }
             csum[j] = point_reduce_sum(s);
         }
         float x[TM][TN];
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
             }
             if (pt_ok && writer)
                 *reinterpret_cast<float4 *>(p.OUT + (size_t)pt * p.ldo + gn) =
-                    make_float4(num[0] / csum[0], num[1] / csum[1], num[2] / csum[2], num[3] / csum[3]);
+                    make_float4(num[0] * rcp_approx(csum[0]), num[1] * rcp_approx(csum[1]), num[2] * rcp_approx(csum[2]),
+                                num[3] * rcp_approx(csum[3]));
         } else {  // EPI_ATT_BWD
             float g[TN] = {0.f, 0.f, 0.f, 0.f};
             if (pt_ok) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmParams p) {
             float dot[TN];
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                const float inv = 1.f / csum[j];
+                const float inv = rcp_approx(csum[j]);
                 float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < TM; ++i) {

@@ -79,6 +79,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per k element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -95,6 +113,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 // round-to-nearest (ties away from zero) to 10 mantissa bits == cvt.rna.tf32.f32 for finite values and infinities, in two
 // integer instructions (ptxas expands the cvt into four); a NaN stays a NaN through the lo = a - hi term
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ float tf32_rn(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u); }
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
@@ -113,9 +140,11 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >
 //   EPI_ATT_FWD  f_agg[p,c] = sum_k x[p,k,c] softmax_k(x w)[c]                          (pu_att_pooling_fwd, K = 16)
 //   EPI_ATT_BWD  d_act = s (g x - sum_k g x s),  dx_direct = g s                        (pu_att_pooling_bwd)
 enum { EPI_STORE = 0, EPI_ATT_FWD = 1, EPI_ATT_BWD = 2 };
-constexpr int STAGES = 2;        // operand (hi/lo) stages consumed by the tensor core
-constexpr int MAX_RAW = 6;       // raw fp32 ring filled by cp.async (no registers held while the bytes are in flight)
-constexpr int P_THREADS = 256;   // 8 producer warps + 8 epilogue warps: the kernel is issue-latency bound with fewer
+constexpr int MAX_TA = 4;        // operand-A stages in TENSOR memory (64 columns each: hi 32 + lo 32)
+constexpr int MAX_RAW = 6;       // raw fp32 ring of the weight-gradient kernel (cp.async, no registers held in flight)
+constexpr int MAX_RAW_P = 10;    // raw fp32 ring of the persistent kernel: up to 9 k-blocks (144 KB) in flight per SM
+constexpr int P_THREADS = 256;   // 8 producer warps
+constexpr int E_THREADS = 512;   // 16 epilogue warps: the epilogue is a chain of dependent ALU work, it needs the thread-level parallelism
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
     const uint32_t d = smem_u32(smem_dst);
@@ -130,45 +159,10 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // wait until 
         case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
         case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
         case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    }
-}
-// raw ring slot: [128 rows][8 chunks of 16 B], chunk (r,c) at (r*8 + c)*16 -- each thread later reads back exactly
-// the chunks it copied itself, so cp.async.wait_group alone orders the hand-over (no CTA barrier)
-__device__ __forceinline__ void raw_issue(char *slot, const float *__restrict__ base, int ld, long long row0, long long row_end,
-                                          int k0, int K, int tid) {
-#pragma unroll
-    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
-        const int idx = tid + P_THREADS * i;
-        const int r = idx >> 3, c = idx & 7;
-        const long long gr = row0 + r;
-        const int gk = k0 + c * 4;
-        const bool valid = gr < row_end && gk < K;
-        const float *src = valid ? base + (size_t)gr * ld + gk : base;
-        cp_async16(slot + (size_t)idx * 16, src, valid);
-    }
-}
-// thread `tid` owns chunk c = tid & 7 of the rows (tid >> 3) + 32 i, i = 0..3: all four share (row & 7), so both the raw
-// offset and the swizzled offset advance by 4096 bytes per i -- no per-chunk address arithmetic in the loop
-__device__ __forceinline__ void raw_issue_full(char *slot_thr, const float *__restrict__ src, size_t row_step) {
-#pragma unroll
-    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
-        const uint32_t d = smem_u32(slot_thr + i * 4096);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i * row_step) : "memory");
-    }
-}
-__device__ __forceinline__ void raw_convert(const char *slot_thr, char *hi_thr, bool split) {
-    constexpr int A_BYTES = BM * 128;
-#pragma unroll
-    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
-        const float4 v = *reinterpret_cast<const float4 *>(slot_thr + i * 4096);
-        if (split) {
-            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-            *reinterpret_cast<float4 *>(hi_thr + i * 4096) = h;
-            *reinterpret_cast<float4 *>(hi_thr + A_BYTES + i * 4096) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        } else {
-            *reinterpret_cast<float4 *>(hi_thr + i * 4096) = v;
-        }
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        case 7: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 8;" ::: "memory"); break;
     }
 }
 
@@ -223,15 +217,17 @@ __global__ void __launch_bounds__(256) tc_pack_weight_kernel(const float *__rest
     }
 }
 
-constexpr int PERSIST_THREADS = 2 * P_THREADS + 32;  // 8 producer warps, 8 epilogue warps, 1 MMA-issuer warp
+constexpr int PERSIST_THREADS = P_THREADS + E_THREADS + 32;  // 8 producer warps, 16 epilogue warps, 1 MMA-issuer warp
 
 template <int BN, int EPI, bool STREAM>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Params2 q) {
     const Params &p = q.g;
-    constexpr int A_BYTES = BM * 128;                 // one 128 x 32 fp32 tile
-    constexpr int A_STAGE = 2 * A_BYTES;              // hi + lo
+    constexpr int A_BYTES = BM * 128;                 // one raw 128 x 32 fp32 k-block
     constexpr int B_KB = 2 * BN * 128;                // hi + lo of one k-block of the weight
-    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (BN in {32,64,128})
+    constexpr int TA = BN <= 64 ? MAX_TA : 2;         // operand-A stages in tensor memory
+    constexpr int ACC_COLS = 2 * BN;                  // double-buffered accumulator; A stage s lives at column ACC_COLS + 64 s
+    constexpr int TMEM_COLS = 512;                    // one CTA per SM: take all of tensor memory
+    static_assert(ACC_COLS + TA * 64 <= TMEM_COLS, "tensor memory budget");
     constexpr int EC = BN > 64 ? 64 : BN;             // epilogue works on EC columns at a time (staging tile fits smem)
     constexpr int NPASS = BN / EC;
     constexpr int LDT = EC + 4;
@@ -239,25 +235,24 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     // 1024-byte alignment by OFFSET (not by an integer round trip): the pointer stays in the shared address space, so the
     // compiler emits LDS/STS with 32-bit addresses instead of generic LD/ST
     char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t stage_free[STAGES], stage_ready[STAGES], b_full[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint64_t stage_free[MAX_TA], stage_ready[MAX_TA], b_full[MAX_TA], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
-    __shared__ float s_red[2 * 4 * P_THREADS];  // statistics partials: [row lane][EC][2]
+    __shared__ float s_red[2 * 16 * 64];  // statistics partials: [16 row lanes][EC][2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = (p.K + BK - 1) / BK;
     const int n0 = blockIdx.y * BN;
     const bool split = p.mode == 3;
     const int D = q.raw_depth;
-    char *a_ring = smem;
-    char *raw_ring = smem + STAGES * A_STAGE;
-    char *b_res = raw_ring + (size_t)D * A_BYTES;     // resident: nkb k-blocks; streamed: STAGES k-blocks
-    float *tile = reinterpret_cast<float *>(b_res + (size_t)(STREAM ? STAGES : nkb) * B_KB);  // epilogue staging [BM][LDT]
+    char *raw_ring = smem;                            // D raw k-blocks, filled by cp.async
+    char *b_res = smem + (size_t)D * A_BYTES;         // resident: nkb k-blocks; streamed: TA k-blocks
+    float *tile = reinterpret_cast<float *>(b_res + (size_t)(STREAM ? TA : nkb) * B_KB);  // epilogue staging [BM][LDT]
     const char *b_packed = STREAM ? q.Bp + (size_t)blockIdx.y * nkb * B_KB : nullptr;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS); mbar_init(&b_full[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P_THREADS); }
+        for (int i = 0; i < MAX_TA; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS); mbar_init(&b_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS); }
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -295,23 +290,45 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 
     if (warp < P_THREADS / 32) {
         // ======================= producers =======================
-        // work items = (tile, k-block) pairs in order; `issue_*` runs D-1 items ahead of `cur_*`
+        // work items = (tile, k-block) pairs in order.
+        //   global --cp.async--> raw ring in shared memory (D-1 k-blocks = up to 144 KB in flight per SM, no registers held)
+        //          --LDS--> registers: hi/lo tf32 split --tcgen05.st--> operand-A stage in TENSOR memory.
+        // The x operand never exists as a hi/lo image in shared memory: the tensor core reads A from TMEM and only the
+        // (small, resident) weight from shared memory, so the shared-memory port carries each x byte twice (in, out).
+        // Copy mapping (coalesced): thread -> 16-byte chunk c = tid & 7 of rows (tid >> 3) + 32 i; the chunk lands at
+        // row*128 + ((c ^ (row & 7)) << 4) so that the row-per-lane reads below are bank-conflict free.
+        // Convert mapping (tensor-memory lanes): warp w owns rows 32 (w & 3) .. +31 (its TMEM lane quarter), lane = row,
+        // and the 16 columns 16 (w >> 2) .. +15 of the k-block.
         long long cur_tile = blockIdx.x, iss_tile = blockIdx.x;
-        int cur_kb = 0, iss_kb = 0;
-        int it = 0, iss_slot = 0, cur_slot = 0;  // ring slots advance with a compare, not a modulo by the runtime depth
+        int cur_kb = 0, iss_kb = 0, iss_slot = 0, cur_slot = 0, slot = 0, use = 0;
         bool ok = true;
         const int pr = tid >> 3, pc = tid & 7;
-        const uint32_t thr_raw = (uint32_t)tid * 16u, thr_sw = sw128(pr, pc);
+        const uint32_t thr_raw = (uint32_t)(pr * 128 + ((pc ^ (pr & 7)) << 4));  // + 4096 i: rows pr + 32 i share (row & 7)
         const size_t row_step = (size_t)32 * p.lda;
         const bool k_full = (p.K % BK) == 0;
+        const int crow = (warp & 3) * 32 + lane, chalf = warp >> 2;
+        uint32_t c_off[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c_off[j] = (uint32_t)(crow * 128 + (((chalf * 4 + j) ^ (crow & 7)) << 4));
+        const uint32_t t_a = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(ACC_COLS + chalf * 16);
         auto issue_one = [&]() {
             if (iss_tile < q.ntiles) {
-                char *slot = raw_ring + (size_t)iss_slot * A_BYTES;
+                const uint32_t dst = smem_u32(raw_ring + (size_t)iss_slot * A_BYTES) + thr_raw;
                 const long long row0 = iss_tile * BM;
-                if (k_full && row0 + BM <= p.M)
-                    raw_issue_full(slot + thr_raw, p.A + (size_t)(row0 + pr) * p.lda + iss_kb * BK + pc * 4, row_step);
-                else
-                    raw_issue(slot, p.A, p.lda, row0, p.M, iss_kb * BK, p.K, tid);
+                const float *src = p.A + (size_t)(row0 + pr) * p.lda + iss_kb * BK + pc * 4;
+                if (k_full && row0 + BM <= p.M) {
+#pragma unroll
+                    for (int i = 0; i < BM * 8 / P_THREADS; ++i)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 4096), "l"(src + i * row_step) : "memory");
+                } else {
+                    const bool kv = iss_kb * BK + pc * 4 < p.K;  // K % 4 == 0: a chunk is entirely inside or outside
+#pragma unroll
+                    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
+                        const int sz = (kv && row0 + pr + 32 * i < p.M) ? 16 : 0;  // src-size 0 => zero fill
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * 4096),
+                                     "l"(sz ? src + i * row_step : p.A), "r"(sz) : "memory");
+                    }
+                }
                 if (++iss_kb == nkb) { iss_kb = 0; iss_tile += gridDim.x; }
             }
             cp_async_commit();  // always commit (possibly empty) so the group arithmetic stays uniform
@@ -319,26 +336,43 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
         };
         for (int i = 0; i < D - 1; ++i) issue_one();
         while (cur_tile < q.ntiles) {
-            issue_one();                 // keep D-1 k-blocks in flight behind the one we are about to convert
-            cp_async_wait_dyn(D - 1);    // the oldest outstanding group (= item `it`) has landed
-            const int s = it % STAGES, u = it / STAGES;
-            char *a_hi = a_ring + (size_t)s * A_STAGE;
-            if (u >= 1) ok = mbar_wait(&stage_free[s], (uint32_t)((u - 1) & 1)) && ok;  // MMAs that read stage s retired
-            raw_convert(raw_ring + (size_t)cur_slot * A_BYTES + thr_raw, a_hi + thr_sw, split);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(&stage_ready[s]);                                 // hand the stage to the issuer; do not wait for it
+            cp_async_wait_dyn(D - 2);        // this thread's chunks of the current item have landed
+            bar_sync_named(1, P_THREADS);    // ... everybody's have, and everybody is done reading the previous item's slot
+            issue_one();                     // refill that slot: D-1 k-blocks stay in flight
+            if (use >= 1) ok = mbar_wait(&stage_free[slot], (uint32_t)((use - 1) & 1)) && ok;  // MMAs that read the stage retired
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const char *src = raw_ring + (size_t)cur_slot * A_BYTES;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = *reinterpret_cast<const float4 *>(src + c_off[j]);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            const uint32_t ta = t_a + (uint32_t)(slot * 64);
+            if (split) {
+                float h[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { h[j] = tf32_rn(v[j]); v[j] -= h[j]; }
+                tmem_st16(ta, h);
+                tmem_st16(ta + 32, v);
+            } else {
+                tmem_st16(ta, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&stage_ready[slot]);  // hand the stage to the issuer; do not wait for it
             if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; }
             if (++cur_slot == D) cur_slot = 0;
-            it++;
+            if (++slot == TA) { slot = 0; ++use; }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (!ok) s_err = 1;
-    } else if (warp == 2 * P_THREADS / 32) {
+    } else if (warp == (P_THREADS + E_THREADS) / 32) {
         // ======================= MMA issuer (one elected lane of its own warp) =======================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BN);
             long long cur_tile = blockIdx.x;
-            int cur_kb = 0, it = 0, tile_count = 0;
+            int cur_kb = 0, slot = 0, use = 0, tile_count = 0;
             bool ok = true;
             if constexpr (STREAM) {
                 if (cur_tile < q.ntiles) {  // weight k-block of item 0
@@ -347,55 +381,55 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 }
             }
             while (cur_tile < q.ntiles) {
-                const int s = it % STAGES, u = it / STAGES;
-                const char *a_hi = a_ring + (size_t)s * A_STAGE, *a_lo = a_hi + A_BYTES;
                 const bool last_kb = cur_kb == nkb - 1;
                 const int buf = tile_count & 1, v = tile_count >> 1;
                 if (cur_kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[buf], (uint32_t)((v - 1) & 1)) && ok;
-                ok = mbar_wait(&stage_ready[s], (uint32_t)(u & 1)) && ok;           // all 256 producers filled stage s
-                const char *b_hi = STREAM ? b_res + (size_t)s * B_KB : b_res + (size_t)cur_kb * B_KB;
+                ok = mbar_wait(&stage_ready[slot], (uint32_t)(use & 1)) && ok;           // all 256 producers filled the stage
+                const char *b_hi = STREAM ? b_res + (size_t)slot * B_KB : b_res + (size_t)cur_kb * B_KB;
                 const char *b_lo = b_hi + BN * 128;
-                if constexpr (STREAM) ok = mbar_wait(&b_full[s], (uint32_t)(u & 1)) && ok;  // this k-block of the weight landed
+                if constexpr (STREAM) ok = mbar_wait(&b_full[slot], (uint32_t)(use & 1)) && ok;  // this k-block of the weight landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t a_tmem = tmem_base + (uint32_t)(ACC_COLS + slot * 64);
 #pragma unroll
                 for (int j = 0; j < BK / UMMA_K; ++j) {
-                    const uint64_t dah = make_desc(smem_u32(a_hi) + j * 32), dbh = make_desc(smem_u32(b_hi) + j * 32);
-                    umma_tf32(d_tmem, dah, dbh, idesc, (cur_kb > 0 || j > 0) ? 1u : 0u);
+                    const uint64_t dbh = make_desc(smem_u32(b_hi) + j * 32);
+                    umma_tf32_ts(d_tmem, a_tmem + j * UMMA_K, dbh, idesc, (cur_kb > 0 || j > 0) ? 1u : 0u);
                     if (split) {
-                        const uint64_t dal = make_desc(smem_u32(a_lo) + j * 32), dbl = make_desc(smem_u32(b_lo) + j * 32);
-                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                        umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+                        const uint64_t dbl = make_desc(smem_u32(b_lo) + j * 32);
+                        umma_tf32_ts(d_tmem, a_tmem + j * UMMA_K, dbl, idesc, 1u);
+                        umma_tf32_ts(d_tmem, a_tmem + 32 + j * UMMA_K, dbh, idesc, 1u);
                     }
                 }
-                umma_commit(&stage_free[s]);
+                umma_commit(&stage_free[slot]);
                 if (last_kb) umma_commit(&acc_full[buf]);
-                if constexpr (STREAM) {  // fetch the weight k-block of the NEXT item into the other stage
+                int slot1 = slot + 1, use1 = use;
+                if (slot1 == TA) { slot1 = 0; ++use1; }
+                if constexpr (STREAM) {  // fetch the weight k-block of the NEXT item into the next stage
                     const int nkb_next = last_kb ? 0 : cur_kb + 1;
                     const long long ntile = last_kb ? cur_tile + gridDim.x : cur_tile;
                     if (ntile < q.ntiles) {
-                        const int s1 = (it + 1) % STAGES, u1 = (it + 1) / STAGES;
-                        if (u1 >= 1) ok = mbar_wait(&stage_free[s1], (uint32_t)((u1 - 1) & 1)) && ok;  // its previous reader retired
-                        mbar_expect_tx(&b_full[s1], (uint32_t)B_KB);
-                        bulk_g2s(b_res + (size_t)s1 * B_KB, b_packed + (size_t)nkb_next * B_KB, (uint32_t)B_KB, &b_full[s1]);
+                        if (use1 >= 1) ok = mbar_wait(&stage_free[slot1], (uint32_t)((use1 - 1) & 1)) && ok;  // its previous reader retired
+                        mbar_expect_tx(&b_full[slot1], (uint32_t)B_KB);
+                        bulk_g2s(b_res + (size_t)slot1 * B_KB, b_packed + (size_t)nkb_next * B_KB, (uint32_t)B_KB, &b_full[slot1]);
                     }
                 }
                 if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
-                it++;
+                slot = slot1; use = use1;
             }
             if (!ok) s_err = 1;
         }
     } else {
         // ======================= epilogue warps =======================
         const int etid = tid - P_THREADS, ewarp = warp - P_THREADS / 32;
-        const int quarter = ewarp & 3, chalf = ewarp >> 2;  // TMEM lane quarter (= warp id % 4) and column half
+        const int quarter = ewarp & 3, cpart = ewarp >> 2;  // TMEM lane quarter (= warp id % 4) and column quarter
         int tile_count = 0;
         bool ok = true;
         for (long long tile_i = blockIdx.x; tile_i < q.ntiles; tile_i += gridDim.x, ++tile_count) {
             const int buf = tile_count & 1, v = tile_count >> 1;
             const long long m0 = tile_i * BM;
             const long long rows_here = min((long long)BM, p.M - m0);
-            constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * EC + P_THREADS - 1) / P_THREADS;
+            constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * EC + E_THREADS - 1) / E_THREADS;
             float xv[PAIRS][16];
             float gv[PAIRS];
 #pragma unroll 1
@@ -407,12 +441,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     const int npts = (int)(rows_here / 16);
 #pragma unroll
                     for (int pp = 0; pp < PAIRS; ++pp) {
-                        const int pair = etid + pp * P_THREADS;
+                        const int pair = etid + pp * E_THREADS;
                         const int pl = pair / EC, c = pair % EC;
                         const bool pv = pair < (BM / 16) * EC && pl < npts && nb + c < p.N;
                         const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + nb + c;
+                        if (q.ldx == BN) {  // contiguous feature_set (the usual case): immediate offsets, one LDG per value
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
+                            for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[k * BN] : 0.f;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
+                        }
                         gv[pp] = 0.f;
                         if constexpr (EPI == EPI_ATT_BWD) gv[pp] = pv ? q.G[(size_t)(m0 / 16 + pl) * q.ldg + nb + c] : 0.f;
                     }
@@ -421,15 +460,23 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                {   // TMEM -> registers -> staging tile: warp (quarter, chalf) moves 32 rows x EC/2 columns
+                {   // TMEM -> registers -> staging tile: warp (quarter, cpart) moves 32 rows x EC/4 columns
                     const int row = quarter * 32 + lane;
-#pragma unroll
-                    for (int cc = 0; cc < EC / 2; cc += 16) {
-                        const int c0 = chalf * (EC / 2) + cc;
+                    constexpr int CW = EC / 4;  // 16 (EC = 64) or 8 (EC = 32)
+                    const int c0 = cpart * CW;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + pass * EC + c0);
+                    if constexpr (CW == 16) {
                         float vals[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + pass * EC + c0), vals);
+                        tmem_ld16(taddr, vals);
 #pragma unroll
                         for (int qd = 0; qd < 16; qd += 4)
+                            *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
+                                make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
+                    } else {
+                        float vals[8];
+                        tmem_ld8(taddr, vals);
+#pragma unroll
+                        for (int qd = 0; qd < 8; qd += 4)
                             *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
                                 make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
                     }
@@ -438,14 +485,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
                 }
-                bar_sync_named(2, P_THREADS);
+                bar_sync_named(2, E_THREADS);
 
                 if constexpr (EPI == EPI_STORE) {
                     const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-                    // thread -> fixed group of 4 columns (P_THREADS % (EC/4) == 0), rows strided: the batch-norm partials
+                    // thread -> fixed group of 4 columns (E_THREADS % (EC/4) == 0), rows strided: the batch-norm partials
                     // accumulate in registers during the copy-out.  Shifted single pass: sums of (v - sh) and (v - sh)^2
                     // with sh = the tile's first stored row, so M2 = S2 - S1^2/n loses nothing to cancellation.
-                    constexpr int CG = EC / 4, RLANES = P_THREADS / CG;
+                    constexpr int CG = EC / 4, RLANES = E_THREADS / CG;
                     const int cg = etid % CG, rl = etid / CG, c = cg * 4, gn = nb + c;
                     float sh[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
                     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -457,7 +504,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                         const float4 t0 = *reinterpret_cast<float4 *>(&tile[c]);
                         sh[0] = t0.x + bias4.x; sh[1] = t0.y + bias4.y; sh[2] = t0.z + bias4.z; sh[3] = t0.w + bias4.w;
                     }
-                    constexpr int RPT = BM / RLANES;  // rows per thread (8 for EC = 64, 4 for EC = 32)
+                    constexpr int RPT = BM / RLANES;  // rows per thread (4 for EC = 64, 2 for EC = 32)
                     const bool fast = gn + 3 < p.N && vecC;
                     float4 old[RPT];
                     if (p.accumulate && fast) {  // all loads of C first: RPT independent requests in flight, not a serial chain
@@ -493,15 +540,30 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                         for (int j = 0; j < 4; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], dv[j], s2[j]); }
                     }
                     if (p.stat_sum) {
+                        // a warp holds 32/CG consecutive row lanes of the same column groups: combine them with shuffles
+                        // first (fixed order), so 16 row lanes per column reach shared memory
+                        constexpr int RL2 = RLANES / (32 / CG);
+                        static_assert(RL2 == 16, "s_red holds 16 row lanes");
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            s_red[(rl * EC + c + j) * 2 + 0] = s1[j];
-                            s_red[(rl * EC + c + j) * 2 + 1] = s2[j];
+#pragma unroll
+                            for (int o = CG; o < 32; o <<= 1) {
+                                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+                            }
                         }
-                        bar_sync_named(2, P_THREADS);
+                        if (lane < CG) {
+                            const int rl2 = etid >> 5;  // one slot per epilogue warp
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                s_red[(rl2 * EC + c + j) * 2 + 0] = s1[j];
+                                s_red[(rl2 * EC + c + j) * 2 + 1] = s2[j];
+                            }
+                        }
+                        bar_sync_named(2, E_THREADS);
                         if (etid < EC && nb + etid < p.N) {
                             float a = 0.f, b = 0.f;
-                            for (int l = 0; l < RLANES; ++l) { a += s_red[(l * EC + etid) * 2]; b += s_red[(l * EC + etid) * 2 + 1]; }
+                            for (int l = 0; l < RL2; ++l) { a += s_red[(l * EC + etid) * 2]; b += s_red[(l * EC + etid) * 2 + 1]; }
                             const float shc = tile[etid] + (p.bias ? p.bias[nb + etid] : 0.f);  // same shift as above
                             const float n = (float)rows_here;
                             p.stat_sum[(size_t)tile_i * p.N + nb + etid] = fmaf(n, shc, a);
@@ -514,7 +576,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     const int npts = (int)(rows_here / 16);
 #pragma unroll
                     for (int pp = 0; pp < PAIRS; ++pp) {
-                        const int pair = etid + pp * P_THREADS;
+                        const int pair = etid + pp * E_THREADS;
                         const int pl = pair / EC, c = pair % EC;
                         const int gn = nb + c;
                         if (pair >= (BM / 16) * EC || pl >= npts || gn >= p.N) continue;
@@ -526,9 +588,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                             mx = fmaxf(mx, a[k]);
                         }
                         float sum = 0.f;
+                        const float mxl = mx * 1.4426950408889634f;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) { a[k] = __expf(a[k] - mx); sum += a[k]; }
-                        const float inv = 1.f / sum;
+                        for (int k = 0; k < 16; ++k) { a[k] = ex2_approx(fmaf(a[k], 1.4426950408889634f, -mxl)); sum += a[k]; }
+                        const float inv = rcp_approx(sum);  // sum in [1, 16]
                         if constexpr (EPI == EPI_ATT_FWD) {
                             float num = 0.f;
 #pragma unroll
@@ -541,15 +604,23 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                             for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * xv[pp][k], a[k], dot); }
                             float *cp = p.C + (size_t)(m0 + pl * 16) * p.ldc + gn;
                             float *op = q.OUT + (size_t)(m0 + pl * 16) * q.ldo + gn;
+                            if (p.ldc == BN && q.ldo == BN) {  // contiguous outputs: immediate offsets
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                cp[(size_t)k * p.ldc] = a[k] * (g * xv[pp][k] - dot);   // d_act
-                                op[(size_t)k * q.ldo] = g * a[k];                       // dx_direct
+                                for (int k = 0; k < 16; ++k) {
+                                    cp[k * BN] = a[k] * (g * xv[pp][k] - dot);   // d_act
+                                    op[k * BN] = g * a[k];                       // dx_direct
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    cp[(size_t)k * p.ldc] = a[k] * (g * xv[pp][k] - dot);
+                                    op[(size_t)k * q.ldo] = g * a[k];
+                                }
                             }
                         }
                     }
                 }
-                bar_sync_named(2, P_THREADS);  // staging tile is reused by the next pass / tile
+                bar_sync_named(2, E_THREADS);  // staging tile is reused by the next pass / tile
             }
         }
         if (!ok) s_err = 1;
@@ -567,14 +638,15 @@ template <int BN, bool STREAM>
 static size_t persist_fixed_bytes(int K) {  // everything except the raw ring
     const int nkb = (K + BK - 1) / BK;
     const int ec = BN > 64 ? 64 : BN;
-    return (size_t)STAGES * 2 * BM * 128 + (size_t)(STREAM ? STAGES : nkb) * 2 * BN * 128 + (size_t)BM * (ec + 4) * 4 + 1024;
+    const int ta = BN <= 64 ? MAX_TA : 2;
+    return (size_t)(STREAM ? ta : nkb) * 2 * BN * 128 + (size_t)BM * (ec + 4) * 4 + 1024;
 }
 template <int BN, bool STREAM>
 static int persist_raw_depth(int K) {  // 0 => does not fit
     const size_t fixed = persist_fixed_bytes<BN, STREAM>(K);
-    if (fixed + 2 * (size_t)BM * 128 > kMaxDynSmem) return 0;
+    if (fixed + 3 * (size_t)BM * 128 > kMaxDynSmem) return 0;
     long long d = (long long)((kMaxDynSmem - fixed) / ((size_t)BM * 128));
-    return (int)(d > MAX_RAW ? MAX_RAW : d);
+    return (int)(d > MAX_RAW_P ? MAX_RAW_P : d);
 }
 
 static inline size_t packed_weight_bytes(int K, int N, int bn) {
@@ -586,7 +658,7 @@ template <int BN, int EPI, bool STREAM>
 static int launch_persist(const Params2 &q, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     Params2 qq = q;
     qq.raw_depth = persist_raw_depth<BN, STREAM>(q.g.K);
-    if (qq.raw_depth < 2) return PU_ERR_UNSUPPORTED;
+    if (qq.raw_depth < 3) return PU_ERR_UNSUPPORTED;
     const size_t smem = persist_fixed_bytes<BN, STREAM>(q.g.K) + (size_t)qq.raw_depth * BM * 128;
     static bool configured = false;
     if (!configured) {
@@ -617,17 +689,17 @@ static int launch_persist(const Params2 &q, void *workspace, size_t workspace_by
 // with BN covering N in at most two slabs; otherwise the streamed-weight variant with the widest tile (BN = 128).
 struct Choice { int bn; bool stream; };
 static Choice choose_linear(int K, int N) {
-    if (N <= 32 && persist_raw_depth<32, false>(K) >= 3) return {32, false};
-    if (N <= 64 && persist_raw_depth<64, false>(K) >= 3) return {64, false};
-    if (N > 64 && persist_raw_depth<128, false>(K) >= 3) return {128, false};
-    if (N > 64 && N <= 128 && persist_raw_depth<64, false>(K) >= 3) return {64, false};
+    if (N <= 32 && persist_raw_depth<32, false>(K) >= 5) return {32, false};
+    if (N <= 64 && persist_raw_depth<64, false>(K) >= 5) return {64, false};
+    if (N > 64 && persist_raw_depth<128, false>(K) >= 5) return {128, false};
+    if (N > 64 && N <= 128 && persist_raw_depth<64, false>(K) >= 5) return {64, false};
     if (N <= 32) return {32, true};
     if (N <= 64) return {64, true};
     return {128, true};
 }
 static Choice choose_att(int d) {
-    if (d <= 32 && persist_raw_depth<32, false>(d) >= 3) return {32, false};
-    if (d <= 64 && persist_raw_depth<64, false>(d) >= 3) return {64, false};
+    if (d <= 32 && persist_raw_depth<32, false>(d) >= 5) return {32, false};
+    if (d <= 64 && persist_raw_depth<64, false>(d) >= 5) return {64, false};
     return {128, true};
 }
 static size_t tc_workspace_bytes(int K, int N) {
