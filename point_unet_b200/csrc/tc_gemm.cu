@@ -97,6 +97,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
 }
+// one lane of a CONVERGED warp; the predicate is taken once and reused (`if (leader) tcgen05.mma ...`): ptxas then emits the
+// MMAs back to back.  Issuing from inside a divergent `if (lane == 0)` region instead wraps every single MMA in an
+// ELECT / BRA.U.ANY loop and costs ~45 cycles per instruction (measured, tools/micro/mma_bench.cu) -- more than a whole
+// 128 x 64 x 8 MMA takes on the tensor core (32 cycles).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -368,14 +377,18 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (!ok) s_err = 1;
     } else if (warp == (P_THREADS + E_THREADS) / 32) {
-        // ======================= MMA issuer (one elected lane of its own warp) =======================
-        if (lane == 0) {
+        // ======================= MMA issuer =======================
+        // The whole warp walks the loop converged (all lanes poll the mbarriers); one elected lane issues.  Descriptors
+        // are base + constant: start address field (bits 0-13, units of 16 B) never carries out for < 256 KB of smem.
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = make_idesc(BN);
+            const uint64_t bdesc0 = make_desc(smem_u32(b_res));
             long long cur_tile = blockIdx.x;
             int cur_kb = 0, slot = 0, use = 0, tile_count = 0;
             bool ok = true;
             if constexpr (STREAM) {
-                if (cur_tile < q.ntiles) {  // weight k-block of item 0
+                if (leader && cur_tile < q.ntiles) {  // weight k-block of item 0
                     mbar_expect_tx(&b_full[0], (uint32_t)B_KB);
                     bulk_g2s(b_res, b_packed, (uint32_t)B_KB, &b_full[0]);
                 }
@@ -385,24 +398,24 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 const int buf = tile_count & 1, v = tile_count >> 1;
                 if (cur_kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[buf], (uint32_t)((v - 1) & 1)) && ok;
                 ok = mbar_wait(&stage_ready[slot], (uint32_t)(use & 1)) && ok;           // all 256 producers filled the stage
-                const char *b_hi = STREAM ? b_res + (size_t)slot * B_KB : b_res + (size_t)cur_kb * B_KB;
-                const char *b_lo = b_hi + BN * 128;
                 if constexpr (STREAM) ok = mbar_wait(&b_full[slot], (uint32_t)(use & 1)) && ok;  // this k-block of the weight landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 const uint32_t a_tmem = tmem_base + (uint32_t)(ACC_COLS + slot * 64);
+                const uint64_t dbh0 = bdesc0 + (uint64_t)((STREAM ? slot : cur_kb) * (B_KB >> 4));
+                const uint64_t dbl0 = dbh0 + (uint64_t)((BN * 128) >> 4);
+                if (leader) {
 #pragma unroll
-                for (int j = 0; j < BK / UMMA_K; ++j) {
-                    const uint64_t dbh = make_desc(smem_u32(b_hi) + j * 32);
-                    umma_tf32_ts(d_tmem, a_tmem + j * UMMA_K, dbh, idesc, (cur_kb > 0 || j > 0) ? 1u : 0u);
-                    if (split) {
-                        const uint64_t dbl = make_desc(smem_u32(b_lo) + j * 32);
-                        umma_tf32_ts(d_tmem, a_tmem + j * UMMA_K, dbl, idesc, 1u);
-                        umma_tf32_ts(d_tmem, a_tmem + 32 + j * UMMA_K, dbh, idesc, 1u);
+                    for (int j = 0; j < BK / UMMA_K; ++j) {
+                        umma_tf32_ts(d_tmem, a_tmem + j * UMMA_K, dbh0 + (uint64_t)(2 * j), idesc, (cur_kb > 0 || j > 0) ? 1u : 0u);
+                        if (split) {
+                            umma_tf32_ts(d_tmem, a_tmem + j * UMMA_K, dbl0 + (uint64_t)(2 * j), idesc, 1u);
+                            umma_tf32_ts(d_tmem, a_tmem + 32 + j * UMMA_K, dbh0 + (uint64_t)(2 * j), idesc, 1u);
+                        }
                     }
+                    umma_commit(&stage_free[slot]);
+                    if (last_kb) umma_commit(&acc_full[buf]);
                 }
-                umma_commit(&stage_free[slot]);
-                if (last_kb) umma_commit(&acc_full[buf]);
                 int slot1 = slot + 1, use1 = use;
                 if (slot1 == TA) { slot1 = 0; ++use1; }
                 if constexpr (STREAM) {  // fetch the weight k-block of the NEXT item into the next stage
@@ -410,8 +423,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     const long long ntile = last_kb ? cur_tile + gridDim.x : cur_tile;
                     if (ntile < q.ntiles) {
                         if (use1 >= 1) ok = mbar_wait(&stage_free[slot1], (uint32_t)((use1 - 1) & 1)) && ok;  // its previous reader retired
-                        mbar_expect_tx(&b_full[slot1], (uint32_t)B_KB);
-                        bulk_g2s(b_res + (size_t)slot1 * B_KB, b_packed + (size_t)nkb_next * B_KB, (uint32_t)B_KB, &b_full[slot1]);
+                        if (leader) {
+                            mbar_expect_tx(&b_full[slot1], (uint32_t)B_KB);
+                            bulk_g2s(b_res + (size_t)slot1 * B_KB, b_packed + (size_t)nkb_next * B_KB, (uint32_t)B_KB, &b_full[slot1]);
+                        }
                     }
                 }
                 if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
@@ -964,27 +979,29 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
             if (++cur_slot == D) cur_slot = 0;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (lane == 0) {
-        // ======================= MMA issuer =======================
+    } else {
+        // ======================= MMA issuer: converged warp, one elected lane issues (see elect_one) =======================
+        const bool leader = elect_one();
+        const uint64_t adesc0 = make_desc_mn(smem_u32(op_ring), WG_ROWS * 128);
         for (int it = 0; it < nsteps; ++it) {
             const int s = it & 1, u = it >> 1;
-            const char *a_hi = op_ring + (size_t)s * STAGE, *a_lo = a_hi + A_BYTES, *b_hi = a_lo + A_BYTES, *b_lo = b_hi + B_BYTES;
             ok = mbar_wait(&stage_ready[s], (uint32_t)(u & 1)) && ok;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t dah0 = adesc0 + (uint64_t)((s * STAGE) >> 4), dal0 = dah0 + (uint64_t)(A_BYTES >> 4);
+            const uint64_t dbh0 = dal0 + (uint64_t)(A_BYTES >> 4), dbl0 = dbh0 + (uint64_t)(B_BYTES >> 4);
+            if (leader) {
 #pragma unroll
-            for (int j = 0; j < WG_ROWS / UMMA_K; ++j) {  // 8 rows = two 512-byte k groups per slab
-                const uint64_t dah = make_desc_mn(smem_u32(a_hi) + j * 1024, WG_ROWS * 128);
-                const uint64_t dbh = make_desc_mn(smem_u32(b_hi) + j * 1024, WG_ROWS * 128);
-                umma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
-                if (split) {
-                    const uint64_t dal = make_desc_mn(smem_u32(a_lo) + j * 1024, WG_ROWS * 128);
-                    const uint64_t dbl = make_desc_mn(smem_u32(b_lo) + j * 1024, WG_ROWS * 128);
-                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                for (int j = 0; j < WG_ROWS / UMMA_K; ++j) {  // 8 rows = two 512-byte k groups per slab
+                    const uint64_t o = (uint64_t)((j * 1024) >> 4);
+                    umma_tf32(tmem_base, dah0 + o, dbh0 + o, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    if (split) {
+                        umma_tf32(tmem_base, dah0 + o, dbl0 + o, idesc, 1u);
+                        umma_tf32(tmem_base, dal0 + o, dbh0 + o, idesc, 1u);
+                    }
                 }
+                umma_commit(&stage_free[s]);
+                if (it == nsteps - 1) umma_commit(&all_done);
             }
-            umma_commit(&stage_free[s]);
-            if (it == nsteps - 1) umma_commit(&all_done);
         }
     }
     if (warp < 8 && nsteps > 0) ok = mbar_wait(&all_done, 0u) && ok;
