@@ -15,6 +15,7 @@
 // The hi/lo split needs a pass through registers anyway, so the tiles are written with st.shared (coalesced loads,
 // conflict-free swizzled stores) and published to the async proxy with fence.proxy.async; accumulators live in TMEM and
 // come back through tcgen05.ld (32 lanes x 16 columns per warp instruction).  Kernel anatomy: see tc_persist_kernel.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <float.h>
 
 #include "common.cuh"
@@ -226,10 +227,10 @@ __global__ void __launch_bounds__(256) tc_pack_weight_kernel(const float *__rest
     }
 }
 
-constexpr int PERSIST_THREADS = P_THREADS + E_THREADS + 32;  // 8 producer warps, 16 epilogue warps, 1 MMA-issuer warp
+constexpr int PERSIST_THREADS = P_THREADS + E_THREADS + 64;  // 8 converter warps, 16 epilogue warps, 1 MMA-issuer warp, 1 TMA warp
 
 template <int BN, int EPI, bool STREAM>
-__global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Params2 q) {
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Params2 q, const __grid_constant__ CUtensorMap tmap_a) {
     const Params &p = q.g;
     constexpr int A_BYTES = BM * 128;                 // one raw 128 x 32 fp32 k-block
     constexpr int B_KB = 2 * BN * 128;                // hi + lo of one k-block of the weight
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     // compiler emits LDS/STS with 32-bit addresses instead of generic LD/ST
     char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t stage_free[MAX_TA], stage_ready[MAX_TA], b_full[MAX_TA], acc_full[2], acc_empty[2];
+    __shared__ uint64_t raw_full[MAX_RAW_P], raw_free[MAX_RAW_P];  // TMA landed a k-block / all converters have read it
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
     __shared__ float s_red[2 * 16 * 64];  // statistics partials: [16 row lanes][EC][2]
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     if (tid == 0) {
         for (int i = 0; i < MAX_TA; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS); mbar_init(&b_full[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS); }
+        for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], P_THREADS); }
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -298,59 +301,29 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp < P_THREADS / 32) {
-        // ======================= producers =======================
+        // ======================= converters =======================
         // work items = (tile, k-block) pairs in order.
-        //   global --cp.async--> raw ring in shared memory (D-1 k-blocks = up to 144 KB in flight per SM, no registers held)
+        //   global --TMA (one elected lane of the loader warp, 128B-swizzled box of 128 rows x 32 floats)--> raw ring in shared
+        //   memory (D k-blocks, up to 160 KB in flight per SM, no registers, no per-thread copy instructions)
         //          --LDS--> registers: hi/lo tf32 split --tcgen05.st--> operand-A stage in TENSOR memory.
         // The x operand never exists as a hi/lo image in shared memory: the tensor core reads A from TMEM and only the
-        // (small, resident) weight from shared memory, so the shared-memory port carries each x byte twice (in, out).
-        // Copy mapping (coalesced): thread -> 16-byte chunk c = tid & 7 of rows (tid >> 3) + 32 i; the chunk lands at
-        // row*128 + ((c ^ (row & 7)) << 4) so that the row-per-lane reads below are bank-conflict free.
-        // Convert mapping (tensor-memory lanes): warp w owns rows 32 (w & 3) .. +31 (its TMEM lane quarter), lane = row,
-        // and the 16 columns 16 (w >> 2) .. +15 of the k-block.
-        long long cur_tile = blockIdx.x, iss_tile = blockIdx.x;
-        int cur_kb = 0, iss_kb = 0, iss_slot = 0, cur_slot = 0, slot = 0, use = 0;
+        // (small, resident) weight from shared memory.  The swizzle puts the 16-byte chunk c of row r at
+        // r*128 + ((c ^ (r & 7)) << 4), so the row-per-lane reads below are bank-conflict free.
+        // Mapping (tensor-memory lanes): warp w owns rows 32 (w & 3) .. +31 (its TMEM lane quarter), lane = row, and the
+        // 16 columns 16 (w >> 2) .. +15 of the k-block.
+        long long cur_tile = blockIdx.x;
+        int cur_kb = 0, rslot = 0, ruse = 0, slot = 0, use = 0;
         bool ok = true;
-        const int pr = tid >> 3, pc = tid & 7;
-        const uint32_t thr_raw = (uint32_t)(pr * 128 + ((pc ^ (pr & 7)) << 4));  // + 4096 i: rows pr + 32 i share (row & 7)
-        const size_t row_step = (size_t)32 * p.lda;
-        const bool k_full = (p.K % BK) == 0;
         const int crow = (warp & 3) * 32 + lane, chalf = warp >> 2;
         uint32_t c_off[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) c_off[j] = (uint32_t)(crow * 128 + (((chalf * 4 + j) ^ (crow & 7)) << 4));
         const uint32_t t_a = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(ACC_COLS + chalf * 16);
-        auto issue_one = [&]() {
-            if (iss_tile < q.ntiles) {
-                const uint32_t dst = smem_u32(raw_ring + (size_t)iss_slot * A_BYTES) + thr_raw;
-                const long long row0 = iss_tile * BM;
-                const float *src = p.A + (size_t)(row0 + pr) * p.lda + iss_kb * BK + pc * 4;
-                if (k_full && row0 + BM <= p.M) {
-#pragma unroll
-                    for (int i = 0; i < BM * 8 / P_THREADS; ++i)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 4096), "l"(src + i * row_step) : "memory");
-                } else {
-                    const bool kv = iss_kb * BK + pc * 4 < p.K;  // K % 4 == 0: a chunk is entirely inside or outside
-#pragma unroll
-                    for (int i = 0; i < BM * 8 / P_THREADS; ++i) {
-                        const int sz = (kv && row0 + pr + 32 * i < p.M) ? 16 : 0;  // src-size 0 => zero fill
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * 4096),
-                                     "l"(sz ? src + i * row_step : p.A), "r"(sz) : "memory");
-                    }
-                }
-                if (++iss_kb == nkb) { iss_kb = 0; iss_tile += gridDim.x; }
-            }
-            cp_async_commit();  // always commit (possibly empty) so the group arithmetic stays uniform
-            if (++iss_slot == D) iss_slot = 0;
-        };
-        for (int i = 0; i < D - 1; ++i) issue_one();
         while (cur_tile < q.ntiles) {
-            cp_async_wait_dyn(D - 2);        // this thread's chunks of the current item have landed
-            bar_sync_named(1, P_THREADS);    // ... everybody's have, and everybody is done reading the previous item's slot
-            issue_one();                     // refill that slot: D-1 k-blocks stay in flight
-            if (use >= 1) ok = mbar_wait(&stage_free[slot], (uint32_t)((use - 1) & 1)) && ok;  // MMAs that read the stage retired
+            ok = mbar_wait(&raw_full[rslot], (uint32_t)(ruse & 1)) && ok;                        // the k-block has landed
+            if (use >= 1) ok = mbar_wait(&stage_free[slot], (uint32_t)((use - 1) & 1)) && ok;    // MMAs that read the stage retired
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const char *src = raw_ring + (size_t)cur_slot * A_BYTES;
+            const char *src = raw_ring + (size_t)rslot * A_BYTES;
             float v[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -367,14 +340,36 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
             } else {
                 tmem_st16(ta, v);
             }
+            // the tensor-memory stores consumed every loaded value, so the shared-memory reads have completed: only now may
+            // the loader refill the slot (an arrive issued right behind the LDS can overtake it in the memory pipeline)
+            mbar_arrive(&raw_free[rslot]);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&stage_ready[slot]);  // hand the stage to the issuer; do not wait for it
             if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; }
-            if (++cur_slot == D) cur_slot = 0;
+            if (++rslot == D) { rslot = 0; ++ruse; }
             if (++slot == TA) { slot = 0; ++use; }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!ok) s_err = 1;
+    } else if (warp == (P_THREADS + E_THREADS) / 32 + 1) {
+        // ======================= loader: one elected lane feeds the raw ring with TMA tile copies =======================
+        // rows >= M and columns >= K are zero-filled by the copy engine (tensor-map bounds), no tail code anywhere
+        const bool leader = elect_one();
+        long long tile_i = blockIdx.x;
+        int kb = 0, rslot = 0, ruse = 0;
+        bool ok = true;
+        while (tile_i < q.ntiles) {
+            if (ruse >= 1) ok = mbar_wait(&raw_free[rslot], (uint32_t)((ruse - 1) & 1)) && ok;   // all converters have read the slot
+            if (leader) {
+                mbar_expect_tx(&raw_full[rslot], (uint32_t)A_BYTES);
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(smem_u32(raw_ring + (size_t)rslot * A_BYTES)), "l"(&tmap_a), "r"(kb * BK), "r"((int)(tile_i * BM)),
+                               "r"(smem_u32(&raw_full[rslot]))
+                             : "memory");
+            }
+            if (++kb == nkb) { kb = 0; tile_i += gridDim.x; }
+            if (++rslot == D) { rslot = 0; ++ruse; }
+        }
         if (!ok) s_err = 1;
     } else if (warp == (P_THREADS + E_THREADS) / 32) {
         // ======================= MMA issuer =======================
@@ -669,6 +664,34 @@ static inline size_t packed_weight_bytes(int K, int N, int bn) {
     return (size_t)nslabs * nkb * 2 * bn * 128;
 }
 
+// 2-D tensor map of the row-major operand x[M, K] (row stride lda floats): box = 128 rows x 32 floats, 128-byte swizzle,
+// out-of-bounds elements read as zero.  cuTensorMapEncodeTiled is a pure host-side encoder; it is looked up through the
+// runtime (cudaGetDriverEntryPoint), so the library has no link-time dependency on libcuda.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (TensorMapEncodeFn)p;
+    }();
+    return fn;
+}
+static int make_tmap_rows(CUtensorMap *map, const float *base, long long M, int K, int lda, int box_rows) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return PU_ERR_UNSUPPORTED;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)lda * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PU_OK : PU_ERR_INVALID_ARG;
+}
+
 template <int BN, int EPI, bool STREAM>
 static int launch_persist(const Params2 &q, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     Params2 qq = q;
@@ -695,7 +718,10 @@ static int launch_persist(const Params2 &q, void *workspace, size_t workspace_by
     if (gx < 1) gx = 1;
     if (gx > q.ntiles) gx = q.ntiles;
     dim3 grid((unsigned)gx, ny);
-    tc_persist_kernel<BN, EPI, STREAM><<<grid, PERSIST_THREADS, smem, st>>>(qq);
+    CUtensorMap tmap;
+    const int trc = make_tmap_rows(&tmap, q.g.A, q.g.M, q.g.K, q.g.lda, BM);
+    if (trc != PU_OK) return trc;
+    tc_persist_kernel<BN, EPI, STREAM><<<grid, PERSIST_THREADS, smem, st>>>(qq, tmap);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

@@ -80,3 +80,23 @@ def test_tc_wgrad_matches_fp64(M, K, N, mode):
     wide = torch.zeros(M, 2 * K, device="cuda"); wide[:, K:] = xg
     dw2, _ = ops.wgrad_raw(wide[:, K:], dg, tc_mode=mode)
     assert torch.equal(dw2, dw)
+
+
+@pytest.mark.gpu
+def test_tc_linear_backed_up_pipeline_is_race_free():
+    """Accumulate mode makes the epilogue the slowest stage, so the TMA ring runs full and every slot is refilled the moment
+    its release barrier completes -- the regime in which a premature release shows up as stale 8-row groups."""
+    g = torch.Generator().manual_seed(7)
+    M, K, N = 100000, 64, 64
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(K, N, generator=g) / 8).cuda()
+    wt = w.t().contiguous()
+    prod = x.double() @ w.double()
+    for trial in range(4):
+        buf = torch.randn(M, 2 * N, generator=g).cuda()
+        want = buf[:, N:].double() + prod
+        ops.tc_error_flag(x.device).zero_()
+        ops.linear_raw(x, None, None, out=buf[:, N:], accumulate=True, wt=wt, tc_mode=3)
+        assert int(ops.tc_error_flag(x.device).item()) == 0
+        err = (buf[:, N:].double() - want).abs().max().item()
+        assert err < 1e-4, (trial, err)
