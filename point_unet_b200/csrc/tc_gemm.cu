@@ -256,7 +256,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     const int n0 = blockIdx.y * BN;
     const bool split = p.mode == 3;
     const int D = q.raw_depth;
-    char *raw_ring = smem;                            // D raw k-blocks, filled by cp.async
+    // att epilogues with d <= 64 take their x values from the raw ring (the tile's k-blocks stay resident until the epilogue
+    // has used them) instead of re-reading them through L2: no load latency in the epilogue's critical path
+    const bool x_ring = EPI != EPI_STORE && !STREAM && nkb <= 2 && p.N == p.K && D >= 7;
+    char *raw_ring = smem;                            // D raw k-blocks, filled by TMA
     char *b_res = smem + (size_t)D * A_BYTES;         // resident: nkb k-blocks; streamed: TA k-blocks
     float *tile = reinterpret_cast<float *>(b_res + (size_t)(STREAM ? TA : nkb) * B_KB);  // epilogue staging [BM][LDT]
     const char *b_packed = STREAM ? q.Bp + (size_t)blockIdx.y * nkb * B_KB : nullptr;
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     if (tid == 0) {
         for (int i = 0; i < MAX_TA; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS); mbar_init(&b_full[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS); }
-        for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], P_THREADS); }
+        for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], P_THREADS + (x_ring ? E_THREADS : 0)); }
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -434,19 +437,31 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
         const int etid = tid - P_THREADS, ewarp = warp - P_THREADS / 32;
         const int quarter = ewarp & 3, cpart = ewarp >> 2;  // TMEM lane quarter (= warp id % 4) and column quarter
         int tile_count = 0;
+        int eslot = 0, euse = 0;  // ring position of the current tile's first k-block (x_ring only)
         bool ok = true;
+        constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * EC + E_THREADS - 1) / E_THREADS;
+        // x_ring: this thread's pair (point pl, channel c) reads rows 16 pl + k of k-block c / 32; the swizzled byte offset
+        // of row 16 pl + k is xo[k & 7] + 1024 (k >> 3)  (16 pl is a multiple of 8, so row & 7 == k & 7)
+        uint32_t xo[8];
+        {
+            const int pl = (etid / EC) % (BM / 16), c = etid % EC;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                xo[k] = (uint32_t)((pl * 16 + k) * 128 + ((((c & 31) >> 2) ^ k) << 4) + (c & 3) * 4);
+        }
         for (long long tile_i = blockIdx.x; tile_i < q.ntiles; tile_i += gridDim.x, ++tile_count) {
             const int buf = tile_count & 1, v = tile_count >> 1;
             const long long m0 = tile_i * BM;
             const long long rows_here = min((long long)BM, p.M - m0);
-            constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * EC + E_THREADS - 1) / E_THREADS;
             float xv[PAIRS][16];
             float gv[PAIRS];
+            int eslot1 = eslot + 1, euse1 = euse;   // second k-block of the tile
+            if (eslot1 == D) { eslot1 = 0; ++euse1; }
 #pragma unroll 1
             for (int pass = 0; pass < NPASS; ++pass) {
                 const int nb = n0 + pass * EC;  // first global column of this pass
                 // att epilogues: fetch this thread's x (and g) values BEFORE waiting for the accumulator -- they do not
-                // depend on the MMA, so (for the first pass) their L2 latency hides behind the tensor-core work
+                // depend on the MMA
                 if constexpr (EPI != EPI_STORE) {
                     const int npts = (int)(rows_here / 16);
 #pragma unroll
@@ -454,16 +469,43 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                         const int pair = etid + pp * E_THREADS;
                         const int pl = pair / EC, c = pair % EC;
                         const bool pv = pair < (BM / 16) * EC && pl < npts && nb + c < p.N;
-                        const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + nb + c;
-                        if (q.ldx == BN) {  // contiguous feature_set (the usual case): immediate offsets, one LDG per value
+                        if (x_ring) {  // PAIRS == 1, NPASS == 1 here (BN <= 64)
+                            const bool second = c >= 32;
+                            ok = mbar_wait(&raw_full[second ? eslot1 : eslot], (uint32_t)((second ? euse1 : euse) & 1)) && ok;
+                            const char *xs = raw_ring + (size_t)(second ? eslot1 : eslot) * A_BYTES;
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[k * BN] : 0.f;
+                            for (int k = 0; k < 16; ++k) xv[pp][k] = *reinterpret_cast<const float *>(xs + xo[k & 7] + (k >> 3) * 1024);
+                            if (!pv) {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) xv[pp][k] = 0.f;
+                            }
                         } else {
+                            const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + nb + c;
+                            if (q.ldx == BN) {  // contiguous feature_set (the usual case): immediate offsets, one LDG per value
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
+                                for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[k * BN] : 0.f;
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
+                            }
                         }
                         gv[pp] = 0.f;
                         if constexpr (EPI == EPI_ATT_BWD) gv[pp] = pv ? q.G[(size_t)(m0 / 16 + pl) * q.ldg + nb + c] : 0.f;
+                    }
+                }
+                // linear epilogue in accumulate mode: the old values of C do not depend on the MMA either -- request them
+                // now, so their HBM latency overlaps the accumulator wait and the TMEM read-out
+                constexpr int S_CG = EC / 4, S_RLANES = E_THREADS / S_CG, S_RPT = BM / S_RLANES;
+                float4 old[EPI == EPI_STORE ? S_RPT : 1];
+                if constexpr (EPI == EPI_STORE) {
+                    const int gn = nb + (etid % S_CG) * 4, rl = etid / S_CG;
+                    if (p.accumulate && gn + 3 < p.N && ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < S_RPT; ++i) {
+                            const int r = rl + i * S_RLANES;
+                            old[i] = r < rows_here ? *reinterpret_cast<const float4 *>(p.C + (size_t)(m0 + r) * p.ldc + gn)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                 }
                 if (pass == 0) {
@@ -516,15 +558,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     }
                     constexpr int RPT = BM / RLANES;  // rows per thread (4 for EC = 64, 2 for EC = 32)
                     const bool fast = gn + 3 < p.N && vecC;
-                    float4 old[RPT];
-                    if (p.accumulate && fast) {  // all loads of C first: RPT independent requests in flight, not a serial chain
-#pragma unroll
-                        for (int i = 0; i < RPT; ++i) {
-                            const int r = rl + i * RLANES;
-                            old[i] = r < rows_here ? *reinterpret_cast<const float4 *>(p.C + (size_t)(m0 + r) * p.ldc + gn)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
+                    static_assert(RPT == S_RPT && RLANES == S_RLANES && CG == S_CG, "accumulate preload uses the same mapping");
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
                         const int r = rl + i * RLANES;
@@ -631,6 +665,12 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     }
                 }
                 bar_sync_named(2, E_THREADS);  // staging tile is reused by the next pass / tile
+            }
+            if (x_ring) {  // every x value has been consumed by the arithmetic above: the loader may refill the tile's slots
+                mbar_arrive(&raw_free[eslot]);
+                if (nkb == 2) mbar_arrive(&raw_free[eslot1]);
+                eslot += nkb; 
+                if (eslot >= D) { eslot -= D; ++euse; }
             }
         }
         if (!ok) s_err = 1;
