@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 
     if (tid == 0) {
         for (int i = 0; i < MAX_TA; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS); mbar_init(&b_full[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS); }
-        for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], P_THREADS + (x_ring ? E_THREADS : 0)); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS / 2); }
+        for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], P_THREADS + (x_ring ? E_THREADS / 2 : 0)); }
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -433,76 +433,50 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
             if (!ok) s_err = 1;
         }
     } else {
-        // ======================= epilogue warps =======================
-        const int etid = tid - P_THREADS, ewarp = warp - P_THREADS / 32;
-        const int quarter = ewarp & 3, cpart = ewarp >> 2;  // TMEM lane quarter (= warp id % 4) and column quarter
-        int tile_count = 0;
-        int eslot = 0, euse = 0;  // ring position of the current tile's first k-block (x_ring only)
+        // ======================= epilogue: two independent groups of 8 warps =======================
+        // Group g finishes the tiles whose accumulator lives in TMEM buffer g (every other tile of this CTA) with its own
+        // staging tile and named barrier: while one group waits for its accumulator and drains tensor memory, the other
+        // one does its arithmetic and stores -- the phases of consecutive tiles overlap instead of queueing behind
+        // CTA-wide barriers.
+        constexpr int G_THREADS = E_THREADS / 2;
+        const int etid = tid - P_THREADS;
+        const int eg = etid / G_THREADS, gtid = etid % G_THREADS, gwarp = gtid >> 5;
+        const int quarter = gwarp & 3, chalf = gwarp >> 2;  // TMEM lane quarter (= warp id % 4) and column half
+        float *tile_g = tile + (size_t)eg * BM * LDT;
+        float *red_g = s_red + eg * (8 * 64 * 2);
+        const int bar_id = 2 + eg;
         bool ok = true;
-        constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * EC + E_THREADS - 1) / E_THREADS;
-        // x_ring: this thread's pair (point pl, channel c) reads rows 16 pl + k of k-block c / 32; the swizzled byte offset
-        // of row 16 pl + k is xo[k & 7] + 1024 (k >> 3)  (16 pl is a multiple of 8, so row & 7 == k & 7)
+        constexpr int PAIRS = EPI == EPI_STORE ? 1 : ((BM / 16) * EC + G_THREADS - 1) / G_THREADS;  // (point, channel) pairs per thread
+        constexpr int PP_ROWS = (G_THREADS / EC) * 16;  // tile rows between a thread's consecutive pairs
+        // x_ring: pair (point pl, channel c) reads rows 16 pl + k of k-block c / 32; the swizzled byte offset of row 16 pl + k
+        // is xo[k & 7] + 1024 (k >> 3)  (16 pl is a multiple of 8, so row & 7 == k & 7)
         uint32_t xo[8];
         {
-            const int pl = (etid / EC) % (BM / 16), c = etid % EC;
+            const int pl = gtid / EC, c = gtid % EC;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                xo[k] = (uint32_t)((pl * 16 + k) * 128 + ((((c & 31) >> 2) ^ k) << 4) + (c & 3) * 4);
+            for (int k = 0; k < 8; ++k) xo[k] = (uint32_t)((pl * 16 + k) * 128 + ((((c & 31) >> 2) ^ k) << 4) + (c & 3) * 4);
         }
-        for (long long tile_i = blockIdx.x; tile_i < q.ntiles; tile_i += gridDim.x, ++tile_count) {
-            const int buf = tile_count & 1, v = tile_count >> 1;
+        int eslot = eg * nkb, euse = 0;  // ring position of this group's current tile (x_ring only: nkb <= 2 < D)
+        int tile_count = eg;
+        for (long long tile_i = blockIdx.x + (long long)eg * gridDim.x; tile_i < q.ntiles; tile_i += 2LL * gridDim.x, tile_count += 2) {
+            const int buf = eg, v = tile_count >> 1;
             const long long m0 = tile_i * BM;
             const long long rows_here = min((long long)BM, p.M - m0);
-            float xv[PAIRS][16];
-            float gv[PAIRS];
-            int eslot1 = eslot + 1, euse1 = euse;   // second k-block of the tile
+            int eslot1 = eslot + 1, euse1 = euse;  // second k-block of the tile
             if (eslot1 == D) { eslot1 = 0; ++euse1; }
 #pragma unroll 1
             for (int pass = 0; pass < NPASS; ++pass) {
                 const int nb = n0 + pass * EC;  // first global column of this pass
-                // att epilogues: fetch this thread's x (and g) values BEFORE waiting for the accumulator -- they do not
-                // depend on the MMA
-                if constexpr (EPI != EPI_STORE) {
-                    const int npts = (int)(rows_here / 16);
-#pragma unroll
-                    for (int pp = 0; pp < PAIRS; ++pp) {
-                        const int pair = etid + pp * E_THREADS;
-                        const int pl = pair / EC, c = pair % EC;
-                        const bool pv = pair < (BM / 16) * EC && pl < npts && nb + c < p.N;
-                        if (x_ring) {  // PAIRS == 1, NPASS == 1 here (BN <= 64)
-                            const bool second = c >= 32;
-                            ok = mbar_wait(&raw_full[second ? eslot1 : eslot], (uint32_t)((second ? euse1 : euse) & 1)) && ok;
-                            const char *xs = raw_ring + (size_t)(second ? eslot1 : eslot) * A_BYTES;
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) xv[pp][k] = *reinterpret_cast<const float *>(xs + xo[k & 7] + (k >> 3) * 1024);
-                            if (!pv) {
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) xv[pp][k] = 0.f;
-                            }
-                        } else {
-                            const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + nb + c;
-                            if (q.ldx == BN) {  // contiguous feature_set (the usual case): immediate offsets, one LDG per value
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[k * BN] : 0.f;
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) xv[pp][k] = pv ? xp[(size_t)k * q.ldx] : 0.f;
-                            }
-                        }
-                        gv[pp] = 0.f;
-                        if constexpr (EPI == EPI_ATT_BWD) gv[pp] = pv ? q.G[(size_t)(m0 / 16 + pl) * q.ldg + nb + c] : 0.f;
-                    }
-                }
-                // linear epilogue in accumulate mode: the old values of C do not depend on the MMA either -- request them
-                // now, so their HBM latency overlaps the accumulator wait and the TMEM read-out
-                constexpr int S_CG = EC / 4, S_RLANES = E_THREADS / S_CG, S_RPT = BM / S_RLANES;
-                float4 old[EPI == EPI_STORE ? S_RPT : 1];
+                // linear epilogue in accumulate mode: the old values of C do not depend on the MMA -- request them now, so
+                // their HBM latency overlaps the accumulator wait and the TMEM read-out
+                constexpr int CG = EC / 4, RLANES = G_THREADS / CG, RPT = BM / RLANES;  // 4-column groups, row lanes, rows per thread
+                float4 old[EPI == EPI_STORE ? RPT : 1];
                 if constexpr (EPI == EPI_STORE) {
-                    const int gn = nb + (etid % S_CG) * 4, rl = etid / S_CG;
+                    const int gn = nb + (gtid % CG) * 4, rl = gtid / CG;
                     if (p.accumulate && gn + 3 < p.N && ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0)) {
 #pragma unroll
-                        for (int i = 0; i < S_RPT; ++i) {
-                            const int r = rl + i * S_RLANES;
+                        for (int i = 0; i < RPT; ++i) {
+                            const int r = rl + i * RLANES;
                             old[i] = r < rows_here ? *reinterpret_cast<const float4 *>(p.C + (size_t)(m0 + r) * p.ldc + gn)
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
@@ -512,24 +486,16 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                {   // TMEM -> registers -> staging tile: warp (quarter, cpart) moves 32 rows x EC/4 columns
+                {   // TMEM -> registers -> staging tile: warp (quarter, chalf) moves 32 rows x EC/2 columns
                     const int row = quarter * 32 + lane;
-                    constexpr int CW = EC / 4;  // 16 (EC = 64) or 8 (EC = 32)
-                    const int c0 = cpart * CW;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + pass * EC + c0);
-                    if constexpr (CW == 16) {
+#pragma unroll
+                    for (int cc = 0; cc < EC / 2; cc += 16) {
+                        const int c0 = chalf * (EC / 2) + cc;
                         float vals[16];
-                        tmem_ld16(taddr, vals);
+                        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + pass * EC + c0), vals);
 #pragma unroll
                         for (int qd = 0; qd < 16; qd += 4)
-                            *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
-                                make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
-                    } else {
-                        float vals[8];
-                        tmem_ld8(taddr, vals);
-#pragma unroll
-                        for (int qd = 0; qd < 8; qd += 4)
-                            *reinterpret_cast<float4 *>(&tile[row * LDT + c0 + qd]) =
+                            *reinterpret_cast<float4 *>(&tile_g[row * LDT + c0 + qd]) =
                                 make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
                     }
                 }
@@ -537,15 +503,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
                 }
-                bar_sync_named(2, E_THREADS);
+                bar_sync_named(bar_id, G_THREADS);
 
                 if constexpr (EPI == EPI_STORE) {
                     const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-                    // thread -> fixed group of 4 columns (E_THREADS % (EC/4) == 0), rows strided: the batch-norm partials
-                    // accumulate in registers during the copy-out.  Shifted single pass: sums of (v - sh) and (v - sh)^2
-                    // with sh = the tile's first stored row, so M2 = S2 - S1^2/n loses nothing to cancellation.
-                    constexpr int CG = EC / 4, RLANES = E_THREADS / CG;
-                    const int cg = etid % CG, rl = etid / CG, c = cg * 4, gn = nb + c;
+                    // thread -> fixed group of 4 columns, rows strided: the batch-norm partials accumulate in registers during
+                    // the copy-out.  Shifted single pass: sums of (v - sh) and (v - sh)^2 with sh = the tile's first stored
+                    // row, so M2 = S2 - S1^2/n loses nothing to cancellation.
+                    const int cg = gtid % CG, rl = gtid / CG, c = cg * 4, gn = nb + c;
                     float sh[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
                     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.bias) {
@@ -553,17 +518,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                         bias4.z = gn + 2 < p.N ? p.bias[gn + 2] : 0.f; bias4.w = gn + 3 < p.N ? p.bias[gn + 3] : 0.f;
                     }
                     if (p.stat_sum) {  // shift = stored value of row 0 (recomputed identically by every thread of the group)
-                        const float4 t0 = *reinterpret_cast<float4 *>(&tile[c]);
+                        const float4 t0 = *reinterpret_cast<float4 *>(&tile_g[c]);
                         sh[0] = t0.x + bias4.x; sh[1] = t0.y + bias4.y; sh[2] = t0.z + bias4.z; sh[3] = t0.w + bias4.w;
                     }
-                    constexpr int RPT = BM / RLANES;  // rows per thread (4 for EC = 64, 2 for EC = 32)
                     const bool fast = gn + 3 < p.N && vecC;
-                    static_assert(RPT == S_RPT && RLANES == S_RLANES && CG == S_CG, "accumulate preload uses the same mapping");
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
                         const int r = rl + i * RLANES;
                         if (r >= rows_here) continue;
-                        float4 val = *reinterpret_cast<float4 *>(&tile[r * LDT + c]);
+                        float4 val = *reinterpret_cast<float4 *>(&tile_g[r * LDT + c]);
                         val.x += bias4.x; val.y += bias4.y; val.z += bias4.z; val.w += bias4.w;
                         float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
                         if (fast) {
@@ -585,9 +548,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     }
                     if (p.stat_sum) {
                         // a warp holds 32/CG consecutive row lanes of the same column groups: combine them with shuffles
-                        // first (fixed order), so 16 row lanes per column reach shared memory
+                        // first (fixed order), so one partial per warp and column reaches shared memory
                         constexpr int RL2 = RLANES / (32 / CG);
-                        static_assert(RL2 == 16, "s_red holds 16 row lanes");
+                        static_assert(RL2 == G_THREADS / 32, "one partial per warp of the group");
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -597,38 +560,50 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                             }
                         }
                         if (lane < CG) {
-                            const int rl2 = etid >> 5;  // one slot per epilogue warp
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                s_red[(rl2 * EC + c + j) * 2 + 0] = s1[j];
-                                s_red[(rl2 * EC + c + j) * 2 + 1] = s2[j];
+                                red_g[(gwarp * EC + c + j) * 2 + 0] = s1[j];
+                                red_g[(gwarp * EC + c + j) * 2 + 1] = s2[j];
                             }
                         }
-                        bar_sync_named(2, E_THREADS);
-                        if (etid < EC && nb + etid < p.N) {
+                        bar_sync_named(bar_id, G_THREADS);
+                        if (gtid < EC && nb + gtid < p.N) {
                             float a = 0.f, b = 0.f;
-                            for (int l = 0; l < RL2; ++l) { a += s_red[(l * EC + etid) * 2]; b += s_red[(l * EC + etid) * 2 + 1]; }
-                            const float shc = tile[etid] + (p.bias ? p.bias[nb + etid] : 0.f);  // same shift as above
+                            for (int l = 0; l < RL2; ++l) { a += red_g[(l * EC + gtid) * 2]; b += red_g[(l * EC + gtid) * 2 + 1]; }
+                            const float shc = tile_g[gtid] + (p.bias ? p.bias[nb + gtid] : 0.f);  // same shift as above
                             const float n = (float)rows_here;
-                            p.stat_sum[(size_t)tile_i * p.N + nb + etid] = fmaf(n, shc, a);
-                            p.stat_m2[(size_t)tile_i * p.N + nb + etid] = fmaxf(b - a * a / n, 0.f);
+                            p.stat_sum[(size_t)tile_i * p.N + nb + gtid] = fmaf(n, shc, a);
+                            p.stat_m2[(size_t)tile_i * p.N + nb + gtid] = fmaxf(b - a * a / n, 0.f);
                         }
                     }
                 } else {
-                    // one (point, channel) pair per thread step: the 16 neighbour rows of a point are consecutive rows of `tile`
+                    // one (point, channel) pair per thread step: the 16 neighbour rows of a point are consecutive rows of the tile
                     const long long pt0 = m0 / 16;
                     const int npts = (int)(rows_here / 16);
 #pragma unroll
                     for (int pp = 0; pp < PAIRS; ++pp) {
-                        const int pair = etid + pp * E_THREADS;
+                        const int pair = gtid + pp * G_THREADS;
                         const int pl = pair / EC, c = pair % EC;
                         const int gn = nb + c;
                         if (pair >= (BM / 16) * EC || pl >= npts || gn >= p.N) continue;
-                        float a[16];
+                        float a[16], x[16];
+                        if (x_ring) {  // the tile's k-blocks are still resident in the TMA ring
+                            const bool second = c >= 32;
+                            ok = mbar_wait(&raw_full[second ? eslot1 : eslot], (uint32_t)((second ? euse1 : euse) & 1)) && ok;
+                            const char *xs = raw_ring + (size_t)(second ? eslot1 : eslot) * A_BYTES + pp * (PP_ROWS * 128);
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) x[k] = *reinterpret_cast<const float *>(xs + xo[k & 7] + (k >> 3) * 1024);
+                        } else {
+                            const float *xp = q.X + (size_t)(m0 + pl * 16) * q.ldx + gn;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) x[k] = xp[(size_t)k * q.ldx];
+                        }
+                        float g = 0.f;
+                        if constexpr (EPI == EPI_ATT_BWD) g = q.G[(size_t)(pt0 + pl) * q.ldg + gn];
                         float mx = -FLT_MAX;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
-                            a[k] = tile[(pl * 16 + k) * LDT + c];
+                            a[k] = tile_g[(pl * 16 + k) * LDT + c];
                             mx = fmaxf(mx, a[k]);
                         }
                         float sum = 0.f;
@@ -639,37 +614,36 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                         if constexpr (EPI == EPI_ATT_FWD) {
                             float num = 0.f;
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) num = fmaf(xv[pp][k], a[k], num);
+                            for (int k = 0; k < 16; ++k) num = fmaf(x[k], a[k], num);
                             q.OUT[(size_t)(pt0 + pl) * q.ldo + gn] = num * inv;
                         } else {
-                            const float g = gv[pp];
                             float dot = 0.f;
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * xv[pp][k], a[k], dot); }
+                            for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * x[k], a[k], dot); }
                             float *cp = p.C + (size_t)(m0 + pl * 16) * p.ldc + gn;
                             float *op = q.OUT + (size_t)(m0 + pl * 16) * q.ldo + gn;
                             if (p.ldc == BN && q.ldo == BN) {  // contiguous outputs: immediate offsets
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
-                                    cp[k * BN] = a[k] * (g * xv[pp][k] - dot);   // d_act
-                                    op[k * BN] = g * a[k];                       // dx_direct
+                                    cp[k * BN] = a[k] * (g * x[k] - dot);   // d_act
+                                    op[k * BN] = g * a[k];                  // dx_direct
                                 }
                             } else {
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
-                                    cp[(size_t)k * p.ldc] = a[k] * (g * xv[pp][k] - dot);
+                                    cp[(size_t)k * p.ldc] = a[k] * (g * x[k] - dot);
                                     op[(size_t)k * q.ldo] = g * a[k];
                                 }
                             }
                         }
                     }
                 }
-                bar_sync_named(2, E_THREADS);  // staging tile is reused by the next pass / tile
+                bar_sync_named(bar_id, G_THREADS);  // the staging tile is reused by the next pass / tile of this group
             }
             if (x_ring) {  // every x value has been consumed by the arithmetic above: the loader may refill the tile's slots
                 mbar_arrive(&raw_free[eslot]);
                 if (nkb == 2) mbar_arrive(&raw_free[eslot1]);
-                eslot += nkb; 
+                eslot += 2 * nkb;  // the other group owns the tile in between
                 if (eslot >= D) { eslot -= D; ++euse; }
             }
         }
@@ -689,7 +663,7 @@ static size_t persist_fixed_bytes(int K) {  // everything except the raw ring
     const int nkb = (K + BK - 1) / BK;
     const int ec = BN > 64 ? 64 : BN;
     const int ta = BN <= 64 ? MAX_TA : 2;
-    return (size_t)(STREAM ? ta : nkb) * 2 * BN * 128 + (size_t)BM * (ec + 4) * 4 + 1024;
+    return (size_t)(STREAM ? ta : nkb) * 2 * BN * 128 + 2 * (size_t)BM * (ec + 4) * 4 + 1024;  // weights, 2 staging tiles
 }
 template <int BN, bool STREAM>
 static int persist_raw_depth(int K) {  // 0 => does not fit
