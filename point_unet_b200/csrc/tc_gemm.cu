@@ -1184,7 +1184,7 @@ int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, co
 /* Tensor-core weight gradient: dw[Kin,N] (+)= x^T dy, db[N] (+)= column sums of dy (db only when Kin % 128 != 0).
  * Supported when Kin >= 32 or N > 32, all of Kin, N, ldx, lddy multiples of 4. */
 int pu_tc_wgrad_supported(long long M, int Kin, int N, int ldx, int lddy, int want_db) {
-    if (M < 4096 || (Kin & 3) || (N & 3) || (ldx & 3) || (lddy & 3) || N < 32 || Kin < 32) return 0;
+    if (M < 512 || (Kin & 3) || (N & 3) || (ldx & 3) || (lddy & 3) || N < 32 || Kin < 32) return 0;
     if (want_db && (Kin % tc::BM) == 0) return 0;
     return 1;
 }

@@ -30,11 +30,14 @@ class Trainer:
         self.bucket = FlatGradBucket(self.params, self.device)
         self.flat_grad = self.bucket.flat
         # tf.train.AdamOptimizer defaults (RandLANet.py:88): beta (0.9, 0.999), eps 1e-8
+        # capturable: the step counter lives on the device, so the whole step (pyramid, forward, backward, all-reduce,
+        # Adam) can be recorded once into a CUDA graph and replayed (capture_step / train_step_graph below)
         self.opt = torch.optim.Adam(self.params, lr=lr if lr is not None else config.learning_rate, betas=(0.9, 0.999),
-                                    eps=1e-8, fused=True)
+                                    eps=1e-8, fused=True, capturable=True)
         self.world_size = world_size
         self._pinned = {}
         self._dev = {}
+        self._graph = None
 
     # -- host staging ----------------------------------------------------------------------------
     def _stage(self, name, arr):
@@ -76,12 +79,47 @@ class Trainer:
         ops.clear_caches()
         return loss.detach()
 
+    # -- CUDA graph: ~1300 kernel launches per step recorded once, replayed with one host call -------
+    def capture_step(self, xyz, features, labels, warmup=3):
+        """Record one optimisation step for inputs of this shape into a CUDA graph.  ``xyz/features/labels`` are device
+        tensors used for the warm-up (workspaces, kernel attributes and the allocator pool are set up outside the
+        capture); afterwards ``train_step_graph`` copies a new batch into the static input buffers and replays.
+        The warm-up steps ARE optimisation steps (they update the weights)."""
+        from . import _lib
+        self._gx, self._gf, self._gl = xyz.clone(), features.clone(), labels.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                self.train_step_device(self._gx, self._gf, self._gl)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self._gloss = self.train_step_device(self._gx, self._gf, self._gl)
+        self.graph_launches = int(_lib.launch_count() - n0)  # our kernels inside one replay (torch's own come on top)
+        self._graph = graph
+        return self
+
+    def train_step_graph(self, xyz, features, labels):
+        """Replay the captured step on a new device-resident batch of the captured shape; returns the loss tensor."""
+        if self._graph is None:
+            raise RuntimeError("capture_step() first")
+        self._gx.copy_(xyz, non_blocking=True)
+        self._gf.copy_(features, non_blocking=True)
+        self._gl.copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._gloss
+
     def train_step(self, xyz, features, labels):
         """Public end-to-end step on HOST buffers (numpy or pinned CPU tensors); returns the loss as a float
-        (device -> host read)."""
+        (device -> host read).  Uses the captured graph when there is one for this shape."""
         x = self._stage("xyz", xyz)
         f = self._stage("features", features)
         l = self._stage("labels", labels)
+        if self._graph is not None and x.shape == self._gx.shape and f.shape == self._gf.shape:
+            return float(self.train_step_graph(x, f, l).item())
         return float(self.train_step_device(x, f, l).item())
 
     @torch.no_grad()

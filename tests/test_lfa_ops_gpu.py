@@ -369,3 +369,28 @@ def test_predict_to_volume_pipeline():
         want = ref.point2prod(probs[b].cpu().numpy(), c["xyz_origin"].astype(np.int64), (shape[2], shape[0], shape[1], 2))
         assert vols[b].shape == (shape[2], shape[1], shape[0], 2)
         assert np.array_equal(vols[b].cpu().numpy().astype(np.float64), want)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_step_matches_eager_training():
+    """The captured step (pyramid + forward + backward + Adam in one CUDA graph) trains like the eager step: same weights
+    after the same number of steps up to dropout noise, loss going down on a fixed batch, one replay per step."""
+    from point_unet_b200.train import Trainer
+    from point_unet_b200 import synthetic
+
+    class cfg(ConfigBraTS):
+        num_points = 8192
+    data = synthetic.batch(synthetic.brats_cloud, 2, cfg.num_points, 11)
+    data = dict(xyz=data["xyz"].astype(np.float32), features=data["features"].astype(np.float32), labels=data["labels"])
+    x = torch.from_numpy(data["xyz"]).cuda(); f = torch.from_numpy(data["features"]).cuda(); l = torch.from_numpy(data["labels"]).cuda()
+    eager = Trainer(cfg, num_features=x.shape[-1] + f.shape[-1], seed=0, device="cuda")
+    graph = Trainer(cfg, num_features=x.shape[-1] + f.shape[-1], seed=0, device="cuda")
+    le = [float(eager.train_step_device(x, f, l)) for _ in range(12)]
+    graph.capture_step(x, f, l, warmup=2)            # two eager steps, then the recording (not executed)
+    lg = [float(graph.train_step_graph(x, f, l)) for _ in range(10)]
+    assert graph.graph_launches > 100
+    assert all(np.isfinite(lg)) and lg[-1] < lg[0]
+    assert abs(lg[-1] - le[-1]) < 0.25 * abs(le[0]) + 0.05, (le, lg)
+    # the public host-buffer entry uses the graph too
+    val = graph.train_step(data["xyz"], data["features"], data["labels"])
+    assert np.isfinite(val)

@@ -57,7 +57,8 @@ def test_tc_used_by_autograd_linear_and_att_pool():
 
 
 @pytest.mark.parametrize("M,K,N", [(8192, 64, 64), (50000, 32, 32), (20000, 128, 128), (9000, 256, 512), (5000, 1536, 512),
-                                   (100000, 64, 32), (4100, 96, 40), (300000, 32, 64), (6000, 160, 32)])
+                                   (100000, 64, 32), (4100, 96, 40), (300000, 32, 64), (6000, 160, 32), (2812, 512, 1024), (1404, 1024, 1024),
+                                   (703, 1536, 512), (600, 64, 64)])
 @pytest.mark.parametrize("mode", [3, 1])
 def test_tc_wgrad_matches_fp64(M, K, N, mode):
     g = torch.Generator().manual_seed(M + K + N + 1)
