@@ -393,7 +393,18 @@ def run_ours(args):
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
     if world > 1:
+        # The captured graph holds NCCL kernels: release it before the communicator goes away, and never let the teardown
+        # (or the interpreter's exit handlers) block the launcher -- the result line is already out.
+        import threading
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        tr._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
