@@ -379,27 +379,48 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
     return out, mean, var
 
 
-def wgrad_raw(x, dy, want_db=False, tc_mode=None):
-    """dw = x^T dy (and db = column sums of dy): tensor cores for wide shapes, CUDA cores otherwise (no autograd)."""
+def wgrad_raw(x, dy, want_db=False, tc_mode=None, out=None, out_db=None, accumulate=False):
+    """dw = x^T dy (and db = column sums of dy): tensor cores for wide shapes, CUDA cores otherwise (no autograd).
+    ``out`` / ``out_db`` (contiguous fp32) receive the result, added to their content when ``accumulate``."""
     xr, M, K, ldx = rows(x)
     gr, Mg, N, ldg = rows(dy)
     assert M == Mg
     L = _L()
-    dw = torch.empty((K, N), dtype=torch.float32, device=x.device)
-    db = torch.empty(N, dtype=torch.float32, device=x.device) if want_db else None
+    dw = out if out is not None else torch.empty((K, N), dtype=torch.float32, device=x.device)
+    assert dw.is_contiguous() and dw.numel() == K * N
+    db = None
+    if want_db:
+        db = out_db if out_db is not None else torch.empty(N, dtype=torch.float32, device=x.device)
+    acc = int(bool(accumulate))
     mode = TC_MODE if tc_mode is None else tc_mode
     if mode in (1, 3) and xr.data_ptr() % 16 == 0 and gr.data_ptr() % 16 == 0 and \
             L.pu_tc_wgrad_supported(M, K, N, ldx, ldg, int(want_db)):
         ws = workspace(L.pu_tc_wgrad_workspace_bytes(M, K, N), x.device, slot=2)
         _call("pu_tc_wgrad", xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
-              db.data_ptr() if want_db else None, 0, mode, ws.data_ptr(), ws.numel(), tc_error_flag(x.device).data_ptr(),
+              db.data_ptr() if want_db else None, acc, mode, ws.data_ptr(), ws.numel(), tc_error_flag(x.device).data_ptr(),
               _stream(x), tag=(M, K, N))
         return dw, db
     nbytes = L.pu_wgrad_workspace_bytes(M, K, N)
     ws = workspace(nbytes, x.device, slot=2)
     _call("pu_wgrad", xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
-          db.data_ptr() if want_db else None, 0, ws.data_ptr(), ws.numel(), _stream(x), tag=(M, K, N))
+          db.data_ptr() if want_db else None, acc, ws.data_ptr(), ws.numel(), _stream(x), tag=(M, K, N))
     return dw, db
+
+
+# Gradient sink: inside a Trainer step every parameter's ``.grad`` is a view of one flat, pre-zeroed buffer.  With the sink
+# on, the backward functions make the kernels add weight / bias / gamma / beta gradients straight into those views and
+# return None for them, instead of handing autograd ~190 small tensors to ``add_`` into the same views one by one.
+GRAD_SINK = False
+
+
+def _sink(param):
+    """The parameter's .grad view if gradients may be written into it directly, else None."""
+    if not GRAD_SINK or param is None or not param.is_leaf or not param.requires_grad:
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape:
+        return None
+    return g
 
 
 class _LinearFn(torch.autograd.Function):
@@ -414,6 +435,7 @@ class _LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.x_needs = x.requires_grad
+        ctx.w_param, ctx.b_param = w, bias
         if want_stats:
             ctx.mark_non_differentiable(mean, var)
             return y, mean, var
@@ -426,14 +448,20 @@ class _LinearFn(torch.autograd.Function):
         if ctx.x_needs:
             dx = linear_raw(dy, None, wt=w)  # dx = dy w^T: the K-major form of w^T is w itself
             dx = dx.view(x.shape)
+        gw, gb = _sink(ctx.w_param), _sink(ctx.b_param)
         if ctx.has_bias and ctx.zero_bias_grad:
             # a bias that feeds a training-mode batch norm has an identically zero gradient (the BN backward makes every
             # column of dy sum to zero); return the exact value instead of accumulating rounding noise
-            dw, _ = wgrad_raw(x, dy, want_db=False)
-            db = torch.zeros(dy.shape[-1], dtype=torch.float32, device=dy.device)
+            dw, _ = wgrad_raw(x, dy, want_db=False, out=gw, accumulate=gw is not None)
+            db = None if gb is not None else torch.zeros(dy.shape[-1], dtype=torch.float32, device=dy.device)
         else:
-            dw, db = wgrad_raw(x, dy, want_db=ctx.has_bias)
-        return dx, dw, db, None, None
+            both = gw is not None and (gb is not None or not ctx.has_bias)
+            dw, db = wgrad_raw(x, dy, want_db=ctx.has_bias, out=gw if both else None, out_db=gb if both else None,
+                               accumulate=both)
+            if both:
+                db = None
+            gw = gw if both else None
+        return dx, (None if gw is not None else dw), db, None, None
 
 
 def linear(x, w, bias=None, want_stats=False, zero_bias_grad=False):
@@ -465,7 +493,12 @@ def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shif
     return out
 
 
-def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training, dz2=None):
+def _bn_sink(gamma, beta):
+    g, b = _sink(gamma), _sink(beta)
+    return (g, b) if g is not None and b is not None else None
+
+
+def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training, dz2=None, sink=None):
     """Gradient of out = lrelu(BN(y)) wrt y, gamma, beta given dout = dz (+ dz2, a second upstream gradient summed on
     the fly inside the kernels)."""
     dzr, R, C, ldd = rows(dz)
@@ -485,6 +518,8 @@ def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training, dz2=N
           float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st)
     co = torch.empty((5, C), dtype=torch.float32, device=y.device)  # dgamma, dbeta, ka, kb, kc
     dgamma, dbeta, ka, kb, kc = co[0], co[1], co[2], co[3], co[4]
+    if sink is not None:  # (gamma.grad, beta.grad): each batch norm runs once per step, its gradients are plain writes
+        dgamma, dbeta = sink
     _call("pu_bn_bwd_coeffs", p1.data_ptr(), p2.data_ptr(), blocks, C, mean.data_ptr(), invstd.data_ptr(),
           gamma.data_ptr(), R, int(bool(training)), dgamma.data_ptr(), dbeta.data_ptr(), ka.data_ptr(), kb.data_ptr(),
           kc.data_ptr(), st)
@@ -509,6 +544,7 @@ class _BNActFn(torch.autograd.Function):
             res = _bn_act_fwd_raw(y, scale, shift, slope)
             ctx.save_for_backward(y, scale, shift, gamma, mean, invstd)
         ctx.two, ctx.slope, ctx.training = two, slope, training
+        ctx.bn_params = (gamma, beta, gamma2, beta2)
         return res
 
     @staticmethod
@@ -516,7 +552,10 @@ class _BNActFn(torch.autograd.Function):
         none5 = (None,) * 5
         if not ctx.two:
             y, scale, shift, gamma, mean, invstd = ctx.saved_tensors
-            dy, dg, db = _bn_bwd_raw(dout, y, scale, shift, ctx.slope, gamma, mean, invstd, ctx.training)
+            sk = _bn_sink(ctx.bn_params[0], ctx.bn_params[1])
+            dy, dg, db = _bn_bwd_raw(dout, y, scale, shift, ctx.slope, gamma, mean, invstd, ctx.training, sink=sk)
+            if sk is not None:
+                dg = db = None
             return (dy, None, None, dg, db, None, None, None) + none5 + (None,)
         y, scale, shift, gamma, mean, invstd, y2, scale2, shift2, gamma2, mean2, invstd2, res = ctx.saved_tensors
         # through the activation first (sign of the output), then each BN branch without activation
@@ -525,8 +564,14 @@ class _BNActFn(torch.autograd.Function):
         dz = torch.empty(res.shape, dtype=torch.float32, device=res.device)
         _call("pu_act_bwd", dr.data_ptr(), ldd, rr.data_ptr(), ldr, float(ctx.slope), R, C, dz.data_ptr(), C,
                                    _stream(res))
-        dy, dg, db = _bn_bwd_raw(dz, y, scale, shift, 1.0, gamma, mean, invstd, ctx.training)
-        dy2, dg2, db2 = _bn_bwd_raw(dz, y2, scale2, shift2, 1.0, gamma2, mean2, invstd2, ctx.training)
+        sk = _bn_sink(ctx.bn_params[0], ctx.bn_params[1])
+        sk2 = _bn_sink(ctx.bn_params[2], ctx.bn_params[3])
+        dy, dg, db = _bn_bwd_raw(dz, y, scale, shift, 1.0, gamma, mean, invstd, ctx.training, sink=sk)
+        dy2, dg2, db2 = _bn_bwd_raw(dz, y2, scale2, shift2, 1.0, gamma2, mean2, invstd2, ctx.training, sink=sk2)
+        if sk is not None:
+            dg = db = None
+        if sk2 is not None:
+            dg2 = db2 = None
         return dy, None, None, dg, db, None, None, None, dy2, None, None, dg2, db2, None
 
 
@@ -572,6 +617,7 @@ class _LFAConcatFn(torch.autograd.Function):
             _bn_act_fwd_raw(y, scale, shift, LEAKY_SLOPE, out=buf[..., h:])
         ctx.save_for_backward(y, scale, shift, gamma, mean, invstd)
         ctx.idx, ctx.dims, ctx.training, ctx.need_fxyz = idx, (B, N, K, h, f_pc.shape[1]), training, need_fxyz
+        ctx.bn_params = (gamma, beta)
         if need_fxyz:
             return buf, f_xyz
         return buf
@@ -584,8 +630,11 @@ class _LFAConcatFn(torch.autograd.Function):
             d_buf = torch.zeros((B, N, K, 2 * h), dtype=torch.float32, device=y.device)
         inv = inverse_of(ctx.idx, n_src)
         d_fpc = segment_sum(d_buf[..., :h], inv, h).view(B, n_src, h)
+        sk = _bn_sink(*ctx.bn_params)
         dy, dg, db = _bn_bwd_raw(d_buf[..., h:], y, scale, shift, LEAKY_SLOPE, gamma, mean, invstd, ctx.training,
-                                 dz2=d_fxyz if ctx.need_fxyz else None)
+                                 dz2=d_fxyz if ctx.need_fxyz else None, sink=sk)
+        if sk is not None:
+            dg = db = None
         return d_fpc, None, dy, None, None, dg, db, None, None, None
 
 
@@ -618,6 +667,7 @@ class _AttPoolFn(torch.autograd.Function):
                   tag=(B * N, K, d))
         ctx.save_for_backward(x, w, wt if use_tc else w)
         ctx.dims = (B, N, K, d, ldx, use_tc)
+        ctx.w_param = w
         return out
 
     @staticmethod
@@ -636,8 +686,9 @@ class _AttPoolFn(torch.autograd.Function):
             _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
                   d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
         linear_raw(d_act, None, wt=w, out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
-        dw, _ = wgrad_raw(x, d_act)
-        return dx, dw
+        gw = _sink(ctx.w_param)
+        dw, _ = wgrad_raw(x, d_act, out=gw, accumulate=gw is not None)
+        return dx, (None if gw is not None else dw)
 
 
 def att_pool(feature_set: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

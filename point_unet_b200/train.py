@@ -72,7 +72,11 @@ class Trainer:
         self.flat_grad.zero_()
         logits = net.inference(inputs, True, dropout_mask)
         loss = net.get_loss(logits, labels)
-        loss.backward()
+        ops.GRAD_SINK = True   # kernels add parameter gradients straight into the flat buffer's views (ops._sink)
+        try:
+            loss.backward()
+        finally:
+            ops.GRAD_SINK = False
         if self.world_size > 1:
             self.bucket.all_reduce_mean()                          # gradients only, NCCL over NVLink
         self.opt.step()

@@ -394,3 +394,36 @@ def test_cuda_graph_step_matches_eager_training():
     # the public host-buffer entry uses the graph too
     val = graph.train_step(data["xyz"], data["features"], data["labels"])
     assert np.isfinite(val)
+
+
+@pytest.mark.gpu
+def test_gradient_sink_matches_autograd_accumulation():
+    """Kernels writing parameter gradients straight into the flat buffer's views (ops.GRAD_SINK) give bit-identical
+    gradients to autograd's own accumulation."""
+    from point_unet_b200.train import Trainer
+    from point_unet_b200 import synthetic
+
+    class cfg(ConfigBraTS):
+        num_points = 4096
+    data = synthetic.batch(synthetic.brats_cloud, 2, cfg.num_points, 5)
+    x = torch.from_numpy(data["xyz"]).cuda(); f = torch.from_numpy(data["features"]).cuda(); l = torch.from_numpy(data["labels"]).cuda()
+    tr = Trainer(cfg, num_features=7, seed=1, device="cuda")
+    pyr = build_pyramid(x, cfg)
+    inputs = dict(pyr, features=torch.cat([x, f], dim=-1))
+    mask = (torch.rand(2, cfg.num_points, 1, 32, device="cuda") < 0.5)
+    flats = []
+    stats0 = {k: v.clone() for k, v in tr.net.stats.items()}
+    for sink in (False, True):
+        for k, v in tr.net.stats.items():
+            v.copy_(stats0[k])
+        tr.flat_grad.zero_()
+        loss = tr.net.get_loss(tr.net.inference(inputs, True, mask), l)
+        ops.GRAD_SINK = sink
+        try:
+            loss.backward()
+        finally:
+            ops.GRAD_SINK = False
+        ops.clear_caches()
+        flats.append(tr.flat_grad.clone())
+    assert float(flats[0].abs().max()) > 0
+    assert torch.equal(flats[0], flats[1])
