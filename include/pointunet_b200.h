@@ -196,6 +196,19 @@ PU_API int pu_att_pooling_bwd(const float *feature_set, int ldx, const float *w,
                               long long P, int K, int d, float *d_act, int ldda, float *dx_direct, int lddx,
                               pu_stream_t stream);
 
+/* The same op for the 16-channel level (K = 16, d = 16: Encoder_layer_0, RandLANet.py:323-335 with d_out = 16), one
+ * kernel each way.  pu_att16_bwd is the COMPLETE gradient in one pass over x: dx [P*16, 16] (row stride lddx) and
+ * dw [16,16] (added to its content when `accumulate`), no d_act / g*s intermediates in HBM.  `w` is the [16,16] kernel in
+ * device memory; each call copies it (stream-ordered) into one of four constant-memory slots used round robin, so at most
+ * four calls may be in flight on DIFFERENT streams at once.  workspace: per-CTA partials of dw. */
+PU_API int pu_att16_supported(int K, int d, int ldx);
+PU_API size_t pu_att16_workspace_bytes(long long P);
+PU_API int pu_att16_fwd(const float *feature_set, int ldx, const float *w, long long P, float *f_agg, int ldo,
+                        pu_stream_t stream);
+PU_API int pu_att16_bwd(const float *feature_set, int ldx, const float *w, const float *g_agg, int ldg, long long P,
+                        float *dx, int lddx, float *dw, int accumulate, void *workspace, size_t workspace_bytes,
+                        pu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

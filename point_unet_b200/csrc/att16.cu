@@ -1,0 +1,415 @@
+// att16.cu -- Network.att_pooling (PointSegment/RandLANet.py:388-401, up to f_agg) for the 16-channel level of the
+// encoder (d = 16, K = 16: Encoder_layer_0 of PointSegment, 4 x 180 000 points per step), forward and FULLY FUSED
+// backward on CUDA cores.
+//
+// Why a kernel of its own.  At d = 16 the op is a 16x16x16 product per point: far too small for a tcgen05 tile (the
+// tensor-core kernels of tc_gemm.cu start at d = 32) and HBM-bound by a wide margin (1 KB of x per point).  The generic
+// tiled kernels of mlp.cu needed three passes for the backward -- d_act and g*s written to HBM, then dx += d_act w^T and
+// dw = x^T d_act read them back: 8 round trips over the [P,16,16] tensor.  Here one pass reads x once and writes dx once:
+//
+//   act = x w            (16 rows x 16 x 16)          s = softmax over the 16 neighbours, per channel
+//   f_agg = sum_k x s                                                                  (forward)
+//   d_act = s (g x - sum_k g x s)      dx = g s + d_act w^T      dw += x^T d_act       (backward)
+//
+// Mapping.  16 lanes own one point, a warp owns two.  A lane plays two roles: ROW owner (neighbour k = its x row in 16
+// registers) for the two products against w, and COLUMN owner (channel c) for the softmax over K, which is then
+// thread-local.  The FC kernel sits in CONSTANT memory: both products are FFMAs whose second operand is a uniform register
+// filled by LDCU.128 on the uniform datapath -- no shared-memory traffic for w at all (a broadcast LDS.128 per 4 FMAs
+// would make the kernel shared-memory bound).  Role changes go through padded shared-memory tiles (row stride 20 floats, the two points of a warp 16 banks
+// apart: every access below is conflict-free).  dw is accumulated as a 4x4 register block per lane over all the points
+// a lane sees and reduced once per CTA in a fixed order (deterministic).  x tiles arrive through a per-warp cp.async
+// ring (3 stages, 2 KB per stage), dx leaves through the same tile with full-line 128-bit stores.
+#include "common.cuh"
+
+namespace pu {
+namespace att16 {
+
+constexpr int D = 16;              // channels
+constexpr int KN = 16;             // neighbours
+constexpr int RS = 20;             // padded row stride of a tile (floats)
+constexpr int TILE = KN * RS + 16; // floats per point tile; 336 = 16 (mod 32): the two half-warps use disjoint banks
+constexpr int WARPS = 8;
+constexpr int STAGES = 3;
+constexpr int SLOTS = 4;           // constant-memory copies of w in flight (one per call, round robin)
+constexpr int FWD_TILES = STAGES * 2 + 2;      // x ring + T
+constexpr int BWD_TILES = STAGES * 2 + 4;      // x ring + T/E + D
+constexpr float LOG2E = 1.4426950408889634f;
+
+}  // namespace att16
+}  // namespace pu
+// w[slot][j][c] (tf.layers.dense kernel [in, out]); C linkage so that the inline PTX below can name it
+extern "C" { __constant__ float pu_att16_cw[4 * 16 * 16]; __constant__ float pu_att16_cw2[4 * 16 * 16]; }
+namespace pu {
+namespace att16 {
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void load_row16(const float *p, float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 a = *reinterpret_cast<const float4 *>(p + 4 * q);
+        v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+    }
+}
+__device__ __forceinline__ void store_row16(float *p, const float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4 *>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+// stage the x tiles of point pair `pair` (2 KB, coalesced 16-byte chunks); points past the end are zero-filled
+__device__ __forceinline__ void issue_pair(const float *__restrict__ x, int ldx, long long P, long long pair, float *stage,
+                                           int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int chunk = lane + 32 * i, h = chunk >> 6, r = chunk & 63, k = r >> 2, q = r & 3;
+        const long long p = pair * 2 + h;
+        float *dst = stage + h * TILE + k * RS + q * 4;
+        if (p < P) cp_async16(dst, x + ((size_t)p * KN + k) * ldx + q * 4);
+        else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// Four consecutive constants.  `volatile`: the load stays where it is written.  Left to itself the compiler treats the 256
+// weights as loop-invariant, hoists every load out of the point loop and spills them (1.8 KB of local-memory traffic per
+// iteration); kept in the loop they become uniform-datapath loads (LDCU.128) feeding FFMAs with a uniform-register operand.
+template <int OFF>  // OFF: float index into pu_att16_cw
+__device__ __forceinline__ float4 ldc4() {
+    float4 r;
+    asm volatile("ld.const.v4.f32 {%0,%1,%2,%3}, [pu_att16_cw+%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "n"(OFF * 4));
+    return r;
+}
+template <int OFF>  // second copy of the weights: every constant has ONE use per loop body (see above)
+__device__ __forceinline__ float4 ldc4b() {
+    float4 r;
+    asm volatile("ld.const.v4.f32 {%0,%1,%2,%3}, [pu_att16_cw2+%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "n"(OFF * 4));
+    return r;
+}
+
+// act[c] = sum_j xr[j] w[j][c]   (compile-time recursion over j so that every constant offset is an immediate)
+template <int SLOT, int J>
+__device__ __forceinline__ void rtw_step(const float (&xr)[16], float (&act)[16]) {
+    const float4 w0 = ldc4<SLOT * D * D + J * D + 0>(), w1 = ldc4<SLOT * D * D + J * D + 4>(),
+                 w2 = ldc4<SLOT * D * D + J * D + 8>(), w3 = ldc4<SLOT * D * D + J * D + 12>();
+    const float xj = xr[J];
+    act[0] = fmaf(xj, w0.x, act[0]); act[1] = fmaf(xj, w0.y, act[1]); act[2] = fmaf(xj, w0.z, act[2]); act[3] = fmaf(xj, w0.w, act[3]);
+    act[4] = fmaf(xj, w1.x, act[4]); act[5] = fmaf(xj, w1.y, act[5]); act[6] = fmaf(xj, w1.z, act[6]); act[7] = fmaf(xj, w1.w, act[7]);
+    act[8] = fmaf(xj, w2.x, act[8]); act[9] = fmaf(xj, w2.y, act[9]); act[10] = fmaf(xj, w2.z, act[10]); act[11] = fmaf(xj, w2.w, act[11]);
+    act[12] = fmaf(xj, w3.x, act[12]); act[13] = fmaf(xj, w3.y, act[13]); act[14] = fmaf(xj, w3.z, act[14]); act[15] = fmaf(xj, w3.w, act[15]);
+    if constexpr (J + 1 < D) rtw_step<SLOT, J + 1>(xr, act);
+}
+template <int SLOT>
+__device__ __forceinline__ void row_times_w(const float (&xr)[16], float (&act)[16]) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) act[c] = 0.f;
+    rtw_step<SLOT, 0>(xr, act);
+}
+// o[j] += sum_c dr[c] w[j][c]
+template <int SLOT, int J>
+__device__ __forceinline__ void rtwt_step(const float (&dr)[16], float (&o)[16]) {
+    const float4 w0 = ldc4b<SLOT * D * D + J * D + 0>(), w1 = ldc4b<SLOT * D * D + J * D + 4>(),
+                 w2 = ldc4b<SLOT * D * D + J * D + 8>(), w3 = ldc4b<SLOT * D * D + J * D + 12>();
+    float s0 = fmaf(dr[0], w0.x, o[J]), s1 = dr[4] * w1.x, s2 = dr[8] * w2.x, s3 = dr[12] * w3.x;
+    s0 = fmaf(dr[1], w0.y, s0); s1 = fmaf(dr[5], w1.y, s1); s2 = fmaf(dr[9], w2.y, s2); s3 = fmaf(dr[13], w3.y, s3);
+    s0 = fmaf(dr[2], w0.z, s0); s1 = fmaf(dr[6], w1.z, s1); s2 = fmaf(dr[10], w2.z, s2); s3 = fmaf(dr[14], w3.z, s3);
+    s0 = fmaf(dr[3], w0.w, s0); s1 = fmaf(dr[7], w1.w, s1); s2 = fmaf(dr[11], w2.w, s2); s3 = fmaf(dr[15], w3.w, s3);
+    o[J] = (s0 + s1) + (s2 + s3);
+    if constexpr (J + 1 < D) rtwt_step<SLOT, J + 1>(dr, o);
+}
+template <int SLOT>
+__device__ __forceinline__ void row_times_wt(const float (&dr)[16], float (&o)[16]) { rtwt_step<SLOT, 0>(dr, o); }
+
+// softmax over the 16 values of a column (in place: a[k] <- e_k, returns 1 / sum)
+__device__ __forceinline__ float softmax16(float (&a)[16]) {
+    float m = a[0];
+#pragma unroll
+    for (int k = 1; k < KN; ++k) m = fmaxf(m, a[k]);
+    const float mb = -m * LOG2E;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {
+        a[k] = ex2_approx(fmaf(a[k], LOG2E, mb));
+        sum += a[k];
+    }
+    return rcp_approx(sum);
+}
+
+template <int SLOT>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+    att16_fwd_kernel(const float *__restrict__ x, int ldx, long long P, float *__restrict__ out, int ldo) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, t = lane & 15;
+    float *wb = smem + (size_t)wib * FWD_TILES * TILE;
+    float *T = wb + (STAGES * 2 + half) * TILE;
+    const long long npairs = (P + 1) >> 1;
+    const long long nw = (long long)gridDim.x * WARPS;
+    long long pair = (long long)blockIdx.x * WARPS + wib;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (pair + s * nw < npairs) issue_pair(x, ldx, P, pair + s * nw, wb + s * 2 * TILE, lane);
+        cp_async_commit();
+    }
+#pragma unroll 1
+    for (int it = 0; pair < npairs; pair += nw, ++it) {
+        const int stage = it % STAGES;
+        {
+            const long long nxt = pair + (STAGES - 1) * nw;
+            if (nxt < npairs) issue_pair(x, ldx, P, nxt, wb + ((it + STAGES - 1) % STAGES) * 2 * TILE, lane);
+            cp_async_commit();
+        }
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        const float *X = wb + (stage * 2 + half) * TILE;
+        const long long p = pair * 2 + half;
+
+        float a[16];
+        {
+            float xr[16];
+            load_row16(X + t * RS, xr);       // row owner: neighbour k = t
+            row_times_w<SLOT>(xr, a);
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) T[c * RS + t] = a[c];   // transposed: T[c][k]
+        __syncwarp();
+        load_row16(T + t * RS, a);            // column owner: channel c = t, a[k] = act[k][c]
+        const float inv = softmax16(a);
+        float num = 0.f;
+#pragma unroll
+        for (int k = 0; k < KN; ++k) num = fmaf(X[k * RS + t], a[k], num);
+        if (p < P) out[(size_t)p * ldo + t] = num * inv;
+        __syncwarp();  // the tiles of this stage and T are free again
+    }
+}
+
+template <int SLOT>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+    att16_bwd_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ g_agg, int ldg, long long P,
+                     float *__restrict__ dx, int lddx, float *__restrict__ dw_part) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, t = lane & 15;
+    const int jq = t >> 2, cq = t & 3;
+    float *wb = smem + (size_t)wib * BWD_TILES * TILE;
+    float *T = wb + (STAGES * 2 + half) * TILE;      // act^T, later E = g*s (row layout)
+    float *Dt = wb + (STAGES * 2 + 2 + half) * TILE; // d_act (row layout)
+    const long long npairs = (P + 1) >> 1;
+    const long long nw = (long long)gridDim.x * WARPS;
+    long long pair = (long long)blockIdx.x * WARPS + wib;
+
+    float wacc[4][4];  // dw[4 jq + a][4 cq + b]
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) wacc[a][b] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (pair + s * nw < npairs) issue_pair(x, ldx, P, pair + s * nw, wb + s * 2 * TILE, lane);
+        cp_async_commit();
+    }
+    float g_next = (pair * 2 + half < P) ? g_agg[(size_t)(pair * 2 + half) * ldg + t] : 0.f;
+#pragma unroll 1
+    for (int it = 0; pair < npairs; pair += nw, ++it) {
+        const int stage = it % STAGES;
+        {
+            const long long nxt = pair + (STAGES - 1) * nw;
+            if (nxt < npairs) issue_pair(x, ldx, P, nxt, wb + ((it + STAGES - 1) % STAGES) * 2 * TILE, lane);
+            cp_async_commit();
+        }
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        float *Xw = wb + stage * 2 * TILE;   // both points of the pair (copy-out)
+        float *X = Xw + half * TILE;
+        const float g = g_next;
+        {
+            const long long pn = (pair + nw) * 2 + half;  // upstream gradient of the next pair: in flight during this one
+            g_next = (pn < P) ? g_agg[(size_t)pn * ldg + t] : 0.f;
+        }
+
+        float a[16];
+        {
+            float xr[16];
+            load_row16(X + t * RS, xr);
+            row_times_w<SLOT>(xr, a);
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) T[c * RS + t] = a[c];
+        __syncwarp();
+        load_row16(T + t * RS, a);            // column owner: a[k] = act[k][c = t]
+        const float inv = softmax16(a);
+        float dot = 0.f;
+        float ds[16];
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {
+            a[k] *= inv;                       // s_k
+            ds[k] = g * X[k * RS + t];         // d s_k = g x_k
+            dot = fmaf(a[k], ds[k], dot);
+        }
+        __syncwarp();                          // every lane has read its T row: T becomes E
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {
+            Dt[k * RS + t] = a[k] * (ds[k] - dot);   // d_act[k][c]
+            T[k * RS + t] = g * a[k];                // direct term g s
+        }
+        __syncwarp();
+        // dw[4jq.., 4cq..] += sum_k x[k][4jq..] (x) d_act[k][4cq..]
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {
+            const float4 xv = *reinterpret_cast<const float4 *>(X + k * RS + 4 * jq);
+            const float4 dv = *reinterpret_cast<const float4 *>(Dt + k * RS + 4 * cq);
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) wacc[a2][b] = fmaf(xa[a2], da[b], wacc[a2][b]);
+        }
+        // row owner again: dx[k = t][j] = g s + sum_c d_act[k][c] w[j][c]
+        float o[16];
+        {
+            float dr[16];
+            load_row16(Dt + t * RS, dr);
+            load_row16(T + t * RS, o);
+            row_times_wt<SLOT>(dr, o);
+        }
+        __syncwarp();                          // all reads of X (dw product) are done: the tile now carries dx
+        store_row16(X + t * RS, o);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int chunk = lane + 32 * i, h = chunk >> 6, r = chunk & 63, k = r >> 2, q = r & 3;
+            const long long pp = pair * 2 + h;
+            if (pp < P)
+                st_stream_f4(reinterpret_cast<float4 *>(dx + ((size_t)pp * KN + k) * lddx + q * 4),
+                             *reinterpret_cast<const float4 *>(Xw + h * TILE + k * RS + q * 4));
+        }
+        __syncwarp();
+    }
+
+    // per-CTA partial of dw: 16 (warp, half) groups summed in a fixed order
+    cp_async_wait<0>();
+    __syncthreads();
+    float *red = smem;  // [16 groups][256]
+    {
+        float *mine = red + (wib * 2 + half) * (D * D);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<float4 *>(mine + (4 * jq + a) * D + 4 * cq) =
+                make_float4(wacc[a][0], wacc[a][1], wacc[a][2], wacc[a][3]);
+    }
+    __syncthreads();
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int gI = 0; gI < WARPS * 2; ++gI) s += red[gI * (D * D) + threadIdx.x];
+        dw_part[(size_t)blockIdx.x * (D * D) + threadIdx.x] = s;
+    }
+}
+
+static int plan_grid(long long P) {
+    const long long npairs = (P + 1) / 2;
+    long long ctas = (npairs + WARPS - 1) / WARPS;
+    const long long cap = 2LL * kNumSMs;  // two resident CTAs per SM, each warp walks its pairs with a grid stride
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    return (int)ctas;
+}
+
+static unsigned g_slot = 0;
+
+template <int SLOT>
+static int launch_fwd(const float *x, int ldx, const float *w, long long P, float *out, int ldo, cudaStream_t st) {
+    constexpr size_t smem = (size_t)WARPS * FWD_TILES * TILE * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        PU_CUDA_TRY(cudaFuncSetAttribute(att16_fwd_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    PU_CUDA_TRY(cudaMemcpyToSymbolAsync(pu_att16_cw, w, D * D * sizeof(float), (size_t)SLOT * D * D * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, st));
+    att16_fwd_kernel<SLOT><<<plan_grid(P), WARPS * 32, smem, st>>>(x, ldx, P, out, ldo);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+template <int SLOT>
+static int launch_bwd(const float *x, int ldx, const float *w, const float *g, int ldg, long long P, float *dx, int lddx,
+                      float *dw, int accumulate, float *part, cudaStream_t st) {
+    constexpr size_t smem = (size_t)WARPS * BWD_TILES * TILE * sizeof(float);
+    static_assert(WARPS * BWD_TILES * TILE >= WARPS * 2 * D * D, "reduction scratch fits");
+    static bool attr = false;
+    if (!attr) {
+        PU_CUDA_TRY(cudaFuncSetAttribute(att16_bwd_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    PU_CUDA_TRY(cudaMemcpyToSymbolAsync(pu_att16_cw, w, D * D * sizeof(float), (size_t)SLOT * D * D * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, st));
+    PU_CUDA_TRY(cudaMemcpyToSymbolAsync(pu_att16_cw2, w, D * D * sizeof(float), (size_t)SLOT * D * D * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, st));
+    const int grid = plan_grid(P);
+    att16_bwd_kernel<SLOT><<<grid, WARPS * 32, smem, st>>>(x, ldx, g, ldg, P, dx, lddx, part);
+    PU_LAUNCH_CHECK();
+    launch_reduce_parts(part, grid, D * D, dw, accumulate, st);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+}  // namespace att16
+}  // namespace pu
+
+extern "C" {
+
+using namespace pu;
+using namespace pu::att16;
+
+int pu_att16_supported(int K, int d, int ldx) { return (K == KN && d == D && ldx >= D && (ldx & 3) == 0) ? 1 : 0; }
+
+size_t pu_att16_workspace_bytes(long long P) {
+    if (P < 0) return 0;
+    return (size_t)plan_grid(P) * D * D * sizeof(float) + 256;
+}
+
+int pu_att16_fwd(const float *feature_set, int ldx, const float *w, long long P, float *f_agg, int ldo,
+                 pu_stream_t stream) {
+    if (!feature_set || !w || !f_agg || P < 0 || ldx < D || (ldx & 3) || ldo < D || (((uintptr_t)feature_set) & 15))
+        return PU_ERR_INVALID_ARG;
+    if (P == 0) return PU_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (__atomic_fetch_add(&g_slot, 1u, __ATOMIC_RELAXED) % SLOTS) {
+        case 0: return launch_fwd<0>(feature_set, ldx, w, P, f_agg, ldo, st);
+        case 1: return launch_fwd<1>(feature_set, ldx, w, P, f_agg, ldo, st);
+        case 2: return launch_fwd<2>(feature_set, ldx, w, P, f_agg, ldo, st);
+        default: return launch_fwd<3>(feature_set, ldx, w, P, f_agg, ldo, st);
+    }
+}
+
+int pu_att16_bwd(const float *feature_set, int ldx, const float *w, const float *g_agg, int ldg, long long P, float *dx,
+                 int lddx, float *dw, int accumulate, void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    if (!feature_set || !w || !g_agg || !dx || !dw || P < 0 || ldx < D || (ldx & 3) || ldg < D || lddx < D || (lddx & 3) ||
+        ((((uintptr_t)feature_set) | ((uintptr_t)dx)) & 15))
+        return PU_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P == 0) {
+        if (!accumulate) PU_CUDA_TRY(cudaMemsetAsync(dw, 0, D * D * sizeof(float), st));
+        return PU_OK;
+    }
+    if (!workspace || workspace_bytes < pu_att16_workspace_bytes(P)) return PU_ERR_WORKSPACE;
+    float *part = (float *)workspace;
+    switch (__atomic_fetch_add(&g_slot, 1u, __ATOMIC_RELAXED) % SLOTS) {
+        case 0: return launch_bwd<0>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
+        case 1: return launch_bwd<1>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
+        case 2: return launch_bwd<2>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
+        default: return launch_bwd<3>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
+    }
+}
+
+}  // extern "C"

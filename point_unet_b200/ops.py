@@ -60,6 +60,9 @@ _lib._OP_SIGS.update({
     "pu_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p],
     "pu_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                            c_int, c_void_p],
+    "pu_att16_fwd": [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_int, c_void_p],
+    "pu_att16_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t,
+                     c_void_p],
 })
 
 import os as _os
@@ -67,6 +70,8 @@ import os as _os
 # Tensor-core policy for the wide contractions (K, N >= 32): 3 = 3xTF32 on tcgen05 (fp32-class accuracy, default),
 # 1 = plain TF32 (stated reduced-precision tolerance), 0 = CUDA-core fp32 tiles only.
 TC_MODE = int(_os.environ.get("PU_TC_MODE", "3"))
+# d = 16 attentive pooling through the dedicated one-pass kernels (att16.cu); 0 = the generic three-pass CUDA-core path
+ATT16 = int(_os.environ.get("PU_ATT16", "1")) != 0
 _tc_error_flag = {}
 
 LEAKY_SLOPE = 0.2  # helper_tf_util.py:169 (alpha is always 0.2, whatever activation_fn was passed)
@@ -94,6 +99,9 @@ def _L():
         L.pu_linear_row_tiles.argtypes = [c_ll, c_int, c_int]
         L.pu_linear_rows_per_tile.argtypes = [c_ll, c_int, c_int]
         L.pu_bn_bwd_reduce_blocks.argtypes = [c_ll, c_int]
+        L.pu_att16_supported.argtypes = [c_int, c_int, c_int]
+        L.pu_att16_workspace_bytes.restype = c_size_t
+        L.pu_att16_workspace_bytes.argtypes = [c_ll]
         L._pu_extra_declared = True
     return L
 
@@ -648,7 +656,9 @@ def lfa_concat(f_pc, idx, y, mean, var, gamma, beta, training=True, moving=None,
 
 # ---------------------------------------------------------------------------------------------
 class _AttPoolFn(torch.autograd.Function):
-    """f_agg[p,c] = sum_k x[p,k,c] softmax_k(x[p,k,:] w)[c]   (RandLANet.py:394-398, one fused kernel)"""
+    """f_agg[p,c] = sum_k x[p,k,c] softmax_k(x[p,k,:] w)[c]   (RandLANet.py:394-398, one fused kernel).
+    Three kernels by channel width: d = 16 -> att16 (CUDA cores, backward fused into ONE pass), d >= 32 -> tcgen05,
+    anything else -> the generic CUDA-core tile."""
 
     @staticmethod
     def forward(ctx, feature_set, w):
@@ -656,27 +666,39 @@ class _AttPoolFn(torch.autograd.Function):
         B, N, K, d = feature_set.shape
         x, R, _, ldx = rows(feature_set)
         out = torch.empty((B, N, 1, d), dtype=torch.float32, device=feature_set.device)
-        use_tc = TC_MODE in (1, 3) and B * N * K >= 128 and x.data_ptr() % 16 == 0 and _L().pu_tc_att_supported(K, d, ldx)
+        L = _L()
+        use16 = ATT16 and x.data_ptr() % 16 == 0 and bool(L.pu_att16_supported(K, d, ldx))
+        use_tc = (not use16) and TC_MODE in (1, 3) and B * N * K >= 128 and x.data_ptr() % 16 == 0 and \
+            L.pu_tc_att_supported(K, d, ldx)
         wt = w.t().contiguous() if use_tc else None
-        if use_tc:
-            tws = workspace(_L().pu_tc_workspace_bytes(d, d), x.device, slot=4)
+        if use16:
+            _call("pu_att16_fwd", x.data_ptr(), ldx, w.data_ptr(), B * N, out.data_ptr(), d, _stream(x), tag=(B * N, K, d))
+        elif use_tc:
+            tws = workspace(L.pu_tc_workspace_bytes(d, d), x.device, slot=4)
             _call("pu_tc_att_pooling_fwd", x.data_ptr(), ldx, wt.data_ptr(), B * N, K, d, out.data_ptr(), d, TC_MODE,
                   tc_error_flag(x.device).data_ptr(), tws.data_ptr(), tws.numel(), _stream(x), tag=(B * N, K, d))
         else:
             _call("pu_att_pooling_fwd", x.data_ptr(), ldx, w.data_ptr(), B * N, K, d, out.data_ptr(), d, _stream(x),
                   tag=(B * N, K, d))
         ctx.save_for_backward(x, w, wt if use_tc else w)
-        ctx.dims = (B, N, K, d, ldx, use_tc)
+        ctx.dims = (B, N, K, d, ldx, use_tc, use16)
         ctx.w_param = w
         return out
 
     @staticmethod
     def backward(ctx, g_agg):
         x, w, wt = ctx.saved_tensors
-        B, N, K, d, ldx, use_tc = ctx.dims
+        B, N, K, d, ldx, use_tc, use16 = ctx.dims
         g, _, _, ldg = rows(g_agg)
-        d_act = torch.empty((B * N * K, d), dtype=torch.float32, device=x.device)
         dx = torch.empty((B, N, K, d), dtype=torch.float32, device=x.device)
+        gw = _sink(ctx.w_param)
+        if use16:
+            dw = gw if gw is not None else torch.empty((d, d), dtype=torch.float32, device=x.device)
+            ws = workspace(_L().pu_att16_workspace_bytes(B * N), x.device, slot=2)
+            _call("pu_att16_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, dx.data_ptr(), d, dw.data_ptr(),
+                  int(gw is not None), ws.data_ptr(), ws.numel(), _stream(x), tag=(B * N, K, d))
+            return dx, (None if gw is not None else dw)
+        d_act = torch.empty((B * N * K, d), dtype=torch.float32, device=x.device)
         if use_tc:
             tws = workspace(_L().pu_tc_workspace_bytes(d, d), x.device, slot=4)
             _call("pu_tc_att_pooling_bwd", x.data_ptr(), ldx, wt.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
@@ -686,7 +708,6 @@ class _AttPoolFn(torch.autograd.Function):
             _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
                   d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
         linear_raw(d_act, None, wt=w, out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
-        gw = _sink(ctx.w_param)
         dw, _ = wgrad_raw(x, d_act, out=gw, accumulate=gw is not None)
         return dx, (None if gw is not None else dw)
 

@@ -228,6 +228,39 @@ def test_att_pool_fwd_bwd(d):
     assert torch.equal(ops.att_pool(wide[..., :d], wg.detach()), agg.detach())
 
 
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 7), (3, 3001), (2, 40000)])
+def test_att16_one_pass_kernels(B, N):
+    """d = 16 level (att16.cu): odd point counts, grid-stride loops (more point pairs than resident warps), agreement
+    with the fp64 restatement and with the generic three-pass path, bit-determinism of the fused dw reduction."""
+    K, d = 16, 16
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    x = torch.randn(B, N, K, d, generator=g)
+    w = torch.randn(d, d, generator=g) * 0.4
+    dy = torch.randn(B, N, 1, d, generator=g)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    act = xr.reshape(-1, K, d) @ wr
+    agg_r = (xr.reshape(-1, K, d) * torch.softmax(act, dim=1)).sum(1).reshape(B, N, 1, d)  # RandLANet.py:394-398
+    (agg_r * dy.double()).sum().backward()
+
+    def run(att16):
+        old = ops.ATT16
+        ops.ATT16 = att16
+        try:
+            xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+            agg = ops.att_pool(xg, wg)
+            (agg * dy.cuda()).sum().backward()
+            return agg.detach(), xg.grad, wg.grad
+        finally:
+            ops.ATT16 = old
+
+    agg, dx, dw = run(True)
+    assert rel_err(agg, agg_r) < 1e-5 and rel_err(dx, xr.grad) < 1e-4 and rel_err(dw, wr.grad) < 1e-4
+    agg2, dx2, dw2 = run(True)
+    assert torch.equal(agg, agg2) and torch.equal(dx, dx2) and torch.equal(dw, dw2)
+    agg3, dx3, dw3 = run(False)
+    assert rel_err(agg, agg3) < 1e-5 and rel_err(dx, dx3) < 1e-4 and rel_err(dw, dw3) < 1e-4
+
+
 def _small_cfg(base, n_points):
     class Cfg(base):
         num_points = n_points
