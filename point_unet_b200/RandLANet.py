@@ -103,23 +103,59 @@ def init_params(cfg, num_features: int, seed: int = 0) -> dict:
     return p
 
 
-def build_pyramid(xyz: torch.Tensor, cfg) -> dict:
+def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = None, inverse: bool = False) -> dict:
     """``tf_map`` (runPancreas.py:124-145 / runBraTS.py:140-161) on the device: per level
     ``neigh_idx = knn(xyz, xyz, k_n)``, ``sub = xyz[:, :N//ratio]``, ``sub_idx = neigh_idx[:, :N//ratio]``,
-    ``interp_idx = knn(sub, xyz, 1)``.  ``xyz`` is a CUDA ``[B,N,3]`` fp32 tensor; everything stays on the GPU."""
+    ``interp_idx = knn(sub, xyz, 1)``.  ``xyz`` is a CUDA ``[B,N,3]`` fp32 tensor; everything stays on the GPU.
+
+    The sub-clouds are prefixes of ``xyz``, so the ten searches do not depend on each other or on the network.  With a
+    ``side`` stream only the level-0 neighbour search runs on the current stream; the other nine (and, with ``inverse``,
+    the fifteen inverse neighbour lists of the scatter-free backward) are queued on ``side`` and overlap the level-0
+    forward, which is HBM-bound while the searches are issue-bound.  The returned dict then carries two callables:
+    ``pyramid_ready()`` makes the current stream wait for the remaining indices (Network.inference calls it before the
+    first ``random_sample``) and ``inverse_ready()`` for the inverse lists (called before the backward).  All result
+    tensors are allocated on the current stream; ``side`` only runs kernels."""
     out = dict(xyz=[], neigh_idx=[], sub_idx=[], interp_idx=[])
     xyz = xyz.contiguous().float()
+    B, dev = xyz.shape[0], xyz.device
     for i in range(cfg.num_layers):
-        neigh = knn_search_cuda(xyz, xyz, cfg.k_n)
-        n_sub = xyz.shape[1] // cfg.sub_sampling_ratio[i]
-        sub_points = xyz[:, :n_sub, :].contiguous()
-        pool_i = neigh[:, :n_sub, :].contiguous()
-        up_i = knn_search_cuda(sub_points, xyz, 1)
+        n = xyz.shape[1]
+        n_sub = n // cfg.sub_sampling_ratio[i]
         out["xyz"].append(xyz)
-        out["neigh_idx"].append(neigh)
-        out["sub_idx"].append(pool_i)
-        out["interp_idx"].append(up_i)
-        xyz = sub_points
+        out["neigh_idx"].append(torch.empty((B, n, cfg.k_n), dtype=torch.int32, device=dev))
+        out["sub_idx"].append(torch.empty((B, n_sub, cfg.k_n), dtype=torch.int32, device=dev))
+        out["interp_idx"].append(torch.empty((B, n, 1), dtype=torch.int32, device=dev))
+        xyz = xyz[:, :n_sub, :].contiguous()
+    subs = out["xyz"][1:] + [xyz]
+
+    def level(i):
+        pts = out["xyz"][i]
+        if i > 0 or side is None:
+            knn_search_cuda(pts, pts, cfg.k_n, out=out["neigh_idx"][i])
+        out["sub_idx"][i].copy_(out["neigh_idx"][i][:, :subs[i].shape[1], :])
+        knn_search_cuda(subs[i], pts, 1, out=out["interp_idx"][i])
+
+    if side is None:
+        for i in range(cfg.num_layers):
+            level(i)
+        return out
+    main = torch.cuda.current_stream(dev)
+    knn_search_cuda(out["xyz"][0], out["xyz"][0], cfg.k_n, out=out["neigh_idx"][0])
+    side.wait_stream(main)
+    ev = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        for i in range(cfg.num_layers):
+            level(i)
+        ev.record(side)
+        if inverse:  # the index tensors whose gathers are differentiated: (idx, rows of the gathered tensor per cloud)
+            for i in range(cfg.num_layers):
+                n, n_sub = out["xyz"][i].shape[1], subs[i].shape[1]
+                ops.inverse_of(out["neigh_idx"][i], n)
+                ops.inverse_of(out["sub_idx"][i], n)
+                ops.inverse_of(out["interp_idx"][i], n_sub)
+    out["_sub_clouds"] = subs  # the last sub-cloud is read by a search still queued on `side`: it must outlive this call
+    out["pyramid_ready"] = lambda: torch.cuda.current_stream(dev).wait_event(ev)
+    out["inverse_ready"] = lambda: torch.cuda.current_stream(dev).wait_stream(side)
     return out
 
 
@@ -268,6 +304,8 @@ class Network(torch.nn.Module):
         for i in range(cfg.num_layers):
             f_encoder_i = self.dilated_res_block(feature, inputs["xyz"][i], inputs["neigh_idx"][i], cfg.d_out[i],
                                                  "Encoder_layer_" + str(i), is_training)
+            if i == 0 and "pyramid_ready" in inputs:
+                inputs["pyramid_ready"]()  # the rest of the index pyramid was built on a side stream (build_pyramid)
             f_sampled_i = self.random_sample(f_encoder_i, inputs["sub_idx"][i])
             feature = f_sampled_i
             if i == 0:

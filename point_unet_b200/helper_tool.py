@@ -71,8 +71,11 @@ def _stream_ptr(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def knn_search_cuda(support: torch.Tensor, query: torch.Tensor, k: int, return_dist: bool = False):
-    """Device-resident entry: ``support [B,N1,3]``, ``query [B,N2,3]`` fp32 CUDA -> int32 ``[B,N2,k]`` CUDA."""
+def knn_search_cuda(support: torch.Tensor, query: torch.Tensor, k: int, return_dist: bool = False,
+                    out: torch.Tensor | None = None):
+    """Device-resident entry: ``support [B,N1,3]``, ``query [B,N2,3]`` fp32 CUDA -> int32 ``[B,N2,k]`` CUDA.
+    ``out`` (optional, contiguous int32 ``[B,N2,k]``) receives the result -- lets a caller allocate on one stream and
+    search on another."""
     if not (support.is_cuda and query.is_cuda):
         raise _lib.PointUnetError("knn_search_cuda needs CUDA tensors (there is no CPU fallback)")
     if support.dim() != 3 or query.dim() != 3 or support.shape[2] != 3 or query.shape[2] != 3 \
@@ -84,7 +87,10 @@ def knn_search_cuda(support: torch.Tensor, query: torch.Tensor, k: int, return_d
     B, N1, _ = support.shape
     N2 = query.shape[1]
     L = _lib.lib()
-    out = torch.empty((B, N2, k), dtype=torch.int32, device=support.device)
+    if out is None:
+        out = torch.empty((B, N2, k), dtype=torch.int32, device=support.device)
+    elif out.dtype != torch.int32 or tuple(out.shape) != (B, N2, k) or not out.is_contiguous() or out.device != support.device:
+        raise ValueError("knn_search_cuda: out must be a contiguous int32 [B,N2,k] tensor on the inputs' device")
     nbytes = L.pu_knn_workspace_bytes(B, N1, N2, k)
     ws = workspace(nbytes, support.device)
     with torch.cuda.device(support.device):

@@ -19,6 +19,10 @@ from . import ops
 from .parallel import FlatGradBucket
 from .RandLANet import Network, build_pyramid
 
+import os as _os
+
+OVERLAP = int(_os.environ.get("PU_OVERLAP", "1")) != 0
+
 
 class Trainer:
     def __init__(self, config, num_features=None, seed=0, device=None, lr=None, world_size=1):
@@ -38,6 +42,7 @@ class Trainer:
         self._pinned = {}
         self._dev = {}
         self._graph = None
+        self._side = None
 
     # -- host staging ----------------------------------------------------------------------------
     def _stage(self, name, arr):
@@ -63,15 +68,24 @@ class Trainer:
             out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
         return out
 
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     # -- steps -----------------------------------------------------------------------------------
     def train_step_device(self, xyz, features, labels, dropout_mask=None):
         """One optimisation step on device-resident inputs: xyz [B,N,3] f32, features [B,N,F-3] f32, labels [B,N]."""
         net = self.net
-        pyr = build_pyramid(xyz, self.cfg)                         # tf_map on the GPU
+        # tf_map on the GPU; levels 1-4 and the inverse lists of the backward are built on a side stream under the
+        # level-0 forward (PU_OVERLAP=0: everything on one stream)
+        pyr = build_pyramid(xyz, self.cfg, side=self._side_stream() if OVERLAP else None, inverse=True)
         inputs = dict(pyr, features=torch.cat([xyz, features], dim=-1))  # runPancreas.py:125
         self.flat_grad.zero_()
         logits = net.inference(inputs, True, dropout_mask)
         loss = net.get_loss(logits, labels)
+        if "inverse_ready" in pyr:
+            pyr["inverse_ready"]()
         ops.GRAD_SINK = True   # kernels add parameter gradients straight into the flat buffer's views (ops._sink)
         try:
             loss.backward()
@@ -132,7 +146,7 @@ class Trainer:
         (testPancreas.py:133-134 ``prob_logits``)."""
         x = self._stage("xyz", xyz)
         f = self._stage("features", features)
-        pyr = build_pyramid(x, self.cfg)
+        pyr = build_pyramid(x, self.cfg, side=self._side_stream() if OVERLAP else None)
         logits = self.net.inference(dict(pyr, features=torch.cat([x, f], dim=-1)), False)
         ops.clear_caches()
         return torch.softmax(logits, dim=-1)
