@@ -387,7 +387,7 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
     return out, mean, var
 
 
-def wgrad_raw(x, dy, want_db=False, tc_mode=None, out=None, out_db=None, accumulate=False):
+def wgrad_raw(x, dy, want_db=False, tc_mode=None, out=None, out_db=None, accumulate=False, ws_slot=2):
     """dw = x^T dy (and db = column sums of dy): tensor cores for wide shapes, CUDA cores otherwise (no autograd).
     ``out`` / ``out_db`` (contiguous fp32) receive the result, added to their content when ``accumulate``."""
     xr, M, K, ldx = rows(x)
@@ -403,13 +403,13 @@ def wgrad_raw(x, dy, want_db=False, tc_mode=None, out=None, out_db=None, accumul
     mode = TC_MODE if tc_mode is None else tc_mode
     if mode in (1, 3) and xr.data_ptr() % 16 == 0 and gr.data_ptr() % 16 == 0 and \
             L.pu_tc_wgrad_supported(M, K, N, ldx, ldg, int(want_db)):
-        ws = workspace(L.pu_tc_wgrad_workspace_bytes(M, K, N), x.device, slot=2)
+        ws = workspace(L.pu_tc_wgrad_workspace_bytes(M, K, N), x.device, slot=ws_slot)
         _call("pu_tc_wgrad", xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
               db.data_ptr() if want_db else None, acc, mode, ws.data_ptr(), ws.numel(), tc_error_flag(x.device).data_ptr(),
               _stream(x), tag=(M, K, N))
         return dw, db
     nbytes = L.pu_wgrad_workspace_bytes(M, K, N)
-    ws = workspace(nbytes, x.device, slot=2)
+    ws = workspace(nbytes, x.device, slot=ws_slot)
     _call("pu_wgrad", xr.data_ptr(), ldx, gr.data_ptr(), ldg, M, K, N, dw.data_ptr(),
           db.data_ptr() if want_db else None, acc, ws.data_ptr(), ws.numel(), _stream(x), tag=(M, K, N))
     return dw, db
@@ -429,6 +429,32 @@ def _sink(param):
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape:
         return None
     return g
+
+
+# Weight gradients off the critical path: nothing in the backward chain consumes dw / db, only the optimiser does.  With a
+# side stream set (Trainer does it for the duration of loss.backward()) and the gradient sink on, a weight-gradient kernel
+# is queued on that stream right after the kernel that produced dy and runs next to the dgrad chain on the main stream --
+# the deep levels launch grids of 20-90 CTAs on 148 SMs, so there is room.  x and dy are kept alive until wgrad_join().
+WGRAD_STREAM = None
+_wgrad_keep: list = []
+
+
+def _wgrad(x, dy, want_db=False, out=None, out_db=None, accumulate=False):
+    side = WGRAD_STREAM
+    if side is None or out is None or (want_db and out_db is None):
+        return wgrad_raw(x, dy, want_db=want_db, out=out, out_db=out_db, accumulate=accumulate)
+    side.wait_stream(torch.cuda.current_stream(x.device))
+    with torch.cuda.stream(side):
+        res = wgrad_raw(x, dy, want_db=want_db, out=out, out_db=out_db, accumulate=accumulate, ws_slot=5)
+    _wgrad_keep.append((x, dy))
+    return res
+
+
+def wgrad_join(device=None):
+    """Make the current stream wait for the weight gradients queued on the side stream and release their operands."""
+    if WGRAD_STREAM is not None:
+        torch.cuda.current_stream(device).wait_stream(WGRAD_STREAM)
+    _wgrad_keep.clear()
 
 
 class _LinearFn(torch.autograd.Function):
@@ -452,23 +478,23 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, *_):
         x, w = ctx.saved_tensors
-        dx = None
-        if ctx.x_needs:
-            dx = linear_raw(dy, None, wt=w)  # dx = dy w^T: the K-major form of w^T is w itself
-            dx = dx.view(x.shape)
         gw, gb = _sink(ctx.w_param), _sink(ctx.b_param)
         if ctx.has_bias and ctx.zero_bias_grad:
             # a bias that feeds a training-mode batch norm has an identically zero gradient (the BN backward makes every
             # column of dy sum to zero); return the exact value instead of accumulating rounding noise
-            dw, _ = wgrad_raw(x, dy, want_db=False, out=gw, accumulate=gw is not None)
+            dw, _ = _wgrad(x, dy, want_db=False, out=gw, accumulate=gw is not None)
             db = None if gb is not None else torch.zeros(dy.shape[-1], dtype=torch.float32, device=dy.device)
         else:
             both = gw is not None and (gb is not None or not ctx.has_bias)
-            dw, db = wgrad_raw(x, dy, want_db=ctx.has_bias, out=gw if both else None, out_db=gb if both else None,
-                               accumulate=both)
+            dw, db = _wgrad(x, dy, want_db=ctx.has_bias, out=gw if both else None, out_db=gb if both else None,
+                            accumulate=both)
             if both:
                 db = None
             gw = gw if both else None
+        dx = None
+        if ctx.x_needs:
+            dx = linear_raw(dy, None, wt=w)  # dx = dy w^T: the K-major form of w^T is w itself
+            dx = dx.view(x.shape)
         return dx, (None if gw is not None else dw), db, None, None
 
 
@@ -707,8 +733,8 @@ class _AttPoolFn(torch.autograd.Function):
         else:
             _call("pu_att_pooling_bwd", x.data_ptr(), ldx, w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
                   d_act.data_ptr(), d, dx.data_ptr(), d, _stream(x), tag=(B * N, K, d))
+        dw, _ = _wgrad(x, d_act, out=gw, accumulate=gw is not None)
         linear_raw(d_act, None, wt=w, out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
-        dw, _ = wgrad_raw(x, d_act, out=gw, accumulate=gw is not None)
         return dx, (None if gw is not None else dw)
 
 

@@ -43,6 +43,7 @@ class Trainer:
         self._dev = {}
         self._graph = None
         self._side = None
+        self._side2 = None
 
     # -- host staging ----------------------------------------------------------------------------
     def _stage(self, name, arr):
@@ -68,6 +69,11 @@ class Trainer:
             out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
         return out
 
+    def _wgrad_stream(self):
+        if self._side2 is None:
+            self._side2 = torch.cuda.Stream(device=self.device)
+        return self._side2
+
     def _side_stream(self):
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -87,10 +93,13 @@ class Trainer:
         if "inverse_ready" in pyr:
             pyr["inverse_ready"]()
         ops.GRAD_SINK = True   # kernels add parameter gradients straight into the flat buffer's views (ops._sink)
+        ops.WGRAD_STREAM = self._wgrad_stream() if OVERLAP else None  # weight gradients next to the dgrad chain
         try:
             loss.backward()
+            ops.wgrad_join(self.device)
         finally:
             ops.GRAD_SINK = False
+            ops.WGRAD_STREAM = None
         if self.world_size > 1:
             self.bucket.all_reduce_mean()                          # gradients only, NCCL over NVLink
         self.opt.step()
