@@ -103,7 +103,8 @@ def init_params(cfg, num_features: int, seed: int = 0) -> dict:
     return p
 
 
-def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = None, inverse: bool = False) -> dict:
+def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = None, inverse: bool = False,
+                  store: "dict | None" = None) -> dict:
     """``tf_map`` (runPancreas.py:124-145 / runBraTS.py:140-161) on the device: per level
     ``neigh_idx = knn(xyz, xyz, k_n)``, ``sub = xyz[:, :N//ratio]``, ``sub_idx = neigh_idx[:, :N//ratio]``,
     ``interp_idx = knn(sub, xyz, 1)``.  ``xyz`` is a CUDA ``[B,N,3]`` fp32 tensor; everything stays on the GPU.
@@ -114,7 +115,27 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
     forward, which is HBM-bound while the searches are issue-bound.  The returned dict then carries two callables:
     ``pyramid_ready()`` makes the current stream wait for the remaining indices (Network.inference calls it before the
     first ``random_sample``) and ``inverse_ready()`` for the inverse lists (called before the backward).  All result
-    tensors are allocated on the current stream; ``side`` only runs kernels."""
+    tensors are allocated on the current stream; ``side`` only runs kernels.
+
+    ``store`` (optional): preallocated result tensors -- ``xyz`` (num_layers + 1 clouds; ``xyz[0]`` receives a copy of the
+    input), ``neigh_idx``, ``sub_idx``, ``interp_idx`` (num_layers each) and, with ``inverse``, ``inv`` = per level three
+    ``(offsets, perm)`` pairs for (neigh_idx, sub_idx, interp_idx).  Everything then runs on the current stream and
+    nothing is allocated (the pipelined step of train.py fills such a store one step ahead)."""
+    if store is not None:
+        assert side is None
+        clouds = store["xyz"]
+        clouds[0].copy_(xyz)
+        for i in range(cfg.num_layers):
+            clouds[i + 1].copy_(clouds[i][:, :clouds[i + 1].shape[1], :])
+            knn_search_cuda(clouds[i], clouds[i], cfg.k_n, out=store["neigh_idx"][i])
+            store["sub_idx"][i].copy_(store["neigh_idx"][i][:, :clouds[i + 1].shape[1], :])
+            knn_search_cuda(clouds[i + 1], clouds[i], 1, out=store["interp_idx"][i])
+            if inverse:
+                n, n_sub = clouds[i].shape[1], clouds[i + 1].shape[1]
+                for idx, n_src, o in zip((store["neigh_idx"][i], store["sub_idx"][i], store["interp_idx"][i]),
+                                         (n, n, n_sub), store["inv"][i]):
+                    ops.InverseIndex(idx, n_src, out=o)
+        return dict(xyz=clouds[:-1], neigh_idx=store["neigh_idx"], sub_idx=store["sub_idx"], interp_idx=store["interp_idx"])
     out = dict(xyz=[], neigh_idx=[], sub_idx=[], interp_idx=[])
     xyz = xyz.contiguous().float()
     B, dev = xyz.shape[0], xyz.device

@@ -500,31 +500,34 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A,
 
 // mean/var (biased) per channel from per-tile (sum, M2) partials: Chan et al. parallel merge, in double.
 //   var = [ sum_t M2_t + sum_t n_t mean_t^2 - n mean^2 ] / n      (the subtraction is done in double)
-// One CTA per channel, 256 threads stride over the tiles, fixed-order block reduction.
-__global__ void __launch_bounds__(256) stats_finalize_kernel(const float *__restrict__ psum, const float *__restrict__ pm2,
-                                                             int tiles, int C, long long count, int rows_per_tile,
-                                                             float *__restrict__ mean, float *__restrict__ var) {
-    __shared__ double red[3][256];
+// One CTA per channel, 1024 threads stride over the tiles (the tensor-core kernels emit one partial per 128 rows: 22 500 of
+// them for the 2.9 M-row tensors, so the per-thread chains must be short), fixed-order block reduction.
+constexpr int SF_THREADS = 1024;
+__global__ void __launch_bounds__(SF_THREADS) stats_finalize_kernel(const float *__restrict__ psum, const float *__restrict__ pm2,
+                                                                    int tiles, int C, long long count, int rows_per_tile,
+                                                                    float *__restrict__ mean, float *__restrict__ var) {
+    constexpr int NT = SF_THREADS;
+    __shared__ double red[3][NT];
     const int c = blockIdx.x;
     double s = 0.0, q = 0.0, r = 0.0;
     int t = threadIdx.x;
-    for (; t + 768 < tiles; t += 1024) {  // four tiles per trip: eight independent loads in flight per thread
+    for (; t + 3 * NT < tiles; t += 4 * NT) {  // four tiles per trip: eight independent loads in flight per thread
         float st[4], mt[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            st[j] = psum[(size_t)(t + 256 * j) * C + c];
-            mt[j] = pm2[(size_t)(t + 256 * j) * C + c];
+            st[j] = psum[(size_t)(t + NT * j) * C + c];
+            mt[j] = pm2[(size_t)(t + NT * j) * C + c];
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const long long r0 = (long long)(t + 256 * j) * rows_per_tile;
+            const long long r0 = (long long)(t + NT * j) * rows_per_tile;
             const double nt = (double)min((long long)rows_per_tile, count - r0);
             s += (double)st[j];
             q += (double)mt[j];
             r += (double)st[j] * (double)st[j] / nt;
         }
     }
-    for (; t < tiles; t += 256) {
+    for (; t < tiles; t += NT) {
         const long long r0 = (long long)t * rows_per_tile;
         const double nt = (double)min((long long)rows_per_tile, count - r0);
         const double st = (double)psum[(size_t)t * C + c];
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float *__rest
     }
     red[0][threadIdx.x] = s; red[1][threadIdx.x] = q; red[2][threadIdx.x] = r;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = NT / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             red[0][threadIdx.x] += red[0][threadIdx.x + o];
             red[1][threadIdx.x] += red[1][threadIdx.x + o];
@@ -803,38 +806,53 @@ __global__ void bn_prepare_kernel(const float *__restrict__ mean, const float *_
         moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * var[c] * unbias;
     }
 }
-//   backward: reduce the [blocks, C] partials (double), emit dgamma, dbeta and the apply coefficients ka, kb, kc
-__global__ void bn_bwd_coeffs_kernel(const float *__restrict__ part_dz, const float *__restrict__ part_dzy, int blocks,
-                                     int C, const float *__restrict__ mean, const float *__restrict__ invstd,
-                                     const float *__restrict__ gamma, double inv_rows, int training,
-                                     float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ ka,
-                                     float *__restrict__ kb, float *__restrict__ kc) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= C) return;
+//   backward: reduce the [blocks, C] partials (double), emit dgamma, dbeta and the apply coefficients ka, kb, kc.
+//   One CTA per channel: with <= 1184 partials every thread has at most five loads, all in flight at once (this kernel
+//   sits between the two passes of every batch-norm backward, 44 times per step -- its latency is on the critical path).
+__global__ void __launch_bounds__(256) bn_bwd_coeffs_kernel(const float *__restrict__ part_dz, const float *__restrict__ part_dzy,
+                                                            int blocks, int C, const float *__restrict__ mean,
+                                                            const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                                            double inv_rows, int training, float *__restrict__ dgamma,
+                                                            float *__restrict__ dbeta, float *__restrict__ ka,
+                                                            float *__restrict__ kb, float *__restrict__ kc) {
+    __shared__ double red[2][8];
+    const int ch = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double s = 0.0, q = 0.0;
-    int t = lane;
-    for (; t + 96 < blocks; t += 128) {  // eight independent loads in flight per lane
+    int t = threadIdx.x;
+    for (; t + 768 < blocks; t += 1024) {  // eight independent loads in flight per thread
         float a[4], b[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { a[j] = part_dz[(size_t)(t + 32 * j) * C + warp]; b[j] = part_dzy[(size_t)(t + 32 * j) * C + warp]; }
+        for (int j = 0; j < 4; ++j) { a[j] = part_dz[(size_t)(t + 256 * j) * C + ch]; b[j] = part_dzy[(size_t)(t + 256 * j) * C + ch]; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) { s += (double)a[j]; q += (double)b[j]; }
     }
-    for (; t < blocks; t += 32) { s += (double)part_dz[(size_t)t * C + warp]; q += (double)part_dzy[(size_t)t * C + warp]; }
+    {
+        float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (t + 256 * j < blocks) { a[j] = part_dz[(size_t)(t + 256 * j) * C + ch]; b[j] = part_dzy[(size_t)(t + 256 * j) * C + ch]; }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { s += (double)a[j]; q += (double)b[j]; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (lane == 0) {
-        const double is = invstd[warp], g = gamma[warp];
+    if (lane == 0) { red[0][wid] = s; red[1][wid] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = 0.0; q = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { s += red[0][w]; q += red[1][w]; }
+        const double is = invstd[ch], g = gamma[ch];
         const double dzx = q * is;  // sum dz * xhat   (q = sum dz * (y - mean), already centered)
-        dgamma[warp] = (float)dzx;
-        dbeta[warp] = (float)s;
+        dgamma[ch] = (float)dzx;
+        dbeta[ch] = (float)s;
         if (training) {
             const double a = g * is, c = -g * is * is * (dzx * inv_rows);
-            ka[warp] = (float)a;
-            kc[warp] = (float)c;
-            kb[warp] = (float)(-g * is * (s * inv_rows));  // applied as ka*dz + kb + kc*(y - mean)
+            ka[ch] = (float)a;
+            kc[ch] = (float)c;
+            kb[ch] = (float)(-g * is * (s * inv_rows));  // applied as ka*dz + kb + kc*(y - mean)
         } else {
-            ka[warp] = (float)(g * is); kb[warp] = 0.f; kc[warp] = 0.f;
+            ka[ch] = (float)(g * is); kb[ch] = 0.f; kc[ch] = 0.f;
         }
     }
 }
@@ -895,7 +913,7 @@ int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, in
                       float *mean, float *var, pu_stream_t stream) {
     if (!stat_sum || !stat_sq || !mean || !var || tiles < 1 || C < 1 || count < 1 || rows_per_tile < 1) return PU_ERR_INVALID_ARG;
     if ((long long)tiles != (count + rows_per_tile - 1) / rows_per_tile) return PU_ERR_INVALID_ARG;
-    stats_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
+    stats_finalize_kernel<<<C, SF_THREADS, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
                                                                                           count, rows_per_tile, mean, var);
     PU_LAUNCH_CHECK();
     return PU_OK;
@@ -1017,7 +1035,7 @@ int pu_bn_bwd_coeffs(const float *part_dz, const float *part_dzy, int blocks, in
     if (!part_dz || !part_dzy || !mean || !invstd || !gamma || !dgamma || !dbeta || !ka || !kb || !kc || blocks < 1 ||
         C < 1 || rows < 1)
         return PU_ERR_INVALID_ARG;
-    bn_bwd_coeffs_kernel<<<ceil_div((long long)C * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    bn_bwd_coeffs_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(
         part_dz, part_dzy, blocks, C, mean, invstd, gamma, 1.0 / (double)rows, training, dgamma, dbeta, ka, kb, kc);
     PU_LAUNCH_CHECK();
     return PU_OK;

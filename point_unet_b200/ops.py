@@ -194,18 +194,27 @@ def _idx32(idx: torch.Tensor) -> torch.Tensor:
 class InverseIndex:
     """offsets/perm of an index tensor ``idx [B, M, K]`` pointing into ``n_src`` rows per cloud."""
 
-    def __init__(self, idx: torch.Tensor, n_src: int):
+    def __init__(self, idx: torch.Tensor, n_src: int, out=None, build: bool = True):
+        """``out = (offsets [B*n_src+1], perm [B*R])`` int32: preallocated storage; ``build=False`` wraps lists that are
+        already there (the pipelined training step builds them one step ahead, train.py)."""
         idx = _idx32(idx)
         B = idx.shape[0]
         R = idx[0].numel()
         L = _L()
-        self.offsets = torch.empty(B * n_src + 1, dtype=torch.int32, device=idx.device)
-        self.perm = torch.empty(B * R, dtype=torch.int32, device=idx.device)
+        self.n_targets = B * n_src
+        if out is not None:
+            self.offsets, self.perm = out
+            assert self.offsets.dtype == torch.int32 and self.offsets.numel() == B * n_src + 1 and self.offsets.is_contiguous()
+            assert self.perm.dtype == torch.int32 and self.perm.numel() == B * R and self.perm.is_contiguous()
+        else:
+            self.offsets = torch.empty(B * n_src + 1, dtype=torch.int32, device=idx.device)
+            self.perm = torch.empty(B * R, dtype=torch.int32, device=idx.device)
+        if not build:
+            return
         nbytes = L.pu_inverse_workspace_bytes(B, R)
         ws = workspace(nbytes, idx.device, slot=1)
         _call("pu_build_inverse", idx.data_ptr(), R, B, n_src, self.offsets.data_ptr(), self.perm.data_ptr(),
                                       ws.data_ptr(), ws.numel(), _stream(idx))
-        self.n_targets = B * n_src
 
 
 _inverse_cache: dict = {}
@@ -222,6 +231,12 @@ def inverse_of(idx: torch.Tensor, n_src: int) -> InverseIndex:
         _inverse_cache[key] = (inv, idx)  # keep idx alive so data_ptr stays unique
         return inv
     return inv[0]
+
+
+def register_inverse(idx: torch.Tensor, n_src: int, offsets: torch.Tensor, perm: torch.Tensor):
+    """Make ``inverse_of(idx, n_src)`` return lists that were built elsewhere (same content as ``idx``)."""
+    key = (idx.data_ptr(), tuple(idx.shape), idx._version, n_src, idx.device.index)
+    _inverse_cache[key] = (InverseIndex(idx, n_src, out=(offsets, perm), build=False), idx)
 
 
 def clear_caches():

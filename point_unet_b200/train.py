@@ -24,6 +24,53 @@ import os as _os
 OVERLAP = int(_os.environ.get("PU_OVERLAP", "1")) != 0
 
 
+class _Slot:
+    """Static storage of one batch, its index pyramid and the inverse neighbour lists of the backward -- all of them
+    views of ONE flat byte buffer, so handing a finished slot over to the training step is a single device copy."""
+
+    def __init__(self, cfg, B, N, n_feat, labels_dtype, device):
+        spec, n = [], N
+        i32, f32 = torch.int32, torch.float32
+        for i in range(cfg.num_layers):
+            n_sub = n // cfg.sub_sampling_ratio[i]
+            spec += [(f"xyz{i}", (B, n, 3), f32), (f"neigh{i}", (B, n, cfg.k_n), i32), (f"sub{i}", (B, n_sub, cfg.k_n), i32),
+                     (f"interp{i}", (B, n, 1), i32),
+                     (f"inv_neigh_off{i}", (B * n + 1,), i32), (f"inv_neigh_perm{i}", (B * n * cfg.k_n,), i32),
+                     (f"inv_sub_off{i}", (B * n + 1,), i32), (f"inv_sub_perm{i}", (B * n_sub * cfg.k_n,), i32),
+                     (f"inv_interp_off{i}", (B * n_sub + 1,), i32), (f"inv_interp_perm{i}", (B * n,), i32)]
+            n = n_sub
+        spec += [(f"xyz{cfg.num_layers}", (B, n, 3), f32), ("features", (B, N, n_feat), f32), ("labels", (B, N), labels_dtype)]
+        offs, total = [], 0
+        for _, shape, dt in spec:
+            offs.append(total)
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            total += (nbytes + 255) // 256 * 256
+        self.flat = torch.zeros(total, dtype=torch.uint8, device=device)
+        self.t = {}
+        for (name, shape, dt), o in zip(spec, offs):
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            self.t[name] = self.flat[o:o + nbytes].view(dt).view(shape)
+        L = range(cfg.num_layers)
+        self.store = dict(xyz=[self.t[f"xyz{i}"] for i in range(cfg.num_layers + 1)],
+                          neigh_idx=[self.t[f"neigh{i}"] for i in L], sub_idx=[self.t[f"sub{i}"] for i in L],
+                          interp_idx=[self.t[f"interp{i}"] for i in L],
+                          inv=[[(self.t[f"inv_{k}_off{i}"], self.t[f"inv_{k}_perm{i}"]) for k in ("neigh", "sub", "interp")]
+                               for i in L])
+        self.features, self.labels = self.t["features"], self.t["labels"]
+
+    def pyramid(self):
+        st = self.store
+        return dict(xyz=st["xyz"][:-1], neigh_idx=st["neigh_idx"], sub_idx=st["sub_idx"], interp_idx=st["interp_idx"])
+
+    def register_inverse(self):
+        """Point ops.inverse_of at this slot's lists (the cache is cleared at the end of every step)."""
+        st = self.store
+        for i, inv in enumerate(st["inv"]):
+            n, n_sub = st["xyz"][i].shape[1], st["xyz"][i + 1].shape[1]
+            for idx, n_src, (off, perm) in zip((st["neigh_idx"][i], st["sub_idx"][i], st["interp_idx"][i]), (n, n, n_sub), inv):
+                ops.register_inverse(idx, n_src, off, perm)
+
+
 class Trainer:
     def __init__(self, config, num_features=None, seed=0, device=None, lr=None, world_size=1):
         self.device = torch.device(device if device is not None else "cuda")
@@ -44,6 +91,8 @@ class Trainer:
         self._graph = None
         self._side = None
         self._side2 = None
+        self.pipelined = False
+        self.dropout_mask = None  # fixed [B,N,1,32] bool mask instead of a fresh tf.nn.dropout draw per step (tests)
 
     # -- host staging ----------------------------------------------------------------------------
     def _stage(self, name, arr):
@@ -82,10 +131,16 @@ class Trainer:
     # -- steps -----------------------------------------------------------------------------------
     def train_step_device(self, xyz, features, labels, dropout_mask=None):
         """One optimisation step on device-resident inputs: xyz [B,N,3] f32, features [B,N,F-3] f32, labels [B,N]."""
-        net = self.net
         # tf_map on the GPU; levels 1-4 and the inverse lists of the backward are built on a side stream under the
         # level-0 forward (PU_OVERLAP=0: everything on one stream)
         pyr = build_pyramid(xyz, self.cfg, side=self._side_stream() if OVERLAP else None, inverse=True)
+        return self._train_on(pyr, xyz, features, labels, dropout_mask)
+
+    def _train_on(self, pyr, xyz, features, labels, dropout_mask=None):
+        """Forward, loss, backward, gradient all-reduce and Adam on a finished index pyramid."""
+        net = self.net
+        if dropout_mask is None:
+            dropout_mask = self.dropout_mask
         inputs = dict(pyr, features=torch.cat([xyz, features], dim=-1))  # runPancreas.py:125
         self.flat_grad.zero_()
         logits = net.inference(inputs, True, dropout_mask)
@@ -107,11 +162,19 @@ class Trainer:
         return loss.detach()
 
     # -- CUDA graph: ~1300 kernel launches per step recorded once, replayed with one host call -------
-    def capture_step(self, xyz, features, labels, warmup=3):
+    def capture_step(self, xyz, features, labels, warmup=3, pipelined=False):
         """Record one optimisation step for inputs of this shape into a CUDA graph.  ``xyz/features/labels`` are device
         tensors used for the warm-up (workspaces, kernel attributes and the allocator pool are set up outside the
         capture); afterwards ``train_step_graph`` copies a new batch into the static input buffers and replays.
-        The warm-up steps ARE optimisation steps (they update the weights)."""
+        The warm-up steps ARE optimisation steps (they update the weights).
+
+        ``pipelined``: software-pipeline the input side one step ahead, the way the reference hides ``tf_map`` behind
+        the training step with ``tf.data ... prefetch`` (runPancreas.py:124-171).  One replay then does two things side by
+        side: the main stream trains on batch i, whose index pyramid and inverse lists were finished by the previous
+        replay, while a side stream builds the pyramid of batch i+1 -- the batch handed to this call -- into the other
+        slot.  Per replay the work is the same (one pyramid, one forward/backward/Adam); the ten searches just leave the
+        critical path.  ``train_step_graph`` therefore returns the loss of the batch submitted ONE CALL EARLIER (the first
+        replay trains on the capture batch)."""
         from . import _lib
         self._gx, self._gf, self._gl = xyz.clone(), features.clone(), labels.clone()
         side = torch.cuda.Stream(device=self.device)
@@ -119,15 +182,42 @@ class Trainer:
         with torch.cuda.stream(side):
             for _ in range(max(int(warmup), 1)):
                 self.train_step_device(self._gx, self._gf, self._gl)
+            if pipelined:
+                B, N = xyz.shape[0], xyz.shape[1]
+                self._slots = [_Slot(self.cfg, B, N, features.shape[-1], labels.dtype, self.device) for _ in range(2)]
+                self._fill_slot(self._slots[1], self._gx, self._gf, self._gl)  # prologue: the first replay trains on this
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
-            self._gloss = self.train_step_device(self._gx, self._gf, self._gl)
+            if pipelined:
+                self._gloss = self._pipelined_step()
+            else:
+                self._gloss = self.train_step_device(self._gx, self._gf, self._gl)
         self.graph_launches = int(_lib.launch_count() - n0)  # our kernels inside one replay (torch's own come on top)
         self._graph = graph
+        self.pipelined = bool(pipelined)
         return self
+
+    def _fill_slot(self, slot, xyz, features, labels):
+        """Batch -> slot on the current stream: copies, the ten searches of tf_map, the fifteen inverse lists."""
+        slot.features.copy_(features)
+        slot.labels.copy_(labels)
+        build_pyramid(xyz, self.cfg, inverse=True, store=slot.store)
+
+    def _pipelined_step(self):
+        cur, nxt = self._slots
+        main = torch.cuda.current_stream(self.device)
+        cur.flat.copy_(nxt.flat)                 # batch i with its pyramid and inverse lists: one 200 MB device copy
+        side = self._side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):            # batch i+1 (just written to the static input buffers)
+            self._fill_slot(nxt, self._gx, self._gf, self._gl)
+        cur.register_inverse()
+        loss = self._train_on(cur.pyramid(), cur.store["xyz"][0], cur.features, cur.labels)
+        main.wait_stream(side)
+        return loss
 
     def train_step_graph(self, xyz, features, labels):
         """Replay the captured step on a new device-resident batch of the captured shape; returns the loss tensor."""

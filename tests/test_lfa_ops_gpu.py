@@ -430,6 +430,36 @@ def test_cuda_graph_step_matches_eager_training():
 
 
 @pytest.mark.gpu
+def test_pipelined_graph_step_equals_sequential_training():
+    """capture_step(pipelined=True): the replay that receives batch i+1 trains on batch i while a side stream builds the
+    pyramid of batch i+1.  With a fixed dropout mask the weights after the same batch sequence are bit-identical to
+    plain sequential steps (all kernels are deterministic), and the returned losses are those of the previous batch."""
+    from point_unet_b200.train import Trainer
+    from point_unet_b200 import synthetic
+
+    class cfg(ConfigBraTS):
+        num_points = 8192
+    batches = []
+    for seed in (21, 22, 23):
+        d = synthetic.batch(synthetic.brats_cloud, 2, cfg.num_points, seed)
+        batches.append((torch.from_numpy(d["xyz"].astype(np.float32)).cuda(), torch.from_numpy(d["features"].astype(np.float32)).cuda(),
+                        torch.from_numpy(d["labels"]).cuda()))
+    mask = torch.rand(2, cfg.num_points, 1, 32, device="cuda", generator=torch.Generator("cuda").manual_seed(3)) < 0.5
+    seq = Trainer(cfg, num_features=7, seed=0, device="cuda")
+    pipe = Trainer(cfg, num_features=7, seed=0, device="cuda")
+    seq.dropout_mask = pipe.dropout_mask = mask
+    order = [0, 0, 1, 2]                                  # warm-up step on batch 0, then the three replays train 0, 1, 2
+    ls = [float(seq.train_step_device(*batches[i])) for i in order]
+    pipe.capture_step(*batches[0], warmup=1, pipelined=True)
+    lp = [float(pipe.train_step_graph(*batches[i])) for i in (1, 2, 2)]   # submit 1 -> trains 0; 2 -> 1; 2 -> 2
+    assert lp == ls[1:], (ls, lp)
+    for (n, a), (_, b) in zip(seq.net.named_variables(), pipe.net.named_variables()):
+        assert torch.equal(a, b), n
+    for k in seq.net.stats:
+        assert torch.equal(seq.net.stats[k], pipe.net.stats[k]), k
+
+
+@pytest.mark.gpu
 def test_gradient_sink_matches_autograd_accumulation():
     """Kernels writing parameter gradients straight into the flat buffer's views (ops.GRAD_SINK) give bit-identical
     gradients to autograd's own accumulation."""
