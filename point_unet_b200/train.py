@@ -22,6 +22,7 @@ from .RandLANet import Network, build_pyramid
 import os as _os
 
 OVERLAP = int(_os.environ.get("PU_OVERLAP", "1")) != 0
+GRAPH_PRIORITY = int(_os.environ.get("PU_GRAPH_PRIORITY", "1")) != 0
 
 
 class _Slot:
@@ -190,7 +191,11 @@ class Trainer:
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
+        # The forward/backward chain is captured from a HIGH-priority stream, the side streams (pyramid, inverse lists,
+        # weight gradients) have the default, lowest priority: kernel nodes inherit it, so whenever an SM frees up the
+        # block scheduler places the chain's CTAs first and the side work fills what is left.
+        hi = torch.cuda.Stream(device=self.device, priority=-5) if GRAPH_PRIORITY else None
+        with torch.cuda.graph(graph, stream=hi):
             if pipelined:
                 self._gloss = self._pipelined_step()
             else:
