@@ -76,58 +76,85 @@ __device__ __forceinline__ void issue_pair(const float *__restrict__ x, int ldx,
     }
 }
 
-// Four consecutive constants.  `volatile`: the load stays where it is written.  Left to itself the compiler treats the 256
-// weights as loop-invariant, hoists every load out of the point loop and spills them (1.8 KB of local-memory traffic per
-// iteration); kept in the loop they become uniform-datapath loads (LDCU.128) feeding FFMAs with a uniform-register operand.
-template <int OFF>  // OFF: float index into pu_att16_cw
-__device__ __forceinline__ float4 ldc4() {
-    float4 r;
-    asm volatile("ld.const.v4.f32 {%0,%1,%2,%3}, [pu_att16_cw+%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "n"(OFF * 4));
+// Packed fp32 pairs: Blackwell's FFMA2 (fma.rn.f32x2) does two FMAs per issue slot.  These kernels are issue-bound (ncu:
+// 80-85 % of the issue slots busy, FMA pipe at 55 %), so halving the FMA instruction count is what makes them faster.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-template <int OFF>  // second copy of the weights: every constant has ONE use per loop body (see above)
-__device__ __forceinline__ float4 ldc4b() {
-    float4 r;
-    asm volatile("ld.const.v4.f32 {%0,%1,%2,%3}, [pu_att16_cw2+%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "n"(OFF * 4));
-    return r;
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 
-// act[c] = sum_j xr[j] w[j][c]   (compile-time recursion over j so that every constant offset is an immediate)
+// Four consecutive constants as two packed pairs.  `volatile`: the load stays where it is written.  Left to itself the
+// compiler treats the 256 weights as loop-invariant, hoists every load out of the point loop and spills them (1.8 KB of
+// local-memory traffic per iteration); kept in the loop they become uniform-datapath loads (LDCU.128) and the FFMA2s take
+// their second operand from uniform registers.  The backward reads the weights twice per iteration and uses a second copy
+// of them (pu_att16_cw2) for the second product: with two uses of the same constant ptxas goes back to hoisting.
+template <int OFF>  // OFF: float index into pu_att16_cw
+__device__ __forceinline__ void ldc4(u64 &p01, u64 &p23) {
+    asm volatile("ld.const.v2.b64 {%0, %1}, [pu_att16_cw+%2];" : "=l"(p01), "=l"(p23) : "n"(OFF * 4));
+}
+template <int OFF>
+__device__ __forceinline__ void ldc4b(u64 &p01, u64 &p23) {
+    asm volatile("ld.const.v2.b64 {%0, %1}, [pu_att16_cw2+%2];" : "=l"(p01), "=l"(p23) : "n"(OFF * 4));
+}
+
+// act[c] += xr[j] w[j][c]   (compile-time recursion over j so that every constant offset is an immediate);
+// act2[i] = (act[2i], act[2i+1])
 template <int SLOT, int J>
-__device__ __forceinline__ void rtw_step(const float (&xr)[16], float (&act)[16]) {
-    const float4 w0 = ldc4<SLOT * D * D + J * D + 0>(), w1 = ldc4<SLOT * D * D + J * D + 4>(),
-                 w2 = ldc4<SLOT * D * D + J * D + 8>(), w3 = ldc4<SLOT * D * D + J * D + 12>();
-    const float xj = xr[J];
-    act[0] = fmaf(xj, w0.x, act[0]); act[1] = fmaf(xj, w0.y, act[1]); act[2] = fmaf(xj, w0.z, act[2]); act[3] = fmaf(xj, w0.w, act[3]);
-    act[4] = fmaf(xj, w1.x, act[4]); act[5] = fmaf(xj, w1.y, act[5]); act[6] = fmaf(xj, w1.z, act[6]); act[7] = fmaf(xj, w1.w, act[7]);
-    act[8] = fmaf(xj, w2.x, act[8]); act[9] = fmaf(xj, w2.y, act[9]); act[10] = fmaf(xj, w2.z, act[10]); act[11] = fmaf(xj, w2.w, act[11]);
-    act[12] = fmaf(xj, w3.x, act[12]); act[13] = fmaf(xj, w3.y, act[13]); act[14] = fmaf(xj, w3.z, act[14]); act[15] = fmaf(xj, w3.w, act[15]);
-    if constexpr (J + 1 < D) rtw_step<SLOT, J + 1>(xr, act);
+__device__ __forceinline__ void rtw_step(const float (&xr)[16], u64 (&act2)[8]) {
+    u64 w[8];
+    ldc4<SLOT * D * D + J * D + 0>(w[0], w[1]);
+    ldc4<SLOT * D * D + J * D + 4>(w[2], w[3]);
+    ldc4<SLOT * D * D + J * D + 8>(w[4], w[5]);
+    ldc4<SLOT * D * D + J * D + 12>(w[6], w[7]);
+    const u64 xx = pack2(xr[J], xr[J]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) act2[i] = fma2(xx, w[i], act2[i]);
+    if constexpr (J + 1 < D) rtw_step<SLOT, J + 1>(xr, act2);
 }
 template <int SLOT>
 __device__ __forceinline__ void row_times_w(const float (&xr)[16], float (&act)[16]) {
+    u64 act2[8];
 #pragma unroll
-    for (int c = 0; c < D; ++c) act[c] = 0.f;
-    rtw_step<SLOT, 0>(xr, act);
+    for (int i = 0; i < 8; ++i) act2[i] = 0ull;
+    rtw_step<SLOT, 0>(xr, act2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) unpack2(act2[i], act[2 * i], act[2 * i + 1]);
 }
-// o[j] += sum_c dr[c] w[j][c]
+// o[j] += sum_c dr[c] w[j][c]: pairs run over c, (even, odd) partial sums per output channel
 template <int SLOT, int J>
-__device__ __forceinline__ void rtwt_step(const float (&dr)[16], float (&o)[16]) {
-    const float4 w0 = ldc4b<SLOT * D * D + J * D + 0>(), w1 = ldc4b<SLOT * D * D + J * D + 4>(),
-                 w2 = ldc4b<SLOT * D * D + J * D + 8>(), w3 = ldc4b<SLOT * D * D + J * D + 12>();
-    float s0 = fmaf(dr[0], w0.x, o[J]), s1 = dr[4] * w1.x, s2 = dr[8] * w2.x, s3 = dr[12] * w3.x;
-    s0 = fmaf(dr[1], w0.y, s0); s1 = fmaf(dr[5], w1.y, s1); s2 = fmaf(dr[9], w2.y, s2); s3 = fmaf(dr[13], w3.y, s3);
-    s0 = fmaf(dr[2], w0.z, s0); s1 = fmaf(dr[6], w1.z, s1); s2 = fmaf(dr[10], w2.z, s2); s3 = fmaf(dr[14], w3.z, s3);
-    s0 = fmaf(dr[3], w0.w, s0); s1 = fmaf(dr[7], w1.w, s1); s2 = fmaf(dr[11], w2.w, s2); s3 = fmaf(dr[15], w3.w, s3);
-    o[J] = (s0 + s1) + (s2 + s3);
-    if constexpr (J + 1 < D) rtwt_step<SLOT, J + 1>(dr, o);
+__device__ __forceinline__ void rtwt_step(const u64 (&dr2)[8], float (&o)[16]) {
+    u64 w[8];
+    ldc4b<SLOT * D * D + J * D + 0>(w[0], w[1]);
+    ldc4b<SLOT * D * D + J * D + 4>(w[2], w[3]);
+    ldc4b<SLOT * D * D + J * D + 8>(w[4], w[5]);
+    ldc4b<SLOT * D * D + J * D + 12>(w[6], w[7]);
+    u64 s0 = pack2(o[J], 0.f), s1 = 0ull;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        s0 = fma2(dr2[i], w[i], s0);
+        s1 = fma2(dr2[i + 1], w[i + 1], s1);
+    }
+    float a, b, c, d;
+    unpack2(s0, a, b);
+    unpack2(s1, c, d);
+    o[J] = (a + b) + (c + d);
+    if constexpr (J + 1 < D) rtwt_step<SLOT, J + 1>(dr2, o);
 }
 template <int SLOT>
-__device__ __forceinline__ void row_times_wt(const float (&dr)[16], float (&o)[16]) { rtwt_step<SLOT, 0>(dr, o); }
+__device__ __forceinline__ void row_times_wt(const float (&dr)[16], float (&o)[16]) {
+    u64 dr2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dr2[i] = pack2(dr[2 * i], dr[2 * i + 1]);
+    rtwt_step<SLOT, 0>(dr2, o);
+}
 
 // softmax over the 16 values of a column (in place: a[k] <- e_k, returns 1 / sum)
 __device__ __forceinline__ float softmax16(float (&a)[16]) {
@@ -206,11 +233,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
     const long long nw = (long long)gridDim.x * WARPS;
     long long pair = (long long)blockIdx.x * WARPS + wib;
 
-    float wacc[4][4];  // dw[4 jq + a][4 cq + b]
+    u64 wacc[4][2];  // dw[4 jq + a][4 cq + (0,1)], [4 cq + (2,3)]
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) wacc[a][b] = 0.f;
+    for (int a = 0; a < 4; ++a) wacc[a][0] = wacc[a][1] = 0ull;
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -267,11 +292,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         for (int k = 0; k < KN; ++k) {
             const float4 xv = *reinterpret_cast<const float4 *>(X + k * RS + 4 * jq);
             const float4 dv = *reinterpret_cast<const float4 *>(Dt + k * RS + 4 * cq);
-            const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+            const u64 d01 = pack2(dv.x, dv.y), d23 = pack2(dv.z, dv.w);
 #pragma unroll
-            for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) wacc[a2][b] = fmaf(xa[a2], da[b], wacc[a2][b]);
+            for (int a2 = 0; a2 < 4; ++a2) {
+                const u64 xx = pack2(xa[a2], xa[a2]);
+                wacc[a2][0] = fma2(xx, d01, wacc[a2][0]);
+                wacc[a2][1] = fma2(xx, d23, wacc[a2][1]);
+            }
         }
         // row owner again: dx[k = t][j] = g s + sum_c d_act[k][c] w[j][c]
         float o[16];
@@ -302,9 +330,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
     {
         float *mine = red + (wib * 2 + half) * (D * D);
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-            *reinterpret_cast<float4 *>(mine + (4 * jq + a) * D + 4 * cq) =
-                make_float4(wacc[a][0], wacc[a][1], wacc[a][2], wacc[a][3]);
+        for (int a = 0; a < 4; ++a) {
+            float4 v;
+            unpack2(wacc[a][0], v.x, v.y);
+            unpack2(wacc[a][1], v.z, v.w);
+            *reinterpret_cast<float4 *>(mine + (4 * jq + a) * D + 4 * cq) = v;
+        }
     }
     __syncthreads();
     {
