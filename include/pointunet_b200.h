@@ -76,7 +76,9 @@ PU_API int pu_knn_read_stats(const void *workspace, unsigned long long *host_sta
 PU_API int pu_gather_rows_fwd(const float *src, int ld_src, int n_src, const int32_t *idx, long long rows_per_cloud,
                               int B, float *dst, int ld_dst, int d, pu_stream_t stream);
 /* Inverse neighbour lists for the scatter-free backward: offsets int32 [B*n_src + 1], perm int32
- * [B*rows_per_cloud] (global row numbers, ascending inside each segment -> deterministic sums). */
+ * [B*rows_per_cloud] (global row numbers, ascending inside each segment -> deterministic sums).  Built as a counting
+ * sort; the workspace holds the unsorted lists, B*n_src + 1 counters and the scan scratch: pu_inverse_workspace_bytes
+ * covers n_src <= 4 * rows_per_cloud, callers with more targets than that add 4 * (B*n_src + 1) bytes. */
 PU_API size_t pu_inverse_workspace_bytes(int B, long long rows_per_cloud);
 PU_API int pu_build_inverse(const int32_t *idx, long long rows_per_cloud, int B, int n_src, int32_t *offsets,
                             int32_t *perm, void *workspace, size_t workspace_bytes, pu_stream_t stream);

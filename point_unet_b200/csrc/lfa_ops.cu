@@ -11,7 +11,7 @@
 // All tensors channels-last fp32; "rows" of d channels are moved as 128-bit vectors when d % 4 == 0 and the
 // row strides allow it.  Outputs take a row stride (ld) so a kernel can write straight into one half of a
 // concat buffer (tf.concat at RandLANet.py:328,333,138 never needs its own copy).
-#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <float.h>
 
 #include "common.cuh"
@@ -129,25 +129,76 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// inverse neighbour lists: stable radix sort of (target = b*n + idx[row]) with payload row
-__global__ void __launch_bounds__(256) inv_keys_kernel(const int32_t *__restrict__ idx, long long R, int B, int n,
-                                                       unsigned *__restrict__ keys, unsigned *__restrict__ vals) {
+// inverse neighbour lists.  off[t] .. off[t+1] delimits the rows (global numbers b*R + r) whose index points at target
+// t = b*n + idx[row]; inside a segment the rows are ASCENDING, so every segmented sum adds in one fixed order.
+// Built as a counting sort -- the lists are short (16 on average, in-degree of a K-NN graph), a general radix sort of
+// 11.5 M (key, row) pairs was three full passes over them:
+//   1. cnt[t]++                 integer atomics (the counts do not depend on their order)
+//   2. off = exclusive scan(cnt)
+//   3. tmp[off[t] + slot] = row slot handed out by atomicSub on cnt[t]: the order inside a segment is arbitrary here ...
+//   4. perm[off[t] + rank] = row  ... and made canonical by ranking every row within its segment (rows are distinct).
+//      Neighbouring threads rank rows of the same segment, so its 64 bytes are read once and broadcast.  Segments longer
+//      than INV_LONG (clouds with thousands of coincident points) are ranked by a whole CTA instead of one thread per row.
+constexpr int INV_LONG = 1024;
+
+__global__ void __launch_bounds__(256) inv_count_kernel(const int32_t *__restrict__ idx, long long R, int B, int n,
+                                                        int32_t *__restrict__ cnt) {
     const long long total = (long long)B * R;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(t / R);
-        keys[t] = (unsigned)b * (unsigned)n + (unsigned)idx[t];
-        vals[t] = (unsigned)t;
+        atomicAdd(&cnt[(size_t)b * n + idx[t]], 1);
     }
 }
-// off[k] = first sorted position whose key >= k, for k in [0, n_targets]; positions i in [0, total]
-__global__ void __launch_bounds__(256) inv_offsets_kernel(const unsigned *__restrict__ keys_sorted, long long total,
-                                                          long long n_targets, int32_t *__restrict__ off) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long prev = i == 0 ? -1 : (long long)keys_sorted[i - 1];
-        const long long cur = i == total ? n_targets : (long long)keys_sorted[i];
-        for (long long k = prev + 1; k <= cur; ++k) off[k] = (int32_t)i;
+__global__ void __launch_bounds__(256) inv_fill_kernel(const int32_t *__restrict__ idx, long long R, int B, int n,
+                                                       const int32_t *__restrict__ off, int32_t *__restrict__ cnt,
+                                                       int32_t *__restrict__ tmp) {
+    const long long total = (long long)B * R;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / R);
+        const size_t key = (size_t)b * n + idx[t];
+        const int slot = atomicSub(&cnt[key], 1) - 1;
+        tmp[off[key] + slot] = (int32_t)t;
+    }
+}
+__global__ void __launch_bounds__(256) inv_rank_kernel(const int32_t *__restrict__ idx, long long R, int n,
+                                                       const int32_t *__restrict__ off, const int32_t *__restrict__ tmp,
+                                                       long long total, int32_t *__restrict__ perm) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int row = tmp[e];
+        const size_t key = (size_t)(row / R) * n + idx[row];
+        const int e0 = off[key], e1 = off[key + 1];
+        if (e1 - e0 > INV_LONG) continue;  // inv_rank_long_kernel
+        int rank = 0;
+        for (int i = e0; i < e1; ++i) rank += tmp[i] < row;
+        perm[e0 + rank] = row;
+    }
+}
+// long segments: each CTA looks at 256 targets at a time, collects the long ones and ranks them with all its threads
+__global__ void __launch_bounds__(256) inv_rank_long_kernel(const int32_t *__restrict__ off, const int32_t *__restrict__ tmp,
+                                                            long long n_targets, int32_t *__restrict__ perm) {
+    __shared__ int s_list[256];
+    __shared__ int s_n;
+    for (long long base = (long long)blockIdx.x * 256; base < n_targets; base += (long long)gridDim.x * 256) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const long long t = base + threadIdx.x;
+        if (t < n_targets && off[t + 1] - off[t] > INV_LONG) s_list[atomicAdd(&s_n, 1)] = (int)threadIdx.x;
+        __syncthreads();
+        const int nl = s_n;
+        for (int q = 0; q < nl; ++q) {
+            const long long tt = base + s_list[q];
+            const int e0 = off[tt], e1 = off[tt + 1];
+            for (int i = e0 + threadIdx.x; i < e1; i += 256) {
+                const int row = tmp[i];
+                int rank = 0;
+                for (int j = e0; j < e1; ++j) rank += tmp[j] < row;
+                perm[e0 + rank] = row;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -433,6 +484,7 @@ int pu_segment_sum(const float *grad_out, int ld_go, const int32_t *offsets, con
 size_t pu_inverse_workspace_bytes(int B, long long rows_per_cloud) {
     if (B <= 0 || rows_per_cloud < 0) return 0;
     const size_t n = (size_t)B * rows_per_cloud;
+    // unsorted lists [n] + counters [<= n + 1 targets ... sized below from n_src at call time] + scan scratch
     return 4 * align_up(n * 4, 256) + (8u << 20) + n;
 }
 
@@ -443,29 +495,30 @@ int pu_build_inverse(const int32_t *idx, long long rows_per_cloud, int B, int n_
     if (total >= (1ll << 31) || n_targets >= (1ll << 31)) return PU_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (!workspace || workspace_bytes < pu_inverse_workspace_bytes(B, rows_per_cloud)) return PU_ERR_WORKSPACE;
-    char *ws = (char *)workspace;
-    const size_t seg = align_up((size_t)total * 4, 256);
-    unsigned *ka = (unsigned *)ws, *kb = (unsigned *)(ws + seg), *va = (unsigned *)(ws + 2 * seg),
-             *vb = (unsigned *)(ws + 3 * seg);
-    void *temp = ws + 4 * seg;
-    const size_t temp_reserved = workspace_bytes - 4 * seg;
-    if (total > 0) {
-        inv_keys_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, B, n_src, ka, va);
-        PU_LAUNCH_CHECK();
-        int bits = 1;
-        while ((1ll << bits) < n_targets) ++bits;
-        cub::DoubleBuffer<unsigned> dk(ka, kb), dv(va, vb);
-        size_t need = 0;
-        PU_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)total, 0, bits, st));
-        if (need > temp_reserved) return PU_ERR_WORKSPACE;
-        PU_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, need, dk, dv, (int)total, 0, bits, st));
-        count_launch(3);
-        PU_CUDA_TRY(cudaMemcpyAsync(perm, dv.Current(), (size_t)total * 4, cudaMemcpyDeviceToDevice, st));
-        inv_offsets_kernel<<<grid_for(total + 1), 256, 0, st>>>(dk.Current(), total, n_targets, offsets);
-        PU_LAUNCH_CHECK();
-    } else {
+    if (total == 0) {
         PU_CUDA_TRY(cudaMemsetAsync(offsets, 0, (size_t)(n_targets + 1) * 4, st));
+        return PU_OK;
     }
+    char *ws = (char *)workspace;
+    const size_t seg_tmp = align_up((size_t)total * 4, 256), seg_cnt = align_up((size_t)(n_targets + 1) * 4, 256);
+    if (seg_tmp + seg_cnt + (1u << 20) > workspace_bytes) return PU_ERR_WORKSPACE;  // many more targets than rows
+    int32_t *tmp = (int32_t *)ws, *cnt = (int32_t *)(ws + seg_tmp);
+    void *temp = ws + seg_tmp + seg_cnt;
+    const size_t temp_reserved = workspace_bytes - seg_tmp - seg_cnt;
+    PU_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(n_targets + 1) * 4, st));
+    inv_count_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, B, n_src, cnt);
+    PU_LAUNCH_CHECK();
+    size_t need = 0;
+    PU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, cnt, offsets, (int)(n_targets + 1), st));
+    if (need > temp_reserved) return PU_ERR_WORKSPACE;
+    PU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, need, cnt, offsets, (int)(n_targets + 1), st));
+    count_launch(1);
+    inv_fill_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, B, n_src, offsets, cnt, tmp);
+    PU_LAUNCH_CHECK();
+    inv_rank_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, n_src, offsets, tmp, total, perm);
+    PU_LAUNCH_CHECK();
+    inv_rank_long_kernel<<<grid_for(n_targets), 256, 0, st>>>(offsets, tmp, n_targets, perm);
+    PU_LAUNCH_CHECK();
     return PU_OK;
 }
 

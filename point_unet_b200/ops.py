@@ -211,7 +211,7 @@ class InverseIndex:
             self.perm = torch.empty(B * R, dtype=torch.int32, device=idx.device)
         if not build:
             return
-        nbytes = L.pu_inverse_workspace_bytes(B, R)
+        nbytes = L.pu_inverse_workspace_bytes(B, R) + 4 * (B * n_src + 1)
         ws = workspace(nbytes, idx.device, slot=1)
         _call("pu_build_inverse", idx.data_ptr(), R, B, n_src, self.offsets.data_ptr(), self.perm.data_ptr(),
                                       ws.data_ptr(), ws.numel(), _stream(idx))
