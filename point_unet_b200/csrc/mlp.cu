@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restri
 // element is read once and costs one FMA -- no shared-memory traffic in the loop.  One block-level reduction per
 // CTA at the end, then the usual fixed-order reduction over CTAs.
 template <int KP>
-__global__ void __launch_bounds__(256) wgrad_narrow_kernel(const float *__restrict__ A, int lda,
+__global__ void __launch_bounds__(256, KP > 8 ? 2 : 4) wgrad_narrow_kernel(const float *__restrict__ A, int lda,
                                                            const float *__restrict__ G, int ldg, long long M, int K,
                                                            int N, long long rows_per_chunk, float *__restrict__ part,
                                                            float *__restrict__ db_part) {
@@ -715,42 +715,65 @@ __global__ void __launch_bounds__(256) wgrad_narrow_kernel(const float *__restri
     const bool va4 = ((lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0) && ((K & 3) == 0);
     const bool va2 = ((lda & 1) == 0) && ((((uintptr_t)A) & 7) == 0) && ((K & 1) == 0);
     const bool vg4 = ((ldg & 3) == 0) && ((((uintptr_t)G) & 15) == 0) && (y * 4 + 3 < N);
+    auto load_row = [&](long long r, float (&av)[KP], float (&gv)[4]) {
+        const float *a = A + (size_t)r * lda;
+        const float *g = G + (size_t)r * ldg + y * 4;
+        if (va4) {
+#pragma unroll
+            for (int i = 0; i < KP; i += 4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < K) v = *reinterpret_cast<const float4 *>(a + i);
+                av[i] = v.x; av[i + 1] = v.y; av[i + 2] = v.z; av[i + 3] = v.w;
+            }
+        } else if (va2) {
+#pragma unroll
+            for (int i = 0; i < KP; i += 2) {
+                float2 v = make_float2(0.f, 0.f);
+                if (i < K) v = *reinterpret_cast<const float2 *>(a + i);
+                av[i] = v.x; av[i + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < KP; ++i) av[i] = i < K ? a[i] : 0.f;
+        }
+        if (vg4) {
+            const float4 v = *reinterpret_cast<const float4 *>(g);
+            gv[0] = v.x; gv[1] = v.y; gv[2] = v.z; gv[3] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[j] = (y * 4 + j < N) ? g[j] : 0.f;
+        }
+    };
+    auto accumulate = [&](const float (&av)[KP], const float (&gv)[4]) {
+#pragma unroll
+        for (int i = 0; i < KP; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dbacc[j] += gv[j];
+    };
     {
-        for (long long r = r_begin + rl; r < r_end; r += RL) {
-            const float *a = A + (size_t)r * lda;
-            const float *g = G + (size_t)r * ldg + y * 4;
-            float av[KP], gv[4];
-            if (va4) {
-#pragma unroll
-                for (int i = 0; i < KP; i += 4) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i < K) v = *reinterpret_cast<const float4 *>(a + i);
-                    av[i] = v.x; av[i + 1] = v.y; av[i + 2] = v.z; av[i + 3] = v.w;
-                }
-            } else if (va2) {
-#pragma unroll
-                for (int i = 0; i < KP; i += 2) {
-                    float2 v = make_float2(0.f, 0.f);
-                    if (i < K) v = *reinterpret_cast<const float2 *>(a + i);
-                    av[i] = v.x; av[i + 1] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < KP; ++i) av[i] = i < K ? a[i] : 0.f;
+        // two rows per trip: all loads of both rows are issued before the first FMA (the row order of the sums is unchanged)
+        long long r = r_begin + rl;
+        if constexpr (KP > 8) {  // (the 8-wide variant already runs at 84 % of the copy bandwidth with one row per trip)
+            for (; r + RL < r_end; r += 2 * RL) {
+                float av0[KP], gv0[4], av1[KP], gv1[4];
+                load_row(r, av0, gv0);
+                load_row(r + RL, av1, gv1);
+                accumulate(av0, gv0);
+                accumulate(av1, gv1);
             }
-            if (vg4) {
-                const float4 v = *reinterpret_cast<const float4 *>(g);
-                gv[0] = v.x; gv[1] = v.y; gv[2] = v.z; gv[3] = v.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) gv[j] = (y * 4 + j < N) ? g[j] : 0.f;
+        } else {
+            for (; r + RL < r_end; r += RL) {
+                float av0[KP], gv0[4];
+                load_row(r, av0, gv0);
+                accumulate(av0, gv0);
             }
-#pragma unroll
-            for (int i = 0; i < KP; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dbacc[j] += gv[j];
+        }
+        if (r < r_end) {
+            float av0[KP], gv0[4];
+            load_row(r, av0, gv0);
+            accumulate(av0, gv0);
         }
     }
     // reduction over row lanes: butterfly over the lanes of a warp that share y, then 8 warps through shared memory
