@@ -487,11 +487,15 @@ class _LinearFn(torch.autograd.Function):
         ctx.w_param, ctx.b_param = w, bias
         if want_stats:
             ctx.mark_non_differentiable(mean, var)
+            # otherwise autograd zero-fills "gradients" for mean / var before every backward: 88 tiny fill launches a step
+            ctx.set_materialize_grads(False)
             return y, mean, var
         return y
 
     @staticmethod
     def backward(ctx, dy, *_):
+        if dy is None:
+            return None, None, None, None, None
         x, w = ctx.saved_tensors
         gw, gb = _sink(ctx.w_param), _sink(ctx.b_param)
         if ctx.has_bias and ctx.zero_bias_grad:
