@@ -204,18 +204,22 @@ __global__ void __launch_bounds__(256) inv_rank_long_kernel(const int32_t *__res
 
 // ---------------------------------------------------------------------------------------------
 // LocSE: out[b,n,k,:] = [ |p - q|, p - q (3), p (3), q (3) ]  with p = xyz[b,n], q = xyz[b, idx[b,n,k]]
-// One CTA = 256 (n,k) rows = 2560 contiguous floats, staged in shared memory and stored as float4.
+// grid (tiles of 256 (n,k) rows inside a cloud, B): the cloud comes from blockIdx.y and the point from a 32-bit shift (K a
+// power of two) or 32-bit division -- the first version spent ~150 of its ~250 instructions per row on two 64-bit
+// divisions (row / K, point / N).  A tile = 2560 contiguous floats, staged in shared memory and stored as float4
+// (the rows of a cloud start at a multiple of 4 floats whenever N*K is even; otherwise the launcher asks for scalar stores).
 __global__ void __launch_bounds__(256) locse_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx,
-                                                    int N, int K, long long rows_total, float *__restrict__ out) {
+                                                    int N, int K, int shiftK, unsigned rows_per_cloud, int vec_ok,
+                                                    float *__restrict__ out) {
     __shared__ __align__(16) float s_out[256 * 10];
-    const long long row0 = (long long)blockIdx.x * 256;
-    const long long row = row0 + threadIdx.x;
-    if (row < rows_total) {
-        const long long pn = row / K;  // global point b*N + n
-        const int b = (int)(pn / N);
-        const int j = idx[row];
-        const float *p = xyz + (size_t)pn * 3;
-        const float *q = xyz + ((size_t)b * N + j) * 3;
+    const unsigned r0 = blockIdx.x * 256u, r = r0 + threadIdx.x;
+    const size_t cloud_row0 = (size_t)blockIdx.y * rows_per_cloud;
+    const float *xb = xyz + (size_t)blockIdx.y * N * 3;
+    if (r < rows_per_cloud) {
+        const unsigned n = shiftK >= 0 ? (r >> shiftK) : (r / (unsigned)K);
+        const int j = idx[cloud_row0 + r];
+        const float *p = xb + (size_t)n * 3;
+        const float *q = xb + (size_t)j * 3;
         const float px = p[0], py = p[1], pz = p[2], qx = q[0], qy = q[1], qz = q[2];
         const float rx = px - qx, ry = py - qy, rz = pz - qz;
         float *o = s_out + threadIdx.x * 10;
@@ -225,11 +229,12 @@ __global__ void __launch_bounds__(256) locse_kernel(const float *__restrict__ xy
         o[7] = qx; o[8] = qy; o[9] = qz;
     }
     __syncthreads();
-    const long long nrows = min((long long)256, rows_total - row0);
-    const int nvec = (int)(nrows * 10 / 4);  // row0*10 floats is a multiple of 4 (row0 % 256 == 0)
-    float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)row0 * 10);
+    const unsigned nrows = min(256u, rows_per_cloud - r0);
+    const int nvec = vec_ok ? (int)(nrows * 10 / 4) : 0;
+    float *ob = out + (cloud_row0 + r0) * 10;
+    float4 *o4 = reinterpret_cast<float4 *>(ob);
     for (int v = threadIdx.x; v < nvec; v += 256) st_stream_f4(o4 + v, reinterpret_cast<float4 *>(s_out)[v]);
-    for (int r = nvec * 4 + threadIdx.x; r < nrows * 10; r += 256) out[(size_t)row0 * 10 + r] = s_out[r];
+    for (int t = nvec * 4 + threadIdx.x; t < (int)nrows * 10; t += 256) ob[t] = s_out[t];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -525,10 +530,15 @@ int pu_build_inverse(const int32_t *idx, long long rows_per_cloud, int B, int n_
 int pu_relative_pos_encoding_fwd(const float *xyz, const int32_t *idx, int B, int N, int K, float *out,
                                  pu_stream_t stream) {
     if (!xyz || !idx || !out || B < 0 || N < 0 || K < 1) return PU_ERR_INVALID_ARG;
-    const long long rows = (long long)B * N * K;
-    if (rows == 0) return PU_OK;
+    const long long rpc = (long long)N * K;
+    if (B == 0 || rpc == 0) return PU_OK;
     if ((((uintptr_t)out) & 15) != 0) return PU_ERR_INVALID_ARG;
-    locse_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(xyz, idx, N, K, rows, out);
+    if (rpc >= (1ll << 31) || B > 65535) return PU_ERR_UNSUPPORTED;
+    const int vec_ok = (B == 1 || (rpc & 1) == 0) ? 1 : 0;  // 128-bit stores need every cloud to start at a multiple of 4 floats
+    int shiftK = -1;
+    if ((K & (K - 1)) == 0) { shiftK = 0; while ((1 << shiftK) < K) ++shiftK; }
+    dim3 grid((unsigned)ceil_div(rpc, 256), (unsigned)B);
+    locse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, idx, N, K, shiftK, (unsigned)rpc, vec_ok, out);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

@@ -56,8 +56,8 @@ def test_gather_neighbour_fwd_bwd(d):
     assert torch.equal(g1, pc_gpu.grad)
 
 
-def test_relative_pos_encoding():
-    B, N, K = 3, 777, 16
+@pytest.mark.parametrize("B,N,K", [(3, 777, 16), (2, 333, 3), (1, 1001, 5), (2, 40, 16)])
+def test_relative_pos_encoding(B, N, K):
     g = torch.Generator().manual_seed(3)
     xyz = torch.rand(B, N, 3, generator=g)
     idx = rand_idx(B, N, K, N, 4)
