@@ -143,20 +143,18 @@ constexpr int INV_LONG = 1024;
 
 __global__ void __launch_bounds__(256) inv_count_kernel(const int32_t *__restrict__ idx, long long R, int B, int n,
                                                         int32_t *__restrict__ cnt) {
-    const long long total = (long long)B * R;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(t / R);
+    const unsigned total = (unsigned)((long long)B * R), Ru = (unsigned)R;  // < 2^31 (checked by the launcher): 32-bit division
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned b = t / Ru;
         atomicAdd(&cnt[(size_t)b * n + idx[t]], 1);
     }
 }
 __global__ void __launch_bounds__(256) inv_fill_kernel(const int32_t *__restrict__ idx, long long R, int B, int n,
                                                        const int32_t *__restrict__ off, int32_t *__restrict__ cnt,
                                                        int32_t *__restrict__ tmp) {
-    const long long total = (long long)B * R;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(t / R);
+    const unsigned total = (unsigned)((long long)B * R), Ru = (unsigned)R;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned b = t / Ru;
         const size_t key = (size_t)b * n + idx[t];
         const int slot = atomicSub(&cnt[key], 1) - 1;
         tmp[off[key] + slot] = (int32_t)t;
@@ -168,7 +166,7 @@ __global__ void __launch_bounds__(256) inv_rank_kernel(const int32_t *__restrict
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const int row = tmp[e];
-        const size_t key = (size_t)(row / R) * n + idx[row];
+        const size_t key = (size_t)((unsigned)row / (unsigned)R) * n + idx[row];
         const int e0 = off[key], e1 = off[key + 1];
         if (e1 - e0 > INV_LONG) continue;  // inv_rank_long_kernel
         int rank = 0;

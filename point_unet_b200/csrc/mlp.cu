@@ -565,21 +565,23 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict
                                                          int ld_y2, const float *__restrict__ scale2,
                                                          const float *__restrict__ shift2, float slope, long long R, int C,
                                                          float *__restrict__ out, int ld_o, float *__restrict__ out2, int ld_o2) {
-    const int cq = C >> 2;
-    const long long total = R * cq;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const long long r = t / cq;
-        const int c = (int)(t - r * cq) * 4;
-        const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
-        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), mu = *reinterpret_cast<const float4 *>(shift + c),
-                     be = *reinterpret_cast<const float4 *>(shift + C + c);
+    // a thread owns ONE float4 column group for its lifetime (coefficients in registers, no index division in the loop)
+    // and walks the rows; consecutive threads still touch consecutive 16-byte chunks
+    const int cq = C >> 2, rpb = 256 / cq;
+    const int c = (threadIdx.x % cq) * 4, rl = threadIdx.x / cq;
+    if (rl >= rpb) return;
+    const float4 sc = *reinterpret_cast<const float4 *>(scale + c), mu = *reinterpret_cast<const float4 *>(shift + c),
+                 be = *reinterpret_cast<const float4 *>(shift + C + c);
+    float4 s2 = sc, m2 = mu, b2 = be;
+    if (y2) {
+        s2 = *reinterpret_cast<const float4 *>(scale2 + c);
+        m2 = *reinterpret_cast<const float4 *>(shift2 + c);
+        b2 = *reinterpret_cast<const float4 *>(shift2 + C + c);
+    }
+    auto emit = [&](long long r, const float4 &v, const float4 &w) {
         const float4 z1 = bn_z(v, mu, sc, be);
         float z[4] = {z1.x, z1.y, z1.z, z1.w};
         if (y2) {
-            const float4 w = *reinterpret_cast<const float4 *>(y2 + (size_t)r * ld_y2 + c);
-            const float4 s2 = *reinterpret_cast<const float4 *>(scale2 + c), m2 = *reinterpret_cast<const float4 *>(shift2 + c),
-                         b2 = *reinterpret_cast<const float4 *>(shift2 + C + c);
             const float4 z2 = bn_z(w, m2, s2, b2);
             z[0] += z2.x; z[1] += z2.y; z[2] += z2.z; z[3] += z2.w;
         }
@@ -587,6 +589,25 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict
         for (int j = 0; j < 4; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * slope;
         *reinterpret_cast<float4 *>(out + (size_t)r * ld_o + c) = make_float4(z[0], z[1], z[2], z[3]);
         if (out2) *reinterpret_cast<float4 *>(out2 + (size_t)r * ld_o2 + c) = make_float4(z[0], z[1], z[2], z[3]);
+    };
+    const long long step = (long long)gridDim.x * rpb;
+    long long r = (long long)blockIdx.x * rpb + rl;
+    for (; r + step < R; r += 2 * step) {  // two rows in flight
+        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        const float4 v1 = *reinterpret_cast<const float4 *>(y + (size_t)(r + step) * ld_y + c);
+        float4 w0 = v0, w1 = v1;
+        if (y2) {
+            w0 = *reinterpret_cast<const float4 *>(y2 + (size_t)r * ld_y2 + c);
+            w1 = *reinterpret_cast<const float4 *>(y2 + (size_t)(r + step) * ld_y2 + c);
+        }
+        emit(r, v0, w0);
+        emit(r + step, v1, w1);
+    }
+    if (r < R) {
+        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        float4 w0 = v0;
+        if (y2) w0 = *reinterpret_cast<const float4 *>(y2 + (size_t)r * ld_y2 + c);
+        emit(r, v0, w0);
     }
 }
 
@@ -662,22 +683,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restri
                                                            const float *__restrict__ ka, const float *__restrict__ kb,
                                                            const float *__restrict__ kc, long long R, int C,
                                                            float *__restrict__ dy, int ld_dy) {
-    const int cq = C >> 2;
-    const long long total = R * cq;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const long long r = t / cq;
-        const int c = (int)(t - r * cq) * 4;
+    // fixed column group per thread (coefficients in registers, no index division), two rows in flight
+    const int cq = C >> 2, rpb = 256 / cq;
+    const int c = (threadIdx.x % cq) * 4, rl = threadIdx.x / cq;
+    if (rl >= rpb) return;
+    const float4 sc = *reinterpret_cast<const float4 *>(scale + c), mu = *reinterpret_cast<const float4 *>(shift + c),
+                 be = *reinterpret_cast<const float4 *>(shift + C + c);
+    const float4 a = *reinterpret_cast<const float4 *>(ka + c), b = *reinterpret_cast<const float4 *>(kb + c),
+                 cc = *reinterpret_cast<const float4 *>(kc + c);
+    auto load_g = [&](long long r) {
         float4 g = *reinterpret_cast<const float4 *>(dout + (size_t)r * ld_d + c);
         if (dout2) {
             const float4 g2 = *reinterpret_cast<const float4 *>(dout2 + (size_t)r * ld_d2 + c);
             g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
         }
-        const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
-        const float4 sc = *reinterpret_cast<const float4 *>(scale + c), mu = *reinterpret_cast<const float4 *>(shift + c),
-                     be = *reinterpret_cast<const float4 *>(shift + C + c);
-        const float4 a = *reinterpret_cast<const float4 *>(ka + c), b = *reinterpret_cast<const float4 *>(kb + c),
-                     cc = *reinterpret_cast<const float4 *>(kc + c);
+        return g;
+    };
+    auto emit = [&](long long r, const float4 &g, const float4 &v) {
         const float4 z = bn_z(v, mu, sc, be);
         const float gz[4] = {z.x > 0.f ? g.x : g.x * slope, z.y > 0.f ? g.y : g.y * slope,
                              z.z > 0.f ? g.z : g.z * slope, z.w > 0.f ? g.w : g.w * slope};
@@ -685,6 +707,20 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restri
         *reinterpret_cast<float4 *>(dy + (size_t)r * ld_dy + c) =
             make_float4(fmaf(a.x, gz[0], fmaf(cc.x, v.x - mu.x, b.x)), fmaf(a.y, gz[1], fmaf(cc.y, v.y - mu.y, b.y)),
                         fmaf(a.z, gz[2], fmaf(cc.z, v.z - mu.z, b.z)), fmaf(a.w, gz[3], fmaf(cc.w, v.w - mu.w, b.w)));
+    };
+    const long long step = (long long)gridDim.x * rpb;
+    long long r = (long long)blockIdx.x * rpb + rl;
+    for (; r + step < R; r += 2 * step) {
+        const float4 g0 = load_g(r), g1 = load_g(r + step);
+        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        const float4 v1 = *reinterpret_cast<const float4 *>(y + (size_t)(r + step) * ld_y + c);
+        emit(r, g0, v0);
+        emit(r + step, g1, v1);
+    }
+    if (r < R) {
+        const float4 g0 = load_g(r);
+        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        emit(r, g0, v0);
     }
 }
 
@@ -1072,6 +1108,7 @@ int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shif
     if (y2 && (!scale2 || !shift2 || (ldy2 & 3) || ldy2 < C)) return PU_ERR_INVALID_ARG;
     if (out2 && ((ldo2 & 3) || ldo2 < C || (((uintptr_t)out2) & 15))) return PU_ERR_INVALID_ARG;
     if (R == 0) return PU_OK;
+    if (C > 1024) return PU_ERR_UNSUPPORTED;  // one float4 column group per thread of a 256-thread CTA
     bn_act_fwd_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, scale, shift, y2, ldy2, scale2, shift2,
                                                                             slope, R, C, out, ldo, out2, ldo2);
     PU_LAUNCH_CHECK();
@@ -1120,6 +1157,7 @@ int pu_bn_bwd_apply(const float *dout, int ldd, const float *dout2, int ldd2, co
         return PU_ERR_INVALID_ARG;
     if (R == 0) return PU_OK;
     if (dout2 && ((ldd2 & 3) || (((uintptr_t)dout2) & 15))) return PU_ERR_INVALID_ARG;
+    if (C > 1024) return PU_ERR_UNSUPPORTED;
     bn_bwd_apply_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dout, ldd, dout2, ldd2, y, ldy, scale, shift, slope,
                                                                               ka, kb, kc, R, C, dy, lddy);
     PU_LAUNCH_CHECK();
