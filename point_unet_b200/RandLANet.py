@@ -343,9 +343,10 @@ class Network(torch.nn.Module):
         f_layer_fc1 = self.conv2d(f_decoder_list[-1], "fc1", True, is_training)
         f_layer_fc2 = self.conv2d(f_layer_fc1, "fc2", True, is_training)
         if is_training:
-            if dropout_mask is None:  # tf.nn.dropout(keep_prob=0.5) (helper_tf_util.py:571-573)
-                dropout_mask = (torch.rand_like(f_layer_fc2) < 0.5)
-            f_layer_drop = f_layer_fc2 * (dropout_mask.to(f_layer_fc2.dtype) * 2.0)
+            if dropout_mask is None:  # tf.nn.dropout(keep_prob=0.5) (helper_tf_util.py:571-573): inverted scaling, x / keep
+                f_layer_drop = torch.nn.functional.dropout(f_layer_fc2, p=0.5, training=True)  # one fused kernel each way
+            else:                      # injected keep-mask (parity tests share it with the oracle)
+                f_layer_drop = f_layer_fc2 * (dropout_mask.to(f_layer_fc2.dtype) * 2.0)
         else:
             f_layer_drop = f_layer_fc2
         f_layer_fc3 = self.conv2d(f_layer_drop, "fc", False, is_training, activation=False)
