@@ -360,10 +360,12 @@ static unsigned g_slot = 0;
 template <int SLOT>
 static int launch_fwd(const float *x, int ldx, const float *w, long long P, float *out, int ldo, cudaStream_t st) {
     constexpr size_t smem = (size_t)WARPS * FWD_TILES * TILE * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};  // per device: the attribute belongs to the device's copy of the function
+    int dev = 0;
+    PU_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         PU_CUDA_TRY(cudaFuncSetAttribute(att16_fwd_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     PU_CUDA_TRY(cudaMemcpyToSymbolAsync(pu_att16_cw, w, D * D * sizeof(float), (size_t)SLOT * D * D * sizeof(float),
                                         cudaMemcpyDeviceToDevice, st));
@@ -377,10 +379,12 @@ static int launch_bwd(const float *x, int ldx, const float *w, const float *g, i
                       float *dw, int accumulate, float *part, cudaStream_t st) {
     constexpr size_t smem = (size_t)WARPS * BWD_TILES * TILE * sizeof(float);
     static_assert(WARPS * BWD_TILES * TILE >= WARPS * 2 * D * D, "reduction scratch fits");
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    int dev = 0;
+    PU_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         PU_CUDA_TRY(cudaFuncSetAttribute(att16_bwd_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     PU_CUDA_TRY(cudaMemcpyToSymbolAsync(pu_att16_cw, w, D * D * sizeof(float), (size_t)SLOT * D * D * sizeof(float),
                                         cudaMemcpyDeviceToDevice, st));

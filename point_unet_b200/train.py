@@ -156,6 +156,7 @@ class Trainer:
         finally:
             ops.GRAD_SINK = False
             ops.WGRAD_STREAM = None
+            ops._wgrad_keep.clear()
         if self.world_size > 1:
             self.bucket.all_reduce_mean()                          # gradients only, NCCL over NVLink
         self.opt.step()
