@@ -737,11 +737,18 @@ __global__ void __launch_bounds__(256, KP > 8 ? 2 : 4) wgrad_narrow_kernel(const
                                                            float *__restrict__ db_part) {
     __shared__ float s_red[8 * (KP + 1) * 8 * 4];  // [warp][(KP+1) rows of NY*4 columns]
     int NY = 1;                               // column groups of 4, rounded up to a power of two (<= 8)
-    while (NY * 4 < N) NY <<= 1;
+    while (NY * 4 < min(N - (int)blockIdx.y * 32, 32)) NY <<= 1;
     const int RL = 256 / NY;                  // row lanes per CTA
     const int y = threadIdx.x % NY, rl = threadIdx.x / NY;
     const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
     const long long r_end = min(M, r_begin + rows_per_chunk);
+    // slab of the output this CTA owns: 32 columns (blockIdx.y) x 16 weight rows (blockIdx.z).  Wider layers are cut into
+    // slabs along ONE axis (the launcher takes this path only when K <= 16 or N <= 32), so the wide operand is still read
+    // once and only the thin one is re-read per slab.
+    const int n0 = blockIdx.y * 32, k0 = blockIdx.z * 16;
+    const int Kfull = K, Nfull = N;
+    A += k0; G += n0;
+    K = min(K - k0, 16); N = min(N - n0, 32);
     float acc[KP][4];
 #pragma unroll
     for (int i = 0; i < KP; ++i)
@@ -839,8 +846,8 @@ __global__ void __launch_bounds__(256, KP > 8 ? 2 : 4) wgrad_narrow_kernel(const
         for (int w = 0; w < 8; ++w) s += s_red[(size_t)w * per + e];
         const int i = e / (NY * 4), col = e % (NY * 4);
         if (col < N) {
-            if (i < K) part[(size_t)blockIdx.x * K * N + (size_t)i * N + col] = s;
-            else if (i == KP && db_part) db_part[(size_t)blockIdx.x * N + col] = s;
+            if (i < K) part[(size_t)blockIdx.x * Kfull * Nfull + (size_t)(k0 + i) * Nfull + n0 + col] = s;
+            else if (i == KP && db_part && k0 == 0) db_part[(size_t)blockIdx.x * Nfull + n0 + col] = s;
         }
     }
 }
@@ -1010,11 +1017,14 @@ int pu_att_pooling_bwd(const float *feature_set, int ldx, const float *w, const 
     return launch_gemm<EPI_ATT_BWD>(p, (cudaStream_t)stream);
 }
 
-static inline bool wgrad_is_narrow(int K, int N) { return K <= 16 && N <= 32; }
+// thread-per-row register kernel: K <= 16 and N <= 32 natively, one of the two axes cut into slabs beyond that
+// (LocSE MLPs 10 -> 64/128/256, the classifier 32 -> 4)
+static inline bool wgrad_is_narrow(int K, int N) { return (K <= 16 && N <= 512) || (N <= 32 && K <= 64); }
 
 static inline void wgrad_plan(long long M, int K, int N, int *chunks, long long *rows_per_chunk) {
     if (wgrad_is_narrow(K, N)) {
-        long long want = (long long)kNumSMs * 8;
+        const int slabs = ceil_div(N, 32) * ceil_div(K, 16);
+        long long want = ((long long)kNumSMs * 8 + slabs - 1) / slabs;
         long long max_chunks = (M + 1023) / 1024;  // at least 1024 rows per CTA
         if (want > max_chunks) want = max_chunks;
         if (want < 1) want = 1;
@@ -1059,10 +1069,11 @@ int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M, in
     float *part = (float *)workspace;
     float *db_part = db ? part + (size_t)chunks * K * N : nullptr;
     if (wgrad_is_narrow(K, N)) {
+        dim3 grid(chunks, ceil_div(N, 32), ceil_div(K, 16));
         if (K <= 8)
-            wgrad_narrow_kernel<8><<<chunks, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
+            wgrad_narrow_kernel<8><<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
         else
-            wgrad_narrow_kernel<16><<<chunks, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
+            wgrad_narrow_kernel<16><<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);
     } else {
         dim3 grid(ceil_div(K, WT), ceil_div(N, WT), chunks);
         wgrad_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, M, K, N, rpc, part, db_part);

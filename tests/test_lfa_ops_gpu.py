@@ -107,7 +107,10 @@ def test_nearest_interpolation_fwd_bwd():
 
 @pytest.mark.parametrize("rows,cin,cout", [(5000, 7, 8), (4096, 10, 8), (3001, 8, 16), (2000, 64, 128), (700, 1536, 512),
                                             (9000, 32, 2), (1500, 160, 32), (300001, 16, 32), (200000, 16, 16),
-                                            (150000, 10, 32), (100000, 8, 8), (50000, 16, 12)])
+                                            (150000, 10, 32), (100000, 8, 8), (50000, 16, 12),
+                                            # slab-cut narrow weight gradients: LocSE MLPs of the deep levels, the classifier
+                                            (60000, 10, 64), (20000, 10, 128), (9001, 10, 256), (70000, 32, 4), (5000, 64, 32),
+                                            (3000, 16, 500)])
 def test_linear_and_wgrad(rows, cin, cout):
     g = torch.Generator().manual_seed(rows)
     x = torch.randn(rows, cin, generator=g)
