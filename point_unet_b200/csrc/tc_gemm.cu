@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     const Params &p = q.g;
     constexpr int A_BYTES = BM * 128;                 // one raw 128 x 32 fp32 k-block
     constexpr int B_KB = 2 * BN * 128;                // hi + lo of one k-block of the weight
-    constexpr int TA = BN <= 64 ? MAX_TA : 2;         // operand-A stages in tensor memory
+    // operand-A stages in tensor memory = weight k-block stages of the streamed variant.  BN = 128: three (96 KB of weights
+    // beside the staging tiles and a 3-deep raw ring); two left only ONE weight fetch in flight and every k-block waited a
+    // full L2 round trip (~1.1 us against 0.39 us of MMA work).
+    constexpr int TA = BN <= 64 ? MAX_TA : 3;
     constexpr int ACC_COLS = 2 * BN;                  // double-buffered accumulator; A stage s lives at column ACC_COLS + 64 s
     constexpr int TMEM_COLS = 512;                    // one CTA per SM: take all of tensor memory
     static_assert(ACC_COLS + TA * 64 <= TMEM_COLS, "tensor memory budget");
@@ -385,11 +388,25 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
             long long cur_tile = blockIdx.x;
             int cur_kb = 0, slot = 0, use = 0, tile_count = 0;
             bool ok = true;
-            if constexpr (STREAM) {
-                if (leader && cur_tile < q.ntiles) {  // weight k-block of item 0
-                    mbar_expect_tx(&b_full[0], (uint32_t)B_KB);
-                    bulk_g2s(b_res, b_packed, (uint32_t)B_KB, &b_full[0]);
+            // streamed weights: the fetch cursor runs PF = TA - 1 items (k-blocks) ahead of the MMA cursor, so PF bulk copies
+            // are in flight while one item computes
+            constexpr int PF = TA - 1;
+            long long f_tile = blockIdx.x;
+            int f_kb = 0, f_slot = 0, f_use = 0;
+            auto fetch_next = [&]() {
+                if (f_tile >= q.ntiles) return;
+                // the stage's previous reader (item - TA) must have retired
+                if (f_use >= 1) ok = mbar_wait(&stage_free[f_slot], (uint32_t)((f_use - 1) & 1)) && ok;
+                if (leader) {
+                    mbar_expect_tx(&b_full[f_slot], (uint32_t)B_KB);
+                    bulk_g2s(b_res + (size_t)f_slot * B_KB, b_packed + (size_t)f_kb * B_KB, (uint32_t)B_KB, &b_full[f_slot]);
                 }
+                if (++f_kb == nkb) { f_kb = 0; f_tile += gridDim.x; }
+                if (++f_slot == TA) { f_slot = 0; ++f_use; }
+            };
+            if constexpr (STREAM) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) fetch_next();  // items 0 .. PF-1 (first use of their stages: nothing to wait for)
             }
             while (cur_tile < q.ntiles) {
                 const bool last_kb = cur_kb == nkb - 1;
@@ -416,17 +433,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 }
                 int slot1 = slot + 1, use1 = use;
                 if (slot1 == TA) { slot1 = 0; ++use1; }
-                if constexpr (STREAM) {  // fetch the weight k-block of the NEXT item into the next stage
-                    const int nkb_next = last_kb ? 0 : cur_kb + 1;
-                    const long long ntile = last_kb ? cur_tile + gridDim.x : cur_tile;
-                    if (ntile < q.ntiles) {
-                        if (use1 >= 1) ok = mbar_wait(&stage_free[slot1], (uint32_t)((use1 - 1) & 1)) && ok;  // its previous reader retired
-                        if (leader) {
-                            mbar_expect_tx(&b_full[slot1], (uint32_t)B_KB);
-                            bulk_g2s(b_res + (size_t)slot1 * B_KB, b_packed + (size_t)nkb_next * B_KB, (uint32_t)B_KB, &b_full[slot1]);
-                        }
-                    }
-                }
+                if constexpr (STREAM) fetch_next();  // item + PF goes into the stage of item - 1 (waits for its MMAs to retire)
                 if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
                 slot = slot1; use = use1;
             }
@@ -662,7 +669,7 @@ template <int BN, bool STREAM>
 static size_t persist_fixed_bytes(int K) {  // everything except the raw ring
     const int nkb = (K + BK - 1) / BK;
     const int ec = BN > 64 ? 64 : BN;
-    const int ta = BN <= 64 ? MAX_TA : 2;
+    const int ta = BN <= 64 ? MAX_TA : 3;
     return (size_t)(STREAM ? ta : nkb) * 2 * BN * 128 + 2 * (size_t)BM * (ec + 4) * 4 + 1024;  // weights, 2 staging tiles
 }
 template <int BN, bool STREAM>
