@@ -46,6 +46,27 @@ def test_knn_argument_validation_without_gpu(L):
     assert L.pu_knn_batch(p, p, 1, 10, 0, 16, p, None, 0, None) == 0       # no queries is a no-op
 
 
+def test_att16_and_inverse_argument_validation_without_gpu(L):
+    """The d = 16 attentive-pooling entries and the inverse-list builder reject bad arguments before any CUDA call."""
+    from point_unet_b200 import ops
+    ops._L()  # declares argument types
+    assert L.pu_att16_supported(16, 16, 16) == 1 and L.pu_att16_supported(16, 16, 32) == 1
+    assert L.pu_att16_supported(16, 32, 32) == 0 and L.pu_att16_supported(8, 16, 16) == 0 and L.pu_att16_supported(16, 16, 18) == 0
+    small, big = L.pu_att16_workspace_bytes(10), L.pu_att16_workspace_bytes(720000)
+    assert 0 < small <= big <= 2 * 148 * 256 * 4 + 256            # one [16,16] partial per CTA, at most 2 CTAs per SM
+    buf = ctypes.create_string_buffer(4096)
+    p = ctypes.cast(buf, ctypes.c_void_p).value
+    p = (p + 15) & ~15
+    assert L.pu_att16_fwd(None, 16, p, 4, p, 16, None) == -1       # null tensor
+    assert L.pu_att16_fwd(p, 8, p, 4, p, 16, None) == -1           # row stride below the channel count
+    assert L.pu_att16_fwd(p, 16, p, 0, p, 16, None) == 0           # no points: no-op
+    assert L.pu_att16_bwd(p, 16, p, p, 16, 4, p, 16, p, 0, None, 0, None) == -2   # no workspace
+    assert L.pu_att16_bwd(p, 16, p, p, 16, 4, p, 18, p, 0, p, 1 << 20, None) == -1  # dx stride not a multiple of 4
+    assert L.pu_build_inverse(None, 16, 1, 4, p, p, p, 1 << 20, None) == -1
+    assert L.pu_build_inverse(p, 16, 1, 4, p, p, None, 0, None) == -2
+    assert L.pu_inverse_workspace_bytes(4, 180000 * 16) > 4 * 4 * 180000 * 16
+
+
 def test_no_cpu_fallback():
     import numpy as np
     import torch
