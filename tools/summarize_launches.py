@@ -31,7 +31,8 @@ ENTRY = [(r"tc::tc_persist_kernel<\d+, 0,", "pu_tc_linear_fwd"), (r"tc::tc_linea
          (r"tc::tc_persist_kernel<\d+, 1,", "pu_tc_att_pooling_fwd"), (r"tc::tc_persist_kernel<\d+, 2,", "pu_tc_att_pooling_bwd"),
          (r"tc::tc_wgrad_kernel", "pu_tc_wgrad"), (r"lfa::gather_rows", "pu_gather_rows_fwd"), (r"lfa::segment_sum", "pu_segment_sum"),
          (r"mlp::wgrad", "pu_wgrad"), (r"mlp::linear_narrow|mlp::gemm_kernel<\d+, \d+, \d+, \d+, 0>", "pu_linear_fwd"),
-         (r"knn::knn_search_kernel", "pu_knn_batch")]
+         (r"knn::knn_search_kernel", "pu_knn_batch"), (r"att16::att16_fwd_kernel", "pu_att16_fwd"),
+         (r"att16::att16_bwd_kernel", "pu_att16_bwd")]
 tr = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for k, a in agg.items():
     for pat, entry in ENTRY:
