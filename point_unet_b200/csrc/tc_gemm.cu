@@ -184,7 +184,24 @@ struct Params2 {
     const float *G; int ldg;   // att bwd: upstream gradient [M/16, N]
     float *OUT; int ldo;       // att fwd: f_agg [M/16, N];  att bwd: dx_direct [M, N]
     long long ntiles;
+#ifdef PU_TC_TIMELINE
+    long long *timeline;       // development builds only (tools/tc_timeline.py): per-role clock64 stamps of CTA (0, 0)
+#endif
 };
+
+// Per-role timeline of the persistent kernel, compiled in only with -DPU_TC_TIMELINE (the product build contains none of
+// it).  CTA (0,0) stamps clock64() at the hand-off points of its first TL_ITEMS work items: role r, item i, event e ->
+// timeline[(r * TL_ITEMS + i) * TL_EVENTS + e].  Roles: 0 loader, 1 converter (warp 0), 2 issuer, 3 / 4 epilogue groups.
+#ifdef PU_TC_TIMELINE
+constexpr int TL_ITEMS = 256, TL_EVENTS = 4, TL_ROLES = 5;
+#define PU_TL(role, item, ev)                                                                              \
+    do {                                                                                                   \
+        if (q.timeline && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (item) < TL_ITEMS) \
+            q.timeline[((size_t)(role) * TL_ITEMS + (item)) * TL_EVENTS + (ev)] = clock64();               \
+    } while (0)
+#else
+#define PU_TL(role, item, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -325,9 +342,18 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 #pragma unroll
         for (int j = 0; j < 4; ++j) c_off[j] = (uint32_t)(crow * 128 + (((chalf * 4 + j) ^ (crow & 7)) << 4));
         const uint32_t t_a = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(ACC_COLS + chalf * 16);
+#ifdef PU_TC_TIMELINE
+        int tl_item = 0;
+#endif
         while (cur_tile < q.ntiles) {
             ok = mbar_wait(&raw_full[rslot], (uint32_t)(ruse & 1)) && ok;                        // the k-block has landed
+#ifdef PU_TC_TIMELINE
+            if (warp == 0) PU_TL(1, tl_item, 0);
+#endif
             if (use >= 1) ok = mbar_wait(&stage_free[slot], (uint32_t)((use - 1) & 1)) && ok;    // MMAs that read the stage retired
+#ifdef PU_TC_TIMELINE
+            if (warp == 0) PU_TL(1, tl_item, 1);
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const char *src = raw_ring + (size_t)rslot * A_BYTES;
             float v[16];
@@ -349,9 +375,16 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
             // the tensor-memory stores consumed every loaded value, so the shared-memory reads have completed: only now may
             // the loader refill the slot (an arrive issued right behind the LDS can overtake it in the memory pipeline)
             mbar_arrive(&raw_free[rslot]);
+#ifdef PU_TC_TIMELINE
+            if (warp == 0) PU_TL(1, tl_item, 2);
+#endif
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&stage_ready[slot]);  // hand the stage to the issuer; do not wait for it
+#ifdef PU_TC_TIMELINE
+            if (warp == 0) PU_TL(1, tl_item, 3);
+            ++tl_item;
+#endif
             if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; }
             if (++rslot == D) { rslot = 0; ++ruse; }
             if (++slot == TA) { slot = 0; ++use; }
@@ -364,8 +397,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
         long long tile_i = blockIdx.x;
         int kb = 0, rslot = 0, ruse = 0;
         bool ok = true;
+#ifdef PU_TC_TIMELINE
+        int tl_item = 0;
+#endif
         while (tile_i < q.ntiles) {
             if (ruse >= 1) ok = mbar_wait(&raw_free[rslot], (uint32_t)((ruse - 1) & 1)) && ok;   // all converters have read the slot
+#ifdef PU_TC_TIMELINE
+            PU_TL(0, tl_item, 0);
+            ++tl_item;
+#endif
             if (leader) {
                 mbar_expect_tx(&raw_full[rslot], (uint32_t)A_BYTES);
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -388,6 +428,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
             long long cur_tile = blockIdx.x;
             int cur_kb = 0, slot = 0, use = 0, tile_count = 0;
             bool ok = true;
+#ifdef PU_TC_TIMELINE
+            int tl_item = 0;
+#endif
             // streamed weights: the fetch cursor runs PF = TA - 1 items (k-blocks) ahead of the MMA cursor, so PF bulk copies
             // are in flight while one item computes
             constexpr int PF = TA - 1;
@@ -413,7 +456,13 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 const int buf = tile_count & 1, v = tile_count >> 1;
                 if (cur_kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[buf], (uint32_t)((v - 1) & 1)) && ok;
                 ok = mbar_wait(&stage_ready[slot], (uint32_t)(use & 1)) && ok;           // all 256 producers filled the stage
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 0);
+#endif
                 if constexpr (STREAM) ok = mbar_wait(&b_full[slot], (uint32_t)(use & 1)) && ok;  // this k-block of the weight landed
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 1);
+#endif
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 const uint32_t a_tmem = tmem_base + (uint32_t)(ACC_COLS + slot * 64);
@@ -433,7 +482,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 }
                 int slot1 = slot + 1, use1 = use;
                 if (slot1 == TA) { slot1 = 0; ++use1; }
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 2);
+#endif
                 if constexpr (STREAM) fetch_next();  // item + PF goes into the stage of item - 1 (waits for its MMAs to retire)
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 3);
+                ++tl_item;
+#endif
                 if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
                 slot = slot1; use = use1;
             }
@@ -489,10 +545,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                         }
                     }
                 }
+#ifdef PU_TC_TIMELINE
+                const int tl_item = (tile_count >> 1) * NPASS + pass;
+                if (gwarp == 0) PU_TL(3 + eg, tl_item, 0);
+#endif
                 if (pass == 0) {
                     ok = mbar_wait(&acc_full[buf], (uint32_t)(v & 1)) && ok;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
+#ifdef PU_TC_TIMELINE
+                if (gwarp == 0) PU_TL(3 + eg, tl_item, 1);
+#endif
                 {   // TMEM -> registers -> staging tile: warp (quarter, chalf) moves 32 rows x EC/2 columns
                     const int row = quarter * 32 + lane;
 #pragma unroll
@@ -511,6 +574,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     mbar_arrive(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
                 }
                 bar_sync_named(bar_id, G_THREADS);
+#ifdef PU_TC_TIMELINE
+                if (gwarp == 0) PU_TL(3 + eg, tl_item, 2);
+#endif
 
                 if constexpr (EPI == EPI_STORE) {
                     const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
@@ -646,6 +712,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                     }
                 }
                 bar_sync_named(bar_id, G_THREADS);  // the staging tile is reused by the next pass / tile of this group
+#ifdef PU_TC_TIMELINE
+                if (gwarp == 0) PU_TL(3 + eg, tl_item, 3);
+#endif
             }
             if (x_ring) {  // every x value has been consumed by the arithmetic above: the loader may refill the tile's slots
                 mbar_arrive(&raw_free[eslot]);
@@ -713,9 +782,21 @@ static int make_tmap_rows(CUtensorMap *map, const float *base, long long M, int 
     return r == CUDA_SUCCESS ? PU_OK : PU_ERR_INVALID_ARG;
 }
 
+#ifdef PU_TC_TIMELINE
+static long long *g_timeline = nullptr;
+extern "C" __attribute__((visibility("default"))) void pu_tc_debug_set_timeline(long long *device_buffer) { g_timeline = device_buffer; }
+extern "C" __attribute__((visibility("default"))) int pu_tc_debug_timeline_dims(int *roles, int *items, int *events) {
+    *roles = TL_ROLES; *items = TL_ITEMS; *events = TL_EVENTS;
+    return 0;
+}
+#endif
+
 template <int BN, int EPI, bool STREAM>
 static int launch_persist(const Params2 &q, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     Params2 qq = q;
+#ifdef PU_TC_TIMELINE
+    qq.timeline = g_timeline;
+#endif
     qq.raw_depth = persist_raw_depth<BN, STREAM>(q.g.K);
     if (qq.raw_depth < 3) return PU_ERR_UNSUPPORTED;
     const size_t smem = persist_fixed_bytes<BN, STREAM>(q.g.K) + (size_t)qq.raw_depth * BM * 128;
