@@ -27,7 +27,8 @@ a = ap.parse_args()
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "point_unet_b200", "csrc")
-subprocess.check_call(["make", "-s", "-C", CSRC, "TL=1"], stderr=subprocess.DEVNULL)
+if not (os.environ.get("PU_TL_NOBUILD") and os.path.exists(os.path.join(ROOT, "point_unet_b200", "libpointunet_b200_tl.so"))):
+    subprocess.check_call(["make", "-s", "-C", CSRC, "TL=1"], stderr=subprocess.DEVNULL)
 L = ctypes.CDLL(os.path.join(ROOT, "point_unet_b200", "libpointunet_b200_tl.so"))
 c_void_p, c_int, c_ll, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t
 L.pu_tc_workspace_bytes.restype = c_size_t
