@@ -31,6 +31,8 @@ N_POINTS = 180000
 BATCH_PER_GPU = 4
 METRIC = "pointsegment_train_points_per_s"
 UNIT = "points/s"
+WORKLOAD = ("PointSegment train step (index pyramid + fwd + bwd + Adam), BraTS-shaped clouds, 4 modality features, "
+            "K=16, d_out [16,64,128,256,512]")
 
 
 def load_peaks():
@@ -165,6 +167,7 @@ def reference_step_factory(n_sample, threads):
     labels = torch.from_numpy(c["labels"][None])
     cw = DP.get_class_weights("BraTS20")
     mask = torch.from_numpy(np.random.default_rng(0).random((1, n_sample, 1, 32)) < 0.5)
+    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=cfg.learning_rate)  # RandLANet.py:88
 
     def step():
         pyr = ref.tf_map(c["xyz"][None], cfg, knn)  # 5x K=16 + 5x K=1, B=1 => one thread, like the reference
@@ -176,10 +179,11 @@ def reference_step_factory(n_sample, threads):
         logits = ref.inference(params, inputs, cfg, True, dropout_mask=mask)
         loss = ref.get_loss(logits, labels, cw)
         loss.backward()
+        opt.step()
         return float(loss.detach())
 
     desc = (f"1 BraTS-shaped cloud x {n_sample} points per step: nanoflann pyramid ({kind}) + torch-CPU fp32 restatement "
-            f"of the TF graph fwd+bwd (TF 1.11 not installable), {threads} threads")
+            f"of the TF graph fwd+bwd + Adam (TF 1.11 not installable), {threads} threads")
     return step, kind, desc
 
 
@@ -201,8 +205,8 @@ def run_reference(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="PointSegment train step fwd+bwd, BraTS-shaped 180k-point clouds, K=16, batch 4/GPU",
-                            sample_points=n_sample),
+                config=dict(workload=WORKLOAD, points_per_cloud=N_POINTS, batch_per_gpu=BATCH_PER_GPU, sample_points=n_sample,
+                            note="CPU arm: one cloud of sample_points points per step (bounded sample of the same workload)"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=kind, sample=desc),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -393,8 +397,7 @@ def run_ours(args):
         pts = B * N * world
         line = dict(metric=METRIC, value=pts / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload="PointSegment train step (GPU index pyramid + fwd + bwd + Adam), BraTS-shaped "
-                                         "clouds, 4 modality features, K=16, d_out [16,64,128,256,512]",
+                    config=dict(workload=WORKLOAD,
                                 points_per_cloud=N, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
                                 l2_policy="working set per step >> 126 MB L2 (no flush needed)",
                                 launch=("one CUDA graph replay per step" if use_graph else "eager launches"),
