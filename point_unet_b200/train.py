@@ -237,7 +237,9 @@ class Trainer:
 
     def train_step(self, xyz, features, labels):
         """Public end-to-end step on HOST buffers (numpy or pinned CPU tensors); returns the loss as a float
-        (device -> host read).  Uses the captured graph when there is one for this shape."""
+        (device -> host read).  Uses the captured graph when there is one for this shape; with a PIPELINED graph
+        (``capture_step(pipelined=True)``) the batch handed in is staged and indexed during this call and trained by the next
+        one, so the value returned is the loss of the batch submitted one call earlier."""
         x = self._stage("xyz", xyz)
         f = self._stage("features", features)
         l = self._stage("labels", labels)
