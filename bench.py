@@ -35,6 +35,12 @@ WORKLOAD = ("PointSegment train step (index pyramid + fwd + bwd + Adam), BraTS-s
             "K=16, d_out [16,64,128,256,512]")
 
 
+def config_dict(world):
+    """The workload description, IDENTICAL for both arms (ours and --impl reference) at the same N."""
+    return dict(workload=WORKLOAD, points_per_cloud=N_POINTS, batch_per_gpu=BATCH_PER_GPU, global_batch=BATCH_PER_GPU * world,
+                parallelism=f"dp{world}", l2_policy="working set per step >> 126 MB L2 (no flush needed)")
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -192,8 +198,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    total = args.steps + args.warmup
-    n_sample = N_POINTS if total <= 4 else max(20000, N_POINTS // ((total + 3) // 4))
+    n_sample = N_POINTS   # the full 180 000-point cloud, every step (about 3.5 s per step on the GPU box's host cores)
     step, kind, desc = reference_step_factory(n_sample, threads)
     for _ in range(args.warmup):
         step()
@@ -204,13 +209,119 @@ def run_reference(args):
     value = n_sample / dt
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, points_per_cloud=N_POINTS, batch_per_gpu=BATCH_PER_GPU, sample_points=n_sample,
-                            note="CPU arm: one cloud of sample_points points per step (bounded sample of the same workload)"),
+                data="synthetic", impl="reference", config=config_dict(int(os.environ.get("WORLD_SIZE", "1"))),
+                note="CPU arm: ONE full cloud of the batch per step (bounded sample of the same workload)",
                 cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=kind, sample=desc),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
+
+
+# ---------------------------------------------------------------------------------------------------------
+def knn_sweep(dev, peaks, with_cpu):
+    """BASELINE.json configs[1]: knn_search K=16 self-query on uniform clouds of 16k / 65k / 180k / 1M points (the
+    reference's own probe, utils/nearest_neighbors/test.py:5-13, draws the same kind of cloud) plus one Pancreas-shaped
+    LATTICE cloud (distance ties in most rows).  Per row: queries/s (CUDA events, build + search of one call), distance
+    evaluations per query, fraction of the 76 B/query HBM roofline; with the CPU leg the reference's nanoflann wrapper timed
+    on the same cloud (B = 1 => one thread, its operating point), the share of rows identical to nanoflann, and bit-exactness
+    against the canonical (distance, index) oracle."""
+    import numpy as np
+    import torch
+    from point_unet_b200 import synthetic as syn
+    from point_unet_b200.helper_tool import knn_last_stats, knn_search_cuda
+    rows = []
+    cases = [("uniform", n) for n in (16384, 65536, 180000, 1000000)] + [("pancreas_lattice", 180000)]
+    for kind, n in cases:
+        pts = np.random.default_rng(n).random((1, n, 3), dtype=np.float32) if kind == "uniform" \
+            else syn.pancreas_cloud(n, 5)["xyz"][None]
+        x = torch.from_numpy(pts).to(dev)
+        for _ in range(3):
+            got = knn_search_cuda(x, x, 16)
+        torch.cuda.synchronize()
+        reps = 5 if n >= 1000000 else 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            got = knn_search_cuda(x, x, 16)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        st = knn_last_stats(dev)
+        row = dict(cloud=kind, n=n, k=16, ms=ms, queries_per_s=n / (ms * 1e-3), evals_per_query=st["dist_evals"] / n,
+                   hbm_frac=76 * n / (ms * 1e-3) / 1e9 / peaks["hbm"], tie_rule="(distance, index)")
+        if with_cpu:
+            from oracle import knn as ok
+            g = got.cpu().numpy()
+            if ok.have_reference():
+                t0 = time.perf_counter()
+                ref = ok.knn_reference(pts, pts, 16)
+                dt = time.perf_counter() - t0
+                row.update(nanoflann_queries_per_s=n / dt, nanoflann_threads=1,
+                           rows_equal_nanoflann=float((g == ref).all(-1).mean()))
+            if n <= 180000:
+                row["bit_exact_vs_canonical_oracle"] = bool(np.array_equal(g, ok.knn_restated(pts, pts, 16, tie_rule=1)))
+        rows.append(row)
+    return rows
+
+
+def inference_leg(dev, rank, world, n_volumes, barrier):
+    """BASELINE.json configs[4]: test-mode inference over 64 synthetic Pancreas volumes (seeds 0..63), volumes dealt
+    round-robin to the ranks with no communication (parallel.shard_round_robin).  Per volume, from PINNED HOST buffers:
+    H2D of the cloud, GPU index pyramid, forward with moving BN statistics, softmax, then
+      (a) testPancreas.py:141-202: probabilities scattered into the dense [Z,Y,X,C] fp32 volume (left on the device: the
+          reference np.save's it), and
+      (b) the fused variant that goes on to the uint8 label volume of utils/genSegmentationPancreas.py:67-77 and copies it
+          back to pinned host memory.
+    Returns volumes/s of the whole job (max over ranks of the wall time)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from point_unet_b200 import synthetic as syn
+    from point_unet_b200.helper_tool import ConfigPancreas
+    from point_unet_b200.parallel import shard_round_robin
+    from point_unet_b200.train import Trainer
+
+    class pcfg(ConfigPancreas):
+        num_points = N_POINTS
+
+    tr = Trainer(pcfg, num_features=4, seed=0, device=dev, world_size=1)
+    X, Y, Z = syn.PANCREAS_SHAPE
+    shape = (Z, X, Y, 2)
+    mine = shard_round_robin(n_volumes, rank, world)
+    vols = []
+    for v in mine:  # host-side preparation of the clouds: untimed (the reference reads them from .ply files)
+        c = syn.pancreas_cloud(N_POINTS, v)
+        vols.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
+                          (c["xyz"][None], c["features"][None], c["xyz_origin"].astype(np.int32)[None])))
+    host_labels = torch.empty((Z, Y, X), dtype=torch.uint8, pin_memory=True)
+    out = {}
+    for name in ("prob_volume", "label_volume"):
+        for xyz, feat, xo in vols[:2]:   # warm-up
+            if name == "prob_volume":
+                tr.predict_to_volume(xyz, feat, xo.to(dev, non_blocking=True), shape)
+            else:
+                host_labels.copy_(tr.predict_to_labels(xyz, feat, xo.to(dev, non_blocking=True), shape)[0])
+        barrier()
+        t0 = time.perf_counter()
+        for xyz, feat, xo in vols:
+            if name == "prob_volume":
+                tr.predict_to_volume(xyz, feat, xo.to(dev, non_blocking=True), shape)
+            else:
+                host_labels.copy_(tr.predict_to_labels(xyz, feat, xo.to(dev, non_blocking=True), shape)[0], non_blocking=True)
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = float(t.item())
+    return dict(workload="64 Pancreas-shaped volumes x 180000 points: H2D + pyramid + forward (BN inference mode) + softmax + "
+                         "scatter to voxels, volumes sharded round-robin over the ranks, no communication",
+                volumes=n_volumes, volumes_per_rank=len(mine), volume_shape_zyxc=[Z, Y, X, 2],
+                volumes_per_s=n_volumes / out["prob_volume"], ms_per_volume_per_gpu=out["prob_volume"] * 1e3 / max(len(mine), 1),
+                label_volumes_per_s=n_volumes / out["label_volume"],
+                label_ms_per_volume_per_gpu=out["label_volume"] * 1e3 / max(len(mine), 1),
+                note="volumes_per_s: dense fp32 probability volume per case, left on the device; label_volumes_per_s: fused "
+                     "argmax label volume (uint8) copied back to pinned host memory")
 
 # ---------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -230,11 +341,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep NCCL's version banner / logger off stdout (rank 0 prints exactly one JSON line there)
-        if "PU_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["PU_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL_DEBUG is left as the caller set it (the driver reads the communicator's rank count from its log); the log
+        # goes to stderr so that stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
@@ -329,7 +437,7 @@ def run_ours(args):
 
     # ---- e2e: public API on pinned host buffers (H2D + D2H inside the timed region)
     pinned = tr.pin_batch(host["xyz"], host["features"], host["labels"])
-    for _ in range(2):
+    for _ in range(3):
         tr.train_step(pinned["xyz"], pinned["features"], pinned["labels"])
     barrier()
     t0 = time.perf_counter()
@@ -342,6 +450,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     h2d = sum(int(v.numel() * v.element_size()) for v in pinned.values())
+
+    # ---- a tensor-core pipeline that timed out trained on garbage: such a run is not a measurement
+    if int(ops.tc_error_flag(dev).item()) != 0:
+        raise SystemExit("bench.py: a tcgen05 mbarrier wait timed out during the run (error flag set) -- results invalid")
+
+    # ---- BASELINE.json configs[4]: sharded test-mode inference over 64 Pancreas volumes (every rank takes part)
+    infer = None
+    if not args.no_extra:
+        tr_graph = tr._graph
+        infer = inference_leg(dev, rank, world, 64, barrier)
+        assert tr._graph is tr_graph
 
     if rank == 0:
         # roofline of the dominant kernel (aggregate over its launches in the timed region)
@@ -368,21 +487,9 @@ def run_ours(args):
                         peak_kind="sustained (kernel timed inside a long step)" if bound == "tensor" else "copy")
         bd = {k: dict(launches=v[0], ms=round(v[1], 3)) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][1])}
 
-        # KNN micro-bench (BASELINE.json configs[1]) on one 180k cloud, K=16 self-query
-        xk = x[:1].contiguous()
-        for _ in range(3):
-            knn_search_cuda(xk, xk, 16)
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(10):
-            knn_search_cuda(xk, xk, 16)
-        k1.record()
-        torch.cuda.synchronize()
-        knn_ms = k0.elapsed_time(k1) / 10
-        knn = dict(queries_per_s=N / (knn_ms * 1e-3), ms=knn_ms, n=N, k=16, algorithmic_bytes=76 * N,
-                   hbm_frac=76 * N / (knn_ms * 1e-3) / 1e9 / peaks["hbm"], tie_rule="(distance, index)")
-
+        # KNN sweep (BASELINE.json configs[1]); the 180k uniform row doubles as the headline KNN number
+        knn_rows = knn_sweep(dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline)) if not args.no_extra else []
+        knn = next((r for r in knn_rows if r["cloud"] == "uniform" and r["n"] == 180000), None)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -397,18 +504,17 @@ def run_ours(args):
         pts = B * N * world
         line = dict(metric=METRIC, value=pts / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=WORKLOAD,
-                                points_per_cloud=N, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world}",
-                                l2_policy="working set per step >> 126 MB L2 (no flush needed)",
-                                launch=("one CUDA graph replay per step" if use_graph else "eager launches"),
-                                input_pipeline=("pyramid of batch i+1 built on a side stream inside the replay that trains "
-                                                "batch i (one pyramid + one train step per replay)" if pipelined and use_graph
-                                                else "pyramid and training of the same batch in one step"),
-                                graph_error=graph_err),
+                    config=dict(config_dict(world), points_per_cloud=N, batch_per_gpu=B, global_batch=B * world),
+                    run=dict(launch=("one CUDA graph replay per step" if use_graph else "eager launches"),
+                             input_pipeline=("pyramid of batch i+1 built on a side stream inside the replay that trains "
+                                             "batch i (one pyramid + one train step per replay)" if pipelined and use_graph
+                                             else "pyramid and training of the same batch in one step"),
+                             host_pipeline="H2D of batch k on a copy stream under the replay of call k (Trainer.train_step)",
+                             graph_error=graph_err, tc_error_flag=0),
                     e2e=dict(value=pts / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
-                             d2h_bytes_per_step=4),
+                             d2h_bytes_per_step=8),
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks, knn=knn,
-                    breakdown_ms_per_step=bd, loss=float(loss_val))
+                    knn_sweep=knn_rows, inference_64_volumes=infer, breakdown_ms_per_step=bd, loss=float(loss_val))
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -436,6 +542,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--cpu-sample", type=int, default=N_POINTS, help="points of the cpu_baseline sample cloud")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the KNN sweep (configs[1]) and the 64-volume inference leg (configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -41,6 +41,9 @@ PU_API const char *pu_version(void);
 PU_API int pu_last_cuda_error(void);
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 PU_API unsigned long long pu_launch_count(void);
+/* CRC32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of TensorFlow V2 checkpoints
+ * (reference: tf.train.Saver snapshots, PointSegment/RandLANet.py:101-102,180-184; restored testPancreas.py:129-132). */
+PU_API unsigned int pu_crc32c(const void *data, size_t n, unsigned int crc);
 
 /* ------------------------------------------------------------------------------------------
  * K-nearest neighbours.
@@ -109,6 +112,18 @@ PU_API int pu_random_sample_bwd(const float *feat, int ld_f, const float *out, i
 PU_API size_t pu_point2prod_workspace_bytes(int Z, int X, int Y);
 PU_API int pu_point2prod(const float *probs, const int32_t *xyz_origin, const int32_t *point_idx, int n, int C, int Z,
                          int X, int Y, float *volume, void *workspace, size_t workspace_bytes, pu_stream_t stream);
+
+/* ref: genSegmentation  utils/genSegmentationPancreas.py:67-77, utils/genSegmentationBraTS.py:67-78: the label volume
+ *   seg = np.argmax(prob_volume, axis=-1).astype(uint8) (first maximum wins; voxels no point fell into are 0), with the
+ *   BraTS relabelling 3 -> 4 as (remap_from, remap_to) = (3, 4) (pass (-1, 0) for none).
+ *   pu_point2label fuses point2prod + argmax: labels u8 [Z,Y,X] straight from the per-point probabilities, the dense
+ *   fp32 probability volume is never written (same workspace as pu_point2prod).  pu_volume_argmax is the stand-alone
+ *   argmax over the last axis of an existing volume [nvox, C]. */
+PU_API int pu_point2label(const float *probs, const int32_t *xyz_origin, const int32_t *point_idx, int n, int C, int Z,
+                          int X, int Y, int remap_from, int remap_to, unsigned char *labels, void *workspace,
+                          size_t workspace_bytes, pu_stream_t stream);
+PU_API int pu_volume_argmax(const float *volume, long long nvox, int C, int remap_from, int remap_to,
+                            unsigned char *labels, pu_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Shared MLP = 1x1 convolution over channels-last rows.

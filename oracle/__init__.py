@@ -11,5 +11,7 @@ knn_oracle.c / knn.py   C restatement of nanoflann v0x123 kd-tree K-NN + canonic
                         brute force; ctypes bindings; binding of the reference's own compiled C++
                         (``oracle/_ref/libknn_ref.so``, built from /root/reference by ``make ref``).
 randla_ref.py           PyTorch-CPU (fp32/fp64) restatement of RandLANet.py / helper_tf_util.py ops.
-clouds.py               Synthetic Pancreas/BraTS-shaped cloud generators.
+prepare_ref.py          numpy restatement of the volume -> cloud preparation (dataPreparePancreas.py / dataPrepareBraTS.py /
+                        runBraTS.py generator), random draws injected.
+(The synthetic Pancreas- / BraTS-shaped cloud generators of SURVEY.md section 8d live in point_unet_b200/synthetic.py.)
 """

@@ -138,15 +138,23 @@ def dilated_res_block(feature, xyz, neigh_idx, d_out, p, name, is_training, upd=
     return leaky_relu(f_pc + shortcut)
 
 
-def inference(p, inputs, cfg, is_training, dropout_mask=None, upd=None, keep=None):
-    """RandLANet.py:110-152.  inputs: dict(xyz=[..5], neigh_idx, sub_idx, interp_idx, features [B,N,F])."""
+def inference(p, inputs, cfg, is_training, dropout_mask=None, upd=None, keep=None, checkpoint=False):
+    """RandLANet.py:110-152.  inputs: dict(xyz=[..5], neigh_idx, sub_idx, interp_idx, features [B,N,F]).
+    ``checkpoint``: recompute each encoder block in the backward instead of keeping its [B,N,K,d] intermediates (same
+    arithmetic, same results; lets the full-size 4 x 180k fp64 golden run fit in host memory)."""
     feature = inputs["features"] @ p["fc0/kernel"] + p["fc0/bias"]
     feature = leaky_relu(batch_norm(feature, p, "fc0/bn", is_training, upd))
     feature = feature.unsqueeze(2)
     f_encoder_list = []
     for i in range(cfg.num_layers):
-        f_encoder_i = dilated_res_block(feature, inputs["xyz"][i], inputs["neigh_idx"][i], cfg.d_out[i], p,
-                                        "Encoder_layer_" + str(i), is_training, upd, keep)
+        if checkpoint:
+            from torch.utils.checkpoint import checkpoint as _ckpt
+            f_encoder_i = _ckpt(lambda f, i=i: dilated_res_block(f, inputs["xyz"][i], inputs["neigh_idx"][i], cfg.d_out[i], p,
+                                                                 "Encoder_layer_" + str(i), is_training, upd, keep),
+                                feature, use_reentrant=False)
+        else:
+            f_encoder_i = dilated_res_block(feature, inputs["xyz"][i], inputs["neigh_idx"][i], cfg.d_out[i], p,
+                                            "Encoder_layer_" + str(i), is_training, upd, keep)
         f_sampled_i = random_sample(f_encoder_i, inputs["sub_idx"][i])
         feature = f_sampled_i
         if i == 0:

@@ -13,8 +13,11 @@ singleton axis-2 convention, int32 indices):
 
 Variables keep the reference's scope names (``Encoder_layer_0LFAatt_pooling_1fc/kernel`` ...), stored in the
 layouts of ``helper_tf_util.py``: conv2d kernels ``[Cin, Cout]`` (the 1x1 ``[1,1,Cin,Cout]`` squeezed),
-conv2d_transpose kernels ``[Cout, Cin]``, dense kernels ``[in, out]``.  ``tf_map`` (``runPancreas.py:124-145``)
-is ``build_pyramid`` here and runs the KNN kernel on the device.
+conv2d_transpose kernels ``[Cout, Cin]``, dense kernels ``[in, out]``.  Batch-norm variables are named
+``<scope>/bn/{gamma,beta,moving_mean,moving_variance}`` here; TensorFlow names them
+``layers/<scope>/batch_normalization/...`` (and ``layers/batch_normalization/...`` for the unnamed BN after ``fc0``,
+RandLANet.py:115): ``tf_variable_name`` / ``Network.load_tf_checkpoint`` translate.  ``tf_map``
+(``runPancreas.py:124-145``) is ``build_pyramid`` here and runs the KNN kernel on the device.
 """
 from __future__ import annotations
 
@@ -103,6 +106,16 @@ def init_params(cfg, num_features: int, seed: int = 0) -> dict:
     return p
 
 
+def tf_variable_name(name: str) -> str:
+    """Name of variable ``name`` in a checkpoint written by the reference's ``tf.train.Saver(GLOBAL_VARIABLES)``
+    (RandLANet.py:56,101-102): everything lives under the ``layers`` variable scope; ``tf.layers.batch_normalization`` is
+    unnamed, so inside ``helper_tf_util.conv2d``'s scope it becomes ``<scope>/batch_normalization`` and the one that follows
+    ``fc0`` directly under ``layers`` (RandLANet.py:115) is ``layers/batch_normalization``."""
+    if name.startswith("fc0/bn/"):
+        return "layers/batch_normalization/" + name[len("fc0/bn/"):]
+    return "layers/" + name.replace("/bn/", "/batch_normalization/")
+
+
 def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = None, inverse: bool = False,
                   store: "dict | None" = None) -> dict:
     """``tf_map`` (runPancreas.py:124-145 / runBraTS.py:140-161) on the device: per level
@@ -121,6 +134,8 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
     input), ``neigh_idx``, ``sub_idx``, ``interp_idx`` (num_layers each) and, with ``inverse``, ``inv`` = per level three
     ``(offsets, perm)`` pairs for (neigh_idx, sub_idx, interp_idx).  Everything then runs on the current stream and
     nothing is allocated (the pipelined step of train.py fills such a store one step ahead)."""
+    if store is None:
+        ops.clear_caches()  # inverse lists cached for a previous pyramid must not be picked up through a recycled buffer
     if store is not None:
         assert side is None
         clouds = store["xyz"]
@@ -171,9 +186,11 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
         if inverse:  # the index tensors whose gathers are differentiated: (idx, rows of the gathered tensor per cloud)
             for i in range(cfg.num_layers):
                 n, n_sub = out["xyz"][i].shape[1], subs[i].shape[1]
-                ops.inverse_of(out["neigh_idx"][i], n)
-                ops.inverse_of(out["sub_idx"][i], n)
-                ops.inverse_of(out["interp_idx"][i], n_sub)
+                for idx, n_src in ((out["neigh_idx"][i], n), (out["sub_idx"][i], n), (out["interp_idx"][i], n_sub)):
+                    inv = ops.inverse_of(idx, n_src)
+                    # allocated while `side` was current but read (and freed) on the main stream
+                    inv.offsets.record_stream(main)
+                    inv.perm.record_stream(main)
     out["_sub_clouds"] = subs  # the last sub-cloud is read by a search still queued on `side`: it must outlive this call
     out["pyramid_ready"] = lambda: torch.cuda.current_stream(dev).wait_event(ev)
     out["inverse_ready"] = lambda: torch.cuda.current_stream(dev).wait_stream(side)
@@ -188,32 +205,90 @@ class Network(torch.nn.Module):
         self.config = config
         self.num_features = num_features if num_features is not None else config.num_features
         self._names = {}
+        self._stat_names = {}  # reference name -> buffer key of moving_mean / moving_variance (not trained)
         self.vars = torch.nn.ParameterDict()
-        self.stats = {}  # moving_mean / moving_variance (not trained)
         self.load_numpy(init_params(config, self.num_features, seed), device)
-        self.class_weights = torch.tensor(DP.get_class_weights(config.name).reshape(-1), dtype=torch.float32,
-                                          device=device)
-        self.is_training = True
+        self.register_buffer("class_weights", torch.tensor(DP.get_class_weights(config.name).reshape(-1), dtype=torch.float32,
+                                                           device=device), persistent=False)
 
     # -- variables -------------------------------------------------------------------------------
     @staticmethod
     def _key(name: str) -> str:
         return name.replace("/", "__").replace(".", "_")
 
-    def load_numpy(self, params: dict, device="cuda"):
-        """Inject variables by reference name (the same dict feeds the oracle)."""
+    @property
+    def is_training(self) -> bool:
+        """The reference's ``is_training`` placeholder (RandLANet.py:54) follows ``nn.Module.train()`` / ``eval()``."""
+        return self.training
+
+    @is_training.setter
+    def is_training(self, value: bool):
+        self.train(bool(value))
+
+    @property
+    def stats(self) -> dict:
+        """{reference name: tensor} of the BN moving statistics.  They are registered BUFFERS, so ``state_dict`` /
+        ``load_state_dict`` / ``.to()`` cover them like the reference's Saver covers all GLOBAL_VARIABLES (RandLANet.py:101)."""
+        return {n: self._buffers[k] for n, k in self._stat_names.items()}
+
+    def load_numpy(self, params: dict, device=None):
+        """Inject variables by reference name (the same dict feeds the oracle).  Existing variables are overwritten in
+        place (views such as the trainer's flat gradient buffer stay valid)."""
         for name, arr in params.items():
-            t = torch.as_tensor(np.asarray(arr), dtype=torch.float32).to(device).contiguous()
-            if name.endswith("moving_mean") or name.endswith("moving_variance"):
-                self.stats[name] = t
+            is_stat = name.endswith("moving_mean") or name.endswith("moving_variance")
+            key = "stat__" + self._key(name) if is_stat else self._key(name)
+            old = self._buffers.get(key) if is_stat else (self.vars[key] if key in self.vars else None)
+            dev = device if device is not None else (old.device if old is not None else "cuda")
+            t = torch.as_tensor(np.asarray(arr), dtype=torch.float32).to(dev).contiguous()
+            if old is not None and old.shape == t.shape and old.device == t.device:
+                with torch.no_grad():
+                    old.copy_(t)
+            elif is_stat:
+                self._stat_names[name] = key
+                self.register_buffer(key, t)
             else:
-                key = self._key(name)
                 self._names[name] = key
                 self.vars[key] = torch.nn.Parameter(t)
 
+    def load_tf_checkpoint(self, prefix: str, strict: bool = True) -> list:
+        """Restore from a checkpoint written by the reference (``snap-<step>``, RandLANet.py:101-102,180-184; restored at
+        testPancreas.py:129-132) by VARIABLE NAME: conv kernels ``[1,1,Cin,Cout]`` / ``[1,1,Cout,Cin]`` are squeezed, BN
+        names translated (``tf_variable_name``), optimizer slots ignored.  Returns the reference names that were loaded."""
+        from .tf_checkpoint import read_checkpoint
+        ck = read_checkpoint(prefix)
+        params, missing = {}, []
+        for name in list(self._names) + list(self._stat_names):
+            tf_name = tf_variable_name(name)
+            if tf_name not in ck:
+                missing.append(tf_name)
+                continue
+            arr = np.asarray(ck[tf_name])
+            want = tuple(self.v(name).shape)
+            if arr.ndim == 4 and arr.shape[:2] == (1, 1):
+                arr = arr[0, 0]
+            if tuple(arr.shape) != want:
+                raise ValueError(f"{tf_name}: checkpoint shape {tuple(arr.shape)} != {want}")
+            params[name] = arr
+        if strict and missing:
+            raise KeyError(f"variables missing from {prefix}: {missing[:5]}{' ...' if len(missing) > 5 else ''}")
+        self.load_numpy(params)
+        return sorted(params)
+
+    def save_tf_checkpoint(self, prefix: str) -> None:
+        """Write the variables (and moving statistics) in the reference's checkpoint format and naming."""
+        from .tf_checkpoint import write_checkpoint
+        out = {}
+        for name in list(self._names) + list(self._stat_names):
+            a = self.v(name).detach().cpu().numpy()
+            if name.endswith("/weights"):
+                a = a[None, None]  # helper_tf_util.py:151-152 / :211-212: 1x1 kernels are 4-D
+            out[tf_variable_name(name)] = a
+        write_checkpoint(prefix, out)
+
     def v(self, name: str) -> torch.Tensor:
-        if name in self.stats:
-            return self.stats[name]
+        k = self._stat_names.get(name)
+        if k is not None:
+            return self._buffers[k]
         return self.vars[self._names[name]]
 
     def named_variables(self):
@@ -227,7 +302,7 @@ class Network(torch.nn.Module):
     def _bn_stats(self, scope, mean, var, count, is_training, fused_4d=True):
         """(mean, var, moving): batch statistics in training plus the moving-average buffers to update (momentum 0.99,
         run with the step like UPDATE_OPS at RandLANet.py:90,163); moving statistics at inference."""
-        mm, mv = self.stats[scope + "/bn/moving_mean"], self.stats[scope + "/bn/moving_variance"]
+        mm, mv = self.v(scope + "/bn/moving_mean"), self.v(scope + "/bn/moving_variance")
         if not is_training:
             return mm, mv, None
         # TF's fused kernel (4-D NHWC inputs) feeds the UNBIASED variance to the moving average
@@ -353,7 +428,7 @@ class Network(torch.nn.Module):
         return f_layer_fc3.squeeze(2)
 
     def forward(self, inputs, dropout_mask=None):
-        return self.inference(inputs, self.is_training, dropout_mask)
+        return self.inference(inputs, self.training, dropout_mask)
 
     def get_loss(self, logits, labels):
         """RandLANet.py:62-84,267-274 (no ignored labels for Pancreas/BraTS): class-weighted CE, mean over points."""

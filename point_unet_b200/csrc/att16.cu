@@ -355,7 +355,30 @@ static int plan_grid(long long P) {
     return (int)ctas;
 }
 
-static unsigned g_slot = 0;
+// The FC kernel travels through one of SLOTS __constant__ copies.  Work queued on ONE stream is serialised, so a stream may
+// keep reusing its slot; two streams must never share one (the second copy would overwrite weights a running kernel still
+// reads).  Slots are therefore handed out per (device, stream) and recycled least-recently-used: a race would need more
+// than SLOTS streams with att16 kernels in flight at the same time (the training step uses one).
+struct SlotOwner { int dev; cudaStream_t st; unsigned long long last; bool used; };
+static SlotOwner g_owner[SLOTS] = {};
+static unsigned long long g_tick = 0;
+static int g_slot_lock = 0;
+static int pick_slot(cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    while (__atomic_exchange_n(&g_slot_lock, 1, __ATOMIC_ACQUIRE)) { }
+    int mine = -1, empty = -1, lru = 0;
+    for (int i = 0; i < SLOTS; ++i) {
+        if (!g_owner[i].used) { if (empty < 0) empty = i; continue; }
+        if (g_owner[i].dev == dev && g_owner[i].st == st) { mine = i; break; }
+        if (!g_owner[lru].used || g_owner[i].last < g_owner[lru].last) lru = i;
+    }
+    // own slot, else a free one, else recycle the least recently used (all SLOTS taken by other streams)
+    const int pick = mine >= 0 ? mine : (empty >= 0 ? empty : lru);
+    g_owner[pick] = SlotOwner{dev, st, ++g_tick, true};
+    __atomic_store_n(&g_slot_lock, 0, __ATOMIC_RELEASE);
+    return pick;
+}
 
 template <int SLOT>
 static int launch_fwd(const float *x, int ldx, const float *w, long long P, float *out, int ldo, cudaStream_t st) {
@@ -419,7 +442,7 @@ int pu_att16_fwd(const float *feature_set, int ldx, const float *w, long long P,
         return PU_ERR_INVALID_ARG;
     if (P == 0) return PU_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (__atomic_fetch_add(&g_slot, 1u, __ATOMIC_RELAXED) % SLOTS) {
+    switch (pick_slot(st)) {
         case 0: return launch_fwd<0>(feature_set, ldx, w, P, f_agg, ldo, st);
         case 1: return launch_fwd<1>(feature_set, ldx, w, P, f_agg, ldo, st);
         case 2: return launch_fwd<2>(feature_set, ldx, w, P, f_agg, ldo, st);
@@ -439,7 +462,7 @@ int pu_att16_bwd(const float *feature_set, int ldx, const float *w, const float 
     }
     if (!workspace || workspace_bytes < pu_att16_workspace_bytes(P)) return PU_ERR_WORKSPACE;
     float *part = (float *)workspace;
-    switch (__atomic_fetch_add(&g_slot, 1u, __ATOMIC_RELAXED) % SLOTS) {
+    switch (pick_slot(st)) {
         case 0: return launch_bwd<0>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
         case 1: return launch_bwd<1>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
         case 2: return launch_bwd<2>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);

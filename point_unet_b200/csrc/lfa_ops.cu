@@ -340,6 +340,41 @@ __global__ void __launch_bounds__(256) p2v_write_kernel(const float *__restrict_
     for (int c = 0; c < C; ++c) vol[v * C + c] = probs[(size_t)i * C + c];
 }
 
+// label volume (utils/genSegmentationPancreas.py:67-77, genSegmentationBraTS.py:67-78): seg = argmax(prob volume, -1) as
+// uint8 (first maximum wins, like np.argmax; untouched voxels hold all-zero probabilities -> label 0), BraTS maps 3 -> 4.
+// Written straight from the per-point probabilities by the voxel's owner: the dense fp32 probability volume
+// (0.25-1 GB per case in the reference) is never materialised.
+__global__ void __launch_bounds__(256) p2v_label_kernel(const float *__restrict__ probs, const int32_t *__restrict__ xyz_origin,
+                                                        const int32_t *__restrict__ point_idx, int n, int C, int Z, int X,
+                                                        int Y, const int32_t *__restrict__ owner, int remap_from, int remap_to,
+                                                        unsigned char *__restrict__ labels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t *o = xyz_origin + (size_t)(point_idx ? point_idx[i] : i) * 3;
+    const int x = o[0], y = o[1], z = o[2];
+    if ((unsigned)x >= (unsigned)X || (unsigned)y >= (unsigned)Y || (unsigned)z >= (unsigned)Z) return;
+    const size_t v = ((size_t)z * Y + y) * X + x;
+    if (owner[v] != i) return;
+    const float *p = probs + (size_t)i * C;
+    int best = 0;
+    float bv = p[0];
+    for (int c = 1; c < C; ++c)
+        if (p[c] > bv) { bv = p[c]; best = c; }
+    labels[v] = (unsigned char)(best == remap_from ? remap_to : best);
+}
+// argmax over the last axis of an existing dense volume [nvox, C] -> uint8 [nvox]
+__global__ void __launch_bounds__(256) volume_argmax_kernel(const float *__restrict__ vol, long long nvox, int C, int remap_from,
+                                                            int remap_to, unsigned char *__restrict__ labels) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+        const float *p = vol + (size_t)v * C;
+        int best = 0;
+        float bv = p[0];
+        for (int c = 1; c < C; ++c)
+            if (p[c] > bv) { bv = p[c]; best = c; }
+        labels[v] = (unsigned char)(best == remap_from ? remap_to : best);
+    }
+}
+
 // 128-bit max-pool forward for K = 16: a thread owns one 16-byte column chunk of one output point, loads the 16
 // neighbour ids as four int4 and keeps all 16 row loads in flight before reducing.
 __global__ void __launch_bounds__(256) maxpool_fwd_v4_kernel(const float *__restrict__ feat, int ld_f, int n_src,
@@ -611,6 +646,33 @@ int pu_point2prod(const float *probs, const int32_t *xyz_origin, const int32_t *
     PU_LAUNCH_CHECK();
     p2v_write_kernel<<<ceil_div(n, 256), 256, 0, st>>>(probs, xyz_origin, point_idx, n, C, Z, X, Y,
                                                        (const int32_t *)workspace, volume);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_point2label(const float *probs, const int32_t *xyz_origin, const int32_t *point_idx, int n, int C, int Z, int X,
+                   int Y, int remap_from, int remap_to, unsigned char *labels, void *workspace, size_t workspace_bytes,
+                   pu_stream_t stream) {
+    if (!probs || !xyz_origin || !labels || n < 0 || C < 1 || C > 255 || Z < 1 || X < 1 || Y < 1) return PU_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < pu_point2prod_workspace_bytes(Z, X, Y)) return PU_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nvox = (size_t)Z * X * Y;
+    PU_CUDA_TRY(cudaMemsetAsync(workspace, 0xFF, nvox * sizeof(int32_t), st));  // owner = -1
+    PU_CUDA_TRY(cudaMemsetAsync(labels, 0, nvox, st));                          // argmax of an all-zero voxel
+    if (n == 0) return PU_OK;
+    p2v_owner_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyz_origin, point_idx, n, Z, X, Y, (int32_t *)workspace);
+    PU_LAUNCH_CHECK();
+    p2v_label_kernel<<<ceil_div(n, 256), 256, 0, st>>>(probs, xyz_origin, point_idx, n, C, Z, X, Y,
+                                                       (const int32_t *)workspace, remap_from, remap_to, labels);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_volume_argmax(const float *volume, long long nvox, int C, int remap_from, int remap_to, unsigned char *labels,
+                     pu_stream_t stream) {
+    if (!volume || !labels || nvox < 0 || C < 1 || C > 255) return PU_ERR_INVALID_ARG;
+    if (nvox == 0) return PU_OK;
+    volume_argmax_kernel<<<grid_for(nvox), 256, 0, (cudaStream_t)stream>>>(volume, nvox, C, remap_from, remap_to, labels);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

@@ -91,6 +91,9 @@ def knn_search_cuda(support: torch.Tensor, query: torch.Tensor, k: int, return_d
         out = torch.empty((B, N2, k), dtype=torch.int32, device=support.device)
     elif out.dtype != torch.int32 or tuple(out.shape) != (B, N2, k) or not out.is_contiguous() or out.device != support.device:
         raise ValueError("knn_search_cuda: out must be a contiguous int32 [B,N2,k] tensor on the inputs' device")
+    else:
+        from . import ops  # the buffer is rewritten through its raw pointer: cached inverse lists of it are stale
+        ops.drop_inverse(out.data_ptr())
     nbytes = L.pu_knn_workspace_bytes(B, N1, N2, k)
     ws = workspace(nbytes, support.device)
     with torch.cuda.device(support.device):

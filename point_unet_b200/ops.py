@@ -57,6 +57,9 @@ _lib._OP_SIGS.update({
                          c_void_p, c_void_p, c_void_p, c_void_p],
     "pu_point2prod": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                       c_void_p],
+    "pu_point2label": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                       c_size_t, c_void_p],
+    "pu_volume_argmax": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p],
     "pu_att_pooling_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p],
     "pu_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                            c_int, c_void_p],
@@ -241,6 +244,13 @@ def register_inverse(idx: torch.Tensor, n_src: int, offsets: torch.Tensor, perm:
 
 def clear_caches():
     _inverse_cache.clear()
+
+
+def drop_inverse(ptr: int):
+    """Forget cached inverse lists of the index buffer at ``ptr``: kernels that fill an index tensor through its raw
+    pointer (``knn_search_cuda(out=...)``) do not bump ``_version``, so a reused buffer would otherwise hit a stale entry."""
+    for key in [k for k in _inverse_cache if k[0] == ptr]:
+        del _inverse_cache[key]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -780,3 +790,33 @@ def point2prod(probs: torch.Tensor, xyz_origin: torch.Tensor, volume_shape, poin
     _call("pu_point2prod", probs.data_ptr(), xo.data_ptr(), pi.data_ptr() if pi is not None else None, probs.shape[0], C,
           Z, X, Y, vol.data_ptr(), ws.data_ptr(), ws.numel(), _stream(probs))
     return vol
+
+
+def point2label(probs: torch.Tensor, xyz_origin: torch.Tensor, volume_shape, point_idx: torch.Tensor | None = None,
+                remap=None) -> torch.Tensor:
+    """utils/genSegmentationPancreas.py:67-77 / genSegmentationBraTS.py:67-78 fused with ``point2prod``: the uint8 label
+    volume ``argmax(prob volume, -1)`` in the layout ``[Z, Y, X]``, written straight from the per-point probabilities
+    (the dense probability volume is never materialised).  ``remap=(3, 4)`` is the BraTS relabelling ``seg[seg == 3] = 4``."""
+    _need_cuda(probs, xyz_origin)
+    Z, X, Y, C = (int(v) for v in volume_shape)
+    probs = probs.contiguous().float()
+    assert probs.dim() == 2 and probs.shape[1] == C
+    xo = xyz_origin.to(torch.int32).contiguous()
+    pi = point_idx.to(torch.int32).contiguous() if point_idx is not None else None
+    lab = torch.empty((Z, Y, X), dtype=torch.uint8, device=probs.device)
+    rf, rt = (int(remap[0]), int(remap[1])) if remap is not None else (-1, 0)
+    ws = workspace(_L().pu_point2prod_workspace_bytes(Z, X, Y), probs.device, slot=3)
+    _call("pu_point2label", probs.data_ptr(), xo.data_ptr(), pi.data_ptr() if pi is not None else None, probs.shape[0], C,
+          Z, X, Y, rf, rt, lab.data_ptr(), ws.data_ptr(), ws.numel(), _stream(probs))
+    return lab
+
+
+def volume_argmax(volume: torch.Tensor, remap=None) -> torch.Tensor:
+    """``np.argmax(volume, axis=-1).astype(uint8)`` (+ optional relabelling) of a dense probability volume on the device."""
+    _need_cuda(volume)
+    v = volume.contiguous().float()
+    C = v.shape[-1]
+    lab = torch.empty(v.shape[:-1], dtype=torch.uint8, device=v.device)
+    rf, rt = (int(remap[0]), int(remap[1])) if remap is not None else (-1, 0)
+    _call("pu_volume_argmax", v.data_ptr(), v.numel() // C, C, rf, rt, lab.data_ptr(), _stream(v))
+    return lab

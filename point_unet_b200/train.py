@@ -84,11 +84,23 @@ class Trainer:
         # tf.train.AdamOptimizer defaults (RandLANet.py:88): beta (0.9, 0.999), eps 1e-8
         # capturable: the step counter lives on the device, so the whole step (pyramid, forward, backward, all-reduce,
         # Adam) can be recorded once into a CUDA graph and replayed (capture_step / train_step_graph below)
-        self.opt = torch.optim.Adam(self.params, lr=lr if lr is not None else config.learning_rate, betas=(0.9, 0.999),
-                                    eps=1e-8, fused=True, capturable=True)
+        # The learning rate is a DEVICE scalar: a Python float would be baked into the captured CUDA graph, a tensor is
+        # read by every replay, so the reference's per-epoch decay (RandLANet.py:190-193) works on the graph path too.
+        self.lr = torch.tensor(float(lr if lr is not None else config.learning_rate), dtype=torch.float32, device=self.device)
+        self.opt = torch.optim.Adam(self.params, lr=self.lr, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
         self.world_size = world_size
         self._pinned = {}
         self._dev = {}
+        self._h2d_done = {}
+        # [loss, tcgen05 error flag] of the last step, written on the device at the end of every step and fetched with ONE
+        # small D2H copy by the host-facing entry points
+        self._report_dev = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._report_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+        self._report_ev = torch.cuda.Event()
+        self._copy_stream = None
+        self._stage_slots = None
+        self._stage_ev = [None, None]
+        self._stage_k = 0
         self._graph = None
         self._side = None
         self._side2 = None
@@ -97,19 +109,31 @@ class Trainer:
 
     # -- host staging ----------------------------------------------------------------------------
     def _stage(self, name, arr):
-        """numpy / CPU tensor -> pinned buffer -> device (async on the current stream)."""
+        """numpy / CPU tensor -> (pinned buffer ->) device, async on the current stream.  A tensor that already lives in
+        pinned memory is copied straight from where it is (no pinned -> pinned memcpy); pageable input goes through a
+        staging buffer that is rewritten only after the previous H2D copy out of it has completed."""
         t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr
         if t.is_cuda:
             return t
-        pin = self._pinned.get(name)
-        if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
-            pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            self._pinned[name] = pin
-            self._dev[name] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
-        if t.data_ptr() != pin.data_ptr():
+        dev = self._dev.get(name)
+        if dev is None or dev.shape != t.shape or dev.dtype != t.dtype:
+            dev = self._dev[name] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        src = t
+        if not t.is_pinned():
+            pin = self._pinned.get(name)
+            if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
+                pin = self._pinned[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            ev = self._h2d_done.get(name)
+            if ev is not None:
+                ev.synchronize()       # the previous copy out of the staging buffer may still be queued
             pin.copy_(t)
-        self._dev[name].copy_(pin, non_blocking=True)
-        return self._dev[name]
+            src = pin
+        dev.copy_(src, non_blocking=True)
+        ev = self._h2d_done.get(name)
+        if ev is None:
+            ev = self._h2d_done[name] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return dev
 
     def pin_batch(self, xyz, features, labels):
         """Pre-place a host batch in pinned memory (what a data-loader worker would hand over)."""
@@ -161,7 +185,37 @@ class Trainer:
             self.bucket.all_reduce_mean()                          # gradients only, NCCL over NVLink
         self.opt.step()
         ops.clear_caches()
-        return loss.detach()
+        loss = loss.detach()
+        self._report_dev[0].copy_(loss)
+        self._report_dev[1].copy_(ops.tc_error_flag(self.device)[0])
+        return loss
+
+    # -- learning-rate schedule, error reporting ----------------------------------------------------------
+    def decay_lr(self, factor=None):
+        """``lr *= lr_decays[epoch]`` after every epoch (RandLANet.py:190-193; 0.95 for both configs).  In place on the device
+        scalar the optimiser reads, so eager steps AND graph replays pick it up."""
+        self.lr.mul_(float(factor if factor is not None else self.cfg.lr_decays))
+        return self
+
+    end_epoch = decay_lr
+
+    def _fetch_report(self):
+        """(loss, error flag) of the last step: one 8-byte D2H copy into pinned memory, then wait for it."""
+        self._report_host.copy_(self._report_dev, non_blocking=True)
+        self._report_ev.record(torch.cuda.current_stream(self.device))
+        self._report_ev.synchronize()
+        return float(self._report_host[0]), float(self._report_host[1])
+
+    def check_errors(self, flag_value=None):
+        """Raise if a tcgen05 kernel's bounded mbarrier wait timed out since the last check (the kernels then carried on
+        with whatever was in tensor / shared memory, so the step's numbers are garbage); the flag is reset."""
+        if flag_value is None:
+            flag_value = float(ops.tc_error_flag(self.device).item())
+        if flag_value != 0.0:
+            ops.tc_error_flag(self.device).zero_()
+            self._report_dev[1].zero_()
+            from ._lib import PointUnetError
+            raise PointUnetError("a tcgen05 pipeline barrier timed out during the last step: its results are invalid")
 
     # -- CUDA graph: ~1300 kernel launches per step recorded once, replayed with one host call -------
     def capture_step(self, xyz, features, labels, warmup=3, pipelined=False):
@@ -237,15 +291,60 @@ class Trainer:
 
     def train_step(self, xyz, features, labels):
         """Public end-to-end step on HOST buffers (numpy or pinned CPU tensors); returns the loss as a float
-        (device -> host read).  Uses the captured graph when there is one for this shape; with a PIPELINED graph
-        (``capture_step(pipelined=True)``) the batch handed in is staged and indexed during this call and trained by the next
-        one, so the value returned is the loss of the batch submitted one call earlier."""
-        x = self._stage("xyz", xyz)
-        f = self._stage("features", features)
-        l = self._stage("labels", labels)
-        if self._graph is not None and x.shape == self._gx.shape and f.shape == self._gf.shape:
-            return float(self.train_step_graph(x, f, l).item())
-        return float(self.train_step_device(x, f, l).item())
+        (device -> host read) and raises if a tensor-core pipeline reported a barrier timeout.
+
+        Without a captured graph: stage, train, read back, in that order.  With a graph the host side is overlapped the way
+        the reference overlaps its input pipeline (``tf.data ... prefetch``, runPancreas.py:158-166): call k queues the
+        host -> device copy of batch k on a COPY stream into staging slot k % 2 and, on the main stream, replays the graph
+        on the batch that finished copying during call k-1 -- so the copy of batch k runs under the replay.  The value
+        returned is therefore the loss of an EARLIER batch: one call back for a plain graph, two for a pipelined one
+        (``capture_step(pipelined=True)`` already trains one batch behind the one it indexes); the first calls train on the
+        capture batch.  Pinned input tensors are read asynchronously: leave them unchanged until the next call returns."""
+        if self._graph is None or tuple(xyz.shape) != tuple(self._gx.shape) or \
+                tuple(features.shape) != tuple(self._gf.shape):
+            x = self._stage("xyz", xyz)
+            f = self._stage("features", features)
+            l = self._stage("labels", labels)
+            self.train_step_device(x, f, l)
+            loss, flag = self._fetch_report()
+            self.check_errors(flag)
+            return loss
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_slots = [(self._gx.clone(), self._gf.clone(), self._gl.clone()) for _ in range(2)]
+        k = self._stage_k
+        cur, prev = self._stage_slots[k % 2], self._stage_slots[(k + 1) % 2]
+        cs = self._copy_stream
+        cs.wait_stream(main)   # slot k % 2 was read by the device copy of call k - 1, queued on `main`
+        with torch.cuda.stream(cs):
+            for dst, src, name in zip(cur, (xyz, features, labels), ("xyz", "features", "labels")):
+                t = torch.from_numpy(np.ascontiguousarray(src)) if isinstance(src, np.ndarray) else src
+                if not t.is_pinned():   # pageable input: through a per-slot pinned buffer (rewritten only once its copy is done)
+                    key = (name, k % 2)
+                    pin = self._pinned.get(key)
+                    if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
+                        pin = self._pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    if self._stage_ev[k % 2] is not None:
+                        self._stage_ev[k % 2].synchronize()
+                    pin.copy_(t)
+                    t = pin
+                dst.copy_(t, non_blocking=True)
+            ev = self._stage_ev[k % 2] or torch.cuda.Event()
+            ev.record(cs)
+            self._stage_ev[k % 2] = ev
+        if self._stage_ev[(k + 1) % 2] is not None:
+            main.wait_event(self._stage_ev[(k + 1) % 2])       # batch k - 1 has landed (first call: the capture batch)
+        self.train_step_graph(*prev)
+        self._stage_k = k + 1
+        loss, flag = self._fetch_report()
+        self.check_errors(flag)
+        return loss
+
+    def flush_inputs(self):
+        """Wait until every queued host -> device copy has completed (pinned inputs may be modified again)."""
+        for ev in list(self._h2d_done.values()) + [e for e in self._stage_ev if e is not None]:
+            ev.synchronize()
 
     @torch.no_grad()
     def predict(self, xyz, features):
@@ -256,7 +355,9 @@ class Trainer:
         pyr = build_pyramid(x, self.cfg, side=self._side_stream() if OVERLAP else None)
         logits = self.net.inference(dict(pyr, features=torch.cat([x, f], dim=-1)), False)
         ops.clear_caches()
-        return torch.softmax(logits, dim=-1)
+        probs = torch.softmax(logits, dim=-1)
+        self.check_errors()   # synchronises: garbage from a timed-out tensor-core pipeline must not leave this call
+        return probs
 
     @torch.no_grad()
     def predict_to_volume(self, xyz, features, xyz_origin, volume_shape, point_idx=None):
@@ -274,3 +375,21 @@ class Trainer:
                 pi = torch.as_tensor(np.ascontiguousarray(pi)).to(self.device) if not torch.is_tensor(pi) else pi.to(self.device)
             vols.append(ops.point2prod(probs[b], xo, volume_shape, pi))
         return vols
+
+    @torch.no_grad()
+    def predict_to_labels(self, xyz, features, xyz_origin, volume_shape, point_idx=None, remap=None):
+        """Test-mode fusion all the way to the segmentation the reference writes as NIfTI
+        (utils/genSegmentationPancreas.py:67-77 / genSegmentationBraTS.py:67-78): uint8 label volumes ``[Z,Y,X]`` =
+        argmax over classes of the scattered probabilities, produced on the device without the dense probability volume.
+        ``remap=(3, 4)`` for BraTS."""
+        probs = self.predict(xyz, features)
+        out = []
+        for b in range(probs.shape[0]):
+            xo = xyz_origin[b]
+            xo = torch.as_tensor(np.ascontiguousarray(xo)).to(self.device) if not torch.is_tensor(xo) else xo.to(self.device)
+            pi = None
+            if point_idx is not None:
+                pi = point_idx[b]
+                pi = torch.as_tensor(np.ascontiguousarray(pi)).to(self.device) if not torch.is_tensor(pi) else pi.to(self.device)
+            out.append(ops.point2label(probs[b], xo, volume_shape, pi, remap=remap))
+        return out
