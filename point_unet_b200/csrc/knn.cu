@@ -5,7 +5,7 @@
 //   -> cpp_knn_batch_omp (utils/nearest_neighbors/knn_.cxx:104-135; nanoflann kd-tree per cloud).
 // Not a port of the kd-tree: a GPU-native bucketed search.
 //
-//   build   (per call, per cloud)  Morton-order the support points (30-bit code, radix sort), cut the
+//   build   (per call, per cloud)  Morton-order the support points (30-bit code, in-tree LSD radix sort), cut the
 //           sorted array into buckets of 32 consecutive points with tight AABBs, and group 32 buckets
 //           into a super-bucket AABB.  The structure adapts to density by construction (every bucket
 //           holds 32 points whether it lies in the dense organ blob or the sparse background).
@@ -24,9 +24,8 @@
 // nearest, NO fused multiply-add (__fmul_rn/__fadd_rn/__fsub_rn are never contracted).
 // Tie rule: ascending (distance, index) -- a total order, hence the result is independent of the visiting
 // order and of scheduling (deterministic).
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/util_type.cuh>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -37,11 +36,14 @@ constexpr int BS = 32;              // points per bucket  (= one warp-wide candi
 constexpr int SBS = 32;             // buckets per super-bucket
 constexpr int SEARCH_WARPS = 4;     // warps per CTA in the search kernel
 constexpr unsigned long long KEY_INIT = 0x7F800000FFFFFFFFull;  // (+inf, id 0xFFFFFFFF)
-constexpr size_t CUB_TEMP_RESERVE_BASE = 8u << 20;              // generous bound, checked at run time
+// Morton sort: stable LSD radix sort of (30-bit key, point index) pairs, one cloud per blockIdx.y, 3 passes of 10 bits
+constexpr int SORT_BITS = 10, SORT_BINS = 1 << SORT_BITS, SORT_PASSES = 3;
+constexpr int SORT_THREADS = 256, SORT_IPT = 16, SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 pairs per CTA
+constexpr int SORT_FUSED_TILES = 64;  // up to this many tiles per cloud the scatter CTAs scan the histogram themselves
 
 struct Layout {
     size_t stats, bbox, keys_a, keys_b, vals_a, vals_b, sp, bk_lo, bk_hi, sb_lo, sb_hi;
-    size_t qkeys_a, qkeys_b, qvals_a, qvals_b, sq, cub_temp, cub_bytes, total;
+    size_t qkeys_a, qkeys_b, qvals_a, qvals_b, sq, sort_hist, hist_one, total;
     int NB, NSB;
 };
 
@@ -58,8 +60,8 @@ static Layout make_layout(int B, int N1, int N2) {
     L.NSB = ceil_div(L.NB, SBS);
     L.stats = take(8 * sizeof(unsigned long long));
     L.bbox = take((size_t)B * 8 * sizeof(unsigned));
-    L.keys_a = take(n1 * 8);
-    L.keys_b = take(n1 * 8);
+    L.keys_a = take(n1 * 4);
+    L.keys_b = take(n1 * 4);
     L.vals_a = take(n1 * 4);
     L.vals_b = take(n1 * 4);
     L.sp = take(n1 * 16);
@@ -67,13 +69,13 @@ static Layout make_layout(int B, int N1, int N2) {
     L.bk_hi = take((size_t)B * L.NB * 16);
     L.sb_lo = take((size_t)B * L.NSB * 16);
     L.sb_hi = take((size_t)B * L.NSB * 16);
-    L.qkeys_a = take(n2 * 8);
-    L.qkeys_b = take(n2 * 8);
+    L.qkeys_a = take(n2 * 4);
+    L.qkeys_b = take(n2 * 4);
     L.qvals_a = take(n2 * 4);
     L.qvals_b = take(n2 * 4);
     L.sq = take(n2 * 16);
-    L.cub_bytes = CUB_TEMP_RESERVE_BASE + (n1 > n2 ? n1 : n2);
-    L.cub_temp = take(L.cub_bytes);
+    L.hist_one = align_up((size_t)B * SORT_BINS * ceil_div(N1 > N2 ? N1 : N2, SORT_TILE) * sizeof(unsigned), 256);
+    L.sort_hist = take(L.hist_one * 2 * SORT_PASSES);   // [support | query][pass] digit histograms, zeroed by one memset
     L.total = off;
     return L;
 }
@@ -132,11 +134,11 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every 
     return v;
 }
 
-// key = (cloud << 30) | morton30(point quantised in the SUPPORT cloud's bounding box); val = global row
+// key = morton30(point quantised in the SUPPORT cloud's bounding box); val = row inside the cloud
 __global__ void __launch_bounds__(256) morton_kernel(const float *__restrict__ pts, int N, int B,
                                                      const unsigned *__restrict__ bbox,
-                                                     unsigned long long *__restrict__ keys,
-                                                     unsigned *__restrict__ vals) {
+                                                     unsigned *__restrict__ keys,
+                                                     unsigned *__restrict__ vals, unsigned *__restrict__ hist0, int ntiles) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)B * N) return;
     const int b = (int)(g / N);
@@ -151,8 +153,158 @@ __global__ void __launch_bounds__(256) morton_kernel(const float *__restrict__ p
         q[c] = (unsigned)t;
     }
     const unsigned m = (spread10(q[0]) << 2) | (spread10(q[1]) << 1) | spread10(q[2]);
-    keys[g] = ((unsigned long long)b << 30) | m;
-    vals[g] = (unsigned)g;
+    const unsigned i = (unsigned)(g - (size_t)b * N);
+    keys[g] = m;
+    vals[g] = i;
+    // digit histogram of the first sort pass, per 4096-pair tile (integer atomics: the counts do not depend on their order)
+    atomicAdd(&hist0[((size_t)b * ntiles + i / SORT_TILE) * SORT_BINS + (m & (SORT_BINS - 1))], 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-tree radix sort (replaces nanoflann's divideTree, nanoflann.hpp:916-964, as the spatial ordering step).  Per pass:
+//   histograms           [cloud][tile][digit] counts of every pass: pass 0 is accumulated by morton_kernel, pass p+1 by the
+//                        scatter kernel of pass p at the pairs' new positions (integer atomics, order-free)
+//   sort_scan_kernel     (only for > SORT_FUSED_TILES tiles) exclusive scan over (digit, tile) = first output slot of every
+//                        (digit, tile) group; otherwise every scatter CTA derives its own slots from the raw counts
+//   sort_scatter_kernel  CTA (tile, cloud): STABLE ranks.  Warp w owns 512 consecutive pairs and walks them 32 at a time;
+//                        inside a round the rank among equal digits comes from __match_any_sync (lower lanes first), across
+//                        rounds and warps from per-warp digit counters that start at the scanned offset -- so equal keys keep
+//                        their input order, every pass is a permutation that depends only on the data (deterministic).
+// many tiles (> SORT_FUSED_TILES): exclusive scan over (digit, tile) as its own launch.  One CTA per cloud, thread d owns
+// digit d's row of tile counts.
+__global__ void __launch_bounds__(SORT_BINS) sort_scan_kernel(unsigned *__restrict__ hist, int ntiles) {
+    __shared__ unsigned s_w[SORT_BINS / 32];
+    unsigned *col = hist + (size_t)blockIdx.x * ntiles * SORT_BINS + threadIdx.x;   // [tile][digit]: coalesced over digits
+    unsigned total = 0;
+    for (int t = 0; t < ntiles; ++t) total += col[(size_t)t * SORT_BINS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned v = s_w[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        s_w[lane] = iv - v;
+    }
+    __syncthreads();
+    unsigned run = s_w[w] + inc - total;
+    for (int t = 0; t < ntiles; ++t) {
+        const unsigned c = col[(size_t)t * SORT_BINS];
+        col[(size_t)t * SORT_BINS] = run;
+        run += c;
+    }
+}
+
+// SCANNED = false: `hist` holds raw counts [tile][digit] and every CTA derives its own first slots (few tiles: the whole
+// matrix is a few hundred KB of L2 reads per CTA, cheaper than a scan launch); SCANNED = true: sort_scan_kernel ran before.
+// `hist_next` (optional) receives the digit histogram of the NEXT pass at the pairs' new positions.
+template <bool SCANNED>
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const unsigned *__restrict__ keys_in,
+                                                                    const unsigned *__restrict__ vals_in, int N, int ntiles,
+                                                                    int shift, const unsigned *__restrict__ hist,
+                                                                    unsigned *__restrict__ keys_out, unsigned *__restrict__ vals_out,
+                                                                    unsigned *__restrict__ hist_next) {
+    constexpr int WARPS = SORT_THREADS / 32, ROUNDS = SORT_TILE / SORT_THREADS;  // 8 warps x 16 rounds of 32 pairs
+    constexpr int DPT = SORT_BINS / SORT_THREADS;                                // digits per thread (consecutive)
+    __shared__ unsigned s_c[WARPS][SORT_BINS];
+    __shared__ unsigned s_w[WARPS];
+    const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < WARPS * SORT_BINS; i += SORT_THREADS) (&s_c[0][0])[i] = 0;
+    __syncthreads();
+    const size_t cb = (size_t)b * N;
+    const int base = tile * SORT_TILE + w * (ROUNDS * 32);
+    unsigned key[ROUNDS], val[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int i = base + r * 32 + lane;
+        key[r] = 0; val[r] = 0;
+        if (i < N) {
+            key[r] = keys_in[cb + i];
+            val[r] = vals_in[cb + i];
+            atomicAdd(&s_c[w][(key[r] >> shift) & (SORT_BINS - 1)], 1u);   // counts only: order-free
+        }
+    }
+    // first output slot of (digit, this tile) for the thread's DPT consecutive digits
+    const unsigned *h = hist + (size_t)b * ntiles * SORT_BINS + threadIdx.x * DPT;   // [tile][digit], 4 digits = one 16-byte load
+    static_assert(DPT == 4, "one uint4 per thread and tile");
+    unsigned first[DPT];
+    if (SCANNED) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(h + (size_t)tile * SORT_BINS);
+        first[0] = v.x; first[1] = v.y; first[2] = v.z; first[3] = v.w;
+        __syncthreads();
+    } else {
+        unsigned tot[DPT] = {0, 0, 0, 0}, mine = 0;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) first[j] = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(h + (size_t)t * SORT_BINS);
+            const unsigned c[DPT] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) {
+                tot[j] += c[j];
+                if (t < tile) first[j] += c[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) mine += tot[j];
+        unsigned inc = mine;   // block-wide exclusive scan of the per-thread totals (digits ascend with the thread id)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        unsigned run = inc - mine;
+#pragma unroll
+        for (int i = 0; i < WARPS; ++i) run += i < w ? s_w[i] : 0u;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) { first[j] += run; run += tot[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {   // counters -> first slot of (digit, warp)
+        const int d = threadIdx.x * DPT + j;
+        unsigned run = first[j];
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ++ww) {
+            const unsigned c = s_c[ww][d];
+            s_c[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    const int shift_next = shift + SORT_BITS;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int i = base + r * 32 + lane;
+        const bool valid = i < N;
+        const unsigned d = valid ? ((key[r] >> shift) & (SORT_BINS - 1)) : (unsigned)SORT_BINS;  // padding lanes form their own group
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned slot = 0;
+        if (valid && lane == leader) {
+            slot = s_c[w][d];
+            s_c[w][d] = slot + __popc(peers);
+        }
+        slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & lt);
+        if (valid) {
+            keys_out[cb + slot] = key[r];
+            vals_out[cb + slot] = val[r];
+            if (hist_next)
+                atomicAdd(&hist_next[((size_t)b * ntiles + slot / SORT_TILE) * SORT_BINS + ((key[r] >> shift_next) & (SORT_BINS - 1))], 1u);
+        }
+        __syncwarp();
+    }
 }
 
 // sorted[g] = (x, y, z, bits(local index))
@@ -161,10 +313,10 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const float *__restr
                                                             float4 *__restrict__ out) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)B * N) return;
-    const unsigned src = vals_sorted[g];
+    const unsigned src = vals_sorted[g];  // row inside the cloud
     const int b = (int)(g / N);
-    const float *p = pts + (size_t)src * 3;
-    out[g] = make_float4(p[0], p[1], p[2], __int_as_float((int)(src - (unsigned)b * (unsigned)N)));
+    const float *p = pts + ((size_t)b * N + src) * 3;
+    out[g] = make_float4(p[0], p[1], p[2], __int_as_float((int)src));
 }
 
 // one warp per group of 32 consecutive items: AABB of the group
@@ -252,15 +404,38 @@ __device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsig
     best[0] = (x < best[0]) ? x : best[0];
 }
 
-template <int K>
+// Deferred insertion.  All 32 lanes look at the same candidate at the same time, each against ITS OWN K-th distance; once the
+// lists are warm a candidate passes for ~2 % of the lanes -- but the ~100-instruction sorted insertion is a divergent branch,
+// so the whole warp paid for it on roughly every second candidate (the kernel was issue-bound on exactly that).  Now a lane
+// that accepts a candidate only APPENDS its key to a small per-lane queue in shared memory (a few instructions); the queues
+// are drained together -- every lane inserts its i-th pending key in the same trip -- when one of them fills up and at the end
+// of every bucket.  The K-th distance used as the filter is the one of the last drain (stale = conservative: the insertion
+// itself re-checks), and the result does not depend on any of this because (distance, index) is a total order.
+constexpr int PEND = 8;  // pending keys per lane
+
+template <int K, bool DEFER>
 struct WarpSearch {
     unsigned long long best[K];
     float qx, qy, qz;
     bool valid;
     unsigned long long n_evals;
     unsigned n_buckets, n_tests;
+    int npend;
+    float kd;                   // K-th distance as of the last drain (+inf until the list is full)
+    unsigned long long *pend;   // this lane's column of the warp's queue: entry i at pend[i * 32]
 
     __device__ __forceinline__ float kth() const { return __uint_as_float((unsigned)(best[K - 1] >> 32)); }
+
+    __device__ __forceinline__ void drain() {
+        const int m = __reduce_max_sync(0xffffffffu, npend);
+        for (int i = 0; i < m; ++i) {
+            // lanes with fewer pending keys insert the largest key, which leaves the list unchanged
+            const unsigned long long key = i < npend ? pend[i * 32] : 0xFFFFFFFFFFFFFFFFull;
+            topk_insert<K>(best, key);
+        }
+        npend = 0;
+        kd = kth();
+    }
 
     // all 32 lanes sweep the `cnt` candidates of one bucket staged in shared memory
     __device__ __forceinline__ void sweep_bucket(const float4 *__restrict__ sp_cloud, int N1, int t, float4 *tile,
@@ -270,34 +445,57 @@ struct WarpSearch {
         __syncwarp();
         if (lane < cnt) tile[lane] = sp_cloud[base + lane];
         __syncwarp();
-        if (valid) {
+        if constexpr (K <= 2 || !DEFER) {  // a one- or two-deep list (or queueing switched off): insert directly
+            if (valid) {
 #pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const float4 p = tile[j];  // broadcast read
-                const float d = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-                const unsigned long long key =
-                    ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-                if (key < best[K - 1]) topk_insert<K>(best, key);
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 p = tile[j];
+                    const float d = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+                    const unsigned long long key =
+                        ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+                    if (key < best[K - 1]) topk_insert<K>(best, key);
+                }
             }
+            n_evals += cnt;
+            n_buckets += 1;
+            return;
         }
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                if (j < cnt) {
+                    const float4 p = tile[j];  // broadcast read
+                    const float d = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+                    if (valid && d <= kd) {    // ties pass here; the 64-bit (distance, index) comparison decides
+                        const unsigned long long key =
+                            ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+                        if (key < best[K - 1]) { pend[npend * 32] = key; ++npend; }
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, npend > PEND - 4)) drain();
+        }
+        drain();
         n_evals += cnt;
         n_buckets += 1;
     }
 };
 
 // grid: (ceil(warps_per_cloud / SEARCH_WARPS), B); one warp = 32 Morton-consecutive queries
-template <int K>
+template <int K, bool DEFER>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
     knn_search_kernel(const float4 *__restrict__ sp, const float4 *__restrict__ sq,
                       const float4 *__restrict__ bk_lo, const float4 *__restrict__ bk_hi,
                       const float4 *__restrict__ sb_lo, const float4 *__restrict__ sb_hi,
-                      const unsigned long long *__restrict__ skeys,  // sorted support keys (NULL for self-query)
-                      const unsigned long long *__restrict__ qkeys,  // sorted query keys   (NULL for self-query)
+                      const unsigned *__restrict__ skeys,  // sorted support keys (NULL for self-query)
+                      const unsigned *__restrict__ qkeys,  // sorted query keys   (NULL for self-query)
                       int N1, int N2, int NB, int NSB, int kout, int32_t *__restrict__ out_idx,
                       float *__restrict__ out_dist, unsigned long long *__restrict__ stats) {
     __shared__ float4 s_tile[SEARCH_WARPS][BS];
     __shared__ float4 s_blo[SEARCH_WARPS][SBS];
     __shared__ float4 s_bhi[SEARCH_WARPS][SBS];
+    __shared__ unsigned long long s_pend[DEFER ? SEARCH_WARPS : 1][PEND][32];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int w = blockIdx.x * SEARCH_WARPS + wib;  // warp index within the cloud
@@ -310,10 +508,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
     const float4 *sb_lo_c = sb_lo + (size_t)b * NSB, *sb_hi_c = sb_hi + (size_t)b * NSB;
     float4 *tile = s_tile[wib];
 
-    WarpSearch<K> S;
+    WarpSearch<K, DEFER> S;
 #pragma unroll
     for (int j = 0; j < K; ++j) S.best[j] = KEY_INIT;
     S.n_evals = 0; S.n_buckets = 0; S.n_tests = 0;
+    S.npend = 0; S.kd = __uint_as_float(0x7F800000u); S.pend = &s_pend[DEFER ? wib : 0][0][lane];
 
     const int qi = w * 32 + lane;
     S.valid = qi < N2;
@@ -343,8 +542,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
         const int nvalid = min(32, N2 - w * 32);
         int pos = 0;
         if (lane == 0) {
-            const unsigned long long key = qkeys[(size_t)b * N2 + w * 32 + (nvalid - 1) / 2];
-            const unsigned long long *sk = skeys + (size_t)b * N1;
+            const unsigned key = qkeys[(size_t)b * N2 + w * 32 + (nvalid - 1) / 2];
+            const unsigned *sk = skeys + (size_t)b * N1;
             int lo = 0, hi = N1;  // lower_bound
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -464,12 +663,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 }
 
 template <int K>
-static int launch_search(const Layout &L, char *ws, bool self, const unsigned long long *skeys,
-                         const unsigned long long *qkeys, const float4 *sq, int B, int N1, int N2, int kout,
+static int launch_search(const Layout &L, char *ws, bool self, const unsigned *skeys,
+                         const unsigned *qkeys, const float4 *sq, int B, int N1, int N2, int kout,
                          int32_t *out_idx, float *out_dist, cudaStream_t st) {
     const int nwarps = ceil_div(N2, 32);
     dim3 grid(ceil_div(nwarps, SEARCH_WARPS), B);
-    knn_search_kernel<K><<<grid, SEARCH_WARPS * 32, 0, st>>>(
+    static const bool defer = [] { const char *e = getenv("PU_KNN_DEFER"); return e && e[0] == '1'; }();
+    auto kern = (defer && K > 2) ? knn_search_kernel<K, true> : knn_search_kernel<K, false>;
+    kern<<<grid, SEARCH_WARPS * 32, 0, st>>>(
         (const float4 *)(ws + L.sp), sq, (const float4 *)(ws + L.bk_lo), (const float4 *)(ws + L.bk_hi),
         (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), self ? nullptr : skeys,
         self ? nullptr : qkeys, N1, N2, L.NB, L.NSB, kout, out_idx, out_dist,
@@ -478,18 +679,31 @@ static int launch_search(const Layout &L, char *ws, bool self, const unsigned lo
     return PU_OK;
 }
 
-static int sort_pairs(void *temp, size_t temp_reserved, unsigned long long *ka, unsigned long long *kb, unsigned *va,
-                      unsigned *vb, size_t n, int end_bit, cudaStream_t st, unsigned long long **k_sorted,
-                      unsigned **v_sorted) {
-    cub::DoubleBuffer<unsigned long long> dk(ka, kb);
-    cub::DoubleBuffer<unsigned> dv(va, vb);
-    size_t need = 0;
-    PU_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)n, 0, end_bit, st));
-    if (need > temp_reserved) return PU_ERR_WORKSPACE;
-    PU_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, need, dk, dv, (int)n, 0, end_bit, st));
-    count_launch(3);
-    *k_sorted = dk.Current();
-    *v_sorted = dv.Current();
+// stable sort of the per-cloud (key, value) pairs by the low 30 bits of the key; `hist` = SORT_PASSES zeroed histogram
+// buffers of `hist_one` bytes, the first already filled by morton_kernel.  The result lands in the "b" buffers (an odd
+// number of passes), which *k_sorted / *v_sorted report.
+static int sort_pairs(char *hist, size_t hist_one, unsigned *ka, unsigned *kb, unsigned *va, unsigned *vb, int B, int N,
+                      cudaStream_t st, unsigned **k_sorted, unsigned **v_sorted) {
+    const int ntiles = ceil_div(N, SORT_TILE);
+    dim3 grid(ntiles, B);
+    unsigned *kin = ka, *vin = va, *kout = kb, *vout = vb;
+    for (int pass = 0; pass < SORT_PASSES; ++pass) {
+        const int shift = pass * SORT_BITS;
+        unsigned *h = (unsigned *)(hist + (size_t)pass * hist_one);
+        unsigned *hn = pass + 1 < SORT_PASSES ? (unsigned *)(hist + (size_t)(pass + 1) * hist_one) : nullptr;
+        if (ntiles > SORT_FUSED_TILES) {
+            sort_scan_kernel<<<B, SORT_BINS, 0, st>>>(h, ntiles);
+            PU_LAUNCH_CHECK();
+            sort_scatter_kernel<true><<<grid, SORT_THREADS, 0, st>>>(kin, vin, N, ntiles, shift, h, kout, vout, hn);
+        } else {
+            sort_scatter_kernel<false><<<grid, SORT_THREADS, 0, st>>>(kin, vin, N, ntiles, shift, h, kout, vout, hn);
+        }
+        PU_LAUNCH_CHECK();
+        unsigned *t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    *k_sorted = kin;
+    *v_sorted = vin;
     return PU_OK;
 }
 
@@ -507,13 +721,11 @@ static int knn_impl(const float *support, const float *query, int B, int N1, int
     if (!workspace || workspace_bytes < L.total) return PU_ERR_WORKSPACE;
     char *ws = (char *)workspace;
     const bool self = (support == query) && (N1 == N2);
-    int batch_bits = 0;
-    while ((1 << batch_bits) < B) ++batch_bits;
-    const int end_bit = 30 + batch_bits;
     const size_t n1 = (size_t)B * N1, n2 = (size_t)B * N2;
     unsigned *bbox = (unsigned *)(ws + L.bbox);
 
     PU_CUDA_TRY(cudaMemsetAsync(ws + L.stats, 0, 8 * sizeof(unsigned long long), st));
+    PU_CUDA_TRY(cudaMemsetAsync(ws + L.sort_hist, 0, L.hist_one * (self ? 1 : 2) * SORT_PASSES, st));
     bbox_init_kernel<<<ceil_div(B * 8, 128), 128, 0, st>>>(bbox, B);
     PU_LAUNCH_CHECK();
     {
@@ -521,14 +733,14 @@ static int knn_impl(const float *support, const float *query, int B, int N1, int
         bbox_kernel<<<grid, 256, 0, st>>>(support, N1, bbox);
         PU_LAUNCH_CHECK();
     }
-    morton_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(support, N1, B, bbox, (unsigned long long *)(ws + L.keys_a),
-                                                     (unsigned *)(ws + L.vals_a));
+    morton_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(support, N1, B, bbox, (unsigned *)(ws + L.keys_a),
+                                                     (unsigned *)(ws + L.vals_a), (unsigned *)(ws + L.sort_hist),
+                                                     ceil_div(N1, SORT_TILE));
     PU_LAUNCH_CHECK();
-    unsigned long long *skeys = nullptr, *qkeys = nullptr;
+    unsigned *skeys = nullptr, *qkeys = nullptr;
     unsigned *svals = nullptr, *qvals = nullptr;
-    int rc = sort_pairs(ws + L.cub_temp, L.cub_bytes, (unsigned long long *)(ws + L.keys_a),
-                        (unsigned long long *)(ws + L.keys_b), (unsigned *)(ws + L.vals_a), (unsigned *)(ws + L.vals_b),
-                        n1, end_bit, st, &skeys, &svals);
+    int rc = sort_pairs(ws + L.sort_hist, L.hist_one, (unsigned *)(ws + L.keys_a), (unsigned *)(ws + L.keys_b),
+                        (unsigned *)(ws + L.vals_a), (unsigned *)(ws + L.vals_b), B, N1, st, &skeys, &svals);
     if (rc != PU_OK) return rc;
     gather_sorted_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(support, N1, B, svals, (float4 *)(ws + L.sp));
     PU_LAUNCH_CHECK();
@@ -542,12 +754,13 @@ static int knn_impl(const float *support, const float *query, int B, int N1, int
 
     const float4 *sq = (const float4 *)(ws + L.sp);
     if (!self) {
-        morton_kernel<<<ceil_div(n2, 256), 256, 0, st>>>(query, N2, B, bbox, (unsigned long long *)(ws + L.qkeys_a),
-                                                         (unsigned *)(ws + L.qvals_a));
+        char *qhist = ws + L.sort_hist + L.hist_one * SORT_PASSES;
+        morton_kernel<<<ceil_div(n2, 256), 256, 0, st>>>(query, N2, B, bbox, (unsigned *)(ws + L.qkeys_a),
+                                                         (unsigned *)(ws + L.qvals_a), (unsigned *)qhist,
+                                                         ceil_div(N2, SORT_TILE));
         PU_LAUNCH_CHECK();
-        rc = sort_pairs(ws + L.cub_temp, L.cub_bytes, (unsigned long long *)(ws + L.qkeys_a),
-                        (unsigned long long *)(ws + L.qkeys_b), (unsigned *)(ws + L.qvals_a),
-                        (unsigned *)(ws + L.qvals_b), n2, end_bit, st, &qkeys, &qvals);
+        rc = sort_pairs(qhist, L.hist_one, (unsigned *)(ws + L.qkeys_a), (unsigned *)(ws + L.qkeys_b),
+                        (unsigned *)(ws + L.qvals_a), (unsigned *)(ws + L.qvals_b), B, N2, st, &qkeys, &qvals);
         if (rc != PU_OK) return rc;
         gather_sorted_kernel<<<ceil_div(n2, 256), 256, 0, st>>>(query, N2, B, qvals, (float4 *)(ws + L.sq));
         PU_LAUNCH_CHECK();

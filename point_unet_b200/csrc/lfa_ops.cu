@@ -11,7 +11,6 @@
 // All tensors channels-last fp32; "rows" of d channels are moved as 128-bit vectors when d % 4 == 0 and the
 // row strides allow it.  Outputs take a row stride (ld) so a kernel can write straight into one half of a
 // concat buffer (tf.concat at RandLANet.py:328,333,138 never needs its own copy).
-#include <cub/device/device_scan.cuh>
 #include <float.h>
 
 #include "common.cuh"
@@ -140,6 +139,86 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float *__restric
 //      Neighbouring threads rank rows of the same segment, so its 64 bytes are read once and broadcast.  Segments longer
 //      than INV_LONG (clouds with thousands of coincident points) are ranked by a whole CTA instead of one thread per row.
 constexpr int INV_LONG = 1024;
+
+// exclusive prefix sum of the per-target counts (in-tree; three launches):
+//   scan_block_sums   CTA i: sum of its 2048 counts -> bsum[i]
+//   scan_block_offs   one CTA: exclusive scan of bsum in place (chunks of 1024 with a running carry)
+//   scan_apply        CTA i: exclusive scan of its 2048 counts (8 per thread, warp shuffles) + bsum[i]
+constexpr int SCAN_THREADS = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int *s_warp, int &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) {
+        const int t = s_warp[i];
+        if (i < w) base += t;
+        tot += t;
+    }
+    total = tot;
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const int32_t *__restrict__ cnt, long long n,
+                                                                       int32_t *__restrict__ bsum) {
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE;
+    int v = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        const long long j = base + (long long)i * SCAN_THREADS + threadIdx.x;  // coalesced
+        if (j < n) v += cnt[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_THREADS / 32; ++i) t += s_warp[i];
+        bsum[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_offs_kernel(int32_t *__restrict__ bsum, int nblocks) {
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    int carry = 0;
+    for (int c0 = 0; c0 < nblocks; c0 += SCAN_THREADS) {
+        const int i = c0 + threadIdx.x;
+        const int v = i < nblocks ? bsum[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan_256(v, s_warp, total);
+        if (i < nblocks) bsum[i] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int32_t *__restrict__ cnt, long long n,
+                                                                  const int32_t *__restrict__ bsum, int32_t *__restrict__ out) {
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_IPT;  // 8 consecutive per thread
+    int v[SCAN_IPT], sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        v[i] = base + i < n ? cnt[base + i] : 0;
+        sum += v[i];
+    }
+    int total;
+    int run = block_exclusive_scan_256(sum, s_warp, total) + bsum[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+}
 
 __global__ void __launch_bounds__(256) inv_count_kernel(const int32_t *__restrict__ idx, long long R, int B, int n,
                                                         int32_t *__restrict__ cnt) {
@@ -546,11 +625,18 @@ int pu_build_inverse(const int32_t *idx, long long rows_per_cloud, int B, int n_
     PU_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(n_targets + 1) * 4, st));
     inv_count_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, B, n_src, cnt);
     PU_LAUNCH_CHECK();
-    size_t need = 0;
-    PU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, cnt, offsets, (int)(n_targets + 1), st));
-    if (need > temp_reserved) return PU_ERR_WORKSPACE;
-    PU_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, need, cnt, offsets, (int)(n_targets + 1), st));
-    count_launch(1);
+    {   // offsets = exclusive scan of the counts (n_targets + 1 entries: the last one is the total)
+        const long long n = n_targets + 1;
+        const int nblocks = ceil_div(n, SCAN_TILE);
+        if ((size_t)nblocks * sizeof(int32_t) > temp_reserved) return PU_ERR_WORKSPACE;
+        int32_t *bsum = (int32_t *)temp;
+        scan_block_sums_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(cnt, n, bsum);
+        PU_LAUNCH_CHECK();
+        scan_block_offs_kernel<<<1, SCAN_THREADS, 0, st>>>(bsum, nblocks);
+        PU_LAUNCH_CHECK();
+        scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(cnt, n, bsum, offsets);
+        PU_LAUNCH_CHECK();
+    }
     inv_fill_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, B, n_src, offsets, cnt, tmp);
     PU_LAUNCH_CHECK();
     inv_rank_kernel<<<grid_for(total), 256, 0, st>>>(idx, rows_per_cloud, n_src, offsets, tmp, total, perm);

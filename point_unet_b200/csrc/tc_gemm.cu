@@ -17,8 +17,13 @@
 // come back through tcgen05.ld (32 lanes x 16 columns per warp instruction).  Kernel anatomy: see tc_persist_kernel.
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+
+#ifndef PU_ISSUER_SWP
+#define PU_ISSUER_SWP 0  // 1: software-pipelined MMA issue (waits of item i+1 taken between the two halves of item i)
+#endif
 
 namespace pu {
 namespace tc {
@@ -44,9 +49,28 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-// bounded spin: returns false on timeout
+// bounded wait: returns false on timeout.  PU_MBAR_HINT=1 builds the variant with a suspend-time hint (the hardware parks the
+// warp until the phase completes or ~10 ms pass instead of returning after the short default limit).  Measured on B200
+// (round 2): no gain for the weight-gradient kernel and 5 % LOSS for the persistent linear kernel (slower wake-up), so the
+// plain polling loop stays the default.
+#ifndef PU_MBAR_HINT
+#define PU_MBAR_HINT 0
+#endif
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#if PU_MBAR_HINT
+    for (int it = 0; it < 64; ++it) {   // 64 x ~10 ms: a pipeline bug still ends in the error flag, not in a hang
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (ok) return true;
+    }
+#else
     for (int it = 0; it < (1 << 22); ++it) {
         uint32_t ok;
         asm volatile(
@@ -58,6 +82,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
         if (ok) return true;
     }
+#endif
     return false;
 }
 
@@ -209,6 +234,23 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP: every mbarrier.arrive is an atomic on one shared-memory word, and arrivals of different warps on the
+// same barrier serialise -- with 256-512 arriving threads per 16 KB hand-off the barriers alone cost as many cycles as the
+// hand-off has at full HBM speed (measured: the weight-gradient kernels sat at ~1100 cycles per 32-row step whatever the
+// operand path).  __syncwarp orders the lanes' preceding shared / tensor-memory accesses before lane 0's releasing arrive.
+// Barriers that use this are initialised with a count of (threads / 32).  PU_WARP_ARRIVE=0 restores per-thread arrivals.
+#ifndef PU_WARP_ARRIVE
+#define PU_WARP_ARRIVE 1
+#endif
+constexpr int ARRIVE_DIV = PU_WARP_ARRIVE ? 32 : 1;
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t *bar) {
+#if PU_WARP_ARRIVE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+    mbar_arrive(bar);
+#endif
+}
 
 // ---- streamed weight operand: pre-split / pre-swizzled image in global memory, fetched with 1-D bulk copies (TMA engine)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
@@ -244,7 +286,8 @@ __global__ void __launch_bounds__(256) tc_pack_weight_kernel(const float *__rest
     }
 }
 
-constexpr int PERSIST_THREADS = P_THREADS + E_THREADS + 64;  // 8 converter warps, 16 epilogue warps, 1 MMA-issuer warp, 1 TMA warp
+// 8 converter warps, 16 epilogue warps, 1 MMA-issuer warp, 1 TMA warp (x), 1 weight-fetch warp (streamed variant)
+constexpr int PERSIST_THREADS = P_THREADS + E_THREADS + 96;
 
 template <int BN, int EPI, bool STREAM>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Params2 q, const __grid_constant__ CUtensorMap tmap_a) {
@@ -285,9 +328,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     const char *b_packed = STREAM ? q.Bp + (size_t)blockIdx.y * nkb * B_KB : nullptr;
 
     if (tid == 0) {
-        for (int i = 0; i < MAX_TA; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS); mbar_init(&b_full[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS / 2); }
-        for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], P_THREADS + (x_ring ? E_THREADS / 2 : 0)); }
+        for (int i = 0; i < MAX_TA; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS / ARRIVE_DIV); mbar_init(&b_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS / 2 / ARRIVE_DIV); }
+        for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], (P_THREADS + (x_ring ? E_THREADS / 2 : 0)) / ARRIVE_DIV); }
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -374,13 +417,13 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
             }
             // the tensor-memory stores consumed every loaded value, so the shared-memory reads have completed: only now may
             // the loader refill the slot (an arrive issued right behind the LDS can overtake it in the memory pipeline)
-            mbar_arrive(&raw_free[rslot]);
+            mbar_arrive_warp(&raw_free[rslot]);
 #ifdef PU_TC_TIMELINE
             if (warp == 0) PU_TL(1, tl_item, 2);
 #endif
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&stage_ready[slot]);  // hand the stage to the issuer; do not wait for it
+            mbar_arrive_warp(&stage_ready[slot]);  // hand the stage to the issuer; do not wait for it
 #ifdef PU_TC_TIMELINE
             if (warp == 0) PU_TL(1, tl_item, 3);
             ++tl_item;
@@ -417,6 +460,28 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
             if (++rslot == D) { rslot = 0; ++ruse; }
         }
         if (!ok) s_err = 1;
+    } else if (warp == (P_THREADS + E_THREADS) / 32 + 2) {
+        // ======================= weight loader (streamed variant): one elected lane feeds the TA weight stages =======================
+        // The per-role timeline (profiles/r1_tc_timeline_*.txt) showed the issuer spending ~1565 cycles per k-block of which
+        // only ~690 issue MMAs: the rest was serial bookkeeping on the same warp, ~300 cycles of it the two single-lane
+        // instructions of the weight fetch.  In a warp of its own the fetch runs up to TA items ahead and costs the issuer
+        // nothing but the b_full wait.
+        if constexpr (STREAM) {
+            const bool leader = elect_one();
+            long long f_tile = blockIdx.x;
+            int f_kb = 0, f_slot = 0, f_use = 0;
+            bool ok = true;
+            while (f_tile < q.ntiles) {
+                if (f_use >= 1) ok = mbar_wait(&stage_free[f_slot], (uint32_t)((f_use - 1) & 1)) && ok;  // previous reader retired
+                if (leader) {
+                    mbar_expect_tx(&b_full[f_slot], (uint32_t)B_KB);
+                    bulk_g2s(b_res + (size_t)f_slot * B_KB, b_packed + (size_t)f_kb * B_KB, (uint32_t)B_KB, &b_full[f_slot]);
+                }
+                if (++f_kb == nkb) { f_kb = 0; f_tile += gridDim.x; }
+                if (++f_slot == TA) { f_slot = 0; ++f_use; }
+            }
+            if (!ok) s_err = 1;
+        }
     } else if (warp == (P_THREADS + E_THREADS) / 32) {
         // ======================= MMA issuer =======================
         // The whole warp walks the loop converged (all lanes poll the mbarriers); one elected lane issues.  Descriptors
@@ -431,26 +496,73 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 #ifdef PU_TC_TIMELINE
             int tl_item = 0;
 #endif
-            // streamed weights: the fetch cursor runs PF = TA - 1 items (k-blocks) ahead of the MMA cursor, so PF bulk copies
-            // are in flight while one item computes
-            constexpr int PF = TA - 1;
-            long long f_tile = blockIdx.x;
-            int f_kb = 0, f_slot = 0, f_use = 0;
-            auto fetch_next = [&]() {
-                if (f_tile >= q.ntiles) return;
-                // the stage's previous reader (item - TA) must have retired
-                if (f_use >= 1) ok = mbar_wait(&stage_free[f_slot], (uint32_t)((f_use - 1) & 1)) && ok;
-                if (leader) {
-                    mbar_expect_tx(&b_full[f_slot], (uint32_t)B_KB);
-                    bulk_g2s(b_res + (size_t)f_slot * B_KB, b_packed + (size_t)f_kb * B_KB, (uint32_t)B_KB, &b_full[f_slot]);
-                }
-                if (++f_kb == nkb) { f_kb = 0; f_tile += gridDim.x; }
-                if (++f_slot == TA) { f_slot = 0; ++f_use; }
+#if PU_ISSUER_SWP
+            // Software-pipelined issue.  The tensor pipe accepts only one or two queued MMAs, so the issuing lane blocks on
+            // every UTCHMMA for about the MMA's own duration (timeline: 690 cycles for the 12 MMAs of a k-block) -- and
+            // whatever else this warp does between two k-blocks (barrier waits, descriptor arithmetic, loop control: ~500
+            // cycles) is time the pipe sits idle.  So the waits and the descriptors of item i+1 are taken in the MIDDLE of
+            // item i: the first half of its MMAs is queued, the bookkeeping for the next item runs in their shadow, then
+            // the second half follows.  No circular wait: stage i+1 only needs item i+1-TA to have retired (TA >= 2).
+            struct Item { uint32_t d_tmem, a_tmem; uint64_t dbh0, dbl0; int slot, buf; bool first_kb, last_kb; };
+            auto acquire = [&](long long tile, int kb, int sl, int us, int tcount, Item &it) {  // whole warp, converged
+                it.buf = tcount & 1;
+                const int v = tcount >> 1;
+                if (kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[it.buf], (uint32_t)((v - 1) & 1)) && ok;
+                ok = mbar_wait(&stage_ready[sl], (uint32_t)(us & 1)) && ok;                    // all 256 producers filled the stage
+                if constexpr (STREAM) ok = mbar_wait(&b_full[sl], (uint32_t)(us & 1)) && ok;   // this k-block of the weight landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                it.slot = sl;
+                it.first_kb = kb == 0;
+                it.last_kb = kb == nkb - 1;
+                it.d_tmem = tmem_base + (uint32_t)(it.buf * BN);
+                it.a_tmem = tmem_base + (uint32_t)(ACC_COLS + sl * 64);
+                it.dbh0 = bdesc0 + (uint64_t)((STREAM ? sl : kb) * (B_KB >> 4));
+                it.dbl0 = it.dbh0 + (uint64_t)((BN * 128) >> 4);
+                (void)tile;
             };
-            if constexpr (STREAM) {
+            auto issue = [&](const Item &it, int j0, int j1) {  // elected lane only
 #pragma unroll
-                for (int i = 0; i < PF; ++i) fetch_next();  // items 0 .. PF-1 (first use of their stages: nothing to wait for)
-            }
+                for (int j = j0; j < j1; ++j) {
+                    umma_tf32_ts(it.d_tmem, it.a_tmem + j * UMMA_K, it.dbh0 + (uint64_t)(2 * j), idesc, (!it.first_kb || j > 0) ? 1u : 0u);
+                    if (split) {
+                        umma_tf32_ts(it.d_tmem, it.a_tmem + j * UMMA_K, it.dbl0 + (uint64_t)(2 * j), idesc, 1u);
+                        umma_tf32_ts(it.d_tmem, it.a_tmem + 32 + j * UMMA_K, it.dbh0 + (uint64_t)(2 * j), idesc, 1u);
+                    }
+                }
+            };
+            constexpr int KSTEPS = BK / UMMA_K, KHALF = KSTEPS / 2;
+            Item cur{};
+            if (cur_tile < q.ntiles) acquire(cur_tile, cur_kb, slot, use, tile_count, cur);
+            while (cur_tile < q.ntiles) {
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 0);
+#endif
+                if (leader) issue(cur, 0, KHALF);
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 1);
+#endif
+                // cursor of the next item
+                long long n_tile = cur_tile;
+                int n_kb = cur_kb + 1, n_slot = slot + 1, n_use = use, n_count = tile_count;
+                if (n_kb == nkb) { n_kb = 0; n_tile += gridDim.x; n_count++; }
+                if (n_slot == TA) { n_slot = 0; ++n_use; }
+                Item nxt{};
+                if (n_tile < q.ntiles) acquire(n_tile, n_kb, n_slot, n_use, n_count, nxt);  // in the shadow of the queued MMAs
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 2);
+#endif
+                if (leader) {
+                    issue(cur, KHALF, KSTEPS);
+                    umma_commit(&stage_free[cur.slot]);
+                    if (cur.last_kb) umma_commit(&acc_full[cur.buf]);
+                }
+#ifdef PU_TC_TIMELINE
+                PU_TL(2, tl_item, 3);
+                ++tl_item;
+#endif
+                cur_tile = n_tile; cur_kb = n_kb; slot = n_slot; use = n_use; tile_count = n_count;
+                cur = nxt;
+#else
             while (cur_tile < q.ntiles) {
                 const bool last_kb = cur_kb == nkb - 1;
                 const int buf = tile_count & 1, v = tile_count >> 1;
@@ -485,13 +597,13 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 #ifdef PU_TC_TIMELINE
                 PU_TL(2, tl_item, 2);
 #endif
-                if constexpr (STREAM) fetch_next();  // item + PF goes into the stage of item - 1 (waits for its MMAs to retire)
 #ifdef PU_TC_TIMELINE
                 PU_TL(2, tl_item, 3);
                 ++tl_item;
 #endif
                 if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
                 slot = slot1; use = use1;
+#endif
             }
             if (!ok) s_err = 1;
         }
@@ -571,7 +683,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 }
                 if (pass == NPASS - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
+                    mbar_arrive_warp(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
                 }
                 bar_sync_named(bar_id, G_THREADS);
 #ifdef PU_TC_TIMELINE
@@ -717,8 +829,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 #endif
             }
             if (x_ring) {  // every x value has been consumed by the arithmetic above: the loader may refill the tile's slots
-                mbar_arrive(&raw_free[eslot]);
-                if (nkb == 2) mbar_arrive(&raw_free[eslot1]);
+                mbar_arrive_warp(&raw_free[eslot]);
+                if (nkb == 2) mbar_arrive_warp(&raw_free[eslot1]);
                 eslot += 2 * nkb;  // the other group owns the tile in between
                 if (eslot >= D) { eslot -= D; ++euse; }
             }
@@ -983,7 +1095,7 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
 
     if (tid == 0) {
         mbar_init(&stage_free[0], 1); mbar_init(&stage_free[1], 1); mbar_init(&all_done, 1);
-        mbar_init(&stage_ready[0], WG_THREADS); mbar_init(&stage_ready[1], WG_THREADS);
+        mbar_init(&stage_ready[0], WG_THREADS / ARRIVE_DIV); mbar_init(&stage_ready[1], WG_THREADS / ARRIVE_DIV);
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1027,7 +1139,7 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
             wg_convert<BM>(slot, a_hi, a_lo, tid, split, ones_col, row0, r_end);
             wg_convert<BN>(slot + A_BYTES, b_hi, b_lo, tid, split, -1, row0, r_end);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&stage_ready[s]);
+            mbar_arrive_warp(&stage_ready[s]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp < WG_THREADS / 32) {
@@ -1103,7 +1215,7 @@ __global__ void __launch_bounds__(WG_TOTAL, 1) tc_wgrad_kernel(const WParams w) 
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&stage_ready[s]);
+            mbar_arrive_warp(&stage_ready[s]);
             if (++cur_slot == D) cur_slot = 0;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1181,7 +1293,7 @@ static WgPlan wgrad_plan_tc(long long M, int Kin, int N) {
     if (gx > max_gx) gx = max_gx;
     if (gx < 1) gx = 1;
     long long rpc = (M + gx - 1) / gx;
-    rpc = (rpc + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+    rpc = (rpc + 63) / 64 * 64;   // whole steps of either kernel (32- or 64-row steps): a CTA never reads its neighbour's rows
     pl.rows_per_cta = rpc;
     pl.gx = (int)((M + rpc - 1) / rpc);
     const size_t stage = 2 * ((size_t)WG_ROWS * BM * 4 + (size_t)WG_ROWS * pl.bn * 4);
@@ -1205,12 +1317,347 @@ static int launch_wgrad(const WParams &w, const WgPlan &pl, cudaStream_t st) {
     return PU_OK;
 }
 
+
+// =============================================================================================================
+// Weight gradient, second generation: the x operand goes through TENSOR MEMORY (TS-form MMA), only dy stays in shared memory.
+// The first kernel (tc_wgrad_kernel above) keeps hi/lo images of BOTH operands in shared memory and is bound by that
+// memory's 128 B/clk port: per 32-row step raw in + LDS + 2 STS + three operand reads by the tensor core come to ~7 bytes of
+// shared-memory traffic per input byte (224 KB per 32 KB of input at BN = 128, 1750 cycles) -- 2.2-3.5 TB/s measured, and
+// worse when Kin < 128 pads the A tile.  Here
+//   * a loader warp brings [32 rows x boxA] of x and [32 x BN] of dy per step with two TMA tile copies (no swizzle; columns
+//     beyond Kin / N and rows beyond M arrive as zeros, so there is no tail code),
+//   * 8 "A" warps read x COLUMN-wise (lane = channel, 16 rows each: conflict-free 128-byte row segments), split hi/lo in
+//     registers and tcgen05.st the values into an operand-A stage in tensor memory (lane = channel = MMA row m, column = k),
+//   * 8 "B" warps convert dy into the MN-major SWIZZLE_128B_BASE32B hi/lo images as before,
+//   * the issuer runs 12 TS-form MMAs per step (A from TMEM, B from shared memory).
+// Shared-memory traffic drops to ~4.5 bytes per input byte at BN = 128 and does not grow when Kin is padded.
+// Work split (second lesson of the per-role timeline, profiles/r2_wgrad_timeline_*.txt): these kernels are INSTRUCTION-ISSUE
+// bound, and most instructions are per-step bookkeeping (two barrier waits, fences, arrivals, ring arithmetic: ~150 per warp
+// and step) rather than conversion work (~700 warp instructions per 16 KB).  So a step is handled by as FEW warps as the
+// tensor-memory lane rule allows -- four "A" warps (one per lane quarter, a thread converts all rows of its channel) and four
+// "B" warps -- and there are TWO such groups per operand that take alternate steps, so two steps are always in conversion.
+// Narrow operand pairs (x block and dy block <= 64 columns) use 64-row steps, which halves the bookkeeping per byte again.
+constexpr int WT_GROUP = 128;                                  // threads per converter group (4 warps)
+constexpr int WT_A_THREADS = 2 * WT_GROUP, WT_B_THREADS = 2 * WT_GROUP;
+constexpr int WT_TOTAL = WT_A_THREADS + WT_B_THREADS + 64;   // + issuer warp + TMA warp
+constexpr int WT_MAX_TA = 4;                                 // operand-A stages in tensor memory
+constexpr int WT_MAX_RAW = 8;
+
+struct WTParams {
+    long long M; int Kin, N;
+    long long rows_per_cta;
+    float *part;               // [gridDim.x][Kin][N]
+    float *db_part;            // [gridDim.x][N] or null
+    int mode;
+    int raw_depth;
+    int box_a;                 // columns of x per step (32 / 64 / 128)
+    int *error_flag;
+    long long *timeline;       // optional (tools/wgrad_timeline.py): clock64 stamps of CTA 0, [role][step][event]
+};
+constexpr int WTL_STEPS = 96, WTL_EVENTS = 4, WTL_ROLES = 4;   // roles: 0 A converter (warp 0), 1 B converter, 2 issuer, 3 loader
+#define WTL(role, step, ev)                                                                                         \
+    do {                                                                                                            \
+        if (w.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && (step) < WTL_STEPS) \
+            w.timeline[((size_t)(role) * WTL_STEPS + (step)) * WTL_EVENTS + (ev)] = clock64();                      \
+    } while (0)
+
+__device__ __forceinline__ uint32_t make_idesc_ts_mn(int n) {  // A from tensor memory (K-major), B MN-major in shared memory
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN, int ROWS>
+__global__ void __launch_bounds__(WT_TOTAL, 1) tc_wgrad_ts_kernel(const WTParams w, const __grid_constant__ CUtensorMap tmap_x,
+                                                                  const __grid_constant__ CUtensorMap tmap_g) {
+    constexpr int B_BYTES = ROWS * BN * 4;             // one image of the dy operand
+    constexpr int B_STAGE = 2 * B_BYTES;               // hi + lo
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    constexpr int A_COLS = 2 * ROWS;                   // tensor-memory columns of one operand-A stage: hi rows, then lo rows
+    constexpr int TA = (512 - ACC_COLS) / A_COLS < WT_MAX_TA ? (512 - ACC_COLS) / A_COLS : WT_MAX_TA;
+    constexpr int TMEM_COLS = 512;
+    static_assert(TA >= 2 && ACC_COLS + TA * A_COLS <= TMEM_COLS, "tensor memory budget");
+    extern __shared__ __align__(1024) char smem_raw[];
+    char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t raw_full[WT_MAX_RAW], raw_free[WT_MAX_RAW], a_ready[WT_MAX_TA], a_free[WT_MAX_TA], b_ready[2], b_free[2], all_done;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ int s_err;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k0 = blockIdx.y * BM, n0 = blockIdx.z * BN;
+    const bool split = w.mode == 3;
+    const int D = w.raw_depth, box_a = w.box_a;
+    const int a_raw_bytes = ROWS * box_a * 4, raw_bytes = a_raw_bytes + B_BYTES;
+    char *b_ring = smem;                        // 2 operand stages of dy (stage g belongs to B group g)
+    char *raw_ring = smem + 2 * B_STAGE;        // D raw slots: [ROWS][box_a] of x, then [ROWS][BN] of dy
+    const long long r_begin = (long long)blockIdx.x * w.rows_per_cta;
+    const long long r_end = min(w.M, r_begin + w.rows_per_cta);
+    const int nsteps = r_end > r_begin ? (int)((r_end - r_begin + ROWS - 1) / ROWS) : 0;
+    const int ones_col = (w.db_part && blockIdx.y == gridDim.y - 1 && (w.Kin % BM) != 0) ? (w.Kin - k0) : -1;
+
+    if (tid == 0) {
+        for (int i = 0; i < WT_MAX_RAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], 2 * WT_GROUP / ARRIVE_DIV); }
+        for (int i = 0; i < WT_MAX_TA; ++i) { mbar_init(&a_ready[i], WT_GROUP / ARRIVE_DIV); mbar_init(&a_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&b_ready[i], WT_GROUP / ARRIVE_DIV); mbar_init(&b_free[i], 1); }
+        mbar_init(&all_done, 1);
+        s_err = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    bool ok = true;
+    if (warp < WT_A_THREADS / 32) {
+        // ======================= A converters: x -> tensor memory =======================
+        // warp (group g, quarter q): channels 32 q .. 32 q + 31 (= its TMEM lane quarter), ALL rows of the steps g, g + 2, ...
+        const int q = warp & 3, g = warp >> 2;
+        const int ch = q * 32 + lane;
+        const bool has_data = ch < box_a;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ACC_COLS;
+        int rs = g % D, ru = g / D, as = g % TA, au = g / TA;
+        for (int it = g; it < nsteps; it += 2) {
+            ok = mbar_wait(&raw_full[rs], (uint32_t)(ru & 1)) && ok;
+            if ((warp & 3) == 0) WTL(0, it, 0);
+            if (au >= 1) ok = mbar_wait(&a_free[as], (uint32_t)((au - 1) & 1)) && ok;   // MMAs that read the stage retired
+            if ((warp & 3) == 0) WTL(0, it, 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float *src = reinterpret_cast<const float *>(raw_ring + (size_t)rs * raw_bytes) + ch;
+            const uint32_t ta = t_lane + (uint32_t)(as * A_COLS);
+#pragma unroll
+            for (int c = 0; c < ROWS / 16; ++c) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = has_data ? src[(c * 16 + i) * box_a] : 0.f;
+                if (ch == ones_col) {   // bias gradient: a row of ones for the valid rows
+                    const long long row0 = r_begin + (long long)it * ROWS + c * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = row0 + i < w.M ? 1.f : 0.f;
+                }
+                if (split) {
+                    float h[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { h[i] = tf32_rn(v[i]); v[i] -= h[i]; }
+                    tmem_st16(ta + c * 16, h);
+                    tmem_st16(ta + ROWS + c * 16, v);
+                } else {
+                    tmem_st16(ta + c * 16, v);
+                }
+            }
+            mbar_arrive_warp(&raw_free[rs]);   // the stores consumed every loaded value: the shared-memory reads have completed
+            if ((warp & 3) == 0) WTL(0, it, 2);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_warp(&a_ready[as]);
+            if ((warp & 3) == 0) WTL(0, it, 3);
+            rs += 2; if (rs >= D) { rs -= D; ++ru; }
+            as += 2; if (as >= TA) { as -= TA; ++au; }
+        }
+    } else if (warp < (WT_A_THREADS + WT_B_THREADS) / 32) {
+        // ======================= B converters: dy -> MN-major hi/lo images in shared memory =======================
+        // group g owns operand stage g and the steps g, g + 2, ...
+        const int bt = (tid - WT_A_THREADS) & (WT_GROUP - 1), g = (tid - WT_A_THREADS) / WT_GROUP;
+        constexpr int CHUNKS = ROWS * BN / 4, CPT = CHUNKS / WT_GROUP;
+        static_assert(CHUNKS % WT_GROUP == 0, "whole chunks per thread");
+        uint32_t c_op[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int idx = bt + WT_GROUP * i;
+            const int r = idx / (BN / 4), c4 = (idx % (BN / 4)) * 4;
+            c_op[i] = (uint32_t)((c4 >> 5) * (ROWS * 128)) + sw128_32b(r, c4 & 31);
+        }
+        char *st_base = b_ring + (size_t)g * B_STAGE;
+        int rs = g % D, ru = g / D, u = 0;
+        for (int it = g; it < nsteps; it += 2, ++u) {
+            ok = mbar_wait(&raw_full[rs], (uint32_t)(ru & 1)) && ok;
+            if (bt < 32) WTL(1, it, 0);
+            if (u >= 1) ok = mbar_wait(&b_free[g], (uint32_t)((u - 1) & 1)) && ok;
+            if (bt < 32) WTL(1, it, 1);
+            const char *src = raw_ring + (size_t)rs * raw_bytes + a_raw_bytes + (size_t)bt * 16;
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                const float4 v = *reinterpret_cast<const float4 *>(src + i * (WT_GROUP * 16));
+                char *dst = st_base + c_op[i];
+                if (split) {
+                    const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                    *reinterpret_cast<float4 *>(dst) = h;
+                    *reinterpret_cast<float4 *>(dst + B_BYTES) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                } else {
+                    *reinterpret_cast<float4 *>(dst) = v;
+                }
+            }
+            mbar_arrive_warp(&raw_free[rs]);
+            if (bt < 32) WTL(1, it, 2);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_warp(&b_ready[g]);
+            if (bt < 32) WTL(1, it, 3);
+            rs += 2; if (rs >= D) { rs -= D; ++ru; }
+        }
+    } else if (warp == (WT_A_THREADS + WT_B_THREADS) / 32 + 1) {
+        // ======================= loader: two TMA tile copies per step =======================
+        const bool leader = elect_one();
+        int rs = 0, ru = 0;
+        for (int it = 0; it < nsteps; ++it) {
+            if (ru >= 1) ok = mbar_wait(&raw_free[rs], (uint32_t)((ru - 1) & 1)) && ok;
+            WTL(3, it, 0);
+            if (leader) {
+                char *slot = raw_ring + (size_t)rs * raw_bytes;
+                const int row0 = (int)(r_begin + (long long)it * ROWS);
+                mbar_expect_tx(&raw_full[rs], (uint32_t)raw_bytes);
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(smem_u32(slot)), "l"(&tmap_x), "r"(k0), "r"(row0), "r"(smem_u32(&raw_full[rs])) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(smem_u32(slot + a_raw_bytes)), "l"(&tmap_g), "r"(n0), "r"(row0), "r"(smem_u32(&raw_full[rs])) : "memory");
+            }
+            if (++rs == D) { rs = 0; ++ru; }
+        }
+    } else {
+        // ======================= MMA issuer: converged warp, one elected lane issues =======================
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_ts_mn(BN);
+        const uint64_t bdesc0 = make_desc_mn(smem_u32(b_ring), ROWS * 128);
+        int as = 0, au = 0;
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it & 1, u = it >> 1;
+            ok = mbar_wait(&a_ready[as], (uint32_t)(au & 1)) && ok;
+            WTL(2, it, 0);
+            ok = mbar_wait(&b_ready[s], (uint32_t)(u & 1)) && ok;
+            WTL(2, it, 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_tmem = tmem_base + (uint32_t)(ACC_COLS + as * A_COLS);
+            const uint64_t dbh0 = bdesc0 + (uint64_t)((s * B_STAGE) >> 4), dbl0 = dbh0 + (uint64_t)(B_BYTES >> 4);
+            if (leader) {
+#pragma unroll
+                for (int j = 0; j < ROWS / UMMA_K; ++j) {  // 8 rows = two 512-byte k groups per slab
+                    const uint64_t o = (uint64_t)((j * 1024) >> 4);
+                    umma_tf32_ts(tmem_base, a_tmem + j * UMMA_K, dbh0 + o, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    if (split) {
+                        umma_tf32_ts(tmem_base, a_tmem + j * UMMA_K, dbl0 + o, idesc, 1u);
+                        umma_tf32_ts(tmem_base, a_tmem + ROWS + j * UMMA_K, dbh0 + o, idesc, 1u);
+                    }
+                }
+                WTL(2, it, 2);
+                umma_commit(&a_free[as]);
+                umma_commit(&b_free[s]);
+                if (it == nsteps - 1) umma_commit(&all_done);
+            }
+            WTL(2, it, 3);
+            if (++as == TA) { as = 0; ++au; }
+        }
+    }
+    if (warp < 8 && nsteps > 0) ok = mbar_wait(&all_done, 0u) && ok;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok) s_err = 1;
+    // epilogue: TMEM lane = Kin index (k0 + lane), column = N index; warps 0-3 and 4-7 split the columns
+    if (warp < 8) {
+        const int quarter = warp & 3, chalf = warp >> 2;
+        const int m = quarter * 32 + lane;
+        const int gk = k0 + m;
+        float *prow = w.part + ((size_t)blockIdx.x * w.Kin + gk) * w.N + n0;
+#pragma unroll
+        for (int cc = 0; cc < BN / 2; cc += 16) {
+            const int c0 = chalf * (BN / 2) + cc;
+            float vals[16];
+            if (nsteps > 0) tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, vals);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vals[i] = 0.f;
+            }
+            if (gk < w.Kin) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n0 + c0 + i < w.N) prow[c0 + i] = vals[i];
+            } else if (m == ones_col && w.db_part) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n0 + c0 + i < w.N) w.db_part[(size_t)blockIdx.x * w.N + n0 + c0 + i] = vals[i];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+    if (tid == 0 && s_err && w.error_flag) *w.error_flag = 1;
+}
+
+// un-swizzled 2-D tensor map over a row-major matrix [rows, cols] (row stride ld floats): box = box_rows x box_cols
+static int make_tmap_plain(CUtensorMap *map, const float *base, long long rows, int cols, int ld, int box_cols, int box_rows) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return PU_ERR_UNSUPPORTED;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PU_OK : PU_ERR_INVALID_ARG;
+}
+
+static long long *g_wgrad_timeline = nullptr;   // development aid, see pu_tc_debug_set_wgrad_timeline
+struct WtPlan { int box_a, rows, depth; size_t smem; };
+static WtPlan wgrad_ts_plan(int Kin, int bn) {
+    WtPlan pl{};
+    const int cols = Kin < BM ? Kin : BM;   // widest A block any CTA sees
+    pl.box_a = cols <= 32 ? 32 : (cols <= 64 ? 64 : 128);
+    pl.rows = (pl.box_a <= 64 && bn <= 64) ? 64 : 32;   // narrow pairs: 64-row steps
+    const size_t b_stage = 2 * (size_t)pl.rows * bn * 4, raw = (size_t)pl.rows * (pl.box_a + bn) * 4;
+    long long d = (long long)((kMaxDynSmem - 2 * b_stage - 1024) / raw);
+    pl.depth = (int)(d > WT_MAX_RAW ? WT_MAX_RAW : d);
+    pl.smem = 2 * b_stage + (size_t)pl.depth * raw + 1024;
+    return pl;
+}
+
+template <int BN, int ROWS>
+static int launch_wgrad_ts_rows(const WParams &w0, const WgPlan &pl, const WtPlan &tp, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        PU_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_ts_kernel<BN, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        configured = true;
+    }
+    CUtensorMap tx, tg;
+    int rc = make_tmap_plain(&tx, w0.X, w0.M, w0.Kin, w0.ldx, tp.box_a, ROWS);
+    if (rc != PU_OK) return rc;
+    rc = make_tmap_plain(&tg, w0.G, w0.M, w0.N, w0.ldg, BN, ROWS);
+    if (rc != PU_OK) return rc;
+    WTParams w{};
+    w.M = w0.M; w.Kin = w0.Kin; w.N = w0.N; w.rows_per_cta = w0.rows_per_cta; w.part = w0.part; w.db_part = w0.db_part;
+    w.mode = w0.mode; w.raw_depth = tp.depth; w.box_a = tp.box_a; w.error_flag = w0.error_flag;
+    w.timeline = g_wgrad_timeline;
+    dim3 grid(pl.gx, pl.gy, pl.gz);
+    tc_wgrad_ts_kernel<BN, ROWS><<<grid, WT_TOTAL, tp.smem, st>>>(w, tx, tg);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+template <int BN>
+static int launch_wgrad_ts(const WParams &w0, const WgPlan &pl, cudaStream_t st) {
+    const WtPlan tp = wgrad_ts_plan(w0.Kin, BN);
+    if (tp.depth < 2) return PU_ERR_UNSUPPORTED;
+    if constexpr (BN <= 64) {
+        if (tp.rows == 64) return launch_wgrad_ts_rows<BN, 64>(w0, pl, tp, st);
+    }
+    return launch_wgrad_ts_rows<BN, 32>(w0, pl, tp, st);
+}
+
 }  // namespace tc
 }  // namespace pu
 
 using namespace pu;
 
 extern "C" {
+
+/* development aid (tools/wgrad_timeline.py): device buffer of roles x steps x events clock64 stamps, or NULL to switch off */
+__attribute__((visibility("default"))) void pu_tc_debug_set_wgrad_timeline(long long *device_buffer) { tc::g_wgrad_timeline = device_buffer; }
+__attribute__((visibility("default"))) int pu_tc_debug_wgrad_timeline_dims(int *roles, int *steps, int *events) {
+    *roles = tc::WTL_ROLES; *steps = tc::WTL_STEPS; *events = tc::WTL_EVENTS;
+    return 0;
+}
 
 /* 1 if (M,K,N, strides) can run on the tensor-core path */
 int pu_tc_linear_supported(long long M, int K, int N, int ldx, int ldwt, int ldy) {
@@ -1297,10 +1744,18 @@ int pu_tc_wgrad(const float *x, int ldx, const float *dy, int lddy, long long M,
     w.part = (float *)workspace;
     w.db_part = db ? w.part + (size_t)pl.gx * Kin * N : nullptr;
     w.mode = mode; w.raw_depth = pl.depth; w.error_flag = error_flag;
+    // PU_WGRAD_TS=0 selects the first-generation kernel (both operands in shared memory) for A/B runs
+    static const bool use_ts = [] { const char *e = getenv("PU_WGRAD_TS"); return !(e && e[0] == '0'); }();
     int rc;
-    if (pl.bn == 32) rc = tc::launch_wgrad<32>(w, pl, st);
-    else if (pl.bn == 64) rc = tc::launch_wgrad<64>(w, pl, st);
-    else rc = tc::launch_wgrad<128>(w, pl, st);
+    if (use_ts) {
+        if (pl.bn == 32) rc = tc::launch_wgrad_ts<32>(w, pl, st);
+        else if (pl.bn == 64) rc = tc::launch_wgrad_ts<64>(w, pl, st);
+        else rc = tc::launch_wgrad_ts<128>(w, pl, st);
+    } else {
+        if (pl.bn == 32) rc = tc::launch_wgrad<32>(w, pl, st);
+        else if (pl.bn == 64) rc = tc::launch_wgrad<64>(w, pl, st);
+        else rc = tc::launch_wgrad<128>(w, pl, st);
+    }
     if (rc != PU_OK) return rc;
     launch_reduce_parts(w.part, pl.gx, (long long)Kin * N, dw, accumulate, st);
     PU_LAUNCH_CHECK();
