@@ -183,6 +183,12 @@ PU_API int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const floa
 PU_API int pu_bn_prepare(const float *mean, const float *var, const float *gamma, const float *beta, float eps, int C,
                          float *invstd, float *scale, float *shift, float *moving_mean, float *moving_var,
                          float momentum, float unbias, pu_stream_t stream);
+/* pu_stats_finalize + pu_bn_prepare in ONE launch (training mode: the statistics come straight from the per-tile partials of
+ * the producing linear kernel; 44 batch norms per step, each saved launch sits on the critical path). */
+PU_API int pu_bn_finalize_prepare(const float *stat_sum, const float *stat_sq, int tiles, int rows_per_tile, int C,
+                                  long long count, const float *gamma, const float *beta, float eps, float *mean,
+                                  float *var, float *invstd, float *scale, float *shift, float *moving_mean,
+                                  float *moving_var, float momentum, float unbias, pu_stream_t stream);
 PU_API int pu_bn_bwd_coeffs(const float *part_dz, const float *part_dzy, int blocks, int C, const float *mean,
                             const float *invstd, const float *gamma, long long rows, int training, float *dgamma,
                             float *dbeta, float *ka, float *kb, float *kc, pu_stream_t stream);

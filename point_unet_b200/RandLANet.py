@@ -322,7 +322,7 @@ class Network(torch.nn.Module):
             return ops.linear(x, w, b)
         rows_n = x.numel() // x.shape[-1]
         if is_training:
-            y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True)
+            y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True, defer_stats=True)
         else:
             y = ops.linear(x, w, b)
             mean = var = None
@@ -356,7 +356,7 @@ class Network(torch.nn.Module):
         w, b = self.v(scope + "/weights"), self.v(scope + "/biases")
         rows_n = x.numel() // x.shape[-1]
         if is_training:
-            y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True)
+            y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True, defer_stats=True)
         else:
             y, mean, var = ops.linear(x, w, b), None, None
         mean, var, moving = self._bn_stats(scope, mean, var, rows_n, is_training)
@@ -382,7 +382,7 @@ class Network(torch.nn.Module):
             w, b = self.v(scope + "/weights"), self.v(scope + "/biases")
             rows_n = x.numel() // x.shape[-1]
             if is_training:
-                y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True)
+                y, mean, var = ops.linear(x, w, b, want_stats=True, zero_bias_grad=True, defer_stats=True)
             else:
                 y, mean, var = ops.linear(x, w, b), None, None
             mean, var, moving = self._bn_stats(scope, mean, var, rows_n, is_training)

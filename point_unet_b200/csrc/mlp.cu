@@ -505,7 +505,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A,
 constexpr int SF_THREADS = 1024;
 __global__ void __launch_bounds__(SF_THREADS) stats_finalize_kernel(const float *__restrict__ psum, const float *__restrict__ pm2,
                                                                     int tiles, int C, long long count, int rows_per_tile,
-                                                                    float *__restrict__ mean, float *__restrict__ var) {
+                                                                    float *__restrict__ mean, float *__restrict__ var,
+                                                                    const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                    float eps, float *__restrict__ invstd, float *__restrict__ scale,
+                                                                    float *__restrict__ shift, float *__restrict__ moving_mean,
+                                                                    float *__restrict__ moving_var, float momentum, float unbias) {
     constexpr int NT = SF_THREADS;
     __shared__ double red[3][NT];
     const int c = blockIdx.x;
@@ -548,8 +552,20 @@ __global__ void __launch_bounds__(SF_THREADS) stats_finalize_kernel(const float 
     if (threadIdx.x == 0) {
         const double n = (double)count, m = red[0][0] / n;
         const double v = (red[1][0] + red[2][0] - n * m * m) / n;
-        mean[c] = (float)m;
-        var[c] = (float)(v > 0.0 ? v : 0.0);
+        const float mf = (float)m, vf = (float)(v > 0.0 ? v : 0.0);
+        mean[c] = mf;
+        var[c] = vf;
+        if (gamma) {   // fused pu_bn_prepare (same arithmetic as bn_prepare_kernel): one launch per batch norm instead of two
+            const float is = rsqrtf(vf + eps);
+            invstd[c] = is;
+            scale[c] = gamma[c] * is;
+            shift[c] = mf;
+            shift[C + c] = beta[c];
+            if (moving_mean) {
+                moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * mf;
+                moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * vf * unbias;
+            }
+        }
     }
 }
 
@@ -979,8 +995,25 @@ int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, in
                       float *mean, float *var, pu_stream_t stream) {
     if (!stat_sum || !stat_sq || !mean || !var || tiles < 1 || C < 1 || count < 1 || rows_per_tile < 1) return PU_ERR_INVALID_ARG;
     if ((long long)tiles != (count + rows_per_tile - 1) / rows_per_tile) return PU_ERR_INVALID_ARG;
-    stats_finalize_kernel<<<C, SF_THREADS, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C,
-                                                                                          count, rows_per_tile, mean, var);
+    stats_finalize_kernel<<<C, SF_THREADS, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C, count, rows_per_tile, mean, var,
+                                                                      nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr,
+                                                                      nullptr, 0.f, 1.f);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
+int pu_bn_finalize_prepare(const float *stat_sum, const float *stat_sq, int tiles, int rows_per_tile, int C, long long count,
+                           const float *gamma, const float *beta, float eps, float *mean, float *var, float *invstd,
+                           float *scale, float *shift, float *moving_mean, float *moving_var, float momentum, float unbias,
+                           pu_stream_t stream) {
+    if (!stat_sum || !stat_sq || !mean || !var || !gamma || !beta || !invstd || !scale || !shift || tiles < 1 || C < 1 ||
+        count < 1 || rows_per_tile < 1)
+        return PU_ERR_INVALID_ARG;
+    if ((long long)tiles != (count + rows_per_tile - 1) / rows_per_tile) return PU_ERR_INVALID_ARG;
+    if ((moving_mean == nullptr) != (moving_var == nullptr)) return PU_ERR_INVALID_ARG;
+    stats_finalize_kernel<<<C, SF_THREADS, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C, count, rows_per_tile, mean, var,
+                                                                      gamma, beta, eps, invstd, scale, shift, moving_mean,
+                                                                      moving_var, momentum, unbias);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

@@ -53,6 +53,8 @@ _lib._OP_SIGS.update({
                         c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p],
     "pu_bn_prepare": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                       c_void_p, c_float, c_float, c_void_p],
+    "pu_bn_finalize_prepare": [c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p],
     "pu_bn_bwd_coeffs": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p],
     "pu_point2prod": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
@@ -365,7 +367,16 @@ def tc_error_flag(device) -> torch.Tensor:
     return _tc_error_flag[key]
 
 
-def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt=None, tc_mode=None):
+class StatPartials:
+    """Per-tile (sum, M2) partials of a linear kernel, not yet reduced: ``bn_prepare`` turns them into mean / variance /
+    invstd / scale / shift in the same launch (pu_bn_finalize_prepare)."""
+    __slots__ = ("ssum", "ssq", "rpt", "rows", "C")
+
+    def __init__(self, ssum, ssq, rpt, rows):
+        self.ssum, self.ssq, self.rpt, self.rows, self.C = ssum, ssq, rpt, rows, ssum.shape[1]
+
+
+def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt=None, tc_mode=None, defer_stats=False):
     """y = x w (+ bias) over rows; optionally the batch-norm mean / biased variance of y. (no autograd)
     ``w`` is [K,N]; ``wt`` (optional) is the same weight stored transposed [N,K] -- the tensor-core path wants the
     K-major form and transposes on the fly (a few hundred KB at most) when only ``w`` is given."""
@@ -405,6 +416,8 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
               tag=(M, K, N, int(accumulate)))
     if not want_stats:
         return out
+    if defer_stats:
+        return out, StatPartials(ssum, ssq, rpt, M), None
     mean = torch.empty(N, dtype=torch.float32, device=x.device)
     var = torch.empty(N, dtype=torch.float32, device=x.device)
     _call("pu_stats_finalize", ssum.data_ptr(), ssq.data_ptr(), ssum.shape[0], rpt, N, M, mean.data_ptr(), var.data_ptr(),
@@ -488,9 +501,13 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, want_stats, zero_bias_grad):
         w = w.contiguous()
-        res = linear_raw(x, w, bias, want_stats=want_stats)
+        defer = want_stats == "defer"
+        res = linear_raw(x, w, bias, want_stats=bool(want_stats), defer_stats=defer)
         ctx.zero_bias_grad = zero_bias_grad
         y, mean, var = res if want_stats else (res, None, None)
+        if defer:   # hand the raw partials through autograd as two plain tensors; ops.linear re-wraps them
+            _LinearFn.last_partials = (mean.rpt, mean.rows)
+            mean, var = mean.ssum, mean.ssq
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.x_needs = x.requires_grad
@@ -527,12 +544,17 @@ class _LinearFn(torch.autograd.Function):
         return dx, (None if gw is not None else dw), db, None, None
 
 
-def linear(x, w, bias=None, want_stats=False, zero_bias_grad=False):
+def linear(x, w, bias=None, want_stats=False, zero_bias_grad=False, defer_stats=False):
     """``y = x w + b`` over the last axis (1x1 conv / dense); with ``want_stats`` also returns the batch mean and
     biased variance of ``y`` per channel (non-differentiable side outputs consumed by :func:`bn_act`).
     ``zero_bias_grad``: the caller asserts that ``y`` goes straight into a training-mode batch norm, whose backward
-    makes the bias gradient identically zero."""
+    makes the bias gradient identically zero.  ``defer_stats``: return ``(y, StatPartials, None)`` instead -- the
+    per-tile partials, reduced later inside :func:`bn_prepare` together with the BN coefficients (one launch less)."""
     _need_cuda(x, w)
+    if want_stats and defer_stats:
+        y, ssum, ssq = _LinearFn.apply(x, w, bias, "defer", zero_bias_grad)
+        rpt, nrows = _LinearFn.last_partials
+        return y, StatPartials(ssum, ssq, rpt, nrows), None
     return _LinearFn.apply(x, w, bias, want_stats, zero_bias_grad)
 
 
@@ -598,9 +620,13 @@ class _BNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, mean, var, gamma, beta, slope, training, moving, y2, mean2, var2, gamma2, beta2, moving2):
         invstd, scale, shift = bn_prepare(mean, var, gamma, beta, moving if training else None)
+        if isinstance(mean, StatPartials):
+            mean = shift[0]   # the fused finalize wrote the batch mean there
         two = y2 is not None
         if two:
             invstd2, scale2, shift2 = bn_prepare(mean2, var2, gamma2, beta2, moving2 if training else None)
+            if isinstance(mean2, StatPartials):
+                mean2 = shift2[0]
             res = _bn_act_fwd_raw(y, scale, shift, slope, y2=y2, scale2=scale2, shift2=shift2)
             ctx.save_for_backward(y, scale, shift, gamma, mean, invstd, y2, scale2, shift2, gamma2, mean2, invstd2, res)
         else:
@@ -641,12 +667,20 @@ class _BNActFn(torch.autograd.Function):
 def bn_prepare(mean, var, gamma, beta, moving=None):
     """invstd / scale / shift per channel in one launch; ``moving = (moving_mean, moving_var, unbias)`` also applies
     the momentum-0.99 moving-average update in place (the reference runs it with the step, RandLANet.py:90,163)."""
-    C = mean.numel()
-    buf = torch.empty((4, C), dtype=torch.float32, device=mean.device)  # invstd, scale, [mean; beta]
     mm = mv = None
     unbias = 1.0
     if moving is not None:
         mm, mv, unbias = moving
+    if isinstance(mean, StatPartials):   # training mode, statistics still as per-tile partials: finalize + prepare fused
+        sp, C = mean, mean.C
+        buf = torch.empty((6, C), dtype=torch.float32, device=sp.ssum.device)  # invstd, scale, [mean; beta], mean, var
+        _call("pu_bn_finalize_prepare", sp.ssum.data_ptr(), sp.ssq.data_ptr(), sp.ssum.shape[0], sp.rpt, C, sp.rows,
+              gamma.data_ptr(), beta.data_ptr(), BN_EPS, buf[4].data_ptr(), buf[5].data_ptr(), buf[0].data_ptr(),
+              buf[1].data_ptr(), buf[2].data_ptr(), mm.data_ptr() if mm is not None else None,
+              mv.data_ptr() if mv is not None else None, BN_MOMENTUM, float(unbias), _stream(sp.ssum))
+        return buf[0], buf[1], buf[2:4]
+    C = mean.numel()
+    buf = torch.empty((4, C), dtype=torch.float32, device=mean.device)  # invstd, scale, [mean; beta]
     _call("pu_bn_prepare", mean.data_ptr(), var.data_ptr(), gamma.data_ptr(), beta.data_ptr(), BN_EPS, C,
           buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), mm.data_ptr() if mm is not None else None,
           mv.data_ptr() if mv is not None else None, BN_MOMENTUM, float(unbias), _stream(mean))
@@ -671,6 +705,8 @@ class _LFAConcatFn(torch.autograd.Function):
     def forward(ctx, f_pc, idx, y, mean, var, gamma, beta, training, moving, need_fxyz):
         B, N, K, h = y.shape
         invstd, scale, shift = bn_prepare(mean, var, gamma, beta, moving if training else None)
+        if isinstance(mean, StatPartials):
+            mean = shift[0]
         buf = torch.empty((B, N, K, 2 * h), dtype=torch.float32, device=y.device)
         gather_rows(f_pc, idx, out=buf[..., :h])
         if need_fxyz:

@@ -30,7 +30,26 @@ def report(op, level, nbytes, ms, **kw):
     print(json.dumps(dict(op=op, level=level, ms=round(ms, 4), algorithmic_mb=round(nbytes / 1e6, 1), gbs=round(gbs, 1),
                           frac_of_measured_hbm=round(gbs / PEAK, 3), **kw)), flush=True)
 
-xyz = torch.from_numpy(syn.batch(syn.brats_cloud, B, NL[0], 0)["xyz"]).cuda()
+import numpy as np
+def locality_order(xyz_np):
+    """(class, Morton) order: class = pyramid level at which a point drops out (prefix sets are preserved)."""
+    n = xyz_np.shape[0]
+    cls = np.zeros(n, np.int64)
+    for lvl, nl in enumerate(NL[:-1]):   # points >= NL[lvl+1] and < NL[lvl] drop out after level lvl
+        cls[NL[lvl + 1]:nl] = len(NL) - 1 - lvl
+    lo, hi = xyz_np.min(0), xyz_np.max(0)
+    q = np.clip(((xyz_np - lo) / np.maximum(hi - lo, 1e-12) * 512).astype(np.int64), 0, 511)
+    def spread(v):
+        r = np.zeros_like(v)
+        for b in range(9):
+            r |= ((v >> b) & 1) << (3 * b)
+        return r
+    m = (spread(q[:, 0]) << 2) | (spread(q[:, 1]) << 1) | spread(q[:, 2])
+    return np.argsort((cls << 27) | m, kind="stable")
+data = syn.batch(syn.brats_cloud, B, NL[0], 0)["xyz"]
+if "--reorder" in sys.argv:
+    data = np.stack([c[locality_order(c)] for c in data])
+xyz = torch.from_numpy(data).cuda()
 for lvl in range(3):
     N, Nn, d = NL[lvl], NL[lvl + 1], DOUT[lvl]
     x = xyz[:, :N].contiguous()
