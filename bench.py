@@ -352,7 +352,7 @@ def run_ours(args):
 
     B, N = args.batch, args.points
     host = make_batch(rank, B, N)
-    tr = Trainer(cfg, num_features=7, seed=0, device=dev, world_size=world)
+    tr = Trainer(cfg, num_features=7, seed=0, device=dev, world_size=world, storage=args.storage)
     x = torch.from_numpy(host["xyz"]).to(dev)
     f = torch.from_numpy(host["features"]).to(dev)
     l = torch.from_numpy(host["labels"]).to(dev)
@@ -510,7 +510,9 @@ def run_ours(args):
                                              "batch i (one pyramid + one train step per replay)" if pipelined and use_graph
                                              else "pyramid and training of the same batch in one step"),
                              host_pipeline="H2D of batch k on a copy stream under the replay of call k (Trainer.train_step)",
-                             graph_error=graph_err, tc_error_flag=0),
+                             graph_error=graph_err, tc_error_flag=0,
+                             storage=("bf16 storage of pre-normalisation activations (opt-in, tolerance 2e-2)"
+                                      if ops.STORAGE_BF16 else "fp32")),
                     e2e=dict(value=pts / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=8),
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks, knn=knn,
@@ -542,6 +544,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--cpu-sample", type=int, default=N_POINTS, help="points of the cpu_baseline sample cloud")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--storage", default=None, choices=["fp32", "bf16"],
+                    help="bf16: opt-in storage mode of the pre-normalisation activations (dtype stays f32: arithmetic is fp32)")
     ap.add_argument("--no-extra", action="store_true", help="skip the KNN sweep (configs[1]) and the 64-volume inference leg (configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

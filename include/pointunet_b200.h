@@ -35,6 +35,12 @@ typedef enum {
     PU_ERR_UNSUPPORTED = -4  /* shape outside the compiled specialisations */
 } pu_status;
 
+/* element type of a tensor that may be STORED at reduced precision (the "bf16 storage mode": the pre-normalisation
+ * activations y of every 1x1 conv -- kept from the forward for the batch-norm backward, the largest saved tensors of a
+ * training step -- are stored as bfloat16; arithmetic and batch statistics stay fp32).  Entry points with an `_ex` suffix
+ * take it; their plain forms mean PU_F32.  Strides stay in ELEMENTS. */
+typedef enum { PU_F32 = 0, PU_BF16 = 1 } pu_dtype;
+
 /* Library / build identification. */
 PU_API const char *pu_version(void);
 /* cudaError_t value of the last failing CUDA call made by this library on this thread (0 = none). */
@@ -137,6 +143,9 @@ PU_API int pu_linear_row_tiles(long long M, int K, int N);
 PU_API int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float *bias, float *y, int ldy,
                          long long M, int K, int N, int accumulate, float *stat_sum, float *stat_sq,
                          pu_stream_t stream);
+PU_API int pu_linear_fwd_ex(const float *x, int ldx, const float *w, int ldw, const float *bias, void *y, int ldy,
+                            long long M, int K, int N, int accumulate, float *stat_sum, float *stat_sq, int y_dtype,
+                            pu_stream_t stream);   /* PU_BF16: narrow shapes only (K <= 16, N <= 32), no accumulate */
 PU_API int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int rows_per_tile, int C,
                              long long count, float *mean, float *var, pu_stream_t stream);
 /* Tensor-core (tcgen05 + TMEM) form of pu_linear_fwd for K >= 32, N >= 32: y[M,N] (+)= x[M,K] wt[N,K]^T + bias, where
@@ -148,6 +157,10 @@ PU_API size_t pu_tc_workspace_bytes(int K, int N); /* scratch for the packed wei
 PU_API int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const float *bias, float *y, int ldy,
                             long long M, int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode,
                             int *error_flag, void *workspace, size_t workspace_bytes, pu_stream_t stream);
+PU_API int pu_tc_linear_fwd_ex(const float *x, int ldx, const float *wt, int ldwt, const float *bias, void *y, int ldy,
+                               long long M, int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode,
+                               int *error_flag, void *workspace, size_t workspace_bytes, int y_dtype,
+                               pu_stream_t stream);   /* PU_BF16: y stored as bf16 (no accumulate); statistics from the fp32 values */
 /* Tensor-core forms of pu_att_pooling_fwd / _bwd (channel width d >= 32, K = 16): same contract, but `wt` is the
  * TRANSPOSED FC kernel [d_out, d_in] (K-major); the softmax-over-K epilogue runs out of TMEM. */
 PU_API int pu_tc_att_supported(int K, int d, int ldx);
@@ -174,6 +187,9 @@ PU_API int pu_wgrad(const float *x, int ldx, const float *dy, int lddy, long lon
 PU_API int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shift, const float *y2, int ldy2,
                          const float *scale2, const float *shift2, float slope, long long R, int C, float *out,
                          int ldo, float *out2, int ldo2, pu_stream_t stream);
+PU_API int pu_bn_act_fwd_ex(const void *y, int ldy, int y_dtype, const float *scale, const float *shift, const void *y2,
+                            int ldy2, int y2_dtype, const float *scale2, const float *shift2, float slope, long long R,
+                            int C, float *out, int ldo, float *out2, int ldo2, pu_stream_t stream);
 /* (`shift` is a [2,C] array: row 0 = mean, row 1 = beta -- z = (y - mean)*scale + beta.  `out2` optionally receives a
  *  second copy of the result, e.g. the right half of an LFA concat buffer, RandLANet.py:328,333.) */
 /* Per-channel batch-norm coefficients, one launch each (tf.layers.batch_normalization, momentum 0.99, eps 1e-6):
@@ -205,6 +221,12 @@ PU_API int pu_bn_bwd_reduce(const float *dout, int ldd, const float *dout2, int 
 PU_API int pu_bn_bwd_apply(const float *dout, int ldd, const float *dout2, int ldd2, const float *y, int ldy,
                            const float *scale, const float *shift, float slope, const float *ka, const float *kb,
                            const float *kc, long long R, int C, float *dy, int lddy, pu_stream_t stream);
+PU_API int pu_bn_bwd_reduce_ex(const float *dout, int ldd, const float *dout2, int ldd2, const void *y, int ldy, int y_dtype,
+                               const float *scale, const float *shift, float slope, long long R, int C, float *part_dz,
+                               float *part_dzy, pu_stream_t stream);
+PU_API int pu_bn_bwd_apply_ex(const float *dout, int ldd, const float *dout2, int ldd2, const void *y, int ldy, int y_dtype,
+                              const float *scale, const float *shift, float slope, const float *ka, const float *kb,
+                              const float *kc, long long R, int C, float *dy, int lddy, pu_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * ref: Network.att_pooling  RandLANet.py:388-401 (up to f_agg; the trailing conv2d is pu_linear_fwd)

@@ -54,6 +54,24 @@ __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
                  : "memory");
 }
 
+// bf16 storage mode (pre-normalisation activations kept in bf16): round-to-nearest-even packing of two floats into one 32-bit
+// word (low half = first value) and the exact widening back
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// 4 consecutive channels of a row that is stored either as fp32 or as bf16 (`ld` and `c` in elements)
+__device__ __forceinline__ float4 load4_any(const void *base, int is_bf16, size_t row, int ld, int c) {
+    if (is_bf16) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned short *>(base) + row * ld + c);
+        return make_float4(bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y));
+    }
+    return *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + row * ld + c);
+}
+
 // 2^x and 1/x on the SFU, one instruction each (arguments of the softmax are <= 0, results in (0, 1]; the denominators >= 1)
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;

@@ -34,6 +34,7 @@ struct GemmParams {
     const float *X; int ldx;   // att: feature_set rows [M,N]
     const float *G; int ldg;   // att bwd: upstream gradient [M/16, N]
     float *OUT; int ldo;       // att fwd: f_agg [M/16, N];  att bwd: g * s  [M,N]
+    int c_bf16;                // narrow linear only: C is stored as bf16 (ldc in elements)
 };
 
 constexpr int BK = 16;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256, 3) linear_narrow_kernel(const GemmParams 
     for (int j = 0; j < 4; ++j) bj[j] = (p.bias && c0 + j < p.N) ? p.bias[c0 + j] : 0.f;
     const bool va4 = ((p.lda & 3) == 0) && ((((uintptr_t)p.A) & 15) == 0) && ((p.K & 3) == 0);
     const bool va2 = ((p.lda & 1) == 0) && ((((uintptr_t)p.A) & 7) == 0) && ((p.K & 1) == 0);
-    const bool vc4 = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0) && (c0 + 3 < p.N);
+    const bool vc4 = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & (p.c_bf16 ? 7 : 15)) == 0) && (c0 + 3 < p.N);
     auto load_row = [&](long long r, float (&xv)[KP]) {
         const float *a = p.A + (size_t)r * p.lda;
         if (va4) {
@@ -345,7 +346,16 @@ __global__ void __launch_bounds__(256, 3) linear_narrow_kernel(const GemmParams 
     }
     auto finish_row = [&](long long r, float (&o)[4], const float4 &old) {
         float *c = p.C + (size_t)r * p.ldc + c0;
-        if (vc4) {
+        if (p.c_bf16) {   // bf16 storage of the pre-normalisation activations; the statistics below stay on the fp32 values
+            unsigned short *cb = reinterpret_cast<unsigned short *>(p.C) + (size_t)r * p.ldc + c0;
+            if (vc4) {
+                *reinterpret_cast<uint2 *>(cb) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c0 + j < p.N) cb[j] = (unsigned short)(pack_bf16x2(o[j], 0.f) & 0xffffu);
+            }
+        } else if (vc4) {
             if (p.accumulate) { o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w; }
             *reinterpret_cast<float4 *>(c) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
@@ -576,11 +586,12 @@ __device__ __forceinline__ float4 bn_z(const float4 v, const float4 mu, const fl
                        fmaf(v.w - mu.w, sc.w, be.w));
 }
 
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict__ y, int ld_y, const float *__restrict__ scale,
-                                                         const float *__restrict__ shift, const float *__restrict__ y2,
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const void *__restrict__ y, int ld_y, const float *__restrict__ scale,
+                                                         const float *__restrict__ shift, const void *__restrict__ y2,
                                                          int ld_y2, const float *__restrict__ scale2,
                                                          const float *__restrict__ shift2, float slope, long long R, int C,
-                                                         float *__restrict__ out, int ld_o, float *__restrict__ out2, int ld_o2) {
+                                                         float *__restrict__ out, int ld_o, float *__restrict__ out2, int ld_o2,
+                                                         int y_bf16, int y2_bf16) {
     // a thread owns ONE float4 column group for its lifetime (coefficients in registers, no index division in the loop)
     // and walks the rows; consecutive threads still touch consecutive 16-byte chunks
     const int cq = C >> 2, rpb = 256 / cq;
@@ -609,20 +620,20 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float *__restrict
     const long long step = (long long)gridDim.x * rpb;
     long long r = (long long)blockIdx.x * rpb + rl;
     for (; r + step < R; r += 2 * step) {  // two rows in flight
-        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
-        const float4 v1 = *reinterpret_cast<const float4 *>(y + (size_t)(r + step) * ld_y + c);
+        const float4 v0 = load4_any(y, y_bf16, (size_t)r, ld_y, c);
+        const float4 v1 = load4_any(y, y_bf16, (size_t)(r + step), ld_y, c);
         float4 w0 = v0, w1 = v1;
         if (y2) {
-            w0 = *reinterpret_cast<const float4 *>(y2 + (size_t)r * ld_y2 + c);
-            w1 = *reinterpret_cast<const float4 *>(y2 + (size_t)(r + step) * ld_y2 + c);
+            w0 = load4_any(y2, y2_bf16, (size_t)r, ld_y2, c);
+            w1 = load4_any(y2, y2_bf16, (size_t)(r + step), ld_y2, c);
         }
         emit(r, v0, w0);
         emit(r + step, v1, w1);
     }
     if (r < R) {
-        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        const float4 v0 = load4_any(y, y_bf16, (size_t)r, ld_y, c);
         float4 w0 = v0;
-        if (y2) w0 = *reinterpret_cast<const float4 *>(y2 + (size_t)r * ld_y2 + c);
+        if (y2) w0 = load4_any(y2, y2_bf16, (size_t)r, ld_y2, c);
         emit(r, v0, w0);
     }
 }
@@ -649,10 +660,10 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float *__restrict__ 
 // grid = fixed number of CTAs; each CTA strides over rows; thread owns one float4 column group.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restrict__ dout, int ld_d,
                                                             const float *__restrict__ dout2, int ld_d2,
-                                                            const float *__restrict__ y, int ld_y,
+                                                            const void *__restrict__ y, int ld_y,
                                                             const float *__restrict__ scale, const float *__restrict__ shift,
                                                             float slope, long long R, int C, float *__restrict__ part_dz,
-                                                            float *__restrict__ part_dzy) {
+                                                            float *__restrict__ part_dzy, int y_bf16) {
     extern __shared__ float sred[];  // [rows_in_flight][C][2]
     const int cq = C >> 2;                 // column groups
     const int rpb = 256 / cq > 0 ? 256 / cq : 1;  // rows processed concurrently by the CTA
@@ -667,7 +678,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restr
                 const float4 g2 = *reinterpret_cast<const float4 *>(dout2 + (size_t)r * ld_d2 + my_c);
                 g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
             }
-            const float4 v = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + my_c);
+            const float4 v = load4_any(y, y_bf16, (size_t)r, ld_y, my_c);
             const float4 z = bn_z(v, mu, sc, be);
             const float gz[4] = {z.x > 0.f ? g.x : g.x * slope, z.y > 0.f ? g.y : g.y * slope,
                                  z.z > 0.f ? g.z : g.z * slope, z.w > 0.f ? g.w : g.w * slope};
@@ -693,12 +704,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float *__restr
 // BN backward, pass 2: dy = ka[c]*dz + kb[c] + kc[c]*y
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restrict__ dout, int ld_d,
                                                            const float *__restrict__ dout2, int ld_d2,
-                                                           const float *__restrict__ y,
+                                                           const void *__restrict__ y,
                                                            int ld_y, const float *__restrict__ scale,
                                                            const float *__restrict__ shift, float slope,
                                                            const float *__restrict__ ka, const float *__restrict__ kb,
                                                            const float *__restrict__ kc, long long R, int C,
-                                                           float *__restrict__ dy, int ld_dy) {
+                                                           float *__restrict__ dy, int ld_dy, int y_bf16) {
     // fixed column group per thread (coefficients in registers, no index division), two rows in flight
     const int cq = C >> 2, rpb = 256 / cq;
     const int c = (threadIdx.x % cq) * 4, rl = threadIdx.x / cq;
@@ -728,14 +739,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restri
     long long r = (long long)blockIdx.x * rpb + rl;
     for (; r + step < R; r += 2 * step) {
         const float4 g0 = load_g(r), g1 = load_g(r + step);
-        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
-        const float4 v1 = *reinterpret_cast<const float4 *>(y + (size_t)(r + step) * ld_y + c);
+        const float4 v0 = load4_any(y, y_bf16, (size_t)r, ld_y, c);
+        const float4 v1 = load4_any(y, y_bf16, (size_t)(r + step), ld_y, c);
         emit(r, g0, v0);
         emit(r + step, g1, v1);
     }
     if (r < R) {
         const float4 g0 = load_g(r);
-        const float4 v0 = *reinterpret_cast<const float4 *>(y + (size_t)r * ld_y + c);
+        const float4 v0 = load4_any(y, y_bf16, (size_t)r, ld_y, c);
         emit(r, g0, v0);
     }
 }
@@ -979,16 +990,22 @@ int pu_linear_rows_per_tile(long long M, int K, int N) {
 }
 int pu_linear_row_tiles(long long M, int K, int N) { return ceil_div(M, pu_linear_rows_per_tile(M, K, N)); }
 
-int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float *bias, float *y, int ldy, long long M,
-                  int K, int N, int accumulate, float *stat_sum, float *stat_sq, pu_stream_t stream) {
+int pu_linear_fwd_ex(const float *x, int ldx, const float *w, int ldw, const float *bias, void *y, int ldy, long long M,
+                     int K, int N, int accumulate, float *stat_sum, float *stat_sq, int y_dtype, pu_stream_t stream) {
     if (!x || !w || !y || M < 0 || K < 1 || N < 1 || ldx < K || ldw < N || ldy < N) return PU_ERR_INVALID_ARG;
     if ((stat_sum == nullptr) != (stat_sq == nullptr)) return PU_ERR_INVALID_ARG;
     if (M == 0) return PU_OK;
     if (ceil_div(M, 128) > 2147483647LL) return PU_ERR_UNSUPPORTED;
+    if (y_dtype != PU_F32 && (y_dtype != PU_BF16 || accumulate || !linear_is_narrow(M, K, N))) return PU_ERR_UNSUPPORTED;
     GemmParams p{};
-    p.A = x; p.lda = ldx; p.B = w; p.ldb = ldw; p.C = y; p.ldc = ldy; p.bias = bias;
+    p.A = x; p.lda = ldx; p.B = w; p.ldb = ldw; p.C = (float *)y; p.c_bf16 = y_dtype == PU_BF16; p.ldc = ldy; p.bias = bias;
     p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
     return launch_gemm<EPI_STORE>(p, (cudaStream_t)stream);
+}
+
+int pu_linear_fwd(const float *x, int ldx, const float *w, int ldw, const float *bias, float *y, int ldy, long long M,
+                  int K, int N, int accumulate, float *stat_sum, float *stat_sq, pu_stream_t stream) {
+    return pu_linear_fwd_ex(x, ldx, w, ldw, bias, y, ldy, M, K, N, accumulate, stat_sum, stat_sq, PU_F32, stream);
 }
 
 int pu_stats_finalize(const float *stat_sum, const float *stat_sq, int tiles, int rows_per_tile, int C, long long count,
@@ -1147,6 +1164,13 @@ int pu_bn_bwd_coeffs(const float *part_dz, const float *part_dzy, int blocks, in
 int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shift, const float *y2, int ldy2,
                   const float *scale2, const float *shift2, float slope, long long R, int C, float *out, int ldo,
                   float *out2, int ldo2, pu_stream_t stream) {
+    return pu_bn_act_fwd_ex(y, ldy, PU_F32, scale, shift, y2, ldy2, PU_F32, scale2, shift2, slope, R, C, out, ldo, out2, ldo2, stream);
+}
+
+int pu_bn_act_fwd_ex(const void *y, int ldy, int y_dtype, const float *scale, const float *shift, const void *y2, int ldy2,
+                     int y2_dtype, const float *scale2, const float *shift2, float slope, long long R, int C, float *out,
+                     int ldo, float *out2, int ldo2, pu_stream_t stream) {
+    if ((y_dtype != PU_F32 && y_dtype != PU_BF16) || (y2_dtype != PU_F32 && y2_dtype != PU_BF16)) return PU_ERR_INVALID_ARG;
     if (!y || !scale || !shift || !out || R < 0 || C < 4 || (C & 3) || ((ldy | ldo) & 3) || ldy < C || ldo < C)
         return PU_ERR_INVALID_ARG;
     if (y2 && (!scale2 || !shift2 || (ldy2 & 3) || ldy2 < C)) return PU_ERR_INVALID_ARG;
@@ -1154,7 +1178,8 @@ int pu_bn_act_fwd(const float *y, int ldy, const float *scale, const float *shif
     if (R == 0) return PU_OK;
     if (C > 1024) return PU_ERR_UNSUPPORTED;  // one float4 column group per thread of a 256-thread CTA
     bn_act_fwd_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, scale, shift, y2, ldy2, scale2, shift2,
-                                                                            slope, R, C, out, ldo, out2, ldo2);
+                                                                            slope, R, C, out, ldo, out2, ldo2,
+                                                                            y_dtype == PU_BF16, y2_dtype == PU_BF16);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
@@ -1178,6 +1203,13 @@ int pu_bn_bwd_reduce_blocks(long long R, int C) {
 int pu_bn_bwd_reduce(const float *dout, int ldd, const float *dout2, int ldd2, const float *y, int ldy, const float *scale,
                      const float *shift, float slope, long long R, int C, float *part_dz, float *part_dzy,
                      pu_stream_t stream) {
+    return pu_bn_bwd_reduce_ex(dout, ldd, dout2, ldd2, y, ldy, PU_F32, scale, shift, slope, R, C, part_dz, part_dzy, stream);
+}
+
+int pu_bn_bwd_reduce_ex(const float *dout, int ldd, const float *dout2, int ldd2, const void *y, int ldy, int y_dtype,
+                        const float *scale, const float *shift, float slope, long long R, int C, float *part_dz,
+                        float *part_dzy, pu_stream_t stream) {
+    if (y_dtype != PU_F32 && y_dtype != PU_BF16) return PU_ERR_INVALID_ARG;
     if (!dout || !y || !scale || !shift || !part_dz || !part_dzy || R < 1 || C < 4 || (C & 3) || C > 1024 * 4 ||
         ((ldd | ldy) & 3))
         return PU_ERR_INVALID_ARG;
@@ -1188,7 +1220,8 @@ int pu_bn_bwd_reduce(const float *dout, int ldd, const float *dout2, int ldd2, c
     if (smem > 48 * 1024) return PU_ERR_UNSUPPORTED;
     if (dout2 && ((ldd2 & 3) || (((uintptr_t)dout2) & 15))) return PU_ERR_INVALID_ARG;
     bn_bwd_reduce_kernel<<<pu_bn_bwd_reduce_blocks(R, C), 256, smem, (cudaStream_t)stream>>>(dout, ldd, dout2, ldd2, y, ldy, scale,
-                                                                                            shift, slope, R, C, part_dz, part_dzy);
+                                                                                            shift, slope, R, C, part_dz, part_dzy,
+                                                                                            y_dtype == PU_BF16);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
@@ -1196,6 +1229,13 @@ int pu_bn_bwd_reduce(const float *dout, int ldd, const float *dout2, int ldd2, c
 int pu_bn_bwd_apply(const float *dout, int ldd, const float *dout2, int ldd2, const float *y, int ldy, const float *scale,
                     const float *shift, float slope, const float *ka, const float *kb, const float *kc, long long R, int C,
                     float *dy, int lddy, pu_stream_t stream) {
+    return pu_bn_bwd_apply_ex(dout, ldd, dout2, ldd2, y, ldy, PU_F32, scale, shift, slope, ka, kb, kc, R, C, dy, lddy, stream);
+}
+
+int pu_bn_bwd_apply_ex(const float *dout, int ldd, const float *dout2, int ldd2, const void *y, int ldy, int y_dtype,
+                       const float *scale, const float *shift, float slope, const float *ka, const float *kb, const float *kc,
+                       long long R, int C, float *dy, int lddy, pu_stream_t stream) {
+    if (y_dtype != PU_F32 && y_dtype != PU_BF16) return PU_ERR_INVALID_ARG;
     if (!dout || !y || !scale || !shift || !ka || !kb || !kc || !dy || R < 0 || C < 4 || (C & 3) ||
         ((ldd | ldy | lddy) & 3))
         return PU_ERR_INVALID_ARG;
@@ -1203,7 +1243,7 @@ int pu_bn_bwd_apply(const float *dout, int ldd, const float *dout2, int ldd2, co
     if (dout2 && ((ldd2 & 3) || (((uintptr_t)dout2) & 15))) return PU_ERR_INVALID_ARG;
     if (C > 1024) return PU_ERR_UNSUPPORTED;
     bn_bwd_apply_kernel<<<ew_grid(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dout, ldd, dout2, ldd2, y, ldy, scale, shift, slope,
-                                                                              ka, kb, kc, R, C, dy, lddy);
+                                                                              ka, kb, kc, R, C, dy, lddy, y_dtype == PU_BF16);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }

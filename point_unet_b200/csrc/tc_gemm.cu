@@ -42,6 +42,7 @@ struct Params {
     float *stat_sum, *stat_m2;  // [row tiles, N] or null
     int mode;                   // 3 = 3xTF32 (fp32-class), 1 = TF32
     int *error_flag;            // set to 1 if an mbarrier wait timed out (never hangs the GPU)
+    int c_bf16;                 // EPI_STORE: C is stored as bf16 (ldc in elements; never with accumulate)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 #endif
 
                 if constexpr (EPI == EPI_STORE) {
-                    const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+                    const bool vecC = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & (p.c_bf16 ? 7 : 15)) == 0);
                     // thread -> fixed group of 4 columns, rows strided: the batch-norm partials accumulate in registers during
                     // the copy-out.  Shifted single pass: sums of (v - sh) and (v - sh)^2 with sh = the tile's first stored
                     // row, so M2 = S2 - S1^2/n loses nothing to cancellation.
@@ -714,7 +715,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                         float4 val = *reinterpret_cast<float4 *>(&tile_g[r * LDT + c]);
                         val.x += bias4.x; val.y += bias4.y; val.z += bias4.z; val.w += bias4.w;
                         float *cptr = p.C + (size_t)(m0 + r) * p.ldc + gn;
-                        if (fast) {
+                        if (p.c_bf16) {   // bf16 storage of the pre-normalisation activations (statistics below: fp32 values)
+                            unsigned short *cb = reinterpret_cast<unsigned short *>(p.C) + (size_t)(m0 + r) * p.ldc + gn;
+                            if (fast) {
+                                *reinterpret_cast<uint2 *>(cb) = make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
+                            } else {
+                                const float vv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (gn + j < p.N) cb[j] = (unsigned short)(pack_bf16x2(vv[j], 0.f) & 0xffffu);
+                            }
+                        } else if (fast) {
                             if (p.accumulate) { val.x += old[i].x; val.y += old[i].y; val.z += old[i].z; val.w += old[i].w; }
                             *reinterpret_cast<float4 *>(cptr) = val;
                         } else {
@@ -1670,6 +1681,15 @@ size_t pu_tc_workspace_bytes(int K, int N) { return tc::tc_workspace_bytes(K, N)
 int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const float *bias, float *y, int ldy, long long M,
                      int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode, int *error_flag,
                      void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    return pu_tc_linear_fwd_ex(x, ldx, wt, ldwt, bias, y, ldy, M, K, N, accumulate, stat_sum, stat_m2, mode, error_flag, workspace,
+                               workspace_bytes, PU_F32, stream);
+}
+
+int pu_tc_linear_fwd_ex(const float *x, int ldx, const float *wt, int ldwt, const float *bias, void *yv, int ldy, long long M,
+                        int K, int N, int accumulate, float *stat_sum, float *stat_m2, int mode, int *error_flag,
+                        void *workspace, size_t workspace_bytes, int y_dtype, pu_stream_t stream) {
+    float *y = (float *)yv;
+    if (y_dtype != PU_F32 && (y_dtype != PU_BF16 || accumulate)) return PU_ERR_INVALID_ARG;
     if (!x || !wt || !y || M < 0 || K < 1 || N < 1 || ldx < K || ldwt < K || ldy < N) return PU_ERR_INVALID_ARG;
     if ((stat_sum == nullptr) != (stat_m2 == nullptr)) return PU_ERR_INVALID_ARG;
     if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
@@ -1679,6 +1699,7 @@ int pu_tc_linear_fwd(const float *x, int ldx, const float *wt, int ldwt, const f
     q.g.A = x; q.g.lda = ldx; q.g.Bt = wt; q.g.ldb = ldwt; q.g.C = y; q.g.ldc = ldy; q.g.bias = bias;
     q.g.M = M; q.g.N = N; q.g.K = K; q.g.accumulate = accumulate; q.g.stat_sum = stat_sum; q.g.stat_m2 = stat_m2; q.g.mode = mode;
     q.g.error_flag = error_flag;
+    q.g.c_bf16 = y_dtype == PU_BF16;
     q.ntiles = (M + tc::BM - 1) / tc::BM;
     return tc::dispatch_persist<tc::EPI_STORE>(q, workspace, workspace_bytes, (cudaStream_t)stream);
 }

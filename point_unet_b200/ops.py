@@ -41,6 +41,16 @@ _lib._OP_SIGS.update({
                               c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     "pu_tc_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
                     c_void_p, c_void_p],
+    "pu_linear_fwd_ex": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
+                         c_void_p, c_int, c_void_p],
+    "pu_tc_linear_fwd_ex": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
+                            c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p],
+    "pu_bn_act_fwd_ex": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_ll,
+                         c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "pu_bn_bwd_reduce_ex": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_ll, c_int,
+                            c_void_p, c_void_p, c_void_p],
+    "pu_bn_bwd_apply_ex": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                           c_void_p, c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p],
     "pu_stats_finalize": [c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p],
     "pu_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                  c_void_p],
@@ -77,6 +87,19 @@ import os as _os
 TC_MODE = int(_os.environ.get("PU_TC_MODE", "3"))
 # d = 16 attentive pooling through the dedicated one-pass kernels (att16.cu); 0 = the generic three-pass CUDA-core path
 ATT16 = int(_os.environ.get("PU_ATT16", "1")) != 0
+# Storage mode of the pre-normalisation activations y (output of every 1x1 conv that feeds a batch norm; kept from the forward
+# for the batch-norm backward -- the largest saved tensors of a training step): "fp32" (default, the parity path) or "bf16"
+# (opt-in: y is rounded to bfloat16 when stored, arithmetic and batch statistics stay fp32; stated tolerance rel-L2 <= 2e-2 on
+# logits and gradients, arg-max agreement >= 99.5 %, tests/test_bf16_storage_gpu.py).
+STORAGE_BF16 = _os.environ.get("PU_STORAGE", "fp32").lower() == "bf16"
+
+
+def set_storage(mode: str) -> None:
+    """``"fp32"`` or ``"bf16"``: see STORAGE_BF16 above.  Global, takes effect for subsequently built graphs / steps."""
+    global STORAGE_BF16
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("storage mode must be 'fp32' or 'bf16'")
+    STORAGE_BF16 = mode == "bf16"
 _tc_error_flag = {}
 
 LEAKY_SLOPE = 0.2  # helper_tf_util.py:169 (alpha is always 0.2, whatever activation_fn was passed)
@@ -141,6 +164,8 @@ class KernelTimer:
 def _call(name, *args, tag=None):
     fn = getattr(_L(), name)
     kt = KernelTimer.active
+    if name.endswith("_ex"):   # same kernel as the plain entry, with an explicit storage dtype: timed under the plain name
+        name = name[:-3]
     if kt is not None and name in kt.names:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -163,10 +188,11 @@ def _need_cuda(*ts):
             raise _lib.PointUnetError("point_unet_b200 ops run on CUDA tensors only (no CPU fallback)")
 
 
-def rows(t: torch.Tensor):
+def rows(t: torch.Tensor, keep_dtype: bool = False):
     """View ``t[..., C]`` as a row-strided matrix: returns (tensor, R, C, ld).  Copies only if the layout
-    cannot be expressed as rows with one constant stride (e.g. a half of a concat buffer is fine)."""
-    if t.dtype != torch.float32:
+    cannot be expressed as rows with one constant stride (e.g. a half of a concat buffer is fine).  ``keep_dtype``: a
+    bfloat16 tensor stays bfloat16 (bf16 storage mode; the stride is in elements either way)."""
+    if t.dtype != torch.float32 and not (keep_dtype and t.dtype == torch.bfloat16):
         t = t.float()
     C = t.shape[-1]
     ok = t.dim() >= 1 and (C == 1 or t.stride(-1) == 1)
@@ -246,6 +272,7 @@ def register_inverse(idx: torch.Tensor, n_src: int, offsets: torch.Tensor, perm:
 
 def clear_caches():
     _inverse_cache.clear()
+    _pre_grads.clear()
 
 
 def drop_inverse(ptr: int):
@@ -367,6 +394,37 @@ def tc_error_flag(device) -> torch.Tensor:
     return _tc_error_flag[key]
 
 
+class PreBN:
+    """bf16 storage mode: the pre-normalisation activation of a 1x1 conv as the batch-norm ops receive it.  ``data`` is the
+    stored bfloat16 tensor; autograd never sees it (it would cast the fp32 gradient of a bf16 tensor to bf16 and back: two
+    extra passes and a rounding of every gradient).  The differentiable link between the conv and the batch norm is
+    ``carrier``, a one-element fp32 tensor produced by the conv's autograd node; the real gradient dy travels from the batch
+    norm's backward to the conv's backward through ``_pre_grads[key]``."""
+    __slots__ = ("data", "carrier", "key", "shape")
+
+    def __init__(self, data, carrier, key):
+        self.data, self.carrier, self.key, self.shape = data, carrier, key, data.shape
+
+
+_pre_grads: dict = {}
+_pre_counter = [0]
+_zero1_cache: dict = {}
+
+
+def _zero1(device):
+    k = device.index if device.index is not None else torch.cuda.current_device()
+    if k not in _zero1_cache:
+        _zero1_cache[k] = torch.zeros(1, dtype=torch.float32, device=device)
+    return _zero1_cache[k]
+
+
+def _unwrap_pre(y):
+    """(tensor handed to autograd, stored tensor, key or None)"""
+    if isinstance(y, PreBN):
+        return y.carrier, y.data, y.key
+    return y, y, None
+
+
 class StatPartials:
     """Per-tile (sum, M2) partials of a linear kernel, not yet reduced: ``bn_prepare`` turns them into mean / variance /
     invstd / scale / shift in the same launch (pu_bn_finalize_prepare)."""
@@ -387,12 +445,17 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
     else:
         assert wt.dim() == 2 and wt.shape[1] == K and wt.is_contiguous()
         N = wt.shape[0]
-    if out is None:
-        out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
-    o, Mo, No, ldo = rows(out)
-    assert o.data_ptr() == out.data_ptr() and Mo == M and No == N
     L = _L()
     mode = TC_MODE if tc_mode is None else tc_mode
+    y_bf16 = False
+    if out is None:
+        # bf16 storage mode: y feeds a batch norm (want_stats) and is produced by a kernel with a bf16 store path
+        tc_ok = mode in (1, 3) and M >= 128 and L.pu_tc_linear_supported(M, K, N, ldx, K, N) and xr.data_ptr() % 16 == 0
+        y_bf16 = STORAGE_BF16 and want_stats and not accumulate and (N & 3) == 0 and \
+            (bool(tc_ok) or L.pu_linear_rows_per_tile(M, K, N) == 2048)
+        out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.bfloat16 if y_bf16 else torch.float32, device=x.device)
+    o, Mo, No, ldo = rows(out, keep_dtype=True)
+    assert o.data_ptr() == out.data_ptr() and Mo == M and No == N and (y_bf16 or o.dtype == torch.float32)
     use_tc = mode in (1, 3) and M >= 128 and L.pu_tc_linear_supported(M, K, N, ldx, K, ldo) and xr.data_ptr() % 16 == 0
     ssum = ssq = None
     if want_stats:
@@ -405,15 +468,16 @@ def linear_raw(x, w, bias=None, out=None, accumulate=False, want_stats=False, wt
         if wt is None:
             wt = w.t().contiguous()
         tws = workspace(L.pu_tc_workspace_bytes(K, N), x.device, slot=4)
-        _call("pu_tc_linear_fwd", xr.data_ptr(), ldx, wt.data_ptr(), K, bptr, o.data_ptr(), ldo, M, K, N, int(accumulate),
-              ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, mode,
-              tc_error_flag(x.device).data_ptr(), tws.data_ptr(), tws.numel(), _stream(x), tag=(M, K, N, int(accumulate)))
+        _call("pu_tc_linear_fwd_ex" if y_bf16 else "pu_tc_linear_fwd", xr.data_ptr(), ldx, wt.data_ptr(), K, bptr, o.data_ptr(), ldo,
+              M, K, N, int(accumulate), ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, mode,
+              tc_error_flag(x.device).data_ptr(), tws.data_ptr(), tws.numel(), *((1,) if y_bf16 else ()), _stream(x),
+              tag=(M, K, N, int(accumulate)))
     else:
         if w is None:
             w = wt.t().contiguous()
-        _call("pu_linear_fwd", xr.data_ptr(), ldx, w.data_ptr(), N, bptr, o.data_ptr(), ldo, M, K, N, int(accumulate),
-              ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None, _stream(x),
-              tag=(M, K, N, int(accumulate)))
+        _call("pu_linear_fwd_ex" if y_bf16 else "pu_linear_fwd", xr.data_ptr(), ldx, w.data_ptr(), N, bptr, o.data_ptr(), ldo, M, K,
+              N, int(accumulate), ssum.data_ptr() if want_stats else None, ssq.data_ptr() if want_stats else None,
+              *((1,) if y_bf16 else ()), _stream(x), tag=(M, K, N, int(accumulate)))
     if not want_stats:
         return out
     if defer_stats:
@@ -508,6 +572,13 @@ class _LinearFn(torch.autograd.Function):
         if defer:   # hand the raw partials through autograd as two plain tensors; ops.linear re-wraps them
             _LinearFn.last_partials = (mean.rpt, mean.rows)
             mean, var = mean.ssum, mean.ssq
+        ctx.pre_key = None
+        _LinearFn.last_pre = None
+        if y.dtype == torch.bfloat16:   # bf16 storage: autograd gets a one-element carrier, see PreBN
+            _pre_counter[0] += 1
+            ctx.pre_key = _pre_counter[0]
+            _LinearFn.last_pre = (y, ctx.pre_key)
+            y = torch.empty(1, dtype=torch.float32, device=x.device)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.x_needs = x.requires_grad
@@ -521,6 +592,8 @@ class _LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, *_):
+        if ctx.pre_key is not None:
+            dy = _pre_grads.pop(ctx.pre_key, None)   # the batch norm's backward left the real gradient here
         if dy is None:
             return None, None, None, None, None
         x, w = ctx.saved_tensors
@@ -554,25 +627,31 @@ def linear(x, w, bias=None, want_stats=False, zero_bias_grad=False, defer_stats=
     if want_stats and defer_stats:
         y, ssum, ssq = _LinearFn.apply(x, w, bias, "defer", zero_bias_grad)
         rpt, nrows = _LinearFn.last_partials
+        if _LinearFn.last_pre is not None:
+            y = PreBN(_LinearFn.last_pre[0], y, _LinearFn.last_pre[1])
         return y, StatPartials(ssum, ssq, rpt, nrows), None
-    return _LinearFn.apply(x, w, bias, want_stats, zero_bias_grad)
+    res = _LinearFn.apply(x, w, bias, want_stats, zero_bias_grad)
+    if want_stats and _LinearFn.last_pre is not None:
+        return (PreBN(_LinearFn.last_pre[0], res[0], _LinearFn.last_pre[1]),) + tuple(res[1:])
+    return res
 
 
 def _bn_act_fwd_raw(y, scale, shift, slope, out=None, y2=None, scale2=None, shift2=None, out2=None):
-    yr, R, C, ldy = rows(y)
+    yr, R, C, ldy = rows(y, keep_dtype=True)
     if out is None:
         out = torch.empty(y.shape, dtype=torch.float32, device=y.device)
     o, Ro, Co, ldo = rows(out)
     assert o.data_ptr() == out.data_ptr() and Ro == R and Co == C
     if y2 is not None:
-        y2r, R2, C2, ldy2 = rows(y2)
+        y2r, R2, C2, ldy2 = rows(y2, keep_dtype=True)
         assert R2 == R and C2 == C
     ldo2 = 0
     if out2 is not None:
         o2, R2o, C2o, ldo2 = rows(out2)
         assert o2.data_ptr() == out2.data_ptr() and R2o == R and C2o == C
-    _call("pu_bn_act_fwd", yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+    _call("pu_bn_act_fwd_ex", yr.data_ptr(), ldy, int(yr.dtype == torch.bfloat16), scale.data_ptr(), shift.data_ptr(),
           y2r.data_ptr() if y2 is not None else None, ldy2 if y2 is not None else 0,
+          int(y2 is not None and y2r.dtype == torch.bfloat16),
           scale2.data_ptr() if y2 is not None else None, shift2.data_ptr() if y2 is not None else None, float(slope), R, C,
           o.data_ptr(), ldo, out2.data_ptr() if out2 is not None else None, ldo2, _stream(y))
     return out
@@ -587,7 +666,8 @@ def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training, dz2=N
     """Gradient of out = lrelu(BN(y)) wrt y, gamma, beta given dout = dz (+ dz2, a second upstream gradient summed on
     the fly inside the kernels)."""
     dzr, R, C, ldd = rows(dz)
-    yr, Ry, Cy, ldy = rows(y)
+    yr, Ry, Cy, ldy = rows(y, keep_dtype=True)
+    yb = int(yr.dtype == torch.bfloat16)
     assert R == Ry and C == Cy
     d2ptr, ldd2 = None, 0
     if dz2 is not None:
@@ -599,7 +679,7 @@ def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training, dz2=N
     p1 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
     p2 = torch.empty((blocks, C), dtype=torch.float32, device=y.device)
     st = _stream(y)
-    _call("pu_bn_bwd_reduce", dzr.data_ptr(), ldd, d2ptr, ldd2, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+    _call("pu_bn_bwd_reduce_ex", dzr.data_ptr(), ldd, d2ptr, ldd2, yr.data_ptr(), ldy, yb, scale.data_ptr(), shift.data_ptr(),
           float(slope), R, C, p1.data_ptr(), p2.data_ptr(), st)
     co = torch.empty((5, C), dtype=torch.float32, device=y.device)  # dgamma, dbeta, ka, kb, kc
     dgamma, dbeta, ka, kb, kc = co[0], co[1], co[2], co[3], co[4]
@@ -609,7 +689,7 @@ def _bn_bwd_raw(dz, y, scale, shift, slope, gamma, mean, invstd, training, dz2=N
           gamma.data_ptr(), R, int(bool(training)), dgamma.data_ptr(), dbeta.data_ptr(), ka.data_ptr(), kb.data_ptr(),
           kc.data_ptr(), st)
     dy = torch.empty(y.shape, dtype=torch.float32, device=y.device)
-    _call("pu_bn_bwd_apply", dzr.data_ptr(), ldd, d2ptr, ldd2, yr.data_ptr(), ldy, scale.data_ptr(), shift.data_ptr(),
+    _call("pu_bn_bwd_apply_ex", dzr.data_ptr(), ldd, d2ptr, ldd2, yr.data_ptr(), ldy, yb, scale.data_ptr(), shift.data_ptr(),
           float(slope), ka.data_ptr(), kb.data_ptr(), kc.data_ptr(), R, C, dy.data_ptr(), C, st)
     return dy, dgamma, dbeta
 
@@ -618,7 +698,13 @@ class _BNActFn(torch.autograd.Function):
     """out = leaky_relu_slope(BN(y) [+ BN2(y2)]) with batch statistics given as (mean, var) of y (and y2)."""
 
     @staticmethod
-    def forward(ctx, y, mean, var, gamma, beta, slope, training, moving, y2, mean2, var2, gamma2, beta2, moving2):
+    def forward(ctx, y, mean, var, gamma, beta, slope, training, moving, y2, mean2, var2, gamma2, beta2, moving2, pre, pre2):
+        # pre / pre2: the stored bf16 tensors and gradient keys when y / y2 are PreBN carriers (bf16 storage mode)
+        ctx.pre_key = ctx.pre_key2 = None
+        if pre is not None:
+            y, ctx.pre_key = pre
+        if pre2 is not None:
+            y2, ctx.pre_key2 = pre2
         invstd, scale, shift = bn_prepare(mean, var, gamma, beta, moving if training else None)
         if isinstance(mean, StatPartials):
             mean = shift[0]   # the fused finalize wrote the batch mean there
@@ -645,7 +731,10 @@ class _BNActFn(torch.autograd.Function):
             dy, dg, db = _bn_bwd_raw(dout, y, scale, shift, ctx.slope, gamma, mean, invstd, ctx.training, sink=sk)
             if sk is not None:
                 dg = db = None
-            return (dy, None, None, dg, db, None, None, None) + none5 + (None,)
+            if ctx.pre_key is not None:
+                _pre_grads[ctx.pre_key] = dy
+                dy = _zero1(dout.device)
+            return (dy, None, None, dg, db, None, None, None) + none5 + (None, None, None)
         y, scale, shift, gamma, mean, invstd, y2, scale2, shift2, gamma2, mean2, invstd2, res = ctx.saved_tensors
         # through the activation first (sign of the output), then each BN branch without activation
         dr, R, C, ldd = rows(dout)
@@ -661,7 +750,13 @@ class _BNActFn(torch.autograd.Function):
             dg = db = None
         if sk2 is not None:
             dg2 = db2 = None
-        return dy, None, None, dg, db, None, None, None, dy2, None, None, dg2, db2, None
+        if ctx.pre_key is not None:
+            _pre_grads[ctx.pre_key] = dy
+            dy = _zero1(dout.device)
+        if ctx.pre_key2 is not None:
+            _pre_grads[ctx.pre_key2] = dy2
+            dy2 = _zero1(dout.device)
+        return dy, None, None, dg, db, None, None, None, dy2, None, None, dg2, db2, None, None, None
 
 
 def bn_prepare(mean, var, gamma, beta, moving=None):
@@ -692,8 +787,11 @@ def bn_act(y, mean, var, gamma, beta, slope=LEAKY_SLOPE, training=True, moving=N
     """``leaky_relu_slope(BN(y) [+ BN2(y2)])`` with the given per-channel statistics (batch stats in training,
     moving stats at inference); ``slope=1`` means no activation (helper_tf_util.py:166-169).  ``moving`` =
     ``(moving_mean, moving_var, unbias)`` is updated in place in training mode."""
-    _need_cuda(y)
-    return _BNActFn.apply(y, mean, var, gamma, beta, slope, training, moving, y2, mean2, var2, gamma2, beta2, moving2)
+    ya, yd, key = _unwrap_pre(y)
+    y2a, y2d, key2 = _unwrap_pre(y2) if y2 is not None else (None, None, None)
+    _need_cuda(yd)
+    return _BNActFn.apply(ya, mean, var, gamma, beta, slope, training, moving, y2a, mean2, var2, gamma2, beta2, moving2,
+                          (yd, key) if key is not None else None, (y2d, key2) if key2 is not None else None)
 
 
 class _LFAConcatFn(torch.autograd.Function):
@@ -702,7 +800,10 @@ class _LFAConcatFn(torch.autograd.Function):
     into the right half (and, if ``need_fxyz``, also into a tensor of its own for the following ``mlp2``)."""
 
     @staticmethod
-    def forward(ctx, f_pc, idx, y, mean, var, gamma, beta, training, moving, need_fxyz):
+    def forward(ctx, f_pc, idx, y, mean, var, gamma, beta, training, moving, need_fxyz, pre):
+        ctx.pre_key = None
+        if pre is not None:   # bf16 storage mode: y is a PreBN carrier, the stored tensor comes separately
+            y, ctx.pre_key = pre
         B, N, K, h = y.shape
         invstd, scale, shift = bn_prepare(mean, var, gamma, beta, moving if training else None)
         if isinstance(mean, StatPartials):
@@ -734,14 +835,19 @@ class _LFAConcatFn(torch.autograd.Function):
                                  dz2=d_fxyz if ctx.need_fxyz else None, sink=sk)
         if sk is not None:
             dg = db = None
-        return d_fpc, None, dy, None, None, dg, db, None, None, None
+        if ctx.pre_key is not None:
+            _pre_grads[ctx.pre_key] = dy
+            dy = _zero1(y.device)
+        return d_fpc, None, dy, None, None, dg, db, None, None, None, None
 
 
 def lfa_concat(f_pc, idx, y, mean, var, gamma, beta, training=True, moving=None, need_fxyz=True):
     """Fused ``concat([gather_neighbour(f_pc, idx), leaky_relu(BN(y))])``; returns ``(concat, f_xyz)`` (f_xyz is None
     when ``need_fxyz`` is False)."""
-    _need_cuda(f_pc, idx, y)
-    res = _LFAConcatFn.apply(f_pc, idx, y, mean, var, gamma, beta, training, moving, need_fxyz)
+    ya, yd, key = _unwrap_pre(y)
+    _need_cuda(f_pc, idx, yd)
+    res = _LFAConcatFn.apply(f_pc, idx, ya, mean, var, gamma, beta, training, moving, need_fxyz,
+                             (yd, key) if key is not None else None)
     return res if need_fxyz else (res, None)
 
 

@@ -73,7 +73,11 @@ class _Slot:
 
 
 class Trainer:
-    def __init__(self, config, num_features=None, seed=0, device=None, lr=None, world_size=1):
+    def __init__(self, config, num_features=None, seed=0, device=None, lr=None, world_size=1, storage=None):
+        """``storage``: "fp32" (default: the 1e-3 parity path) or "bf16" -- store the pre-normalisation activations as
+        bfloat16 (ops.set_storage; stated tolerance 2e-2, tests/test_bf16_storage_gpu.py).  Process-wide switch."""
+        if storage is not None:
+            ops.set_storage(storage)
         self.device = torch.device(device if device is not None else "cuda")
         self.cfg = config
         self.net = Network(config, num_features, seed=seed, device=self.device)
