@@ -288,26 +288,32 @@ def inference_leg(dev, rank, world, n_volumes, barrier):
     X, Y, Z = syn.PANCREAS_SHAPE
     shape = (Z, X, Y, 2)
     mine = shard_round_robin(n_volumes, rank, world)
+    VB = 4   # volumes per forward pass on a GPU: test mode uses moving BN statistics, so batching changes no result
     vols = []
     for v in mine:  # host-side preparation of the clouds: untimed (the reference reads them from .ply files)
         c = syn.pancreas_cloud(N_POINTS, v)
-        vols.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
-                          (c["xyz"][None], c["features"][None], c["xyz_origin"].astype(np.int32)[None])))
-    host_labels = torch.empty((Z, Y, X), dtype=torch.uint8, pin_memory=True)
+        vols.append((c["xyz"], c["features"], c["xyz_origin"].astype(np.int32)))
+    batches = []
+    for i in range(0, len(vols), VB):
+        grp = vols[i:i + VB]
+        batches.append(tuple(torch.from_numpy(np.ascontiguousarray(np.stack([g[j] for g in grp]))).pin_memory() for j in range(3)))
+    host_labels = torch.empty((VB, Z, Y, X), dtype=torch.uint8, pin_memory=True)
     out = {}
     for name in ("prob_volume", "label_volume"):
-        for xyz, feat, xo in vols[:2]:   # warm-up
+        def run(xyz, feat, xo, blocking):
+            xo_d = xo.to(dev, non_blocking=True)
             if name == "prob_volume":
-                tr.predict_to_volume(xyz, feat, xo.to(dev, non_blocking=True), shape)
+                tr.predict_to_volume(xyz, feat, xo_d, shape)
             else:
-                host_labels.copy_(tr.predict_to_labels(xyz, feat, xo.to(dev, non_blocking=True), shape)[0])
+                labs = tr.predict_to_labels(xyz, feat, xo_d, shape)
+                for b, lab in enumerate(labs):
+                    host_labels[b].copy_(lab, non_blocking=not blocking)
+        for bt in batches[:2]:   # warm-up
+            run(*bt, True)
         barrier()
         t0 = time.perf_counter()
-        for xyz, feat, xo in vols:
-            if name == "prob_volume":
-                tr.predict_to_volume(xyz, feat, xo.to(dev, non_blocking=True), shape)
-            else:
-                host_labels.copy_(tr.predict_to_labels(xyz, feat, xo.to(dev, non_blocking=True), shape)[0], non_blocking=True)
+        for bt in batches:
+            run(*bt, False)
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -316,7 +322,7 @@ def inference_leg(dev, rank, world, n_volumes, barrier):
         out[name] = float(t.item())
     return dict(workload="64 Pancreas-shaped volumes x 180000 points: H2D + pyramid + forward (BN inference mode) + softmax + "
                          "scatter to voxels, volumes sharded round-robin over the ranks, no communication",
-                volumes=n_volumes, volumes_per_rank=len(mine), volume_shape_zyxc=[Z, Y, X, 2],
+                volumes=n_volumes, volumes_per_rank=len(mine), volumes_per_forward=VB, volume_shape_zyxc=[Z, Y, X, 2],
                 volumes_per_s=n_volumes / out["prob_volume"], ms_per_volume_per_gpu=out["prob_volume"] * 1e3 / max(len(mine), 1),
                 label_volumes_per_s=n_volumes / out["label_volume"],
                 label_ms_per_volume_per_gpu=out["label_volume"] * 1e3 / max(len(mine), 1),
