@@ -11,9 +11,7 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# PU_LIB=<file name inside the package directory> selects a development variant of the library (A/B runs of one kernel
-# change, e.g. `make SWP=1`); the product is always the default name.
-LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("PU_LIB", "libpointunet_b200.so")))
+LIB_PATH = os.path.join(_HERE, "libpointunet_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pointunet_b200.h")
 
 PU_OK = 0

@@ -25,7 +25,6 @@
 // Tie rule: ascending (distance, index) -- a total order, hence the result is independent of the visiting
 // order and of scheduling (deterministic).
 #include <float.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -404,40 +403,21 @@ __device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsig
     best[0] = (x < best[0]) ? x : best[0];
 }
 
-// Deferred insertion.  All 32 lanes look at the same candidate at the same time, each against ITS OWN K-th distance; once the
-// lists are warm a candidate passes for ~2 % of the lanes -- but the ~100-instruction sorted insertion is a divergent branch,
-// so the whole warp paid for it on roughly every second candidate (the kernel was issue-bound on exactly that).  Now a lane
-// that accepts a candidate only APPENDS its key to a small per-lane queue in shared memory (a few instructions); the queues
-// are drained together -- every lane inserts its i-th pending key in the same trip -- when one of them fills up and at the end
-// of every bucket.  The K-th distance used as the filter is the one of the last drain (stale = conservative: the insertion
-// itself re-checks), and the result does not depend on any of this because (distance, index) is a total order.
-constexpr int PEND = 8;  // pending keys per lane
-
-template <int K, bool DEFER>
+template <int K>
 struct WarpSearch {
     unsigned long long best[K];
     float qx, qy, qz;
     bool valid;
     unsigned long long n_evals;
     unsigned n_buckets, n_tests;
-    int npend;
-    float kd;                   // K-th distance as of the last drain (+inf until the list is full)
-    unsigned long long *pend;   // this lane's column of the warp's queue: entry i at pend[i * 32]
 
     __device__ __forceinline__ float kth() const { return __uint_as_float((unsigned)(best[K - 1] >> 32)); }
 
-    __device__ __forceinline__ void drain() {
-        const int m = __reduce_max_sync(0xffffffffu, npend);
-        for (int i = 0; i < m; ++i) {
-            // lanes with fewer pending keys insert the largest key, which leaves the list unchanged
-            const unsigned long long key = i < npend ? pend[i * 32] : 0xFFFFFFFFFFFFFFFFull;
-            topk_insert<K>(best, key);
-        }
-        npend = 0;
-        kd = kth();
-    }
-
-    // all 32 lanes sweep the `cnt` candidates of one bucket staged in shared memory
+    // all 32 lanes sweep the `cnt` candidates of one bucket staged in shared memory (broadcast reads).
+    // Measured alternatives that were SLOWER on B200 (round 2, 180k uniform cloud, this kernel 0.55 ms): queueing accepted
+    // keys per lane and draining the queues together (15 % fewer instructions, 23 % more time: the drains serialise), and
+    // per-lane bucket sweeps (3.1x fewer distance evaluations, 467 instead of 1462 per query, but 37 % more time: a 16-byte
+    // load per lane and candidate instead of one broadcast) -- ncu: 62 % of the instructions are the sorted insertion.
     __device__ __forceinline__ void sweep_bucket(const float4 *__restrict__ sp_cloud, int N1, int t, float4 *tile,
                                                  int lane) {
         const int base = t * BS;
@@ -445,45 +425,23 @@ struct WarpSearch {
         __syncwarp();
         if (lane < cnt) tile[lane] = sp_cloud[base + lane];
         __syncwarp();
-        if constexpr (K <= 2 || !DEFER) {  // a one- or two-deep list (or queueing switched off): insert directly
-            if (valid) {
+        if (valid) {
 #pragma unroll 4
-                for (int j = 0; j < cnt; ++j) {
-                    const float4 p = tile[j];
-                    const float d = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-                    const unsigned long long key =
-                        ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-                    if (key < best[K - 1]) topk_insert<K>(best, key);
-                }
+            for (int j = 0; j < cnt; ++j) {
+                const float4 p = tile[j];  // broadcast read
+                const float d = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+                if (key < best[K - 1]) topk_insert<K>(best, key);
             }
-            n_evals += cnt;
-            n_buckets += 1;
-            return;
         }
-        for (int j0 = 0; j0 < cnt; j0 += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u;
-                if (j < cnt) {
-                    const float4 p = tile[j];  // broadcast read
-                    const float d = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-                    if (valid && d <= kd) {    // ties pass here; the 64-bit (distance, index) comparison decides
-                        const unsigned long long key =
-                            ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-                        if (key < best[K - 1]) { pend[npend * 32] = key; ++npend; }
-                    }
-                }
-            }
-            if (__any_sync(0xffffffffu, npend > PEND - 4)) drain();
-        }
-        drain();
         n_evals += cnt;
         n_buckets += 1;
     }
 };
 
 // grid: (ceil(warps_per_cloud / SEARCH_WARPS), B); one warp = 32 Morton-consecutive queries
-template <int K, bool DEFER>
+template <int K>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
     knn_search_kernel(const float4 *__restrict__ sp, const float4 *__restrict__ sq,
                       const float4 *__restrict__ bk_lo, const float4 *__restrict__ bk_hi,
@@ -495,7 +453,6 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
     __shared__ float4 s_tile[SEARCH_WARPS][BS];
     __shared__ float4 s_blo[SEARCH_WARPS][SBS];
     __shared__ float4 s_bhi[SEARCH_WARPS][SBS];
-    __shared__ unsigned long long s_pend[DEFER ? SEARCH_WARPS : 1][PEND][32];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int w = blockIdx.x * SEARCH_WARPS + wib;  // warp index within the cloud
@@ -508,11 +465,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
     const float4 *sb_lo_c = sb_lo + (size_t)b * NSB, *sb_hi_c = sb_hi + (size_t)b * NSB;
     float4 *tile = s_tile[wib];
 
-    WarpSearch<K, DEFER> S;
+    WarpSearch<K> S;
 #pragma unroll
     for (int j = 0; j < K; ++j) S.best[j] = KEY_INIT;
     S.n_evals = 0; S.n_buckets = 0; S.n_tests = 0;
-    S.npend = 0; S.kd = __uint_as_float(0x7F800000u); S.pend = &s_pend[DEFER ? wib : 0][0][lane];
 
     const int qi = w * 32 + lane;
     S.valid = qi < N2;
@@ -668,9 +624,7 @@ static int launch_search(const Layout &L, char *ws, bool self, const unsigned *s
                          int32_t *out_idx, float *out_dist, cudaStream_t st) {
     const int nwarps = ceil_div(N2, 32);
     dim3 grid(ceil_div(nwarps, SEARCH_WARPS), B);
-    static const bool defer = [] { const char *e = getenv("PU_KNN_DEFER"); return e && e[0] == '1'; }();
-    auto kern = (defer && K > 2) ? knn_search_kernel<K, true> : knn_search_kernel<K, false>;
-    kern<<<grid, SEARCH_WARPS * 32, 0, st>>>(
+    knn_search_kernel<K><<<grid, SEARCH_WARPS * 32, 0, st>>>(
         (const float4 *)(ws + L.sp), sq, (const float4 *)(ws + L.bk_lo), (const float4 *)(ws + L.bk_hi),
         (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), self ? nullptr : skeys,
         self ? nullptr : qkeys, N1, N2, L.NB, L.NSB, kout, out_idx, out_dist,

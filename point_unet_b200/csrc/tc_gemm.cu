@@ -21,10 +21,6 @@
 
 #include "common.cuh"
 
-#ifndef PU_ISSUER_SWP
-#define PU_ISSUER_SWP 0  // 1: software-pipelined MMA issue (waits of item i+1 taken between the two halves of item i)
-#endif
-
 namespace pu {
 namespace tc {
 
@@ -497,73 +493,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 #ifdef PU_TC_TIMELINE
             int tl_item = 0;
 #endif
-#if PU_ISSUER_SWP
-            // Software-pipelined issue.  The tensor pipe accepts only one or two queued MMAs, so the issuing lane blocks on
-            // every UTCHMMA for about the MMA's own duration (timeline: 690 cycles for the 12 MMAs of a k-block) -- and
-            // whatever else this warp does between two k-blocks (barrier waits, descriptor arithmetic, loop control: ~500
-            // cycles) is time the pipe sits idle.  So the waits and the descriptors of item i+1 are taken in the MIDDLE of
-            // item i: the first half of its MMAs is queued, the bookkeeping for the next item runs in their shadow, then
-            // the second half follows.  No circular wait: stage i+1 only needs item i+1-TA to have retired (TA >= 2).
-            struct Item { uint32_t d_tmem, a_tmem; uint64_t dbh0, dbl0; int slot, buf; bool first_kb, last_kb; };
-            auto acquire = [&](long long tile, int kb, int sl, int us, int tcount, Item &it) {  // whole warp, converged
-                it.buf = tcount & 1;
-                const int v = tcount >> 1;
-                if (kb == 0 && v >= 1) ok = mbar_wait(&acc_empty[it.buf], (uint32_t)((v - 1) & 1)) && ok;
-                ok = mbar_wait(&stage_ready[sl], (uint32_t)(us & 1)) && ok;                    // all 256 producers filled the stage
-                if constexpr (STREAM) ok = mbar_wait(&b_full[sl], (uint32_t)(us & 1)) && ok;   // this k-block of the weight landed
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                it.slot = sl;
-                it.first_kb = kb == 0;
-                it.last_kb = kb == nkb - 1;
-                it.d_tmem = tmem_base + (uint32_t)(it.buf * BN);
-                it.a_tmem = tmem_base + (uint32_t)(ACC_COLS + sl * 64);
-                it.dbh0 = bdesc0 + (uint64_t)((STREAM ? sl : kb) * (B_KB >> 4));
-                it.dbl0 = it.dbh0 + (uint64_t)((BN * 128) >> 4);
-                (void)tile;
-            };
-            auto issue = [&](const Item &it, int j0, int j1) {  // elected lane only
-#pragma unroll
-                for (int j = j0; j < j1; ++j) {
-                    umma_tf32_ts(it.d_tmem, it.a_tmem + j * UMMA_K, it.dbh0 + (uint64_t)(2 * j), idesc, (!it.first_kb || j > 0) ? 1u : 0u);
-                    if (split) {
-                        umma_tf32_ts(it.d_tmem, it.a_tmem + j * UMMA_K, it.dbl0 + (uint64_t)(2 * j), idesc, 1u);
-                        umma_tf32_ts(it.d_tmem, it.a_tmem + 32 + j * UMMA_K, it.dbh0 + (uint64_t)(2 * j), idesc, 1u);
-                    }
-                }
-            };
-            constexpr int KSTEPS = BK / UMMA_K, KHALF = KSTEPS / 2;
-            Item cur{};
-            if (cur_tile < q.ntiles) acquire(cur_tile, cur_kb, slot, use, tile_count, cur);
-            while (cur_tile < q.ntiles) {
-#ifdef PU_TC_TIMELINE
-                PU_TL(2, tl_item, 0);
-#endif
-                if (leader) issue(cur, 0, KHALF);
-#ifdef PU_TC_TIMELINE
-                PU_TL(2, tl_item, 1);
-#endif
-                // cursor of the next item
-                long long n_tile = cur_tile;
-                int n_kb = cur_kb + 1, n_slot = slot + 1, n_use = use, n_count = tile_count;
-                if (n_kb == nkb) { n_kb = 0; n_tile += gridDim.x; n_count++; }
-                if (n_slot == TA) { n_slot = 0; ++n_use; }
-                Item nxt{};
-                if (n_tile < q.ntiles) acquire(n_tile, n_kb, n_slot, n_use, n_count, nxt);  // in the shadow of the queued MMAs
-#ifdef PU_TC_TIMELINE
-                PU_TL(2, tl_item, 2);
-#endif
-                if (leader) {
-                    issue(cur, KHALF, KSTEPS);
-                    umma_commit(&stage_free[cur.slot]);
-                    if (cur.last_kb) umma_commit(&acc_full[cur.buf]);
-                }
-#ifdef PU_TC_TIMELINE
-                PU_TL(2, tl_item, 3);
-                ++tl_item;
-#endif
-                cur_tile = n_tile; cur_kb = n_kb; slot = n_slot; use = n_use; tile_count = n_count;
-                cur = nxt;
-#else
             while (cur_tile < q.ntiles) {
                 const bool last_kb = cur_kb == nkb - 1;
                 const int buf = tile_count & 1, v = tile_count >> 1;
@@ -571,7 +500,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 ok = mbar_wait(&stage_ready[slot], (uint32_t)(use & 1)) && ok;           // all 256 producers filled the stage
 #ifdef PU_TC_TIMELINE
                 PU_TL(2, tl_item, 0);
-#endif
                 if constexpr (STREAM) ok = mbar_wait(&b_full[slot], (uint32_t)(use & 1)) && ok;  // this k-block of the weight landed
 #ifdef PU_TC_TIMELINE
                 PU_TL(2, tl_item, 1);
