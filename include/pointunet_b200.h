@@ -171,6 +171,12 @@ PU_API int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float 
                                  long long P, int K, int d, float *d_act, int ldda, float *dx_direct, int lddx,
                                  int mode, int *error_flag, void *workspace, size_t workspace_bytes,
                                  pu_stream_t stream);
+/* d = 64: the dgrad through the FC fused into the same kernel -- `dx` receives the complete gradient g s + d_act w^T, the
+ * separate accumulate GEMM (pu_tc_linear_fwd with accumulate) is not needed; `w` = FC kernel [d,d], `wt` = its transpose. */
+PU_API int pu_tc_att_bwd_fused_supported(int K, int d, int ldx);
+PU_API int pu_tc_att_pooling_bwd_fused(const float *feature_set, int ldx, const float *wt, const float *w, const float *g_agg,
+                                       int ldg, long long P, int K, int d, float *d_act, int ldda, float *dx, int lddx,
+                                       int mode, int *error_flag, pu_stream_t stream);
 /* Tensor-core weight gradient (tcgen05, MN-major operands, all rows of a CTA accumulated in TMEM): same contract as
  * pu_wgrad for Kin, N >= 32 and M >= 4096; db is produced through a ones row and needs Kin % 128 != 0. */
 PU_API int pu_tc_wgrad_supported(long long M, int Kin, int N, int ldx, int lddy, int want_db);

@@ -171,7 +171,10 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >
 //   EPI_STORE    y (+)= x wt^T + bias, optional per-tile batch-norm partials           (pu_tc_linear_fwd)
 //   EPI_ATT_FWD  f_agg[p,c] = sum_k x[p,k,c] softmax_k(x w)[c]                          (pu_att_pooling_fwd, K = 16)
 //   EPI_ATT_BWD  d_act = s (g x - sum_k g x s),  dx_direct = g s                        (pu_att_pooling_bwd)
-enum { EPI_STORE = 0, EPI_ATT_FWD = 1, EPI_ATT_BWD = 2 };
+//   EPI_ATT_BWD_F  the same plus the dgrad through the FC in the SAME kernel (d = 64): d_act goes back into tensor memory as
+//                the A operand of a second MMA against the resident weight, dx = g s + d_act w^T leaves once -- the separate
+//                accumulate-GEMM (read d_act, read dx_direct, write dx: 2.2 GB per launch at level 1) disappears
+enum { EPI_STORE = 0, EPI_ATT_FWD = 1, EPI_ATT_BWD = 2, EPI_ATT_BWD_F = 3 };
 constexpr int MAX_TA = 4;        // operand-A stages in TENSOR memory (64 columns each: hi 32 + lo 32)
 constexpr int MAX_RAW = 6;       // raw fp32 ring of the weight-gradient kernel (cp.async, no registers held in flight)
 constexpr int MAX_RAW_P = 10;    // raw fp32 ring of the persistent kernel: up to 9 k-blocks (144 KB) in flight per SM
@@ -204,7 +207,9 @@ struct Params2 {
     Params g;                  // the GEMM proper (A = x rows, Bt = weight in K-major form, C, bias, stats, mode)
     const float *X; int ldx;   // att: feature_set rows (same memory as A)
     const float *G; int ldg;   // att bwd: upstream gradient [M/16, N]
-    float *OUT; int ldo;       // att fwd: f_agg [M/16, N];  att bwd: dx_direct [M, N]
+    float *OUT; int ldo;       // att fwd: f_agg [M/16, N];  att bwd: dx_direct [M, N] (fused: the complete dx)
+    int dbg;                   // development: timing experiments of the fused att backward (0 in the product)
+    const float *W2; int ldw2; // EPI_ATT_BWD_F: the FC kernel in its own orientation w[c_in][j_out] (= K-major B operand of d_act w^T)
     long long ntiles;
 #ifdef PU_TC_TIMELINE
     long long *timeline;       // development builds only (tools/tc_timeline.py): per-role clock64 stamps of CTA (0, 0)
@@ -298,6 +303,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     constexpr int ACC_COLS = 2 * BN;                  // double-buffered accumulator; A stage s lives at column ACC_COLS + 64 s
     constexpr int TMEM_COLS = 512;                    // one CTA per SM: take all of tensor memory
     static_assert(ACC_COLS + TA * 64 <= TMEM_COLS, "tensor memory budget");
+    constexpr bool FUSED = EPI == EPI_ATT_BWD_F;      // second MMA (d_act w^T) inside the epilogue
+    constexpr int A2_COL = ACC_COLS + TA * 64;        // operand A of the second MMA: BN columns hi, BN columns lo
+    static_assert(!FUSED || (!STREAM && BN == 64 && A2_COL + 2 * BN <= TMEM_COLS), "fused att_pooling backward: d = 64 only");
     constexpr int EC = BN > 64 ? 64 : BN;             // epilogue works on EC columns at a time (staging tile fits smem)
     constexpr int NPASS = BN / EC;
     constexpr int LDT = EC + 4;
@@ -307,6 +315,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t stage_free[MAX_TA], stage_ready[MAX_TA], b_full[MAX_TA], acc_full[2], acc_empty[2];
     __shared__ uint64_t raw_full[MAX_RAW_P], raw_free[MAX_RAW_P];  // TMA landed a k-block / all converters have read it
+    __shared__ uint64_t a2_free, acc2_full[2];                      // fused att backward: second-MMA operand / result hand-offs
     __shared__ uint32_t tmem_base_slot;
     __shared__ int s_err;
     __shared__ float s_red[2 * 16 * 64];  // statistics partials: [16 row lanes][EC][2]
@@ -319,15 +328,18 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
     // att epilogues with d <= 64 take their x values from the raw ring (the tile's k-blocks stay resident until the epilogue
     // has used them) instead of re-reading them through L2: no load latency in the epilogue's critical path
     const bool x_ring = EPI != EPI_STORE && !STREAM && nkb <= 2 && p.N == p.K && D >= 7;
+    constexpr bool ATT_BWD = EPI == EPI_ATT_BWD || EPI == EPI_ATT_BWD_F;
     char *raw_ring = smem;                            // D raw k-blocks, filled by TMA
     char *b_res = smem + (size_t)D * A_BYTES;         // resident: nkb k-blocks; streamed: TA k-blocks
-    float *tile = reinterpret_cast<float *>(b_res + (size_t)(STREAM ? TA : nkb) * B_KB);  // epilogue staging [BM][LDT]
+    char *b2_res = b_res + (size_t)(STREAM ? TA : nkb) * B_KB;   // fused att backward: second resident weight image
+    float *tile = reinterpret_cast<float *>(b2_res + (FUSED ? (size_t)nkb * B_KB : 0));  // epilogue staging [BM][LDT]
     const char *b_packed = STREAM ? q.Bp + (size_t)blockIdx.y * nkb * B_KB : nullptr;
 
     if (tid == 0) {
         for (int i = 0; i < MAX_TA; ++i) { mbar_init(&stage_free[i], 1); mbar_init(&stage_ready[i], P_THREADS / ARRIVE_DIV); mbar_init(&b_full[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], E_THREADS / 2 / ARRIVE_DIV); }
         for (int i = 0; i < MAX_RAW_P; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], (P_THREADS + (x_ring ? E_THREADS / 2 : 0)) / ARRIVE_DIV); }
+        mbar_init(&a2_free, 1); mbar_init(&acc2_full[0], 1); mbar_init(&acc2_full[1], 1);
         s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -338,14 +350,18 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if constexpr (!STREAM) {
-        // resident weight: all threads load + split every k-block once
-        for (int kb = 0; kb < nkb; ++kb) {
-            char *b_hi = b_res + (size_t)kb * B_KB, *b_lo = b_hi + BN * 128;
+        // resident weight: all threads load + split every k-block once (fused att backward: both orientations)
+        for (int kb = 0; kb < (FUSED ? 2 * nkb : nkb); ++kb) {
+            const bool second = kb >= nkb;
+            const int kbb = second ? kb - nkb : kb;
+            const float *wsrc = second ? q.W2 : p.Bt;
+            const int wld = second ? q.ldw2 : p.ldb;
+            char *b_hi = (second ? b2_res : b_res) + (size_t)kbb * B_KB, *b_lo = b_hi + BN * 128;
             for (int idx = tid; idx < BN * 8; idx += PERSIST_THREADS) {
                 const int r = idx >> 3, c = idx & 7;
-                const int gn = n0 + r, gk = kb * BK + c * 4;
+                const int gn = n0 + r, gk = kbb * BK + c * 4;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (gn < p.N && gk < p.K) v = *reinterpret_cast<const float4 *>(p.Bt + (size_t)gn * p.ldb + gk);
+                if (gn < p.N && gk < p.K) v = *reinterpret_cast<const float4 *>(wsrc + (size_t)gn * wld + gk);
                 const uint32_t off = sw128(r, c);
                 if (split) {
                     const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
@@ -500,6 +516,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                 ok = mbar_wait(&stage_ready[slot], (uint32_t)(use & 1)) && ok;           // all 256 producers filled the stage
 #ifdef PU_TC_TIMELINE
                 PU_TL(2, tl_item, 0);
+#endif
                 if constexpr (STREAM) ok = mbar_wait(&b_full[slot], (uint32_t)(use & 1)) && ok;  // this k-block of the weight landed
 #ifdef PU_TC_TIMELINE
                 PU_TL(2, tl_item, 1);
@@ -532,7 +549,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 #endif
                 if (++cur_kb == nkb) { cur_kb = 0; cur_tile += gridDim.x; tile_count++; }
                 slot = slot1; use = use1;
-#endif
             }
             if (!ok) s_err = 1;
         }
@@ -610,10 +626,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                                 make_float4(vals[qd], vals[qd + 1], vals[qd + 2], vals[qd + 3]);
                     }
                 }
-                if (pass == NPASS - 1) {
+                if (pass == NPASS - 1 && !FUSED) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive_warp(&acc_empty[buf]);  // the tensor core may overwrite this accumulator now
-                }
+                }   // (fused att backward: the buffer becomes the accumulator of the second MMA and is released after that)
                 bar_sync_named(bar_id, G_THREADS);
 #ifdef PU_TC_TIMELINE
                 if (gwarp == 0) PU_TL(3 + eg, tl_item, 2);
@@ -723,7 +739,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                             for (int k = 0; k < 16; ++k) x[k] = xp[(size_t)k * q.ldx];
                         }
                         float g = 0.f;
-                        if constexpr (EPI == EPI_ATT_BWD) g = q.G[(size_t)(pt0 + pl) * q.ldg + gn];
+                        if constexpr (ATT_BWD) g = q.G[(size_t)(pt0 + pl) * q.ldg + gn];
                         float mx = -FLT_MAX;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
@@ -746,6 +762,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                             for (int k = 0; k < 16; ++k) { a[k] *= inv; dot = fmaf(g * x[k], a[k], dot); }
                             float *cp = p.C + (size_t)(m0 + pl * 16) * p.ldc + gn;
                             float *op = q.OUT + (size_t)(m0 + pl * 16) * q.ldo + gn;
+                            if constexpr (FUSED) {   // d_act also goes back into the staging tile: operand of the second MMA
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) tile_g[(pl * 16 + k) * LDT + c] = a[k] * (g * x[k] - dot);
+                            }
                             if (p.ldc == BN && q.ldo == BN) {  // contiguous outputs: immediate offsets
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
@@ -761,6 +781,90 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
                             }
                         }
                     }
+                }
+                if constexpr (FUSED) {
+                    // ---- dx += d_act w^T on the tensor core, inside this epilogue ----
+                    // tile_count is the CTA-local tile number; the single A2 operand buffer is used in that order by the two
+                    // groups: tile t may write it once the second MMA of tile t - 1 has retired (a2_free phase t - 1).
+                    bar_sync_named(bar_id, G_THREADS);                     // d_act tile complete, dx_direct stores issued
+                    if (tile_count >= 1) ok = mbar_wait(&a2_free, (uint32_t)((tile_count - 1) & 1)) && ok;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    {   // rows of d_act -> hi/lo -> tensor memory: warp (quarter, chalf) = 32 rows x 32 columns
+                        const int row = quarter * 32 + lane;
+                        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(A2_COL + chalf * 32);
+#pragma unroll
+                        for (int cc = 0; cc < 32; cc += 16) {
+                            float vv[16], hh[16];
+#pragma unroll
+                            for (int qd = 0; qd < 16; qd += 4) {
+                                const float4 t4 = *reinterpret_cast<const float4 *>(&tile_g[row * LDT + chalf * 32 + cc + qd]);
+                                vv[qd] = t4.x; vv[qd + 1] = t4.y; vv[qd + 2] = t4.z; vv[qd + 3] = t4.w;
+                            }
+                            if (split) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) { hh[i] = tf32_rn(vv[i]); vv[i] -= hh[i]; }
+                                tmem_st16(ta + cc, hh);
+                                tmem_st16(ta + BN + cc, vv);
+                            } else {
+                                tmem_st16(ta + cc, vv);
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    bar_sync_named(bar_id, G_THREADS);                     // operand complete
+                    if (gwarp == 0) {                                      // converged warp, one elected lane issues
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const bool leader2 = elect_one();
+                        const uint32_t idesc2 = make_idesc(BN);
+                        const uint64_t b2desc0 = make_desc(smem_u32(b2_res));
+                        const uint32_t d2 = tmem_base + (uint32_t)(buf * BN);      // the drained accumulator of this tile
+                        const uint32_t a2 = tmem_base + (uint32_t)A2_COL;
+                        if (leader2) {
+#pragma unroll
+                            for (int kk = 0; kk < BN / UMMA_K; ++kk) {             // contraction over the BN channels of d_act
+                                const uint64_t bh = b2desc0 + (uint64_t)((kk >> 2) * (B_KB >> 4)) + (uint64_t)(2 * (kk & 3));
+                                const uint64_t bl = bh + (uint64_t)((BN * 128) >> 4);
+                                umma_tf32_ts(d2, a2 + kk * UMMA_K, bh, idesc2, kk > 0 ? 1u : 0u);
+                                if (split) {
+                                    umma_tf32_ts(d2, a2 + kk * UMMA_K, bl, idesc2, 1u);
+                                    umma_tf32_ts(d2, a2 + BN + kk * UMMA_K, bh, idesc2, 1u);
+                                }
+                            }
+                            umma_commit(&a2_free);
+                            umma_commit(&acc2_full[buf]);
+                        }
+                    }
+                    {   // dx = dx_direct (written above, still in L2) + d_act w^T: lane = row, 32 columns per warp.  The old
+                        // values are requested BEFORE the wait for the second MMA, so their L2 latency hides behind it.
+                        const int row = quarter * 32 + lane;
+                        float *op = q.OUT + (size_t)(m0 + row) * q.ldo + n0 + chalf * 32;
+                        float4 o4[8];
+                        if (row < rows_here && !(q.dbg & 1)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o4[i] = *reinterpret_cast<const float4 *>(op + 4 * i);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (!(q.dbg & 2)) ok = mbar_wait(&acc2_full[buf], (uint32_t)(v & 1)) && ok;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                        for (int cc = 0; cc < 32; cc += 16) {
+                            float vals[16];
+                            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + chalf * 32 + cc), vals);
+                            if (row < rows_here) {
+#pragma unroll
+                                for (int qd = 0; qd < 16; qd += 4) {
+                                    float4 t4 = o4[(cc + qd) >> 2];
+                                    t4.x += vals[qd]; t4.y += vals[qd + 1]; t4.z += vals[qd + 2]; t4.w += vals[qd + 3];
+                                    *reinterpret_cast<float4 *>(op + cc + qd) = t4;
+                                }
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive_warp(&acc_empty[buf]);  // now the first MMA of tile + 2 may overwrite the buffer
                 }
                 bar_sync_named(bar_id, G_THREADS);  // the staging tile is reused by the next pass / tile of this group
 #ifdef PU_TC_TIMELINE
@@ -786,15 +890,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) tc_persist_kernel(const Pa
 
 constexpr size_t kMaxDynSmem = 227 * 1024 - 10 * 1024;  // dynamic budget: 227 KB minus the kernel's static shared memory (~9 KB)
 template <int BN, bool STREAM>
-static size_t persist_fixed_bytes(int K) {  // everything except the raw ring
+static size_t persist_fixed_bytes(int K, bool second_weight = false) {  // everything except the raw ring
     const int nkb = (K + BK - 1) / BK;
     const int ec = BN > 64 ? 64 : BN;
     const int ta = BN <= 64 ? MAX_TA : 3;
-    return (size_t)(STREAM ? ta : nkb) * 2 * BN * 128 + 2 * (size_t)BM * (ec + 4) * 4 + 1024;  // weights, 2 staging tiles
+    return (size_t)(STREAM ? ta : nkb) * 2 * BN * 128 * (second_weight ? 2 : 1) + 2 * (size_t)BM * (ec + 4) * 4 + 1024;  // weights, 2 staging tiles
 }
 template <int BN, bool STREAM>
-static int persist_raw_depth(int K) {  // 0 => does not fit
-    const size_t fixed = persist_fixed_bytes<BN, STREAM>(K);
+static int persist_raw_depth(int K, bool second_weight = false) {  // 0 => does not fit
+    const size_t fixed = persist_fixed_bytes<BN, STREAM>(K, second_weight);
     if (fixed + 3 * (size_t)BM * 128 > kMaxDynSmem) return 0;
     long long d = (long long)((kMaxDynSmem - fixed) / ((size_t)BM * 128));
     return (int)(d > MAX_RAW_P ? MAX_RAW_P : d);
@@ -848,9 +952,10 @@ static int launch_persist(const Params2 &q, void *workspace, size_t workspace_by
 #ifdef PU_TC_TIMELINE
     qq.timeline = g_timeline;
 #endif
-    qq.raw_depth = persist_raw_depth<BN, STREAM>(q.g.K);
+    constexpr bool kSecondWeight = EPI == EPI_ATT_BWD_F;
+    qq.raw_depth = persist_raw_depth<BN, STREAM>(q.g.K, kSecondWeight);
     if (qq.raw_depth < 3) return PU_ERR_UNSUPPORTED;
-    const size_t smem = persist_fixed_bytes<BN, STREAM>(q.g.K) + (size_t)qq.raw_depth * BM * 128;
+    const size_t smem = persist_fixed_bytes<BN, STREAM>(q.g.K, kSecondWeight) + (size_t)qq.raw_depth * BM * 128;
     static bool configured = false;
     if (!configured) {
         PU_CUDA_TRY(cudaFuncSetAttribute(tc_persist_kernel<BN, EPI, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
@@ -1663,6 +1768,31 @@ int pu_tc_att_pooling_bwd(const float *feature_set, int ldx, const float *wt, co
     q.X = feature_set; q.ldx = ldx; q.G = g_agg; q.ldg = ldg; q.OUT = dx_direct; q.ldo = lddx;
     q.ntiles = (q.g.M + tc::BM - 1) / tc::BM;
     return tc::dispatch_persist<tc::EPI_ATT_BWD>(q, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+/* Fused att_pooling backward for d = 64 (K = 16): as pu_tc_att_pooling_bwd, but `dx` receives the COMPLETE gradient
+ * g s + d_act w^T (the dgrad through the FC runs as a second tensor-core MMA inside the kernel); d_act is still written for
+ * the weight gradient.  `w` is the FC kernel [d, d] in its own orientation, `wt` its transpose. */
+int pu_tc_att_bwd_fused_supported(int K, int d, int ldx) { return K == 16 && d == 64 && (ldx & 3) == 0; }
+
+int pu_tc_att_pooling_bwd_fused(const float *feature_set, int ldx, const float *wt, const float *w, const float *g_agg, int ldg,
+                                long long P, int K, int d, float *d_act, int ldda, float *dx, int lddx, int mode,
+                                int *error_flag, pu_stream_t stream) {
+    if (!feature_set || !wt || !w || !g_agg || !d_act || !dx || P < 0 || ldx < d || ldg < d || ldda < d || lddx < d)
+        return PU_ERR_INVALID_ARG;
+    const int dbg = mode >> 8;   // development: timing experiments (results are wrong with dbg != 0)
+    mode &= 0xff;
+    if (mode != 1 && mode != 3) return PU_ERR_INVALID_ARG;
+    if (!pu_tc_att_bwd_fused_supported(K, d, ldx) || (lddx & 3) ||
+        (((uintptr_t)feature_set | (uintptr_t)wt | (uintptr_t)w | (uintptr_t)dx) & 15))
+        return PU_ERR_UNSUPPORTED;
+    if (P == 0) return PU_OK;
+    tc::Params2 q{};
+    q.g.A = feature_set; q.g.lda = ldx; q.g.Bt = wt; q.g.ldb = d; q.g.M = P * K; q.g.N = d; q.g.K = d; q.g.mode = mode;
+    q.g.C = d_act; q.g.ldc = ldda; q.g.error_flag = error_flag;
+    q.X = feature_set; q.ldx = ldx; q.G = g_agg; q.ldg = ldg; q.OUT = dx; q.ldo = lddx; q.W2 = w; q.ldw2 = d; q.dbg = dbg;
+    q.ntiles = (q.g.M + tc::BM - 1) / tc::BM;
+    return tc::launch_persist<64, tc::EPI_ATT_BWD_F, false>(q, nullptr, 0, (cudaStream_t)stream);
 }
 
 /* Tensor-core weight gradient: dw[Kin,N] (+)= x^T dy, db[N] (+)= column sums of dy (db only when Kin % 128 != 0).

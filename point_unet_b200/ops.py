@@ -39,6 +39,8 @@ _lib._OP_SIGS.update({
                               c_size_t, c_void_p],
     "pu_tc_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    "pu_tc_att_pooling_bwd_fused": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int,
+                                    c_void_p, c_int, c_int, c_void_p, c_void_p],
     "pu_tc_wgrad": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
                     c_void_p, c_void_p],
     "pu_linear_fwd_ex": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p,
@@ -87,6 +89,8 @@ import os as _os
 TC_MODE = int(_os.environ.get("PU_TC_MODE", "3"))
 # d = 16 attentive pooling through the dedicated one-pass kernels (att16.cu); 0 = the generic three-pass CUDA-core path
 ATT16 = int(_os.environ.get("PU_ATT16", "1")) != 0
+# d = 64 attentive pooling backward with the dgrad through the FC fused into the tcgen05 kernel; 0 = separate accumulate GEMM
+ATT_BWD_FUSED = int(_os.environ.get("PU_ATT_BWD_FUSED", "1")) != 0
 # Storage mode of the pre-normalisation activations y (output of every 1x1 conv that feeds a batch norm; kept from the forward
 # for the batch-norm backward -- the largest saved tensors of a training step): "fp32" (default, the parity path) or "bf16"
 # (opt-in: y is rounded to bfloat16 when stored, arithmetic and batch statistics stay fp32; stated tolerance rel-L2 <= 2e-2 on
@@ -119,6 +123,7 @@ def _L():
         L.pu_point2prod_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.pu_tc_linear_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
         L.pu_tc_att_supported.argtypes = [c_int, c_int, c_int]
+        L.pu_tc_att_bwd_fused_supported.argtypes = [c_int, c_int, c_int]
         L.pu_tc_workspace_bytes.restype = c_size_t
         L.pu_tc_workspace_bytes.argtypes = [c_int, c_int]
         L.pu_tc_wgrad_supported.argtypes = [c_ll, c_int, c_int, c_int, c_int, c_int]
@@ -896,6 +901,13 @@ class _AttPoolFn(torch.autograd.Function):
                   int(gw is not None), ws.data_ptr(), ws.numel(), _stream(x), tag=(B * N, K, d))
             return dx, (None if gw is not None else dw)
         d_act = torch.empty((B * N * K, d), dtype=torch.float32, device=x.device)
+        if use_tc and ATT_BWD_FUSED and _L().pu_tc_att_bwd_fused_supported(K, d, ldx):
+            # d = 64: dx = g s + d_act w^T leaves the kernel complete (second MMA inside the epilogue)
+            _call("pu_tc_att_pooling_bwd_fused", x.data_ptr(), ldx, wt.data_ptr(), w.data_ptr(), g.data_ptr(), ldg, B * N, K, d,
+                  d_act.data_ptr(), d, dx.data_ptr(), d, TC_MODE, tc_error_flag(x.device).data_ptr(), _stream(x),
+                  tag=(B * N, K, d))
+            dw, _ = _wgrad(x, d_act, out=gw, accumulate=gw is not None)
+            return dx, (None if gw is not None else dw)
         if use_tc:
             tws = workspace(_L().pu_tc_workspace_bytes(d, d), x.device, slot=4)
             _call("pu_tc_att_pooling_bwd", x.data_ptr(), ldx, wt.data_ptr(), g.data_ptr(), ldg, B * N, K, d,

@@ -326,3 +326,42 @@ def test_overlapped_host_staging_trains_the_submitted_batches():
     lo = [ovl.train_step(batches[i]["xyz"], batches[i]["features"], batches[i]["labels"]) for i in (1, 2, 2, 2)]
     # call 0 trains the capture batch (0), call 1 trains batch 1, call 2 trains batch 2 (call 3 trains batch 2 again)
     assert lo[:3] == pytest.approx(ls[1:], rel=0, abs=0), (ls, lo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [8, 1000, 45001])
+def test_fused_att_pooling_backward_d64(P):
+    """d = 64: dx = g s + d_act w^T from ONE kernel (second tcgen05 MMA inside the epilogue) against the fp64 restatement
+    (RandLANet.py:394-398) and against the two-kernel path (att backward + accumulate GEMM); bit-deterministic."""
+    from point_unet_b200 import ops
+    K, d = 16, 64
+    g = torch.Generator().manual_seed(P)
+    x = torch.randn(1, P, K, d, generator=g)
+    w = torch.randn(d, d, generator=g) * 0.2
+    dy = torch.randn(1, P, 1, d, generator=g)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    act = xr.reshape(-1, K, d) @ wr
+    agg_r = (xr.reshape(-1, K, d) * torch.softmax(act, dim=1)).sum(1).reshape(1, P, 1, d)
+    (agg_r * dy.double()).sum().backward()
+
+    def run(fused):
+        old = ops.ATT_BWD_FUSED
+        ops.ATT_BWD_FUSED = fused
+        try:
+            xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+            ops.tc_error_flag(xg.device).zero_()
+            agg = ops.att_pool(xg, wg)
+            (agg * dy.cuda()).sum().backward()
+            assert int(ops.tc_error_flag(xg.device).item()) == 0, "tcgen05 pipeline barrier timed out"
+            return xg.grad, wg.grad
+        finally:
+            ops.ATT_BWD_FUSED = old
+
+    def rel(a, b):
+        return float((a.detach().cpu().double() - b).abs().max() / b.abs().max())
+    dx1, dw1 = run(True)
+    assert rel(dx1, xr.grad) < 1e-4 and rel(dw1, wr.grad) < 1e-4, (rel(dx1, xr.grad), rel(dw1, wr.grad))
+    dx0, dw0 = run(False)
+    assert rel(dx1, dx0.cpu().double()) < 1e-5 and torch.equal(dw1, dw0)   # d_act (hence dw) is produced identically
+    dx2, dw2 = run(True)
+    assert torch.equal(dx1, dx2) and torch.equal(dw1, dw2)
