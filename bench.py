@@ -113,6 +113,9 @@ def algorithmic(name, tag):
     if name in ("pu_att_pooling_bwd", "pu_tc_att_pooling_bwd"):
         P, K, d = tag  # reads x and g, writes d_act and dx_direct
         return 3 * 4 * P * K * d + 4 * d * d + 4 * P * d, 2 * P * K * d * d, "tensor" if d >= 64 else "hbm"
+    if name == "pu_tc_att_pooling_bwd_fused":
+        P, K, d = tag  # reads x and g, writes d_act and the complete dx; two GEMMs (scores, d_act w^T)
+        return 3 * 4 * P * K * d + 8 * d * d + 4 * P * d, 4 * P * K * d * d, "hbm"
     if name == "pu_gather_rows_fwd":
         R, n_src, d = tag
         return 4 * R + 4 * n_src * d + 4 * R * d, 0, "hbm"
@@ -131,10 +134,11 @@ def algorithmic(name, tag):
 def load_traffic():
     """Measured DRAM bytes per launch of each C-ABI entry (ncu dram__bytes_read+write), written by
     tools/summarize_launches.py into profiles/; null if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f)
+    for rnd in ("r2", "r1"):   # newest round first
+        path = os.path.join(ROOT, "profiles", rnd + "_kernel_traffic.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f)
     return {}
 
 

@@ -103,3 +103,17 @@ def test_rows_view_of_concat_halves():
     assert ld == 32 and t.is_contiguous()
     t, R, C, ld = rows(torch.zeros(7, 1, 8).squeeze(1))
     assert (R, C, ld) == (7, 8, 8)
+
+
+def test_oracle_sources_are_frozen():
+    """The restatements are the single point of failure of the TF half ("parity unpinned"): they are frozen.  A deliberate
+    edit updates the digest here together with the golden fixtures that were generated from them."""
+    import hashlib
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    want = {"randla_ref.py": "0f73b0757a37a218bf8ea2abaa48b6b01ac077ccae3bd6764a4ccf9bd0b3a9af",
+            "knn_oracle.c": "7cd921ae4f9024103ee93f62cb34074188177626edb5e0d9bb43818b4ff63220",
+            "prepare_ref.py": "0a596fa462389fc50ee05bc3952f70e4e8bce64472e82cb6040307741af51321"}
+    for name, digest in want.items():
+        with open(os.path.join(root, name), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == digest, name

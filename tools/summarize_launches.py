@@ -1,5 +1,6 @@
 """Turns an ncu launch list (CSV with gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum per launch)
-into profiles/<tag>_launch_summary.txt and profiles/r1_kernel_traffic.json.   python tools/summarize_launches.py <csv> <tag>"""
+into profiles/<tag>_launch_summary.txt and profiles/<round>_kernel_traffic.json (<round> = the tag up to its first "_", e.g.
+r2_step -> r2).   python tools/summarize_launches.py <csv> <tag>"""
 import collections, csv, json, os, re, sys
 src, tag = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,7 +30,10 @@ open(os.path.join(ROOT, "profiles", f"{tag}_launch_summary.txt"), "w").write("\n
 # per C-ABI entry traffic (bytes per launch), mapping kernel names to the entry points bench.py times
 ENTRY = [(r"tc::tc_persist_kernel<\d+, 0,", "pu_tc_linear_fwd"), (r"tc::tc_linear_kernel", "pu_tc_linear_fwd"),
          (r"tc::tc_persist_kernel<\d+, 1,", "pu_tc_att_pooling_fwd"), (r"tc::tc_persist_kernel<\d+, 2,", "pu_tc_att_pooling_bwd"),
-         (r"tc::tc_wgrad_kernel", "pu_tc_wgrad"), (r"lfa::gather_rows", "pu_gather_rows_fwd"), (r"lfa::segment_sum", "pu_segment_sum"),
+         (r"tc::tc_persist_kernel<\d+, 3,", "pu_tc_att_pooling_bwd_fused"),
+         (r"tc::tc_wgrad_kernel|tc::tc_wgrad_ts_kernel", "pu_tc_wgrad"), (r"mlp::bn_act_fwd", "pu_bn_act_fwd"),
+         (r"mlp::bn_bwd_reduce", "pu_bn_bwd_reduce"), (r"mlp::bn_bwd_apply", "pu_bn_bwd_apply"),
+         (r"lfa::maxpool_bwd", "pu_random_sample_bwd"), (r"lfa::maxpool_fwd", "pu_random_sample_fwd"), (r"lfa::gather_rows", "pu_gather_rows_fwd"), (r"lfa::segment_sum", "pu_segment_sum"),
          (r"mlp::wgrad", "pu_wgrad"), (r"mlp::linear_narrow|mlp::gemm_kernel<\d+, \d+, \d+, \d+, 0>", "pu_linear_fwd"),
          (r"knn::knn_search_kernel", "pu_knn_batch"), (r"att16::att16_fwd_kernel", "pu_att16_fwd"),
          (r"att16::att16_bwd_kernel", "pu_att16_bwd")]
@@ -41,5 +45,5 @@ for k, a in agg.items():
             break
 json.dump({e: dict(dram_bytes_per_launch=v[1] / v[0], launches_per_step=v[0], ncu_ms_per_step=v[2] / 1e3,
                    dram_gbs_under_ncu=v[1] / max(v[2], 1e-9) / 1e3) for e, v in tr.items() if v[0]},
-          open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json"), "w"), indent=1)
+          open(os.path.join(ROOT, "profiles", tag.split("_")[0] + "_kernel_traffic.json"), "w"), indent=1)
 print("\n".join(out[:30]))
