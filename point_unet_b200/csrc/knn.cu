@@ -24,6 +24,7 @@
 // nearest, NO fused multiply-add (__fmul_rn/__fadd_rn/__fsub_rn are never contracted).
 // Tie rule: ascending (distance, index) -- a total order, hence the result is independent of the visiting
 // order and of scheduling (deterministic).
+#include <cstdlib>
 #include <float.h>
 
 #include "common.cuh"
@@ -42,8 +43,8 @@ constexpr int SORT_FUSED_TILES = 64;  // up to this many tiles per cloud the sca
 
 struct Layout {
     size_t stats, bbox, keys_a, keys_b, vals_a, vals_b, sp, bk_lo, bk_hi, sb_lo, sb_hi;
-    size_t qkeys_a, qkeys_b, qvals_a, qvals_b, sq, sort_hist, hist_one, total;
-    int NB, NSB;
+    size_t qkeys_a, qkeys_b, qvals_a, qvals_b, sq, sort_hist, hist_one, cb_lo, cb_hi, total;
+    int NB, NSB, NCB;
 };
 
 static Layout make_layout(int B, int N1, int N2) {
@@ -57,6 +58,7 @@ static Layout make_layout(int B, int N1, int N2) {
     const size_t n1 = (size_t)B * N1, n2 = (size_t)B * N2;
     L.NB = ceil_div(N1, BS);
     L.NSB = ceil_div(L.NB, SBS);
+    L.NCB = ceil_div(L.NSB, SBS);   // third level (32 super-buckets = 32 768 points): used by the warp-per-query search
     L.stats = take(8 * sizeof(unsigned long long));
     L.bbox = take((size_t)B * 8 * sizeof(unsigned));
     L.keys_a = take(n1 * 4);
@@ -75,6 +77,8 @@ static Layout make_layout(int B, int N1, int N2) {
     L.sq = take(n2 * 16);
     L.hist_one = align_up((size_t)B * SORT_BINS * ceil_div(N1 > N2 ? N1 : N2, SORT_TILE) * sizeof(unsigned), 256);
     L.sort_hist = take(L.hist_one * 2 * SORT_PASSES);   // [support | query][pass] digit histograms, zeroed by one memset
+    L.cb_lo = take((size_t)B * L.NCB * 16);
+    L.cb_hi = take((size_t)B * L.NCB * 16);
     L.total = off;
     return L;
 }
@@ -115,12 +119,21 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float *__restrict__ pts
             hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one atomic per CTA and bound (every warp hitting the same six words serialises in L2: 74 us at 4 x 180 k points)
+    __shared__ float s_lo[8][3], s_hi[8][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            atomicMin(&bbox[b * 8 + c], f2ord(lo[c]));
-            atomicMax(&bbox[b * 8 + 4 + c], f2ord(hi[c]));
-        }
+        for (int c = 0; c < 3; ++c) { s_lo[warp][c] = lo[c]; s_hi[warp][c] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        float l = s_lo[0][c], h = s_hi[0][c];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { l = fminf(l, s_lo[w][c]); h = fmaxf(h, s_hi[w][c]); }
+        atomicMin(&bbox[b * 8 + c], f2ord(l));
+        atomicMax(&bbox[b * 8 + 4 + c], f2ord(h));
     }
 }
 
@@ -618,6 +631,169 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-query search (self-queries, K <= 32).  The per-lane kernel above makes 32 queries share every candidate
+// bucket, so each lane evaluates the union of 32 neighbourhoods (~1 460 distances per query at 180 k points) and the warp
+// runs the 16-deep sorted insertion whenever ANY lane accepts a candidate -- i.e. almost always.  Here a warp owns ONE
+// query: lane l evaluates candidate l of a bucket (one coalesced 512-byte load), the K best keys live as an ascending list
+// ACROSS the lanes, a candidate is inserted with one ballot + one shuffle-up, many candidates at once by a warp bitonic sort
+// + bitonic merge, and boxes are pruned against the query's OWN K-th distance on three levels (32 768 / 1 024 / 32 points).
+// Same distance arithmetic, same conservative bounds, same (distance, index) total order => bit-identical results.
+constexpr int QW_WARPS = 8;      // warps per CTA
+constexpr int QW_QPW = 8;        // queries per warp: a CTA covers 64 Morton-consecutive queries (shared L1 working set)
+constexpr int QW_MERGE_MIN = 12;  // more accepted candidates than this in one bucket: sort + merge instead of insertions
+
+__device__ __forceinline__ unsigned long long qw_sort32(unsigned long long x, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, x, j);
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            x = ((x < o) == keep_min) ? x : o;
+        }
+    return x;
+}
+// `list` and `y` ascending by lane -> the 32 smallest keys of their union, ascending by lane
+__device__ __forceinline__ unsigned long long qw_merge32(unsigned long long list, unsigned long long y, int lane) {
+    const unsigned long long yr = __shfl_sync(0xffffffffu, y, 31 - lane);
+    unsigned long long z = list < yr ? list : yr;  // bitonic
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, z, j);
+        const bool keep_min = (lane & j) == 0;
+        z = ((z < o) == keep_min) ? z : o;
+    }
+    return z;
+}
+
+__global__ void __launch_bounds__(QW_WARPS * 32)
+    knn_query_warp_kernel(const float4 *__restrict__ sp, const float4 *__restrict__ bk_lo, const float4 *__restrict__ bk_hi,
+                          const float4 *__restrict__ sb_lo, const float4 *__restrict__ sb_hi,
+                          const float4 *__restrict__ cb_lo, const float4 *__restrict__ cb_hi, int N, int NB, int NSB,
+                          int NCB, int kout, int32_t *__restrict__ out_idx, float *__restrict__ out_dist,
+                          unsigned long long *__restrict__ stats) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, b = blockIdx.y;
+    const float4 *sp_cloud = sp + (size_t)b * N;
+    const float4 *bk_lo_c = bk_lo + (size_t)b * NB, *bk_hi_c = bk_hi + (size_t)b * NB;
+    const float4 *sb_lo_c = sb_lo + (size_t)b * NSB, *sb_hi_c = sb_hi + (size_t)b * NSB;
+    const float4 *cb_lo_c = cb_lo + (size_t)b * NCB, *cb_hi_c = cb_hi + (size_t)b * NCB;
+    unsigned long long n_evals = 0;
+    unsigned n_buckets = 0, n_tests = 0;
+
+    for (int i = 0; i < QW_QPW; ++i) {
+        const int qi = (blockIdx.x * QW_QPW + i) * QW_WARPS + wib;  // warp-uniform
+        if (qi >= N) break;
+        const float4 q = sp_cloud[qi];
+        unsigned long long list = KEY_INIT, thr = KEY_INIT;  // ascending across the lanes; thr = the kout-th key
+        unsigned q_evals = 0;
+        float kd = __uint_as_float(0x7F800000u);
+
+        // candidate keys of bucket t, one per lane (KEY_INIT beyond the end of the cloud)
+        auto load_keys = [&](int t) -> unsigned long long {
+            const int base = t * BS;
+            const int cnt = min(BS, N - base);
+            unsigned long long key = KEY_INIT;
+            if (lane < cnt) {
+                const float4 p = sp_cloud[base + lane];
+                const float d = dist2_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+            }
+            q_evals += cnt;
+            return key;
+        };
+        auto set_thr = [&]() {
+            thr = __shfl_sync(0xffffffffu, list, kout - 1);
+            kd = __uint_as_float((unsigned)(thr >> 32));
+        };
+        // fold one bucket's keys into the list
+        auto absorb = [&](unsigned long long key) {
+            unsigned m = __ballot_sync(0xffffffffu, key < thr);
+            if (m == 0) return;
+            if (__popc(m) > QW_MERGE_MIN) {
+                list = qw_merge32(list, qw_sort32(key, lane), lane);
+            } else {
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned long long x = __shfl_sync(0xffffffffu, key, bit);
+                    // position = number of smaller keys; everything from there on moves up one lane
+                    const int pos = __popc(__ballot_sync(0xffffffffu, list < x));
+                    const unsigned long long up = __shfl_up_sync(0xffffffffu, list, 1);
+                    list = lane < pos ? list : (lane == pos ? x : up);
+                }
+            }
+            set_thr();
+        };
+
+        // seed: the query's own bucket and its two Morton neighbours (three loads in flight)
+        const int home = min(qi / BS, NB - 1);
+        const int seed_lo = max(home - 1, 0), seed_hi = min(home + 1, NB - 1);
+        {
+            const unsigned long long k0 = load_keys(home);
+            const unsigned long long k1 = seed_lo != home ? load_keys(seed_lo) : KEY_INIT;
+            const unsigned long long k2 = seed_hi != home ? load_keys(seed_hi) : KEY_INIT;
+            list = qw_sort32(k0, lane);
+            set_thr();
+            absorb(k1);
+            absorb(k2);
+        }
+
+        // Boxes are visited NEAREST FIRST on the two lower levels (one REDUX over the lanes' bound bits picks the next box;
+        // non-negative floats order like their bit patterns), so the radius shrinks early and the walk of a level stops at
+        // the first remaining box that lies beyond it.
+        for (int c0 = 0; c0 < NCB; c0 += 32) {
+            float cd = FLT_MAX;
+            const bool c_ok = c0 + lane < NCB;   // (kd is +inf while the list is not full: validity is its own predicate)
+            if (c_ok) cd = point_box_dist2(q.x, q.y, q.z, cb_lo_c[c0 + lane], cb_hi_c[c0 + lane]);
+            unsigned mc = __ballot_sync(0xffffffffu, c_ok && cd <= kd);
+            n_tests += 1;
+            while (mc) {
+                const int bc = __ffs(mc) - 1;
+                mc &= mc - 1;
+                if (__shfl_sync(0xffffffffu, cd, bc) > kd) continue;  // the radius shrank since the ballot
+                const int s0 = (c0 + bc) * SBS;
+                unsigned sbits = 0xFFFFFFFFu;   // bound of this lane's super-bucket; all ones = nothing (left) to visit
+                if (s0 + lane < NSB)
+                    sbits = __float_as_uint(point_box_dist2(q.x, q.y, q.z, sb_lo_c[s0 + lane], sb_hi_c[s0 + lane]));
+                n_tests += 1;
+                for (;;) {
+                    const unsigned smin = __reduce_min_sync(0xffffffffu, sbits);
+                    if (smin == 0xFFFFFFFFu || __uint_as_float(smin) > kd) break;
+                    const int bs = __ffs(__ballot_sync(0xffffffffu, sbits == smin)) - 1;
+                    if (lane == bs) sbits = 0xFFFFFFFFu;
+                    const int t0 = (s0 + bs) * SBS, t = t0 + lane;
+                    unsigned bbits = 0xFFFFFFFFu;
+                    if (t < NB && (t < seed_lo || t > seed_hi))   // the seed buckets were swept already
+                        bbits = __float_as_uint(point_box_dist2(q.x, q.y, q.z, bk_lo_c[t], bk_hi_c[t]));
+                    n_tests += 1;
+                    for (;;) {
+                        const unsigned bmin = __reduce_min_sync(0xffffffffu, bbits);
+                        if (bmin == 0xFFFFFFFFu || __uint_as_float(bmin) > kd) break;
+                        const int bb = __ffs(__ballot_sync(0xffffffffu, bbits == bmin)) - 1;
+                        if (lane == bb) bbits = 0xFFFFFFFFu;
+                        absorb(load_keys(t0 + bb));   // (fetching the two nearest buckets together bought nothing: issue-bound)
+                    }
+                }
+            }
+        }
+
+        n_evals += q_evals;
+        n_buckets += (q_evals + BS - 1) / BS;
+        if (lane < kout) {
+            const size_t o = ((size_t)b * N + (size_t)__float_as_int(q.w)) * kout + lane;
+            out_idx[o] = list == KEY_INIT ? 0 : (int)(unsigned)list;
+            if (out_dist) out_dist[o] = list == KEY_INIT ? FLT_MAX : __uint_as_float((unsigned)(list >> 32));
+        }
+    }
+    if (stats && lane == 0) {
+        atomicAdd(&stats[0], n_evals);
+        atomicAdd(&stats[1], (unsigned long long)n_buckets);
+        atomicAdd(&stats[2], (unsigned long long)n_tests);
+    }
+}
+
 template <int K>
 static int launch_search(const Layout &L, char *ws, bool self, const unsigned *skeys,
                          const unsigned *qkeys, const float4 *sq, int B, int N1, int N2, int kout,
@@ -683,7 +859,7 @@ static int knn_impl(const float *support, const float *query, int B, int N1, int
     bbox_init_kernel<<<ceil_div(B * 8, 128), 128, 0, st>>>(bbox, B);
     PU_LAUNCH_CHECK();
     {
-        dim3 grid(min(ceil_div(N1, 256), 4 * kNumSMs), B);
+        dim3 grid(min(ceil_div(N1, 1024), kNumSMs), B);
         bbox_kernel<<<grid, 256, 0, st>>>(support, N1, bbox);
         PU_LAUNCH_CHECK();
     }
@@ -705,6 +881,25 @@ static int knn_impl(const float *support, const float *query, int B, int N1, int
         (const float4 *)(ws + L.bk_lo), (const float4 *)(ws + L.bk_hi), L.NB, L.NSB, B, (float4 *)(ws + L.sb_lo),
         (float4 *)(ws + L.sb_hi));
     PU_LAUNCH_CHECK();
+
+    static const int warp_query = []() {
+        const char *e = getenv("PU_KNN_WARP_QUERY");
+        return e ? atoi(e) : 1;
+    }();
+    if (self && warp_query && K > 4) {  // one warp per query (see knn_query_warp_kernel)
+        super_box_kernel<<<ceil_div((long long)B * L.NCB * 32, 128), 128, 0, st>>>(
+            (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), L.NSB, L.NCB, B, (float4 *)(ws + L.cb_lo),
+            (float4 *)(ws + L.cb_hi));
+        PU_LAUNCH_CHECK();
+        dim3 grid(ceil_div(N1, QW_WARPS * QW_QPW), B);
+        knn_query_warp_kernel<<<grid, QW_WARPS * 32, 0, st>>>(
+            (const float4 *)(ws + L.sp), (const float4 *)(ws + L.bk_lo), (const float4 *)(ws + L.bk_hi),
+            (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), (const float4 *)(ws + L.cb_lo),
+            (const float4 *)(ws + L.cb_hi), N1, L.NB, L.NSB, L.NCB, K, out_idx, out_dist,
+            (unsigned long long *)(ws + L.stats));
+        PU_LAUNCH_CHECK();
+        return PU_OK;
+    }
 
     const float4 *sq = (const float4 *)(ws + L.sp);
     if (!self) {
