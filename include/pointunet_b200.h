@@ -100,6 +100,32 @@ PU_API int pu_segment_sum(const float *grad_out, int ld_go, const int32_t *offse
 PU_API int pu_relative_pos_encoding_fwd(const float *xyz, const int32_t *idx, int B, int N, int K, float *out,
                                         pu_stream_t stream);
 
+/* ref: building_block, position branch  RandLANet.py:323-326:  relative_pos_encoding -> conv2d(10 -> h, 'mlp1') ->
+ *   BN(0.99, 1e-6) -> LeakyReLU(0.2), as recompute kernels (csrc/locse_mlp.cu): neither the 10-channel LocSE rows nor the
+ *   pre-normalisation tensor nor its gradient are ever stored.  h = power of two in [4, 1024].
+ *   pu_locse_moments:    mom[0:10] = column sums of the LocSE rows over all B*N*K rows, mom[10:65] = centred second-moment
+ *                        sums (upper triangle, row-major); the batch statistics of the conv output follow from them.
+ *   pu_locse_bn_prepare: coef (5h + 110 floats, 16-byte aligned): scale | t | invstd | mean_y | var_y | xbar(10) | Cov(100).
+ *                        training != 0: batch statistics (moving_mean / moving_var, when given, receive the momentum update
+ *                        with `unbias`, like pu_bn_finalize_prepare); training == 0: the moving statistics are used.
+ *   pu_locse_mlp_fwd:    out[row, 0:h] (row stride ldo; optionally also out2) = lrelu(scale * ((x - xbar) W) + t).
+ *   pu_locse_mlp_bwd:    backward given dz (+ dz2, summed on the fly) and the coef of the forward (same `training`): dW [10,h]
+ *                        ((+)= when accumulate_dw), dbias (optional; identically 0 in training mode), dgamma, dbeta [h]; there
+ *                        is no dgrad (xyz is data).  Deterministic. */
+PU_API int pu_locse_mlp_supported(int K, int h);
+PU_API size_t pu_locse_mlp_workspace_bytes(int h);
+PU_API int pu_locse_moments(const float *xyz, const int32_t *idx, int B, int N, int K, float *mom, void *workspace,
+                            size_t workspace_bytes, pu_stream_t stream);
+PU_API int pu_locse_bn_prepare(const float *mom, long long count, const float *w, int h, const float *bias,
+                               const float *gamma, const float *beta, float eps, int training, float *moving_mean,
+                               float *moving_var, float momentum, float unbias, float *coef, pu_stream_t stream);
+PU_API int pu_locse_mlp_fwd(const float *xyz, const int32_t *idx, int B, int N, int K, const float *w, int h,
+                            const float *coef, float slope, float *out, int ldo, float *out2, int ldo2, pu_stream_t stream);
+PU_API int pu_locse_mlp_bwd(const float *xyz, const int32_t *idx, int B, int N, int K, const float *w, int h,
+                            const float *coef, const float *gamma, const float *bias, int training, float slope,
+                            const float *dz, int ldz, const float *dz2, int ldz2, float *dw, int accumulate_dw, float *dbias, float *dgamma, float *dbeta,
+                            void *workspace, size_t workspace_bytes, pu_stream_t stream);
+
 /* ref: Network.random_sample  RandLANet.py:345-360   out[b,m,:] = max_k feat[b, pool_idx[b,m,k], :]
  *   ties (uint8 [B*M, d], optional) = how many neighbours attain the max; the backward splits the gradient
  *   evenly among exact ties like tf.reduce_max and walks the inverse list of pool_idx (scatter-free). */

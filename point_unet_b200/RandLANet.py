@@ -365,9 +365,18 @@ class Network(torch.nn.Module):
     def building_block(self, xyz, feature, neigh_idx, d_out, name, is_training):
         """RandLANet.py:323-335.  Same dataflow; the two tf.concat's are produced in place by ops.lfa_concat (gather into
         the left half, BN + LeakyReLU of the position MLP into the right half)."""
-        f_xyz = self.relative_pos_encoding(xyz, neigh_idx)
-        y, m, v, g, b, mv = self._linear_stats(f_xyz, name + "mlp1", is_training)
-        f_concat, f_xyz = ops.lfa_concat(feature.squeeze(2), neigh_idx, y, m, v, g, b, is_training, mv, need_fxyz=True)
+        scope = name + "mlp1"
+        h = self.v(scope + "/weights").shape[1]
+        if ops.locse_mlp_supported(neigh_idx.shape[-1], h):   # LocSE + mlp1 + BN + LeakyReLU recomputed inside one kernel each way (csrc/locse_mlp.cu)
+            rows_n = neigh_idx.numel()
+            f_concat, f_xyz = ops.locse_mlp_concat(
+                xyz, feature.squeeze(2), neigh_idx, self.v(scope + "/weights"), self.v(scope + "/biases"),
+                self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta"), is_training, self.v(scope + "/bn/moving_mean"),
+                self.v(scope + "/bn/moving_variance"), rows_n / max(rows_n - 1, 1), is_training and torch.is_grad_enabled())
+        else:
+            f_xyz = self.relative_pos_encoding(xyz, neigh_idx)
+            y, m, v, g, b, mv = self._linear_stats(f_xyz, scope, is_training)
+            f_concat, f_xyz = ops.lfa_concat(feature.squeeze(2), neigh_idx, y, m, v, g, b, is_training, mv, need_fxyz=True)
         f_pc_agg = self.att_pooling(f_concat, d_out // 2, name + "att_pooling_1", is_training)
         y, m, v, g, b, mv = self._linear_stats(f_xyz, name + "mlp2", is_training)
         f_concat, _ = ops.lfa_concat(f_pc_agg.squeeze(2), neigh_idx, y, m, v, g, b, is_training, mv, need_fxyz=False)

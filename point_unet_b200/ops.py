@@ -78,6 +78,14 @@ _lib._OP_SIGS.update({
     "pu_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                            c_int, c_void_p],
     "pu_att16_fwd": [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_int, c_void_p],
+    "pu_locse_moments": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    "pu_locse_bn_prepare": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
+                            c_float, c_float, c_void_p, c_void_p],
+    "pu_locse_mlp_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                         c_int, c_void_p],
+    "pu_locse_mlp_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                         c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                         c_void_p],
     "pu_att16_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t,
                      c_void_p],
 })
@@ -91,6 +99,9 @@ TC_MODE = int(_os.environ.get("PU_TC_MODE", "3"))
 ATT16 = int(_os.environ.get("PU_ATT16", "1")) != 0
 # d = 64 attentive pooling backward with the dgrad through the FC fused into the tcgen05 kernel; 0 = separate accumulate GEMM
 ATT_BWD_FUSED = int(_os.environ.get("PU_ATT_BWD_FUSED", "1")) != 0
+# position branch of building_block (LocSE -> 10->h conv -> BN -> LeakyReLU) as recompute kernels (csrc/locse_mlp.cu);
+# 0 = the separate relative_pos_encoding / linear / batch-norm kernels
+LOCSE_FUSED = int(_os.environ.get("PU_LOCSE_FUSED", "1")) != 0
 # Storage mode of the pre-normalisation activations y (output of every 1x1 conv that feeds a batch norm; kept from the forward
 # for the batch-norm backward -- the largest saved tensors of a training step): "fp32" (default, the parity path) or "bf16"
 # (opt-in: y is rounded to bfloat16 when stored, arithmetic and batch statistics stay fp32; stated tolerance rel-L2 <= 2e-2 on
@@ -135,6 +146,9 @@ def _L():
         L.pu_att16_supported.argtypes = [c_int, c_int, c_int]
         L.pu_att16_workspace_bytes.restype = c_size_t
         L.pu_att16_workspace_bytes.argtypes = [c_ll]
+        L.pu_locse_mlp_supported.argtypes = [c_int, c_int]
+        L.pu_locse_mlp_workspace_bytes.restype = c_size_t
+        L.pu_locse_mlp_workspace_bytes.argtypes = [c_int]
         L._pu_extra_declared = True
     return L
 
@@ -854,6 +868,93 @@ def lfa_concat(f_pc, idx, y, mean, var, gamma, beta, training=True, moving=None,
     res = _LFAConcatFn.apply(f_pc, idx, ya, mean, var, gamma, beta, training, moving, need_fxyz,
                              (yd, key) if key is not None else None)
     return res if need_fxyz else (res, None)
+
+
+class _LocSEMlpConcatFn(torch.autograd.Function):
+    """``concat([gather_neighbour(f_pc, idx), lrelu(BN(conv2d(relative_pos_encoding(xyz, idx))))], -1)`` -- the first half of
+    building_block (RandLANet.py:323-328) -- through the recompute kernels of csrc/locse_mlp.cu: the LocSE rows, the
+    pre-normalisation tensor and its gradient are never stored; the batch statistics come from the 10x10 covariance of the
+    LocSE rows and the weight gradient from the closed form given in that file."""
+
+    @staticmethod
+    def forward(ctx, f_pc, idx, xyz, w, bias, gamma, beta, training, mm, mv, unbias, update_moving):
+        xyz = xyz.detach().contiguous().float()
+        idx = _idx32(idx)
+        w = w.contiguous()
+        B, N, K = idx.shape
+        h = w.shape[1]
+        dev = xyz.device
+        L = _L()
+        st = _stream(xyz)
+        coef = torch.empty(5 * h + 112, dtype=torch.float32, device=dev)
+        mom = None
+        if training:
+            mom = torch.empty(65, dtype=torch.float32, device=dev)
+            ws = workspace(L.pu_locse_mlp_workspace_bytes(h), dev, slot=6)
+            _call("pu_locse_moments", xyz.data_ptr(), idx.data_ptr(), B, N, K, mom.data_ptr(), ws.data_ptr(), ws.numel(), st,
+                  tag=(B * N * K,))
+        upd = training and update_moving
+        _call("pu_locse_bn_prepare", mom.data_ptr() if training else None, B * N * K, w.data_ptr(), h, bias.data_ptr(),
+              gamma.data_ptr(), beta.data_ptr(), BN_EPS, int(bool(training)),
+              mm.data_ptr() if (upd or not training) else None, mv.data_ptr() if (upd or not training) else None, BN_MOMENTUM,
+              float(unbias), coef.data_ptr(), st)
+        buf = torch.empty((B, N, K, 2 * h), dtype=torch.float32, device=dev)
+        gather_rows(f_pc, idx, out=buf[..., :h])
+        f_xyz = torch.empty((B, N, K, h), dtype=torch.float32, device=dev)
+        _call("pu_locse_mlp_fwd", xyz.data_ptr(), idx.data_ptr(), B, N, K, w.data_ptr(), h, coef.data_ptr(), LEAKY_SLOPE,
+              buf.data_ptr() + 4 * h, 2 * h, f_xyz.data_ptr(), h, st, tag=(B * N * K, h))
+        ctx.save_for_backward(xyz, w, coef, gamma, bias)
+        ctx.idx, ctx.dims = idx, (B, N, K, h, f_pc.shape[1])
+        ctx.params = (w, bias, gamma, beta)
+        ctx.training = training
+        ctx.set_materialize_grads(False)
+        return buf, f_xyz
+
+    @staticmethod
+    def backward(ctx, d_buf, d_fxyz):
+        xyz, w, coef, gamma, bias = ctx.saved_tensors
+        B, N, K, h, n_src = ctx.dims
+        dev = xyz.device
+        if d_buf is None:
+            d_buf = torch.zeros((B, N, K, 2 * h), dtype=torch.float32, device=dev)
+        inv = inverse_of(ctx.idx, n_src)
+        d_fpc = segment_sum(d_buf[..., :h], inv, h).view(B, n_src, h)
+        dz, R, _, ldz = rows(d_buf[..., h:])
+        d2ptr, ld2 = None, 0
+        if d_fxyz is not None:
+            d2, R2, _, ld2 = rows(d_fxyz)
+            assert R2 == R
+            d2ptr = d2.data_ptr()
+        wp, bp, gp, bep = ctx.params
+        gw, gb, sk = _sink(wp), _sink(bp), _bn_sink(gp, bep)
+        dw = gw if gw is not None else torch.empty((10, h), dtype=torch.float32, device=dev)
+        if sk is not None:
+            dg, dbeta = sk
+        else:
+            dg = torch.empty(h, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(h, dtype=torch.float32, device=dev)
+        db = None if gb is not None else torch.empty(h, dtype=torch.float32, device=dev)
+        ws = workspace(_L().pu_locse_mlp_workspace_bytes(h), dev, slot=6)
+        _call("pu_locse_mlp_bwd", xyz.data_ptr(), ctx.idx.data_ptr(), B, N, K, w.data_ptr(), h, coef.data_ptr(), gamma.data_ptr(),
+              bias.data_ptr(), int(bool(ctx.training)), LEAKY_SLOPE, dz.data_ptr(), ldz, d2ptr, ld2, dw.data_ptr(), int(gw is not None),
+              db.data_ptr() if db is not None else None, dg.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(),
+              _stream(xyz), tag=(B * N * K, h))
+        return (d_fpc, None, None, None if gw is not None else dw, db, None if sk is not None else dg,
+                None if sk is not None else dbeta, None, None, None, None, None)
+
+
+def locse_mlp_supported(K: int, h: int) -> bool:
+    return LOCSE_FUSED and bool(_L().pu_locse_mlp_supported(int(K), int(h)))
+
+
+def locse_mlp_concat(xyz, f_pc, idx, w, bias, gamma, beta, training=True, moving_mean=None, moving_var=None, unbias=1.0,
+                     update_moving=False):
+    """Fused position branch of building_block; returns ``(concat [B,N,K,2h], f_xyz [B,N,K,h])``.  ``moving_mean`` /
+    ``moving_var`` are the statistics used at inference and, with ``update_moving``, updated in place in training."""
+    _need_cuda(xyz, f_pc, idx, w)
+    return _LocSEMlpConcatFn.apply(f_pc, idx, xyz, w, bias, gamma, beta, bool(training), moving_mean, moving_var, float(unbias),
+                                   bool(update_moving))
+
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,132 @@
+"""GPU parity of the fused position branch of building_block (csrc/locse_mlp.cu) against the oracle restatement in fp64
+(oracle/randla_ref.py: relative_pos_encoding -> conv2d 'mlp1' -> BN -> LeakyReLU -> concat with the gathered features,
+RandLANet.py:323-328) and against the unfused kernels.  Tolerance 1e-3 relative per tensor (north_star); measured ~1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import randla_ref as ref
+from point_unet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+def make_case(B, N, K, h, seed, offset=0.0):
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.rand(B, N, 3, generator=g) * 2.0 + offset   # an off-centre cloud: the centring of x must cope with it
+    idx = torch.randint(0, N, (B, N, K), generator=g, dtype=torch.int32)
+    idx[:, :, 0] = torch.arange(N, dtype=torch.int32)[None]
+    f_pc = torch.randn(B, N, h, generator=g)
+    p = {"s/weights": torch.randn(10, h, generator=g) * (2 / h) ** 0.5, "s/biases": torch.randn(h, generator=g) * 0.1,
+         "s/bn/gamma": torch.rand(h, generator=g) + 0.5, "s/bn/beta": torch.randn(h, generator=g) * 0.1,
+         "s/bn/moving_mean": torch.randn(h, generator=g) * 0.1, "s/bn/moving_variance": torch.rand(h, generator=g) + 0.5}
+    d_buf = torch.randn(B, N, K, 2 * h, generator=g)
+    d_fxyz = torch.randn(B, N, K, h, generator=g)
+    return xyz, idx, f_pc, p, d_buf, d_fxyz
+
+
+def oracle_branch(xyz, idx, f_pc, p, training, upd=None):
+    f_xyz = ref.relative_pos_encoding(xyz, idx)
+    f_xyz = ref.conv2d(f_xyz, p, "s", True, training, True, upd)
+    return torch.cat([ref.gather_neighbour(f_pc, idx), f_xyz], dim=-1), f_xyz
+
+
+@pytest.mark.parametrize("B,N,K,h,offset", [(2, 1500, 16, 8, 0.0), (3, 700, 16, 32, 50.0), (1, 333, 5, 64, 0.0),
+                                            (2, 300, 16, 128, 3.0), (1, 130, 16, 256, 0.0), (1, 1, 16, 8, 0.0)])
+def test_locse_mlp_training_fwd_bwd_vs_oracle(B, N, K, h, offset):
+    if not ops.locse_mlp_supported(K, h):
+        pytest.skip("fused LocSE branch switched off")
+    xyz, idx, f_pc, p, d_buf, d_fxyz = make_case(B, N, K, h, 100 + h, offset)
+    pr = {k: v.double().requires_grad_(not k.startswith("s/bn/moving")) for k, v in p.items()}
+    fr = f_pc.double().requires_grad_(True)
+    upd = {}
+    cat_r, fx_r = oracle_branch(xyz.double(), idx, fr, pr, True, upd)
+    ((cat_r * d_buf.double()).sum() + (fx_r * d_fxyz.double()).sum()).backward()
+
+    pg = {k: v.cuda().requires_grad_(not k.startswith("s/bn/moving")) for k, v in p.items()}
+    fg = f_pc.cuda().requires_grad_(True)
+    rows_n = B * N * K
+    unbias = rows_n / max(rows_n - 1, 1)
+    cat, fx = ops.locse_mlp_concat(xyz.cuda(), fg, idx.cuda(), pg["s/weights"], pg["s/biases"], pg["s/bn/gamma"], pg["s/bn/beta"],
+                                   True, pg["s/bn/moving_mean"], pg["s/bn/moving_variance"], unbias, True)
+    assert cat.shape == (B, N, K, 2 * h) and fx.shape == (B, N, K, h)
+    assert torch.equal(cat[..., :h].cpu(), cat_r[..., :h].detach().float())   # the gathered half is a copy
+    assert torch.equal(cat[..., h:], fx)
+    assert rel_err(cat, cat_r) < TOL * 0.1
+    # moving statistics: momentum 0.99 with TF's unbiased-variance quirk (helper_tf_util.py:553-574)
+    mean, var, cnt = upd["s/bn"]
+    want_mm = 0.99 * p["s/bn/moving_mean"].double() + 0.01 * mean
+    want_mv = 0.99 * p["s/bn/moving_variance"].double() + 0.01 * var * cnt / max(cnt - 1, 1)
+    assert rel_err(pg["s/bn/moving_mean"], want_mm) < 1e-5
+    assert rel_err(pg["s/bn/moving_variance"], want_mv) < 1e-5
+    if rows_n < 64:   # a batch norm over a handful of rows: the backward is all cancellation, forward checked above
+        return
+    ((cat * d_buf.cuda()).sum() + (fx * d_fxyz.cuda()).sum()).backward()
+    assert rel_err(fg.grad, fr.grad) < 1e-5
+    for k in ("s/weights", "s/bn/gamma", "s/bn/beta"):
+        assert rel_err(pg[k].grad, pr[k].grad) < TOL, (k, rel_err(pg[k].grad, pr[k].grad))
+    assert float(pg["s/biases"].grad.abs().max()) == 0.0   # analytically zero through a training-mode batch norm
+
+
+def test_locse_mlp_matches_unfused_kernels_and_is_deterministic():
+    B, N, K, h = 2, 4000, 16, 32
+    xyz, idx, f_pc, p, d_buf, d_fxyz = make_case(B, N, K, h, 7)
+    xyz, idx, d_buf, d_fxyz = xyz.cuda(), idx.cuda(), d_buf.cuda(), d_fxyz.cuda()
+
+    def run(fused):
+        pg = {k: v.cuda().requires_grad_(not k.startswith("s/bn/moving")) for k, v in p.items()}
+        fg = f_pc.cuda().requires_grad_(True)
+        if fused:
+            cat, fx = ops.locse_mlp_concat(xyz, fg, idx, pg["s/weights"], pg["s/biases"], pg["s/bn/gamma"], pg["s/bn/beta"], True,
+                                           pg["s/bn/moving_mean"], pg["s/bn/moving_variance"], 1.0, False)
+        else:
+            x = ops.relative_pos_encoding(xyz, idx)
+            y, m, v = ops.linear(x, pg["s/weights"], pg["s/biases"], want_stats=True, zero_bias_grad=True, defer_stats=True)
+            cat, fx = ops.lfa_concat(fg, idx, y, m, v, pg["s/bn/gamma"], pg["s/bn/beta"], True, None, need_fxyz=True)
+        ((cat * d_buf).sum() + (fx * d_fxyz).sum()).backward()
+        return [cat.detach(), fg.grad] + [pg[k].grad for k in ("s/weights", "s/bn/gamma", "s/bn/beta")]
+
+    a, b, c = run(True), run(True), run(False)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)            # bit-deterministic
+    for u, v in zip(a, c):
+        assert rel_err(u, v) < 1e-4
+
+
+@pytest.mark.parametrize("h", [8, 64])
+def test_locse_mlp_inference_mode(h):
+    B, N, K = 2, 900, 16
+    xyz, idx, f_pc, p, d_buf, d_fxyz = make_case(B, N, K, h, 31 + h)
+    pr = {k: v.double().requires_grad_(not k.startswith("s/bn/moving")) for k, v in p.items()}
+    fr = f_pc.double().requires_grad_(True)
+    cat_r, fx_r = oracle_branch(xyz.double(), idx, fr, pr, False)
+    ((cat_r * d_buf.double()).sum() + (fx_r * d_fxyz.double()).sum()).backward()
+    pg = {k: v.cuda().requires_grad_(not k.startswith("s/bn/moving")) for k, v in p.items()}
+    fg = f_pc.cuda().requires_grad_(True)
+    mm0 = pg["s/bn/moving_mean"].clone()
+    cat, fx = ops.locse_mlp_concat(xyz.cuda(), fg, idx.cuda(), pg["s/weights"], pg["s/biases"], pg["s/bn/gamma"], pg["s/bn/beta"],
+                                   False, pg["s/bn/moving_mean"], pg["s/bn/moving_variance"], 1.0, False)
+    assert rel_err(cat, cat_r) < TOL * 0.1
+    assert torch.equal(pg["s/bn/moving_mean"], mm0)   # untouched at inference
+    ((cat * d_buf.cuda()).sum() + (fx * d_fxyz.cuda()).sum()).backward()
+    for k in ("s/weights", "s/biases", "s/bn/gamma", "s/bn/beta"):
+        assert rel_err(pg[k].grad, pr[k].grad) < TOL, k
+    assert rel_err(fg.grad, fr.grad) < 1e-5
+
+
+def test_locse_mlp_argument_validation():
+    L = ops._L()
+    assert L.pu_locse_mlp_supported(16, 8) == 1 and L.pu_locse_mlp_supported(16, 24) == 0
+    x = torch.zeros(1, 8, 3, device="cuda")
+    i = torch.zeros(1, 8, 16, dtype=torch.int32, device="cuda")
+    mom = torch.zeros(65, device="cuda")
+    assert L.pu_locse_moments(x.data_ptr(), i.data_ptr(), 1, 8, 16, mom.data_ptr(), None, 0, None) == -2   # PU_ERR_WORKSPACE
+    assert L.pu_locse_moments(None, i.data_ptr(), 1, 8, 16, mom.data_ptr(), None, 0, None) == -1            # PU_ERR_INVALID_ARG
