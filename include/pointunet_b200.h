@@ -103,6 +103,8 @@ PU_API int pu_relative_pos_encoding_fwd(const float *xyz, const int32_t *idx, in
 /* ref: building_block, position branch  RandLANet.py:323-326:  relative_pos_encoding -> conv2d(10 -> h, 'mlp1') ->
  *   BN(0.99, 1e-6) -> LeakyReLU(0.2), as recompute kernels (csrc/locse_mlp.cu): neither the 10-channel LocSE rows nor the
  *   pre-normalisation tensor nor its gradient are ever stored.  h = power of two in [4, 1024].
+ *   The kernels read the cloud as padded points xyz4 [B,N,4] = (x, y, z, 0), 16-byte aligned (one 128-bit access per end
+ *   point instead of three scalar gathers): pu_locse_pack_xyz makes that copy from xyz [n_points, 3].
  *   pu_locse_moments:    mom[0:10] = column sums of the LocSE rows over all B*N*K rows, mom[10:65] = centred second-moment
  *                        sums (upper triangle, row-major); the batch statistics of the conv output follow from them.
  *   pu_locse_bn_prepare: coef (5h + 110 floats, 16-byte aligned): scale | t | invstd | mean_y | var_y | xbar(10) | Cov(100).
@@ -114,14 +116,15 @@ PU_API int pu_relative_pos_encoding_fwd(const float *xyz, const int32_t *idx, in
  *                        is no dgrad (xyz is data).  Deterministic. */
 PU_API int pu_locse_mlp_supported(int K, int h);
 PU_API size_t pu_locse_mlp_workspace_bytes(int h);
-PU_API int pu_locse_moments(const float *xyz, const int32_t *idx, int B, int N, int K, float *mom, void *workspace,
+PU_API int pu_locse_pack_xyz(const float *xyz, long long n_points, float *xyz4, pu_stream_t stream);
+PU_API int pu_locse_moments(const float *xyz4, const int32_t *idx, int B, int N, int K, float *mom, void *workspace,
                             size_t workspace_bytes, pu_stream_t stream);
 PU_API int pu_locse_bn_prepare(const float *mom, long long count, const float *w, int h, const float *bias,
                                const float *gamma, const float *beta, float eps, int training, float *moving_mean,
                                float *moving_var, float momentum, float unbias, float *coef, pu_stream_t stream);
-PU_API int pu_locse_mlp_fwd(const float *xyz, const int32_t *idx, int B, int N, int K, const float *w, int h,
+PU_API int pu_locse_mlp_fwd(const float *xyz4, const int32_t *idx, int B, int N, int K, const float *w, int h,
                             const float *coef, float slope, float *out, int ldo, float *out2, int ldo2, pu_stream_t stream);
-PU_API int pu_locse_mlp_bwd(const float *xyz, const int32_t *idx, int B, int N, int K, const float *w, int h,
+PU_API int pu_locse_mlp_bwd(const float *xyz4, const int32_t *idx, int B, int N, int K, const float *w, int h,
                             const float *coef, const float *gamma, const float *bias, int training, float slope,
                             const float *dz, int ldz, const float *dz2, int ldz2, float *dw, int accumulate_dw, float *dbias, float *dgamma, float *dbeta,
                             void *workspace, size_t workspace_bytes, pu_stream_t stream);
@@ -285,6 +288,15 @@ PU_API int pu_att16_fwd(const float *feature_set, int ldx, const float *w, long 
 PU_API int pu_att16_bwd(const float *feature_set, int ldx, const float *w, const float *g_agg, int ldg, long long P,
                         float *dx, int lddx, float *dw, int accumulate, void *workspace, size_t workspace_bytes,
                         pu_stream_t stream);
+/* The same kernels with the 16 channels of a row in TWO tensors (x_lo: channels 0-7, x_hi: channels 8-15; likewise dx): the
+ * two halves of building_block's concat (RandLANet.py:328,333) kept as separate contiguous tensors -- at 8 channels a half
+ * row is 32 bytes, and reading / writing it inside a 64-byte row costs a full DRAM burst per half. */
+PU_API int pu_att16_supported_split(int K, int d, int ld_lo, int ld_hi);
+PU_API int pu_att16_fwd_split(const float *x_lo, int ld_lo, const float *x_hi, int ld_hi, const float *w, long long P,
+                              float *f_agg, int ldo, pu_stream_t stream);
+PU_API int pu_att16_bwd_split(const float *x_lo, int ld_lo, const float *x_hi, int ld_hi, const float *w, const float *g_agg,
+                              int ldg, long long P, float *dx_lo, int lddx_lo, float *dx_hi, int lddx_hi, float *dw,
+                              int accumulate, void *workspace, size_t workspace_bytes, pu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -117,7 +117,7 @@ def tf_variable_name(name: str) -> str:
 
 
 def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = None, inverse: bool = False,
-                  store: "dict | None" = None) -> dict:
+                  store: "dict | None" = None, locse: bool = False) -> dict:
     """``tf_map`` (runPancreas.py:124-145 / runBraTS.py:140-161) on the device: per level
     ``neigh_idx = knn(xyz, xyz, k_n)``, ``sub = xyz[:, :N//ratio]``, ``sub_idx = neigh_idx[:, :N//ratio]``,
     ``interp_idx = knn(sub, xyz, 1)``.  ``xyz`` is a CUDA ``[B,N,3]`` fp32 tensor; everything stays on the GPU.
@@ -129,6 +129,9 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
     ``pyramid_ready()`` makes the current stream wait for the remaining indices (Network.inference calls it before the
     first ``random_sample``) and ``inverse_ready()`` for the inverse lists (called before the backward).  All result
     tensors are allocated on the current stream; ``side`` only runs kernels.
+
+    ``locse``: also prepare, per level, what the fused position branch needs from the pyramid alone (``ops.locse_prepare``:
+    padded cloud + moments of the LocSE rows) as ``out["locse"]`` -- level 0 on the current stream, the others on ``side``.
 
     ``store`` (optional): preallocated result tensors -- ``xyz`` (num_layers + 1 clouds; ``xyz[0]`` receives a copy of the
     input), ``neigh_idx``, ``sub_idx``, ``interp_idx`` (num_layers each) and, with ``inverse``, ``inv`` = per level three
@@ -145,12 +148,17 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
             knn_search_cuda(clouds[i], clouds[i], cfg.k_n, out=store["neigh_idx"][i])
             store["sub_idx"][i].copy_(store["neigh_idx"][i][:, :clouds[i + 1].shape[1], :])
             knn_search_cuda(clouds[i + 1], clouds[i], 1, out=store["interp_idx"][i])
+            if "locse" in store:
+                ops.locse_prepare(clouds[i], store["neigh_idx"][i], out=store["locse"][i])
             if inverse:
                 n, n_sub = clouds[i].shape[1], clouds[i + 1].shape[1]
                 for idx, n_src, o in zip((store["neigh_idx"][i], store["sub_idx"][i], store["interp_idx"][i]),
                                          (n, n, n_sub), store["inv"][i]):
                     ops.InverseIndex(idx, n_src, out=o)
-        return dict(xyz=clouds[:-1], neigh_idx=store["neigh_idx"], sub_idx=store["sub_idx"], interp_idx=store["interp_idx"])
+        res = dict(xyz=clouds[:-1], neigh_idx=store["neigh_idx"], sub_idx=store["sub_idx"], interp_idx=store["interp_idx"])
+        if "locse" in store:
+            res["locse"] = store["locse"]
+        return res
     out = dict(xyz=[], neigh_idx=[], sub_idx=[], interp_idx=[])
     xyz = xyz.contiguous().float()
     B, dev = xyz.shape[0], xyz.device
@@ -161,6 +169,9 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
         out["neigh_idx"].append(torch.empty((B, n, cfg.k_n), dtype=torch.int32, device=dev))
         out["sub_idx"].append(torch.empty((B, n_sub, cfg.k_n), dtype=torch.int32, device=dev))
         out["interp_idx"].append(torch.empty((B, n, 1), dtype=torch.int32, device=dev))
+        if locse:
+            out.setdefault("locse", []).append((torch.empty((B, n, 4), dtype=torch.float32, device=dev),
+                                                torch.empty(68, dtype=torch.float32, device=dev)))
         xyz = xyz[:, :n_sub, :].contiguous()
     subs = out["xyz"][1:] + [xyz]
 
@@ -168,6 +179,8 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
         pts = out["xyz"][i]
         if i > 0 or side is None:
             knn_search_cuda(pts, pts, cfg.k_n, out=out["neigh_idx"][i])
+            if locse:
+                ops.locse_prepare(pts, out["neigh_idx"][i], out=out["locse"][i])
         out["sub_idx"][i].copy_(out["neigh_idx"][i][:, :subs[i].shape[1], :])
         knn_search_cuda(subs[i], pts, 1, out=out["interp_idx"][i])
 
@@ -177,6 +190,8 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
         return out
     main = torch.cuda.current_stream(dev)
     knn_search_cuda(out["xyz"][0], out["xyz"][0], cfg.k_n, out=out["neigh_idx"][0])
+    if locse:
+        ops.locse_prepare(out["xyz"][0], out["neigh_idx"][0], out=out["locse"][0])
     side.wait_stream(main)
     ev = torch.cuda.Event()
     with torch.cuda.stream(side):
@@ -362,29 +377,43 @@ class Network(torch.nn.Module):
         mean, var, moving = self._bn_stats(scope, mean, var, rows_n, is_training)
         return y, mean, var, self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta"), moving
 
-    def building_block(self, xyz, feature, neigh_idx, d_out, name, is_training):
-        """RandLANet.py:323-335.  Same dataflow; the two tf.concat's are produced in place by ops.lfa_concat (gather into
-        the left half, BN + LeakyReLU of the position MLP into the right half)."""
+    def building_block(self, xyz, feature, neigh_idx, d_out, name, is_training, locse_pre=None):
+        """RandLANet.py:323-335.  Same dataflow.  The position branch (LocSE -> mlp1 -> BN -> LeakyReLU) runs as recompute
+        kernels (csrc/locse_mlp.cu); the two tf.concat's are produced in place by ops.lfa_concat (gather into the left half,
+        BN + LeakyReLU of the position MLP into the right half) -- or, at the 16-channel level, not at all: the att16 kernels
+        take the two halves as separate tensors (32-byte half rows inside 64-byte rows waste half of every DRAM burst)."""
         scope = name + "mlp1"
         h = self.v(scope + "/weights").shape[1]
-        if ops.locse_mlp_supported(neigh_idx.shape[-1], h):   # LocSE + mlp1 + BN + LeakyReLU recomputed inside one kernel each way (csrc/locse_mlp.cu)
+        K = neigh_idx.shape[-1]
+        fused = ops.locse_mlp_supported(K, h)
+        split = fused and ops.att_pool_split_supported(K, 2 * h)
+        if fused:   # LocSE + mlp1 + BN + LeakyReLU recomputed inside one kernel each way
             rows_n = neigh_idx.numel()
             f_concat, f_xyz = ops.locse_mlp_concat(
-                xyz, feature.squeeze(2), neigh_idx, self.v(scope + "/weights"), self.v(scope + "/biases"),
+                xyz, None if split else feature.squeeze(2), neigh_idx, self.v(scope + "/weights"), self.v(scope + "/biases"),
                 self.v(scope + "/bn/gamma"), self.v(scope + "/bn/beta"), is_training, self.v(scope + "/bn/moving_mean"),
-                self.v(scope + "/bn/moving_variance"), rows_n / max(rows_n - 1, 1), is_training and torch.is_grad_enabled())
+                self.v(scope + "/bn/moving_variance"), rows_n / max(rows_n - 1, 1), is_training and torch.is_grad_enabled(),
+                pre=locse_pre)
         else:
             f_xyz = self.relative_pos_encoding(xyz, neigh_idx)
             y, m, v, g, b, mv = self._linear_stats(f_xyz, scope, is_training)
             f_concat, f_xyz = ops.lfa_concat(feature.squeeze(2), neigh_idx, y, m, v, g, b, is_training, mv, need_fxyz=True)
+        if split:   # f_concat is the first alias of f_xyz here
+            f_agg = ops.att_pool_split(self.gather_neighbour(feature.squeeze(2), neigh_idx), f_concat,
+                                       self.v(name + "att_pooling_1fc/kernel"))
+            f_pc_agg = self.conv2d(f_agg, name + "att_pooling_1mlp", True, is_training, True)
+            f_xyz = self.conv2d(f_xyz, name + "mlp2", True, is_training, True)
+            f_agg = ops.att_pool_split(self.gather_neighbour(f_pc_agg.squeeze(2), neigh_idx), f_xyz,
+                                       self.v(name + "att_pooling_2fc/kernel"))
+            return self.conv2d(f_agg, name + "att_pooling_2mlp", True, is_training, True)
         f_pc_agg = self.att_pooling(f_concat, d_out // 2, name + "att_pooling_1", is_training)
         y, m, v, g, b, mv = self._linear_stats(f_xyz, name + "mlp2", is_training)
         f_concat, _ = ops.lfa_concat(f_pc_agg.squeeze(2), neigh_idx, y, m, v, g, b, is_training, mv, need_fxyz=False)
         return self.att_pooling(f_concat, d_out, name + "att_pooling_2", is_training)
 
-    def dilated_res_block(self, feature, xyz, neigh_idx, d_out, name, is_training):
+    def dilated_res_block(self, feature, xyz, neigh_idx, d_out, name, is_training, locse_pre=None):
         f_pc = self.conv2d(feature, name + "mlp1", True, is_training)
-        f_pc = self.building_block(xyz, f_pc, neigh_idx, d_out, name + "LFA", is_training)
+        f_pc = self.building_block(xyz, f_pc, neigh_idx, d_out, name + "LFA", is_training, locse_pre)
         # mlp2 / shortcut: BN without activation, then leaky_relu(sum)  (RandLANet.py:317-321), one fused kernel
         outs = []
         for x, scope in ((f_pc, name + "mlp2"), (feature, name + "shortcut")):
@@ -406,9 +435,10 @@ class Network(torch.nn.Module):
         feature = self.conv2d(inputs["features"], "fc0", True, is_training, True, dense_names=True)
         feature = feature.unsqueeze(2)
         f_encoder_list = []
+        pre = inputs.get("locse") if is_training else None   # (padded cloud, LocSE moments) per level, from build_pyramid
         for i in range(cfg.num_layers):
             f_encoder_i = self.dilated_res_block(feature, inputs["xyz"][i], inputs["neigh_idx"][i], cfg.d_out[i],
-                                                 "Encoder_layer_" + str(i), is_training)
+                                                 "Encoder_layer_" + str(i), is_training, pre[i] if pre is not None else None)
             if i == 0 and "pyramid_ready" in inputs:
                 inputs["pyramid_ready"]()  # the rest of the index pyramid was built on a side stream (build_pyramid)
             f_sampled_i = self.random_sample(f_encoder_i, inputs["sub_idx"][i])

@@ -64,14 +64,19 @@ __device__ __forceinline__ void store_row16(float *p, const float (&v)[16]) {
 }
 
 // stage the x tiles of point pair `pair` (2 KB, coalesced 16-byte chunks); points past the end are zero-filled
-__device__ __forceinline__ void issue_pair(const float *__restrict__ x, int ldx, long long P, long long pair, float *stage,
+// The 16 channels of a row may live in two tensors (xa: channels 0-7, row stride lda; xb: channels 8-15, row stride ldb) --
+// the two halves of building_block's concat kept as separate, contiguous tensors (a 32-byte half row inside a 64-byte row
+// costs a full DRAM burst per half).  One concat tensor is the special case xb = xa + 8, ldb = lda.
+// (a lane always moves the same 16-byte column chunk q = lane & 3 of a row, so the tensor and stride it addresses are fixed
+// for its lifetime: xq = base of its chunk's tensor + column offset, ldq = that tensor's row stride)
+__device__ __forceinline__ void issue_pair(const float *__restrict__ xq, int ldq, long long P, long long pair, float *stage,
                                            int lane) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int chunk = lane + 32 * i, h = chunk >> 6, r = chunk & 63, k = r >> 2, q = r & 3;
         const long long p = pair * 2 + h;
         float *dst = stage + h * TILE + k * RS + q * 4;
-        if (p < P) cp_async16(dst, x + ((size_t)p * KN + k) * ldx + q * 4);
+        if (p < P) cp_async16(dst, xq + ((size_t)p * KN + k) * ldq);
         else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
@@ -173,9 +178,12 @@ __device__ __forceinline__ float softmax16(float (&a)[16]) {
 
 template <int SLOT>
 __global__ void __launch_bounds__(WARPS * 32, 2)
-    att16_fwd_kernel(const float *__restrict__ x, int ldx, long long P, float *__restrict__ out, int ldo) {
+    att16_fwd_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ xb, int ldxb, long long P,
+                     float *__restrict__ out, int ldo) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, t = lane & 15;
+    const float *xq = (lane & 2) ? xb + ((lane & 3) - 2) * 4 : x + (lane & 3) * 4;
+    const int ldq = (lane & 2) ? ldxb : ldx;
     float *wb = smem + (size_t)wib * FWD_TILES * TILE;
     float *T = wb + (STAGES * 2 + half) * TILE;
     const long long npairs = (P + 1) >> 1;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (pair + s * nw < npairs) issue_pair(x, ldx, P, pair + s * nw, wb + s * 2 * TILE, lane);
+        if (pair + s * nw < npairs) issue_pair(xq, ldq, P, pair + s * nw, wb + s * 2 * TILE, lane);
         cp_async_commit();
     }
 #pragma unroll 1
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         const int stage = it % STAGES;
         {
             const long long nxt = pair + (STAGES - 1) * nw;
-            if (nxt < npairs) issue_pair(x, ldx, P, nxt, wb + ((it + STAGES - 1) % STAGES) * 2 * TILE, lane);
+            if (nxt < npairs) issue_pair(xq, ldq, P, nxt, wb + ((it + STAGES - 1) % STAGES) * 2 * TILE, lane);
             cp_async_commit();
         }
         cp_async_wait<STAGES - 1>();
@@ -221,11 +229,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
 
 template <int SLOT>
 __global__ void __launch_bounds__(WARPS * 32, 2)
-    att16_bwd_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ g_agg, int ldg, long long P,
-                     float *__restrict__ dx, int lddx, float *__restrict__ dw_part) {
+    att16_bwd_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ xb, int ldxb,
+                     const float *__restrict__ g_agg, int ldg, long long P, float *__restrict__ dx, int lddx,
+                     float *__restrict__ dxb, int lddxb, float *__restrict__ dw_part) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, t = lane & 15;
     const int jq = t >> 2, cq = t & 3;
+    const float *xq = (lane & 2) ? xb + ((lane & 3) - 2) * 4 : x + (lane & 3) * 4;
+    const int ldq = (lane & 2) ? ldxb : ldx;
+    float *dxq = (lane & 2) ? dxb + ((lane & 3) - 2) * 4 : dx + (lane & 3) * 4;
+    const int lddq = (lane & 2) ? lddxb : lddx;
     float *wb = smem + (size_t)wib * BWD_TILES * TILE;
     float *T = wb + (STAGES * 2 + half) * TILE;      // act^T, later E = g*s (row layout)
     float *Dt = wb + (STAGES * 2 + 2 + half) * TILE; // d_act (row layout)
@@ -239,7 +252,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (pair + s * nw < npairs) issue_pair(x, ldx, P, pair + s * nw, wb + s * 2 * TILE, lane);
+        if (pair + s * nw < npairs) issue_pair(xq, ldq, P, pair + s * nw, wb + s * 2 * TILE, lane);
         cp_async_commit();
     }
     float g_next = (pair * 2 + half < P) ? g_agg[(size_t)(pair * 2 + half) * ldg + t] : 0.f;
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         const int stage = it % STAGES;
         {
             const long long nxt = pair + (STAGES - 1) * nw;
-            if (nxt < npairs) issue_pair(x, ldx, P, nxt, wb + ((it + STAGES - 1) % STAGES) * 2 * TILE, lane);
+            if (nxt < npairs) issue_pair(xq, ldq, P, nxt, wb + ((it + STAGES - 1) % STAGES) * 2 * TILE, lane);
             cp_async_commit();
         }
         cp_async_wait<STAGES - 1>();
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
             const int chunk = lane + 32 * i, h = chunk >> 6, r = chunk & 63, k = r >> 2, q = r & 3;
             const long long pp = pair * 2 + h;
             if (pp < P)
-                st_stream_f4(reinterpret_cast<float4 *>(dx + ((size_t)pp * KN + k) * lddx + q * 4),
+                st_stream_f4(reinterpret_cast<float4 *>(dxq + ((size_t)pp * KN + k) * lddq),
                              *reinterpret_cast<const float4 *>(Xw + h * TILE + k * RS + q * 4));
         }
         __syncwarp();
@@ -381,7 +394,8 @@ static int pick_slot(cudaStream_t st) {
 }
 
 template <int SLOT>
-static int launch_fwd(const float *x, int ldx, const float *w, long long P, float *out, int ldo, cudaStream_t st) {
+static int launch_fwd(const float *x, int ldx, const float *xb, int ldxb, const float *w, long long P, float *out, int ldo,
+                      cudaStream_t st) {
     constexpr size_t smem = (size_t)WARPS * FWD_TILES * TILE * sizeof(float);
     static bool attr[64] = {};  // per device: the attribute belongs to the device's copy of the function
     int dev = 0;
@@ -392,14 +406,14 @@ static int launch_fwd(const float *x, int ldx, const float *w, long long P, floa
     }
     PU_CUDA_TRY(cudaMemcpyToSymbolAsync(pu_att16_cw, w, D * D * sizeof(float), (size_t)SLOT * D * D * sizeof(float),
                                         cudaMemcpyDeviceToDevice, st));
-    att16_fwd_kernel<SLOT><<<plan_grid(P), WARPS * 32, smem, st>>>(x, ldx, P, out, ldo);
+    att16_fwd_kernel<SLOT><<<plan_grid(P), WARPS * 32, smem, st>>>(x, ldx, xb, ldxb, P, out, ldo);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
 
 template <int SLOT>
-static int launch_bwd(const float *x, int ldx, const float *w, const float *g, int ldg, long long P, float *dx, int lddx,
-                      float *dw, int accumulate, float *part, cudaStream_t st) {
+static int launch_bwd(const float *x, int ldx, const float *xb, int ldxb, const float *w, const float *g, int ldg, long long P,
+                      float *dx, int lddx, float *dxb, int lddxb, float *dw, int accumulate, float *part, cudaStream_t st) {
     constexpr size_t smem = (size_t)WARPS * BWD_TILES * TILE * sizeof(float);
     static_assert(WARPS * BWD_TILES * TILE >= WARPS * 2 * D * D, "reduction scratch fits");
     static bool attr[64] = {};
@@ -414,7 +428,7 @@ static int launch_bwd(const float *x, int ldx, const float *w, const float *g, i
     PU_CUDA_TRY(cudaMemcpyToSymbolAsync(pu_att16_cw2, w, D * D * sizeof(float), (size_t)SLOT * D * D * sizeof(float),
                                         cudaMemcpyDeviceToDevice, st));
     const int grid = plan_grid(P);
-    att16_bwd_kernel<SLOT><<<grid, WARPS * 32, smem, st>>>(x, ldx, g, ldg, P, dx, lddx, part);
+    att16_bwd_kernel<SLOT><<<grid, WARPS * 32, smem, st>>>(x, ldx, xb, ldxb, g, ldg, P, dx, lddx, dxb, lddxb, part);
     PU_LAUNCH_CHECK();
     launch_reduce_parts(part, grid, D * D, dw, accumulate, st);
     PU_LAUNCH_CHECK();
@@ -436,24 +450,37 @@ size_t pu_att16_workspace_bytes(long long P) {
     return (size_t)plan_grid(P) * D * D * sizeof(float) + 256;
 }
 
-int pu_att16_fwd(const float *feature_set, int ldx, const float *w, long long P, float *f_agg, int ldo,
-                 pu_stream_t stream) {
-    if (!feature_set || !w || !f_agg || P < 0 || ldx < D || (ldx & 3) || ldo < D || (((uintptr_t)feature_set) & 15))
+int pu_att16_supported_split(int K, int d, int ld_lo, int ld_hi) {
+    return (K == KN && d == D && ld_lo >= D / 2 && ld_hi >= D / 2 && ((ld_lo | ld_hi) & 3) == 0) ? 1 : 0;
+}
+
+int pu_att16_fwd_split(const float *x_lo, int ld_lo, const float *x_hi, int ld_hi, const float *w, long long P, float *f_agg,
+                       int ldo, pu_stream_t stream) {
+    if (!x_lo || !x_hi || !w || !f_agg || P < 0 || ld_lo < D / 2 || ld_hi < D / 2 || ((ld_lo | ld_hi) & 3) || ldo < D ||
+        ((((uintptr_t)x_lo) | ((uintptr_t)x_hi)) & 15))
         return PU_ERR_INVALID_ARG;
     if (P == 0) return PU_OK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pick_slot(st)) {
-        case 0: return launch_fwd<0>(feature_set, ldx, w, P, f_agg, ldo, st);
-        case 1: return launch_fwd<1>(feature_set, ldx, w, P, f_agg, ldo, st);
-        case 2: return launch_fwd<2>(feature_set, ldx, w, P, f_agg, ldo, st);
-        default: return launch_fwd<3>(feature_set, ldx, w, P, f_agg, ldo, st);
+        case 0: return launch_fwd<0>(x_lo, ld_lo, x_hi, ld_hi, w, P, f_agg, ldo, st);
+        case 1: return launch_fwd<1>(x_lo, ld_lo, x_hi, ld_hi, w, P, f_agg, ldo, st);
+        case 2: return launch_fwd<2>(x_lo, ld_lo, x_hi, ld_hi, w, P, f_agg, ldo, st);
+        default: return launch_fwd<3>(x_lo, ld_lo, x_hi, ld_hi, w, P, f_agg, ldo, st);
     }
 }
 
-int pu_att16_bwd(const float *feature_set, int ldx, const float *w, const float *g_agg, int ldg, long long P, float *dx,
-                 int lddx, float *dw, int accumulate, void *workspace, size_t workspace_bytes, pu_stream_t stream) {
-    if (!feature_set || !w || !g_agg || !dx || !dw || P < 0 || ldx < D || (ldx & 3) || ldg < D || lddx < D || (lddx & 3) ||
-        ((((uintptr_t)feature_set) | ((uintptr_t)dx)) & 15))
+int pu_att16_fwd(const float *feature_set, int ldx, const float *w, long long P, float *f_agg, int ldo,
+                 pu_stream_t stream) {
+    if (!feature_set || ldx < D) return PU_ERR_INVALID_ARG;
+    return pu_att16_fwd_split(feature_set, ldx, feature_set + D / 2, ldx, w, P, f_agg, ldo, stream);
+}
+
+int pu_att16_bwd_split(const float *x_lo, int ld_lo, const float *x_hi, int ld_hi, const float *w, const float *g_agg, int ldg,
+                       long long P, float *dx_lo, int lddx_lo, float *dx_hi, int lddx_hi, float *dw, int accumulate,
+                       void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    if (!x_lo || !x_hi || !w || !g_agg || !dx_lo || !dx_hi || !dw || P < 0 || ld_lo < D / 2 || ld_hi < D / 2 || ldg < D ||
+        lddx_lo < D / 2 || lddx_hi < D / 2 || ((ld_lo | ld_hi | lddx_lo | lddx_hi) & 3) ||
+        ((((uintptr_t)x_lo) | ((uintptr_t)x_hi) | ((uintptr_t)dx_lo) | ((uintptr_t)dx_hi)) & 15))
         return PU_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (P == 0) {
@@ -463,11 +490,18 @@ int pu_att16_bwd(const float *feature_set, int ldx, const float *w, const float 
     if (!workspace || workspace_bytes < pu_att16_workspace_bytes(P)) return PU_ERR_WORKSPACE;
     float *part = (float *)workspace;
     switch (pick_slot(st)) {
-        case 0: return launch_bwd<0>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
-        case 1: return launch_bwd<1>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
-        case 2: return launch_bwd<2>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
-        default: return launch_bwd<3>(feature_set, ldx, w, g_agg, ldg, P, dx, lddx, dw, accumulate, part, st);
+        case 0: return launch_bwd<0>(x_lo, ld_lo, x_hi, ld_hi, w, g_agg, ldg, P, dx_lo, lddx_lo, dx_hi, lddx_hi, dw, accumulate, part, st);
+        case 1: return launch_bwd<1>(x_lo, ld_lo, x_hi, ld_hi, w, g_agg, ldg, P, dx_lo, lddx_lo, dx_hi, lddx_hi, dw, accumulate, part, st);
+        case 2: return launch_bwd<2>(x_lo, ld_lo, x_hi, ld_hi, w, g_agg, ldg, P, dx_lo, lddx_lo, dx_hi, lddx_hi, dw, accumulate, part, st);
+        default: return launch_bwd<3>(x_lo, ld_lo, x_hi, ld_hi, w, g_agg, ldg, P, dx_lo, lddx_lo, dx_hi, lddx_hi, dw, accumulate, part, st);
     }
+}
+
+int pu_att16_bwd(const float *feature_set, int ldx, const float *w, const float *g_agg, int ldg, long long P, float *dx,
+                 int lddx, float *dw, int accumulate, void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    if (!feature_set || !dx || ldx < D || lddx < D) return PU_ERR_INVALID_ARG;
+    return pu_att16_bwd_split(feature_set, ldx, feature_set + D / 2, ldx, w, g_agg, ldg, P, dx, lddx, dx + D / 2, lddx, dw,
+                              accumulate, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -78,6 +78,10 @@ _lib._OP_SIGS.update({
     "pu_att_pooling_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                            c_int, c_void_p],
     "pu_att16_fwd": [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_int, c_void_p],
+    "pu_att16_fwd_split": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_int, c_void_p],
+    "pu_att16_bwd_split": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p, c_int,
+                           c_void_p, c_int, c_void_p, c_size_t, c_void_p],
+    "pu_locse_pack_xyz": [c_void_p, c_ll, c_void_p, c_void_p],
     "pu_locse_moments": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     "pu_locse_bn_prepare": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
                             c_float, c_float, c_void_p, c_void_p],
@@ -102,6 +106,9 @@ ATT_BWD_FUSED = int(_os.environ.get("PU_ATT_BWD_FUSED", "1")) != 0
 # position branch of building_block (LocSE -> 10->h conv -> BN -> LeakyReLU) as recompute kernels (csrc/locse_mlp.cu);
 # 0 = the separate relative_pos_encoding / linear / batch-norm kernels
 LOCSE_FUSED = int(_os.environ.get("PU_LOCSE_FUSED", "1")) != 0
+# 16-channel level: keep the two halves of building_block's concat as separate contiguous tensors (att16 reads / writes both);
+# 0 = one [.., 16] concat buffer whose 32-byte half rows are written and read by different kernels
+ATT16_SPLIT = int(_os.environ.get("PU_ATT16_SPLIT", "1")) != 0
 # Storage mode of the pre-normalisation activations y (output of every 1x1 conv that feeds a batch norm; kept from the forward
 # for the batch-norm backward -- the largest saved tensors of a training step): "fp32" (default, the parity path) or "bf16"
 # (opt-in: y is rounded to bfloat16 when stored, arithmetic and batch statistics stay fp32; stated tolerance rel-L2 <= 2e-2 on
@@ -147,6 +154,7 @@ def _L():
         L.pu_att16_workspace_bytes.restype = c_size_t
         L.pu_att16_workspace_bytes.argtypes = [c_ll]
         L.pu_locse_mlp_supported.argtypes = [c_int, c_int]
+        L.pu_att16_supported_split.argtypes = [c_int, c_int, c_int, c_int]
         L.pu_locse_mlp_workspace_bytes.restype = c_size_t
         L.pu_locse_mlp_workspace_bytes.argtypes = [c_int]
         L._pu_extra_declared = True
@@ -877,7 +885,7 @@ class _LocSEMlpConcatFn(torch.autograd.Function):
     LocSE rows and the weight gradient from the closed form given in that file."""
 
     @staticmethod
-    def forward(ctx, f_pc, idx, xyz, w, bias, gamma, beta, training, mm, mv, unbias, update_moving):
+    def forward(ctx, f_pc, idx, xyz, w, bias, gamma, beta, training, mm, mv, unbias, update_moving, pre):
         xyz = xyz.detach().contiguous().float()
         idx = _idx32(idx)
         w = w.contiguous()
@@ -887,27 +895,32 @@ class _LocSEMlpConcatFn(torch.autograd.Function):
         L = _L()
         st = _stream(xyz)
         coef = torch.empty(5 * h + 112, dtype=torch.float32, device=dev)
-        mom = None
-        if training:
-            mom = torch.empty(65, dtype=torch.float32, device=dev)
-            ws = workspace(L.pu_locse_mlp_workspace_bytes(h), dev, slot=6)
-            _call("pu_locse_moments", xyz.data_ptr(), idx.data_ptr(), B, N, K, mom.data_ptr(), ws.data_ptr(), ws.numel(), st,
-                  tag=(B * N * K,))
+        if pre is not None:      # (padded cloud, moments) prepared with the index pyramid, off the critical path
+            xyz, mom = pre
+        else:
+            xyz, mom = locse_prepare(xyz, idx, moments=training)
         upd = training and update_moving
         _call("pu_locse_bn_prepare", mom.data_ptr() if training else None, B * N * K, w.data_ptr(), h, bias.data_ptr(),
               gamma.data_ptr(), beta.data_ptr(), BN_EPS, int(bool(training)),
               mm.data_ptr() if (upd or not training) else None, mv.data_ptr() if (upd or not training) else None, BN_MOMENTUM,
               float(unbias), coef.data_ptr(), st)
-        buf = torch.empty((B, N, K, 2 * h), dtype=torch.float32, device=dev)
-        gather_rows(f_pc, idx, out=buf[..., :h])
         f_xyz = torch.empty((B, N, K, h), dtype=torch.float32, device=dev)
-        _call("pu_locse_mlp_fwd", xyz.data_ptr(), idx.data_ptr(), B, N, K, w.data_ptr(), h, coef.data_ptr(), LEAKY_SLOPE,
-              buf.data_ptr() + 4 * h, 2 * h, f_xyz.data_ptr(), h, st, tag=(B * N * K, h))
         ctx.save_for_backward(xyz, w, coef, gamma, bias)
-        ctx.idx, ctx.dims = idx, (B, N, K, h, f_pc.shape[1])
+        ctx.idx, ctx.dims = idx, (B, N, K, h, f_pc.shape[1] if f_pc is not None else 0)
         ctx.params = (w, bias, gamma, beta)
         ctx.training = training
+        ctx.concat = f_pc is not None
         ctx.set_materialize_grads(False)
+        if f_pc is None:
+            # no concat buffer: the result is handed out TWICE (two aliases of one tensor) so that the gradients of its two
+            # consumers -- att_pooling_1 and mlp2 -- arrive separately and are summed inside the backward kernel
+            _call("pu_locse_mlp_fwd", xyz.data_ptr(), idx.data_ptr(), B, N, K, w.data_ptr(), h, coef.data_ptr(), LEAKY_SLOPE,
+                  f_xyz.data_ptr(), h, None, 0, st, tag=(B * N * K, h))
+            return f_xyz, f_xyz.view(f_xyz.shape)
+        buf = torch.empty((B, N, K, 2 * h), dtype=torch.float32, device=dev)
+        gather_rows(f_pc, idx, out=buf[..., :h])
+        _call("pu_locse_mlp_fwd", xyz.data_ptr(), idx.data_ptr(), B, N, K, w.data_ptr(), h, coef.data_ptr(), LEAKY_SLOPE,
+              buf.data_ptr() + 4 * h, 2 * h, f_xyz.data_ptr(), h, st, tag=(B * N * K, h))
         return buf, f_xyz
 
     @staticmethod
@@ -915,11 +928,19 @@ class _LocSEMlpConcatFn(torch.autograd.Function):
         xyz, w, coef, gamma, bias = ctx.saved_tensors
         B, N, K, h, n_src = ctx.dims
         dev = xyz.device
-        if d_buf is None:
-            d_buf = torch.zeros((B, N, K, 2 * h), dtype=torch.float32, device=dev)
-        inv = inverse_of(ctx.idx, n_src)
-        d_fpc = segment_sum(d_buf[..., :h], inv, h).view(B, n_src, h)
-        dz, R, _, ldz = rows(d_buf[..., h:])
+        d_fpc = None
+        if ctx.concat:
+            if d_buf is None:
+                d_buf = torch.zeros((B, N, K, 2 * h), dtype=torch.float32, device=dev)
+            inv = inverse_of(ctx.idx, n_src)
+            d_fpc = segment_sum(d_buf[..., :h], inv, h).view(B, n_src, h)
+            dz, R, _, ldz = rows(d_buf[..., h:])
+        else:   # (d_buf, d_fxyz) are the gradients of the two aliases of f_xyz
+            if d_buf is None:
+                d_buf, d_fxyz = d_fxyz, None
+            if d_buf is None:
+                d_buf = torch.zeros((B, N, K, h), dtype=torch.float32, device=dev)
+            dz, R, _, ldz = rows(d_buf)
         d2ptr, ld2 = None, 0
         if d_fxyz is not None:
             d2, R2, _, ld2 = rows(d_fxyz)
@@ -940,21 +961,46 @@ class _LocSEMlpConcatFn(torch.autograd.Function):
               db.data_ptr() if db is not None else None, dg.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(),
               _stream(xyz), tag=(B * N * K, h))
         return (d_fpc, None, None, None if gw is not None else dw, db, None if sk is not None else dg,
-                None if sk is not None else dbeta, None, None, None, None, None)
+                None if sk is not None else dbeta, None, None, None, None, None, None)
 
 
 def locse_mlp_supported(K: int, h: int) -> bool:
     return LOCSE_FUSED and bool(_L().pu_locse_mlp_supported(int(K), int(h)))
 
 
-def locse_mlp_concat(xyz, f_pc, idx, w, bias, gamma, beta, training=True, moving_mean=None, moving_var=None, unbias=1.0,
-                     update_moving=False):
-    """Fused position branch of building_block; returns ``(concat [B,N,K,2h], f_xyz [B,N,K,h])``.  ``moving_mean`` /
-    ``moving_var`` are the statistics used at inference and, with ``update_moving``, updated in place in training."""
-    _need_cuda(xyz, f_pc, idx, w)
-    return _LocSEMlpConcatFn.apply(f_pc, idx, xyz, w, bias, gamma, beta, bool(training), moving_mean, moving_var, float(unbias),
-                                   bool(update_moving))
+def locse_prepare(xyz, idx, moments=True, out=None):
+    """What the fused position branch needs from the index pyramid alone (no weights involved, so it can be computed with
+    the pyramid, off the critical path): the padded cloud ``xyz4 [B,N,4]`` and, with ``moments``, the sums / centred second
+    moments ``mom [65]`` of the LocSE rows of ``(xyz, idx)``.  ``out = (xyz4, mom)``: preallocated storage.  No autograd."""
+    _need_cuda(xyz, idx)
+    xyz = xyz.detach().contiguous().float()
+    idx = _idx32(idx)
+    B, N, K = idx.shape
+    dev = xyz.device
+    st = _stream(xyz)
+    if out is not None:
+        xyz4, mom = out
+        assert xyz4.is_contiguous() and xyz4.numel() == B * N * 4 and mom.numel() >= 65
+    else:
+        xyz4 = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+        mom = torch.empty(65, dtype=torch.float32, device=dev) if moments else None
+    _call("pu_locse_pack_xyz", xyz.data_ptr(), B * N, xyz4.data_ptr(), st)
+    if moments:
+        ws = workspace(_L().pu_locse_mlp_workspace_bytes(1), dev, slot=7)
+        _call("pu_locse_moments", xyz4.data_ptr(), idx.data_ptr(), B, N, K, mom.data_ptr(), ws.data_ptr(), ws.numel(), st,
+              tag=(B * N * K,))
+    return xyz4, mom
 
+
+def locse_mlp_concat(xyz, f_pc, idx, w, bias, gamma, beta, training=True, moving_mean=None, moving_var=None, unbias=1.0,
+                     update_moving=False, pre=None):
+    """Fused position branch of building_block; returns ``(concat [B,N,K,2h], f_xyz [B,N,K,h])``.  ``moving_mean`` /
+    ``moving_var`` are the statistics used at inference and, with ``update_moving``, updated in place in training.
+    ``f_pc=None``: no concat -- returns ``(f_xyz, f_xyz')``, two aliases of the same tensor, one per consumer.
+    ``pre``: the result of :func:`locse_prepare` for ``(xyz, idx)`` when the caller has it already (build_pyramid)."""
+    _need_cuda(xyz, idx, w)
+    return _LocSEMlpConcatFn.apply(f_pc, idx, xyz, w, bias, gamma, beta, bool(training), moving_mean, moving_var, float(unbias),
+                                   bool(update_moving), pre)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -1020,6 +1066,51 @@ class _AttPoolFn(torch.autograd.Function):
         dw, _ = _wgrad(x, d_act, out=gw, accumulate=gw is not None)
         linear_raw(d_act, None, wt=w, out=dx.view(B * N * K, d), accumulate=True)  # dx += d_act w^T
         return dx, (None if gw is not None else dw)
+
+
+class _AttPoolSplitFn(torch.autograd.Function):
+    """:class:`_AttPoolFn` for d = 16 with the two halves of the feature set in separate tensors (att16 kernels)."""
+
+    @staticmethod
+    def forward(ctx, left, right, w):
+        w = w.contiguous()
+        B, N, K, h = left.shape
+        xl, R, _, ldl = rows(left)
+        xr, R2, _, ldr = rows(right)
+        assert R == R2 and right.shape[-1] == h and 2 * h == w.shape[0]
+        out = torch.empty((B, N, 1, 2 * h), dtype=torch.float32, device=left.device)
+        _call("pu_att16_fwd_split", xl.data_ptr(), ldl, xr.data_ptr(), ldr, w.data_ptr(), B * N, out.data_ptr(), 2 * h, _stream(xl),
+              tag=(B * N, K, 2 * h))
+        ctx.save_for_backward(xl, xr, w)
+        ctx.dims = (B, N, K, h, ldl, ldr)
+        ctx.w_param = w
+        return out
+
+    @staticmethod
+    def backward(ctx, g_agg):
+        xl, xr, w = ctx.saved_tensors
+        B, N, K, h, ldl, ldr = ctx.dims
+        g, _, _, ldg = rows(g_agg)
+        dl = torch.empty((B, N, K, h), dtype=torch.float32, device=xl.device)
+        dr = torch.empty((B, N, K, h), dtype=torch.float32, device=xl.device)
+        gw = _sink(ctx.w_param)
+        dw = gw if gw is not None else torch.empty((2 * h, 2 * h), dtype=torch.float32, device=xl.device)
+        ws = workspace(_L().pu_att16_workspace_bytes(B * N), xl.device, slot=2)
+        _call("pu_att16_bwd_split", xl.data_ptr(), ldl, xr.data_ptr(), ldr, w.data_ptr(), g.data_ptr(), ldg, B * N, dl.data_ptr(), h,
+              dr.data_ptr(), h, dw.data_ptr(), int(gw is not None), ws.data_ptr(), ws.numel(), _stream(xl), tag=(B * N, K, 2 * h))
+        return dl, dr, (None if gw is not None else dw)
+
+
+def att_pool_split_supported(K: int, d: int) -> bool:
+    return ATT16 and ATT16_SPLIT and bool(_L().pu_att16_supported_split(int(K), int(d), d // 2, d // 2))
+
+
+def att_pool_split(left: torch.Tensor, right: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``att_pool(concat([left, right], -1), w)`` without the concat: ``[B,N,K,8]`` x 2, ``w [16,16]`` -> ``[B,N,1,16]``."""
+    _need_cuda(left, right, w)
+    if left.data_ptr() % 16 or right.data_ptr() % 16:
+        return att_pool(torch.cat([left, right], dim=-1), w)
+    return _AttPoolSplitFn.apply(left, right, w)
 
 
 def att_pool(feature_set: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

@@ -35,7 +35,7 @@ class _Slot:
         for i in range(cfg.num_layers):
             n_sub = n // cfg.sub_sampling_ratio[i]
             spec += [(f"xyz{i}", (B, n, 3), f32), (f"neigh{i}", (B, n, cfg.k_n), i32), (f"sub{i}", (B, n_sub, cfg.k_n), i32),
-                     (f"interp{i}", (B, n, 1), i32),
+                     (f"interp{i}", (B, n, 1), i32), (f"xyz4_{i}", (B, n, 4), f32), (f"locse_mom{i}", (68,), f32),
                      (f"inv_neigh_off{i}", (B * n + 1,), i32), (f"inv_neigh_perm{i}", (B * n * cfg.k_n,), i32),
                      (f"inv_sub_off{i}", (B * n + 1,), i32), (f"inv_sub_perm{i}", (B * n_sub * cfg.k_n,), i32),
                      (f"inv_interp_off{i}", (B * n_sub + 1,), i32), (f"inv_interp_perm{i}", (B * n,), i32)]
@@ -55,13 +55,15 @@ class _Slot:
         self.store = dict(xyz=[self.t[f"xyz{i}"] for i in range(cfg.num_layers + 1)],
                           neigh_idx=[self.t[f"neigh{i}"] for i in L], sub_idx=[self.t[f"sub{i}"] for i in L],
                           interp_idx=[self.t[f"interp{i}"] for i in L],
+                          locse=[(self.t[f"xyz4_{i}"], self.t[f"locse_mom{i}"]) for i in L],
                           inv=[[(self.t[f"inv_{k}_off{i}"], self.t[f"inv_{k}_perm{i}"]) for k in ("neigh", "sub", "interp")]
                                for i in L])
         self.features, self.labels = self.t["features"], self.t["labels"]
 
     def pyramid(self):
         st = self.store
-        return dict(xyz=st["xyz"][:-1], neigh_idx=st["neigh_idx"], sub_idx=st["sub_idx"], interp_idx=st["interp_idx"])
+        return dict(xyz=st["xyz"][:-1], neigh_idx=st["neigh_idx"], sub_idx=st["sub_idx"], interp_idx=st["interp_idx"],
+                    locse=st["locse"])
 
     def register_inverse(self):
         """Point ops.inverse_of at this slot's lists (the cache is cleared at the end of every step)."""
@@ -162,7 +164,7 @@ class Trainer:
         """One optimisation step on device-resident inputs: xyz [B,N,3] f32, features [B,N,F-3] f32, labels [B,N]."""
         # tf_map on the GPU; levels 1-4 and the inverse lists of the backward are built on a side stream under the
         # level-0 forward (PU_OVERLAP=0: everything on one stream)
-        pyr = build_pyramid(xyz, self.cfg, side=self._side_stream() if OVERLAP else None, inverse=True)
+        pyr = build_pyramid(xyz, self.cfg, side=self._side_stream() if OVERLAP else None, inverse=True, locse=True)
         return self._train_on(pyr, xyz, features, labels, dropout_mask)
 
     def _train_on(self, pyr, xyz, features, labels, dropout_mask=None):

@@ -40,7 +40,8 @@ def oracle_branch(xyz, idx, f_pc, p, training, upd=None):
 
 
 @pytest.mark.parametrize("B,N,K,h,offset", [(2, 1500, 16, 8, 0.0), (3, 700, 16, 32, 50.0), (1, 333, 5, 64, 0.0),
-                                            (2, 300, 16, 128, 3.0), (1, 130, 16, 256, 0.0), (1, 1, 16, 8, 0.0)])
+                                            (2, 300, 16, 128, 3.0), (1, 130, 16, 256, 0.0), (1, 1, 16, 8, 0.0),
+                                            (2, 257, 3, 16, 0.0), (1, 100, 16, 4, 0.0), (4, 9000, 16, 8, 0.0)])
 def test_locse_mlp_training_fwd_bwd_vs_oracle(B, N, K, h, offset):
     if not ops.locse_mlp_supported(K, h):
         pytest.skip("fused LocSE branch switched off")
@@ -125,8 +126,65 @@ def test_locse_mlp_inference_mode(h):
 def test_locse_mlp_argument_validation():
     L = ops._L()
     assert L.pu_locse_mlp_supported(16, 8) == 1 and L.pu_locse_mlp_supported(16, 24) == 0
-    x = torch.zeros(1, 8, 3, device="cuda")
+    x = torch.zeros(1, 8, 4, device="cuda")
     i = torch.zeros(1, 8, 16, dtype=torch.int32, device="cuda")
     mom = torch.zeros(65, device="cuda")
     assert L.pu_locse_moments(x.data_ptr(), i.data_ptr(), 1, 8, 16, mom.data_ptr(), None, 0, None) == -2   # PU_ERR_WORKSPACE
     assert L.pu_locse_moments(None, i.data_ptr(), 1, 8, 16, mom.data_ptr(), None, 0, None) == -1            # PU_ERR_INVALID_ARG
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (2, 777), (3, 20001)])
+def test_att_pool_split_equals_concat(B, N):
+    """att16 with the halves of the feature set in two tensors == the same kernels on the concatenated tensor, bit for bit
+    (only the addressing differs), forward and backward."""
+    K, h = 16, 8
+    if not ops.att_pool_split_supported(K, 2 * h):
+        pytest.skip("split att16 switched off")
+    g = torch.Generator().manual_seed(N)
+    left = torch.randn(B, N, K, h, generator=g).cuda()
+    right = torch.randn(B, N, K, h, generator=g).cuda()
+    w = (torch.randn(2 * h, 2 * h, generator=g) * 0.3).cuda()
+    go = torch.randn(B, N, 1, 2 * h, generator=g).cuda()
+    l1, r1, w1 = left.clone().requires_grad_(True), right.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    o1 = ops.att_pool_split(l1, r1, w1)
+    (o1 * go).sum().backward()
+    cat = torch.cat([left, right], dim=-1).requires_grad_(True)
+    w2 = w.clone().requires_grad_(True)
+    o2 = ops.att_pool(cat, w2)
+    (o2 * go).sum().backward()
+    assert torch.equal(o1, o2)
+    assert torch.equal(l1.grad, cat.grad[..., :h]) and torch.equal(r1.grad, cat.grad[..., h:])
+    assert torch.equal(w1.grad, w2.grad)
+    # and against the oracle in fp64
+    pr = {"afc/kernel": w.double().cpu().requires_grad_(True)}
+    xr = torch.cat([left, right], dim=-1).double().cpu().requires_grad_(True)
+    f = xr.reshape(-1, K, 2 * h)
+    s = torch.softmax(f @ pr["afc/kernel"], dim=1)
+    want = (f * s).sum(dim=1).reshape(B, N, 1, 2 * h)
+    (want * go.double().cpu()).sum().backward()
+    assert rel_err(o1, want) < TOL
+    assert rel_err(l1.grad, xr.grad[..., :h]) < TOL and rel_err(r1.grad, xr.grad[..., h:]) < TOL
+    assert rel_err(w1.grad, pr["afc/kernel"].grad) < TOL
+
+
+def test_locse_mlp_without_concat_sums_both_consumers():
+    """f_pc=None: the result comes back as two aliases; the gradients of both reach the backward kernel and are summed."""
+    B, N, K, h = 2, 3000, 16, 8
+    xyz, idx, f_pc, p, d_buf, d_fxyz = make_case(B, N, K, h, 55)
+    d1, d2 = d_buf[..., :h].contiguous().cuda(), d_fxyz.cuda()
+
+    def run(split):
+        pg = {k: v.cuda().requires_grad_(not k.startswith("s/bn/moving")) for k, v in p.items()}
+        args = (pg["s/weights"], pg["s/biases"], pg["s/bn/gamma"], pg["s/bn/beta"], True, pg["s/bn/moving_mean"],
+                pg["s/bn/moving_variance"], 1.0, False)
+        if split:
+            a, b = ops.locse_mlp_concat(xyz.cuda(), None, idx.cuda(), *args)
+            assert a.data_ptr() == b.data_ptr()
+        else:
+            cat, b = ops.locse_mlp_concat(xyz.cuda(), f_pc.cuda(), idx.cuda(), *args)
+            a = cat[..., h:]
+        ((a * d1).sum() + (b * d2).sum()).backward()
+        return [b.detach()] + [pg[k].grad for k in ("s/weights", "s/bn/gamma", "s/bn/beta")]
+
+    for u, v in zip(run(True), run(False)):
+        assert rel_err(u, v) < 1e-6
