@@ -114,8 +114,11 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const float *__restri
     if (g == 0 && i < n) out[i] = accumulate ? out[i] + (float)red[0][e] : (float)red[0][e];
 }
 // launch helper: narrow CTAs (8 elements x 32 chunk groups) for small outputs, wide ones (32 x 8) otherwise
+// (few chunks: wide CTAs of 128 x 2 -- with 3 partials of a 1024 x 1024 weight gradient five of the eight chunk groups of
+// the 32 x 8 shape had nothing to do, 60 us per launch)
 inline void launch_reduce_parts(const float *part, int chunks, long long n, float *out, int accumulate, cudaStream_t st) {
-    if (n <= 8192) reduce_parts_kernel<8><<<ceil_div(n, 8), 256, 0, st>>>(part, chunks, n, out, accumulate);
+    if (chunks <= 8 && n > 8192) reduce_parts_kernel<128><<<ceil_div(n, 128), 256, 0, st>>>(part, chunks, n, out, accumulate);
+    else if (n <= 8192) reduce_parts_kernel<8><<<ceil_div(n, 8), 256, 0, st>>>(part, chunks, n, out, accumulate);
     else reduce_parts_kernel<32><<<ceil_div(n, 32), 256, 0, st>>>(part, chunks, n, out, accumulate);
 }
 

@@ -579,6 +579,55 @@ __global__ void __launch_bounds__(SF_THREADS) stats_finalize_kernel(const float 
     }
 }
 
+// The same for SHORT partial lists (the deep levels: 3-350 tiles, but 256-1024 channels): one WARP per channel, eight channels
+// per CTA, lanes stride over the tiles, xor-shuffle reduction in double.  One 1024-thread CTA per channel spent its time in
+// the ten barrier rounds of the block reduction with most threads idle: 28 us per launch at 1024 channels (ncu launch list),
+// between a conv and its batch norm on the critical path.  Same arithmetic; the summation order depends only on `tiles`.
+__global__ void __launch_bounds__(256) stats_finalize_warp_kernel(const float *__restrict__ psum, const float *__restrict__ pm2,
+                                                                  int tiles, int C, long long count, int rows_per_tile,
+                                                                  float *__restrict__ mean, float *__restrict__ var,
+                                                                  const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                  float eps, float *__restrict__ invstd, float *__restrict__ scale,
+                                                                  float *__restrict__ shift, float *__restrict__ moving_mean,
+                                                                  float *__restrict__ moving_var, float momentum, float unbias) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0, r = 0.0;
+    for (int t = lane; t < tiles; t += 32) {
+        const long long r0 = (long long)t * rows_per_tile;
+        const double nt = (double)min((long long)rows_per_tile, count - r0);
+        const double st = (double)psum[(size_t)t * C + c];
+        s += st;
+        q += (double)pm2[(size_t)t * C + c];
+        r += st * st / nt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    if (lane == 0) {
+        const double n = (double)count, m = s / n;
+        const double v = (q + r - n * m * m) / n;
+        const float mf = (float)m, vf = (float)(v > 0.0 ? v : 0.0);
+        mean[c] = mf;
+        var[c] = vf;
+        if (gamma) {
+            const float is = rsqrtf(vf + eps);
+            invstd[c] = is;
+            scale[c] = gamma[c] * is;
+            shift[c] = mf;
+            shift[C + c] = beta[c];
+            if (moving_mean) {
+                moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * mf;
+                moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * vf * unbias;
+            }
+        }
+    }
+}
+constexpr int SF_WARP_MAX_TILES = 512;   // up to 16 rounds per lane
+
 // NOTE on "shift": all batch-norm kernels below evaluate z = (y - mean[c]) * scale[c] + beta[c] (centered form, no
 // cancellation between y*scale and mean*scale); `shift` is a [2,C] array: row 0 = mean, row 1 = beta.
 __device__ __forceinline__ float4 bn_z(const float4 v, const float4 mu, const float4 sc, const float4 be) {
@@ -1028,9 +1077,15 @@ int pu_bn_finalize_prepare(const float *stat_sum, const float *stat_sq, int tile
         return PU_ERR_INVALID_ARG;
     if ((long long)tiles != (count + rows_per_tile - 1) / rows_per_tile) return PU_ERR_INVALID_ARG;
     if ((moving_mean == nullptr) != (moving_var == nullptr)) return PU_ERR_INVALID_ARG;
-    stats_finalize_kernel<<<C, SF_THREADS, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C, count, rows_per_tile, mean, var,
-                                                                      gamma, beta, eps, invstd, scale, shift, moving_mean,
-                                                                      moving_var, momentum, unbias);
+    if (tiles <= SF_WARP_MAX_TILES)
+        stats_finalize_warp_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C, count,
+                                                                                    rows_per_tile, mean, var, gamma, beta, eps,
+                                                                                    invstd, scale, shift, moving_mean, moving_var,
+                                                                                    momentum, unbias);
+    else
+        stats_finalize_kernel<<<C, SF_THREADS, 0, (cudaStream_t)stream>>>(stat_sum, stat_sq, tiles, C, count, rows_per_tile, mean,
+                                                                          var, gamma, beta, eps, invstd, scale, shift, moving_mean,
+                                                                          moving_var, momentum, unbias);
     PU_LAUNCH_CHECK();
     return PU_OK;
 }
