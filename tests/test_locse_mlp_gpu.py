@@ -188,3 +188,49 @@ def test_locse_mlp_without_concat_sums_both_consumers():
 
     for u, v in zip(run(True), run(False)):
         assert rel_err(u, v) < 1e-6
+
+
+@pytest.mark.parametrize("fused,split", [(False, False), (True, False)])
+def test_network_switches_agree_with_default_path(fused, split):
+    """PU_LOCSE_FUSED / PU_ATT16_SPLIT select older kernel paths (one concat buffer; separate LocSE / conv / BN kernels): the
+    whole network must give the same logits and gradients either way (different kernels, same mathematics)."""
+    from point_unet_b200 import synthetic as syn
+    from point_unet_b200.helper_tool import ConfigBraTS
+    from point_unet_b200.RandLANet import Network, build_pyramid
+
+    class Cfg(ConfigBraTS):
+        num_points = 8192
+
+    B = 2
+    data = syn.batch(syn.brats_cloud, B, Cfg.num_points, seed0=3)
+    xyz = torch.from_numpy(data["xyz"]).cuda()
+    feats = torch.cat([xyz, torch.from_numpy(data["features"]).cuda()], dim=-1)
+    labels = torch.from_numpy(data["labels"]).cuda()
+    mask = (torch.rand(B, Cfg.num_points, 1, 32, generator=torch.Generator().manual_seed(1)) < 0.5).cuda()
+
+    def run():
+        net = Network(Cfg, feats.shape[-1], seed=5, device="cuda")
+        pyr = build_pyramid(xyz, Cfg, locse=True)
+        logits = net.inference(dict(pyr, features=feats), True, dropout_mask=mask)
+        net.get_loss(logits, labels).backward()
+        return logits.detach(), {n: t.grad.clone() for n, t in net.named_variables()}, dict(net.stats)
+
+    keep = (ops.LOCSE_FUSED, ops.ATT16_SPLIT)
+    try:
+        ref_logits, ref_grads, ref_stats = run()
+        ops.LOCSE_FUSED, ops.ATT16_SPLIT = fused, split
+        logits, grads, stats = run()
+    finally:
+        ops.LOCSE_FUSED, ops.ATT16_SPLIT = keep
+    assert rel_err(logits, ref_logits) < 1e-4
+    for n in ref_stats:
+        assert rel_err(stats[n], ref_stats[n]) < 1e-4, n
+    bad = []
+    for n, g in ref_grads.items():
+        scale = float(g.abs().max())
+        if scale < 1e-8:      # a bias under a batch norm: analytically zero
+            continue
+        e = float((grads[n] - g).double().norm() / max(float(g.double().norm()), 1e-30))
+        if e > 5e-3:          # routing flips (max-pool winners, LeakyReLU signs) between two fp32 evaluations, see DESIGN
+            bad.append((n, e))
+    assert not bad, bad
