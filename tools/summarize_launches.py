@@ -35,7 +35,8 @@ ENTRY = [(r"tc::tc_persist_kernel<\d+, 0,", "pu_tc_linear_fwd"), (r"tc::tc_linea
          (r"mlp::bn_bwd_reduce", "pu_bn_bwd_reduce"), (r"mlp::bn_bwd_apply", "pu_bn_bwd_apply"),
          (r"lfa::maxpool_bwd", "pu_random_sample_bwd"), (r"lfa::maxpool_fwd", "pu_random_sample_fwd"), (r"lfa::gather_rows", "pu_gather_rows_fwd"), (r"lfa::segment_sum", "pu_segment_sum"),
          (r"mlp::wgrad", "pu_wgrad"), (r"mlp::linear_narrow|mlp::gemm_kernel<\d+, \d+, \d+, \d+, 0>", "pu_linear_fwd"),
-         (r"knn::knn_search_kernel", "pu_knn_batch"), (r"att16::att16_fwd_kernel", "pu_att16_fwd"),
+         (r"knn::knn_search_kernel|knn::knn_query_warp_kernel", "pu_knn_batch"), (r"locse::locse_mlp_fwd", "pu_locse_mlp_fwd"),
+         (r"locse::locse_mlp_bwd_kernel|locse::locse_mlp_bwd_direct", "pu_locse_mlp_bwd"), (r"locse::locse_moment", "pu_locse_moments"), (r"att16::att16_fwd_kernel", "pu_att16_fwd"),
          (r"att16::att16_bwd_kernel", "pu_att16_bwd")]
 tr = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for k, a in agg.items():
