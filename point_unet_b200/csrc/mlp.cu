@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(256) stats_finalize_warp_kernel(const float *_
         }
     }
 }
-constexpr int SF_WARP_MAX_TILES = 512;   // up to 16 rounds per lane
+constexpr int SF_WARP_MAX_TILES = 64;   // two rounds per lane; longer lists: the 1024-thread kernel (measured: 15 us here vs 7 us there at 352 tiles)
 
 // NOTE on "shift": all batch-norm kernels below evaluate z = (y - mean[c]) * scale[c] + beta[c] (centered form, no
 // cancellation between y*scale and mean*scale); `shift` is a [2,C] array: row 0 = mean, row 1 = beta.

@@ -14,9 +14,9 @@ full() {  # name, regex on the demangled kernel name
     ncu -i $out/${tag}_full_$1.ncu-rep --page raw --csv > $out/${tag}_ncu_full_$1.csv 2>/dev/null
     rm -f $out/${tag}_full_$1.ncu-rep
 }
-full tc_persist_stream 'tc_persist_kernel<128, 0, '
-full tc_persist_tma 'tc_persist_kernel<64, 0, '
-full tc_att_bwd_fused 'tc_persist_kernel<64, 3, '
+full tc_persist_stream 'tc_persist_kernel<\(int\)128, \(int\)0, \(bool\)1'
+full tc_persist_tma 'tc_persist_kernel<\(int\)64, \(int\)0, '
+full tc_att_bwd_fused 'tc_persist_kernel<\(int\)64, \(int\)3, '
 full locse_mlp_bwd 'locse_mlp_bwd_kernel'
 full locse_mlp_fwd 'locse_mlp_fwd_kernel'
 full bn_bwd_apply 'bn_bwd_apply_kernel'
