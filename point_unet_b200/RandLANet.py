@@ -28,7 +28,12 @@ import torch
 
 from . import ops
 from .helper_tool import DataProcessing as DP
-from .helper_tool import knn_search_cuda
+from .helper_tool import knn_search_cuda, knn_self_interp_cuda
+
+import os as _os
+
+# neigh_idx and interp_idx of a pyramid level from ONE search structure (pu_knn_self_interp); 0 = two separate searches
+KNN_FUSED_INTERP = int(_os.environ.get("PU_KNN_FUSED_INTERP", "1")) != 0
 
 
 def layer_table(cfg, num_features: int):
@@ -145,9 +150,12 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
         clouds[0].copy_(xyz)
         for i in range(cfg.num_layers):
             clouds[i + 1].copy_(clouds[i][:, :clouds[i + 1].shape[1], :])
-            knn_search_cuda(clouds[i], clouds[i], cfg.k_n, out=store["neigh_idx"][i])
+            if KNN_FUSED_INTERP:
+                knn_self_interp_cuda(clouds[i], cfg.k_n, clouds[i + 1].shape[1], store["neigh_idx"][i], store["interp_idx"][i])
+            else:
+                knn_search_cuda(clouds[i], clouds[i], cfg.k_n, out=store["neigh_idx"][i])
+                knn_search_cuda(clouds[i + 1], clouds[i], 1, out=store["interp_idx"][i])
             store["sub_idx"][i].copy_(store["neigh_idx"][i][:, :clouds[i + 1].shape[1], :])
-            knn_search_cuda(clouds[i + 1], clouds[i], 1, out=store["interp_idx"][i])
             if "locse" in store:
                 ops.locse_prepare(clouds[i], store["neigh_idx"][i], out=store["locse"][i])
             if inverse:
@@ -175,21 +183,29 @@ def build_pyramid(xyz: torch.Tensor, cfg, side: "torch.cuda.Stream | None" = Non
         xyz = xyz[:, :n_sub, :].contiguous()
     subs = out["xyz"][1:] + [xyz]
 
+    def search(i):   # neigh_idx (and, fused, interp_idx) of level i
+        pts = out["xyz"][i]
+        if KNN_FUSED_INTERP:
+            knn_self_interp_cuda(pts, cfg.k_n, subs[i].shape[1], out["neigh_idx"][i], out["interp_idx"][i])
+        else:
+            knn_search_cuda(pts, pts, cfg.k_n, out=out["neigh_idx"][i])
+
     def level(i):
         pts = out["xyz"][i]
         if i > 0 or side is None:
-            knn_search_cuda(pts, pts, cfg.k_n, out=out["neigh_idx"][i])
+            search(i)
             if locse:
                 ops.locse_prepare(pts, out["neigh_idx"][i], out=out["locse"][i])
         out["sub_idx"][i].copy_(out["neigh_idx"][i][:, :subs[i].shape[1], :])
-        knn_search_cuda(subs[i], pts, 1, out=out["interp_idx"][i])
+        if not KNN_FUSED_INTERP:
+            knn_search_cuda(subs[i], pts, 1, out=out["interp_idx"][i])
 
     if side is None:
         for i in range(cfg.num_layers):
             level(i)
         return out
     main = torch.cuda.current_stream(dev)
-    knn_search_cuda(out["xyz"][0], out["xyz"][0], cfg.k_n, out=out["neigh_idx"][0])
+    search(0)
     if locse:
         ops.locse_prepare(out["xyz"][0], out["neigh_idx"][0], out=out["locse"][0])
     side.wait_stream(main)

@@ -794,6 +794,99 @@ __global__ void __launch_bounds__(QW_WARPS * 32)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Up-sampling indices from the neighbour lists (tf_map: interp_idx = knn(sub_points, points, 1) with sub_points = the
+// first n_sub points, runPancreas.py:135-137).  The nearest sub-cloud point of point n is the FIRST entry of n's own
+// K-neighbour row whose index is below n_sub: the row holds the K smallest (distance, index) keys among ALL points in
+// ascending order, so every sub-cloud point outside the row has a larger key than every point inside it.  Only rows without
+// such an entry (about 0.75^16 = 1 % of them at a sub-sampling ratio of 4) need a search; they are collected in a list and
+// searched, one warp per row, on the structure the self-query has just built -- candidates filtered by index < n_sub, same
+// distance arithmetic, same bounds, same (distance, index) order, hence bit-identical to a separate K = 1 search over the
+// sub-cloud.  That search used to cost a Morton sort of the sub-cloud, one of all query points and a full K = 1 sweep per level.
+__global__ void __launch_bounds__(256) interp_from_neigh_kernel(const int32_t *__restrict__ neigh, int N, int K, int kvalid,
+                                                                int n_sub, int32_t *__restrict__ interp,
+                                                                unsigned *__restrict__ cnt, unsigned *__restrict__ list) {
+    const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const int32_t *row = neigh + ((size_t)b * N + n) * K;
+    int found = -1;
+    for (int k = 0; k < kvalid; ++k) {
+        const int j = row[k];
+        if (j < n_sub) { found = j; break; }
+    }
+    if (found >= 0) interp[(size_t)b * N + n] = found;
+    else list[(size_t)b * N + atomicAdd(&cnt[b], 1u)] = (unsigned)n;   // the ORDER of the list is immaterial
+}
+
+constexpr int NP_WARPS = 8;
+__global__ void __launch_bounds__(NP_WARPS * 32)
+    knn_nearest_prefix_kernel(const float *__restrict__ cloud, const float4 *__restrict__ sp, const float4 *__restrict__ bk_lo,
+                              const float4 *__restrict__ bk_hi, const float4 *__restrict__ sb_lo,
+                              const float4 *__restrict__ sb_hi, const float4 *__restrict__ cb_lo,
+                              const float4 *__restrict__ cb_hi, int N, int NB, int NSB, int NCB, int n_sub,
+                              const unsigned *__restrict__ cnt, const unsigned *__restrict__ list,
+                              int32_t *__restrict__ interp) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, b = blockIdx.y;
+    const float4 *sp_cloud = sp + (size_t)b * N;
+    const float4 *bk_lo_c = bk_lo + (size_t)b * NB, *bk_hi_c = bk_hi + (size_t)b * NB;
+    const float4 *sb_lo_c = sb_lo + (size_t)b * NSB, *sb_hi_c = sb_hi + (size_t)b * NSB;
+    const float4 *cb_lo_c = cb_lo + (size_t)b * NCB, *cb_hi_c = cb_hi + (size_t)b * NCB;
+    const unsigned total = cnt[b];
+    for (unsigned u = blockIdx.x * NP_WARPS + wib; u < total; u += gridDim.x * NP_WARPS) {   // warp-uniform
+        const unsigned n = list[(size_t)b * N + u];
+        const float *qp = cloud + ((size_t)b * N + n) * 3;
+        const float qx = qp[0], qy = qp[1], qz = qp[2];
+        unsigned long long best = KEY_INIT;
+        float kd = __uint_as_float(0x7F800000u);
+        // nearest first on all three levels; a box is skipped only when its lower bound EXCEEDS the best distance so far
+        for (int c0 = 0; c0 < NCB; c0 += 32) {
+            unsigned cbits = 0xFFFFFFFFu;
+            if (c0 + lane < NCB) cbits = __float_as_uint(point_box_dist2(qx, qy, qz, cb_lo_c[c0 + lane], cb_hi_c[c0 + lane]));
+            for (;;) {
+                const unsigned cmin = __reduce_min_sync(0xffffffffu, cbits);
+                if (cmin == 0xFFFFFFFFu || __uint_as_float(cmin) > kd) break;
+                const int bc = __ffs(__ballot_sync(0xffffffffu, cbits == cmin)) - 1;
+                if (lane == bc) cbits = 0xFFFFFFFFu;
+                const int s0 = (c0 + bc) * SBS;
+                unsigned sbits = 0xFFFFFFFFu;
+                if (s0 + lane < NSB)
+                    sbits = __float_as_uint(point_box_dist2(qx, qy, qz, sb_lo_c[s0 + lane], sb_hi_c[s0 + lane]));
+                for (;;) {
+                    const unsigned smin = __reduce_min_sync(0xffffffffu, sbits);
+                    if (smin == 0xFFFFFFFFu || __uint_as_float(smin) > kd) break;
+                    const int bs = __ffs(__ballot_sync(0xffffffffu, sbits == smin)) - 1;
+                    if (lane == bs) sbits = 0xFFFFFFFFu;
+                    const int t0 = (s0 + bs) * SBS, t = t0 + lane;
+                    unsigned bbits = 0xFFFFFFFFu;
+                    if (t < NB) bbits = __float_as_uint(point_box_dist2(qx, qy, qz, bk_lo_c[t], bk_hi_c[t]));
+                    for (;;) {
+                        const unsigned bmin = __reduce_min_sync(0xffffffffu, bbits);
+                        if (bmin == 0xFFFFFFFFu || __uint_as_float(bmin) > kd) break;
+                        const int bb = __ffs(__ballot_sync(0xffffffffu, bbits == bmin)) - 1;
+                        if (lane == bb) bbits = 0xFFFFFFFFu;
+                        const int base = (t0 + bb) * BS;
+                        unsigned hi = 0xFFFFFFFFu, lo = 0xFFFFFFFFu;
+                        if (base + lane < N) {
+                            const float4 p = sp_cloud[base + lane];
+                            const unsigned pi = (unsigned)__float_as_int(p.w);
+                            if (pi < (unsigned)n_sub) {
+                                hi = __float_as_uint(dist2_rn(qx, qy, qz, p.x, p.y, p.z));
+                                lo = pi;
+                            }
+                        }
+                        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                        if (mh == 0xFFFFFFFFu) continue;   // no sub-cloud point in this bucket
+                        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
+                        const unsigned long long cand = ((unsigned long long)mh << 32) | ml;
+                        if (cand < best) { best = cand; kd = __uint_as_float(mh); }
+                    }
+                }
+            }
+        }
+        if (lane == 0) interp[(size_t)b * N + n] = best == KEY_INIT ? 0 : (int)(unsigned)best;
+    }
+}
+
 template <int K>
 static int launch_search(const Layout &L, char *ws, bool self, const unsigned *skeys,
                          const unsigned *qkeys, const float4 *sq, int B, int N1, int N2, int kout,
@@ -929,6 +1022,43 @@ static int knn_impl(const float *support, const float *query, int B, int N1, int
     return PU_ERR_UNSUPPORTED;
 }
 
+// neighbour lists of a cloud AND the up-sampling index of every point into the cloud's first n_sub points, from ONE
+// search structure (one Morton sort per pyramid level instead of three)
+static int knn_self_interp_impl(const float *cloud, int B, int N, int K, int n_sub, int32_t *out_neigh, int32_t *out_interp,
+                                void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (!cloud || !out_neigh || !out_interp || n_sub < 0 || n_sub > N) return PU_ERR_INVALID_ARG;
+    int rc = knn_impl(cloud, cloud, B, N, N, K, out_neigh, nullptr, workspace, workspace_bytes, st);
+    if (rc != PU_OK) return rc;
+    if (B == 0 || N == 0) return PU_OK;
+    if (n_sub == 0) {
+        PU_CUDA_TRY(cudaMemsetAsync(out_interp, 0, (size_t)B * N * sizeof(int32_t), st));
+        return PU_OK;
+    }
+    const Layout L = make_layout(B, N, N);
+    char *ws = (char *)workspace;
+    // the query-side sort buffers are unused by a self-query: counters and row lists live there
+    unsigned *cnt = (unsigned *)(ws + L.qkeys_a), *list = (unsigned *)(ws + L.qvals_a);
+    if ((size_t)B * sizeof(unsigned) > (size_t)B * N * 4) return PU_ERR_WORKSPACE;
+    PU_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)B * sizeof(unsigned), st));
+    interp_from_neigh_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(out_neigh, N, K, K < N ? K : N, n_sub, out_interp, cnt,
+                                                                        list);
+    PU_LAUNCH_CHECK();
+    // third box level (the warp-per-query self search builds it too; rebuilt here for the K <= 4 / per-lane path)
+    super_box_kernel<<<ceil_div((long long)B * L.NCB * 32, 128), 128, 0, st>>>(
+        (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), L.NSB, L.NCB, B, (float4 *)(ws + L.cb_lo),
+        (float4 *)(ws + L.cb_hi));
+    PU_LAUNCH_CHECK();
+    int gx = ceil_div(N, NP_WARPS * 16);   // a warp per 16 rows would cover a list of ALL rows; ~1 % of them are expected
+    const int cap = kNumSMs * 2 / (B > 0 ? B : 1) + 1;
+    if (gx > cap) gx = cap;
+    knn_nearest_prefix_kernel<<<dim3(gx, B), NP_WARPS * 32, 0, st>>>(
+        cloud, (const float4 *)(ws + L.sp), (const float4 *)(ws + L.bk_lo), (const float4 *)(ws + L.bk_hi),
+        (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), (const float4 *)(ws + L.cb_lo),
+        (const float4 *)(ws + L.cb_hi), N, L.NB, L.NSB, L.NCB, n_sub, cnt, list, out_interp);
+    PU_LAUNCH_CHECK();
+    return PU_OK;
+}
+
 }  // namespace knn
 }  // namespace pu
 
@@ -951,6 +1081,12 @@ int pu_knn_batch_dist(const float *support, const float *query, int B, int N1, i
     if (!out_dist) return PU_ERR_INVALID_ARG;
     return pu::knn::knn_impl(support, query, B, N1, N2, K, out_idx, out_dist, workspace, workspace_bytes,
                              (cudaStream_t)stream);
+}
+
+int pu_knn_self_interp(const float *cloud, int B, int N, int K, int n_sub, int32_t *out_neigh, int32_t *out_interp,
+                       void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    return pu::knn::knn_self_interp_impl(cloud, B, N, K, n_sub, out_neigh, out_interp, workspace, workspace_bytes,
+                                         (cudaStream_t)stream);
 }
 
 int pu_knn_read_stats(const void *workspace, unsigned long long *host_stats3, pu_stream_t stream) {

@@ -109,6 +109,36 @@ def knn_search_cuda(support: torch.Tensor, query: torch.Tensor, k: int, return_d
     return out
 
 
+def knn_self_interp_cuda(points: torch.Tensor, k: int, n_sub: int, out_neigh: torch.Tensor | None = None,
+                         out_interp: torch.Tensor | None = None):
+    """One pyramid level of ``tf_map`` (runPancreas.py:131-137) from a single search structure: returns
+    ``(knn_search(points, points, k) [B,N,k], knn_search(points[:, :n_sub], points, 1) [B,N,1])``, both int32 and
+    bit-identical to the two separate searches (C-ABI ``pu_knn_self_interp``)."""
+    if not points.is_cuda:
+        raise _lib.PointUnetError("knn_self_interp_cuda needs CUDA tensors (there is no CPU fallback)")
+    if points.dim() != 3 or points.shape[2] != 3:
+        raise ValueError(f"expected points [B,N,3], got {tuple(points.shape)}")
+    points = points.contiguous().float()
+    B, N, _ = points.shape
+    dev = points.device
+    from . import ops
+    if out_neigh is None:
+        out_neigh = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+    if out_interp is None:
+        out_interp = torch.empty((B, N, 1), dtype=torch.int32, device=dev)
+    for t, shape in ((out_neigh, (B, N, k)), (out_interp, (B, N, 1))):
+        if t.dtype != torch.int32 or tuple(t.shape) != shape or not t.is_contiguous() or t.device != dev:
+            raise ValueError("knn_self_interp_cuda: outputs must be contiguous int32 [B,N,k] / [B,N,1] tensors on the inputs' device")
+        ops.drop_inverse(t.data_ptr())   # rewritten through the raw pointer: cached inverse lists of it are stale
+    L = _lib.lib()
+    ws = workspace(L.pu_knn_workspace_bytes(B, N, N, k), dev)
+    with torch.cuda.device(dev):
+        st = L.pu_knn_self_interp(points.data_ptr(), B, N, int(k), int(n_sub), out_neigh.data_ptr(), out_interp.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _lib.check(st, "pu_knn_self_interp")
+    return out_neigh, out_interp
+
+
 def knn_last_stats(device=None) -> dict:
     """Counters of the last KNN call on ``device``: candidate distance evaluations, buckets swept, box tests."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

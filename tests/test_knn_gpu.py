@@ -165,3 +165,32 @@ def test_deterministic_and_numpy_boundary():
     assert np.array_equal(a, ok.knn_restated(p, p, 16, tie_rule=1))
     pd = p.astype(np.float64)  # the reference coerces to contiguous float32 (knn.pyx:95-96)
     assert np.array_equal(DP.knn_search(pd, pd, 16), a)
+
+
+@pytest.mark.parametrize("kind,N,ratio,K", [("uniform", 20000, 4, 16), ("uniform", 5000, 2, 16), ("lattice", 30000, 4, 16),
+                                            ("uniform", 703, 2, 16), ("uniform", 3000, 4, 3), ("dup", 8000, 4, 16),
+                                            ("uniform", 12, 4, 16), ("uniform", 4096, 64, 16)])
+def test_self_interp_equals_two_searches(kind, N, ratio, K):
+    """pu_knn_self_interp: neigh_idx and interp_idx of a pyramid level from one structure == the two separate searches of
+    tf_map (runPancreas.py:131-137), bit for bit -- including rows whose K neighbours hold no sub-cloud point (forced by a
+    large ratio), lattices with distance ties and duplicated points."""
+    import torch
+    from point_unet_b200.helper_tool import knn_search_cuda, knn_self_interp_cuda
+    rng = np.random.default_rng(N + K)
+    B = 3
+    if kind == "lattice":
+        pts = rng.integers(0, 40, size=(B, N, 3)).astype(np.float32)          # many exact ties and coincident points
+    else:
+        pts = rng.random((B, N, 3)).astype(np.float32)
+        if kind == "dup":
+            pts[:, N // 2:] = pts[:, :N - N // 2]                             # every point of the second half duplicates one
+    x = torch.from_numpy(pts).cuda()
+    n_sub = max(N // ratio, 1)
+    neigh, interp = knn_self_interp_cuda(x, K, n_sub)
+    want_neigh = knn_search_cuda(x, x, K)
+    want_interp = knn_search_cuda(x[:, :n_sub].contiguous(), x, 1)
+    assert torch.equal(neigh, want_neigh)
+    assert torch.equal(interp, want_interp)
+    # deterministic (the unresolved-row list is filled in arbitrary order)
+    neigh2, interp2 = knn_self_interp_cuda(x, K, n_sub)
+    assert torch.equal(interp, interp2) and torch.equal(neigh, neigh2)
