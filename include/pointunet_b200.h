@@ -75,9 +75,12 @@ PU_API int pu_knn_batch_dist(const float *support, const float *query, int B, in
  *   out_neigh  [B,N,K] = pu_knn_batch(cloud, cloud, K)                      (neigh_idx; sub_idx is its first n_sub rows)
  *   out_interp [B,N]   = pu_knn_batch(cloud[:, :n_sub], cloud, 1)           (interp_idx), bit-identical to that call:
  * the nearest sub-cloud point of a point is the first entry of its own neighbour row with index < n_sub; the ~1 % of rows
- * without one are searched on the same structure with candidates filtered by index.  Workspace: pu_knn_workspace_bytes(B,N,N,K). */
+ * without one are searched on the same structure with candidates filtered by index (boxes without a prefix point are
+ * skipped).  out_unresolved (optional, uint32 [B], device): how many rows per cloud needed that search -- when the prefix is a
+ * spatial region instead of a random subset most rows do, and two separate pu_knn_batch calls are the faster way
+ * (both are exact; the host mirror switches on the previous call's count).  Workspace: pu_knn_workspace_bytes(B,N,N,K). */
 PU_API int pu_knn_self_interp(const float *cloud, int B, int N, int K, int n_sub, int32_t *out_neigh, int32_t *out_interp,
-                              void *workspace, size_t workspace_bytes, pu_stream_t stream);
+                              unsigned *out_unresolved, void *workspace, size_t workspace_bytes, pu_stream_t stream);
 /* Search statistics of the last pu_knn_batch* call on this stream (device counters copied by the caller):
  * stats[0] = candidate distance evaluations, stats[1] = buckets visited, stats[2] = bucket box tests. */
 PU_API int pu_knn_read_stats(const void *workspace, unsigned long long *host_stats3, pu_stream_t stream);

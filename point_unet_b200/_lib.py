@@ -58,7 +58,8 @@ def lib() -> ctypes.CDLL:
         L.pu_knn_batch.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
         L.pu_knn_batch_dist.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_size_t, c_void_p]
-        L.pu_knn_self_interp.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+        L.pu_knn_self_interp.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_void_p]
         L.pu_knn_read_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong), c_void_p]
         _lib = L
     return _lib

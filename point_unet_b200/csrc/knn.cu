@@ -803,6 +803,24 @@ __global__ void __launch_bounds__(QW_WARPS * 32)
 // searched, one warp per row, on the structure the self-query has just built -- candidates filtered by index < n_sub, same
 // distance arithmetic, same bounds, same (distance, index) order, hence bit-identical to a separate K = 1 search over the
 // sub-cloud.  That search used to cost a Morton sort of the sub-cloud, one of all query points and a full K = 1 sweep per level.
+// smallest ORIGINAL point index inside every box of the three levels (one warp per box: 32 points, 32 buckets, 32
+// super-buckets).  The filtered search below skips a box that holds no point of the prefix at all; without this, a cloud
+// whose first n_sub points are a spatial REGION rather than a random subset (a volume listed organ first, say) sends most
+// rows into the filtered search AND makes every such row wade through all the non-prefix points that lie nearer (measured:
+// 94 ms instead of 1.6 ms per level).
+__global__ void __launch_bounds__(128) box_min_idx_kernel(const float4 *__restrict__ sp, const int *__restrict__ child, int n_items,
+                                                          int n_boxes, int B, int *__restrict__ out) {
+    const long long gw = ((long long)blockIdx.x * 128 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)B * n_boxes) return;
+    const int b = (int)(gw / n_boxes), t = (int)(gw % n_boxes);
+    const int i = t * 32 + lane;
+    unsigned v = 0xFFFFFFFFu;
+    if (i < n_items) v = sp ? (unsigned)__float_as_int(sp[(size_t)b * n_items + i].w) : (unsigned)child[(size_t)b * n_items + i];
+    v = __reduce_min_sync(0xffffffffu, v);
+    if (lane == 0) out[(size_t)b * n_boxes + t] = (int)v;
+}
+
 __global__ void __launch_bounds__(256) interp_from_neigh_kernel(const int32_t *__restrict__ neigh, int N, int K, int kvalid,
                                                                 int n_sub, int32_t *__restrict__ interp,
                                                                 unsigned *__restrict__ cnt, unsigned *__restrict__ list) {
@@ -823,14 +841,16 @@ __global__ void __launch_bounds__(NP_WARPS * 32)
     knn_nearest_prefix_kernel(const float *__restrict__ cloud, const float4 *__restrict__ sp, const float4 *__restrict__ bk_lo,
                               const float4 *__restrict__ bk_hi, const float4 *__restrict__ sb_lo,
                               const float4 *__restrict__ sb_hi, const float4 *__restrict__ cb_lo,
-                              const float4 *__restrict__ cb_hi, int N, int NB, int NSB, int NCB, int n_sub,
-                              const unsigned *__restrict__ cnt, const unsigned *__restrict__ list,
+                              const float4 *__restrict__ cb_hi, const int *__restrict__ bk_min,
+                              const int *__restrict__ sb_min, const int *__restrict__ cb_min, int N, int NB, int NSB, int NCB,
+                              int n_sub, const unsigned *__restrict__ cnt, const unsigned *__restrict__ list,
                               int32_t *__restrict__ interp) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, b = blockIdx.y;
     const float4 *sp_cloud = sp + (size_t)b * N;
     const float4 *bk_lo_c = bk_lo + (size_t)b * NB, *bk_hi_c = bk_hi + (size_t)b * NB;
     const float4 *sb_lo_c = sb_lo + (size_t)b * NSB, *sb_hi_c = sb_hi + (size_t)b * NSB;
     const float4 *cb_lo_c = cb_lo + (size_t)b * NCB, *cb_hi_c = cb_hi + (size_t)b * NCB;
+    const int *bk_min_c = bk_min + (size_t)b * NB, *sb_min_c = sb_min + (size_t)b * NSB, *cb_min_c = cb_min + (size_t)b * NCB;
     const unsigned total = cnt[b];
     for (unsigned u = blockIdx.x * NP_WARPS + wib; u < total; u += gridDim.x * NP_WARPS) {   // warp-uniform
         const unsigned n = list[(size_t)b * N + u];
@@ -841,7 +861,8 @@ __global__ void __launch_bounds__(NP_WARPS * 32)
         // nearest first on all three levels; a box is skipped only when its lower bound EXCEEDS the best distance so far
         for (int c0 = 0; c0 < NCB; c0 += 32) {
             unsigned cbits = 0xFFFFFFFFu;
-            if (c0 + lane < NCB) cbits = __float_as_uint(point_box_dist2(qx, qy, qz, cb_lo_c[c0 + lane], cb_hi_c[c0 + lane]));
+            if (c0 + lane < NCB && cb_min_c[c0 + lane] < n_sub)   // (boxes without a prefix point are never entered)
+                cbits = __float_as_uint(point_box_dist2(qx, qy, qz, cb_lo_c[c0 + lane], cb_hi_c[c0 + lane]));
             for (;;) {
                 const unsigned cmin = __reduce_min_sync(0xffffffffu, cbits);
                 if (cmin == 0xFFFFFFFFu || __uint_as_float(cmin) > kd) break;
@@ -849,7 +870,7 @@ __global__ void __launch_bounds__(NP_WARPS * 32)
                 if (lane == bc) cbits = 0xFFFFFFFFu;
                 const int s0 = (c0 + bc) * SBS;
                 unsigned sbits = 0xFFFFFFFFu;
-                if (s0 + lane < NSB)
+                if (s0 + lane < NSB && sb_min_c[s0 + lane] < n_sub)
                     sbits = __float_as_uint(point_box_dist2(qx, qy, qz, sb_lo_c[s0 + lane], sb_hi_c[s0 + lane]));
                 for (;;) {
                     const unsigned smin = __reduce_min_sync(0xffffffffu, sbits);
@@ -858,7 +879,7 @@ __global__ void __launch_bounds__(NP_WARPS * 32)
                     if (lane == bs) sbits = 0xFFFFFFFFu;
                     const int t0 = (s0 + bs) * SBS, t = t0 + lane;
                     unsigned bbits = 0xFFFFFFFFu;
-                    if (t < NB) bbits = __float_as_uint(point_box_dist2(qx, qy, qz, bk_lo_c[t], bk_hi_c[t]));
+                    if (t < NB && bk_min_c[t] < n_sub) bbits = __float_as_uint(point_box_dist2(qx, qy, qz, bk_lo_c[t], bk_hi_c[t]));
                     for (;;) {
                         const unsigned bmin = __reduce_min_sync(0xffffffffu, bbits);
                         if (bmin == 0xFFFFFFFFu || __uint_as_float(bmin) > kd) break;
@@ -1025,13 +1046,14 @@ static int knn_impl(const float *support, const float *query, int B, int N1, int
 // neighbour lists of a cloud AND the up-sampling index of every point into the cloud's first n_sub points, from ONE
 // search structure (one Morton sort per pyramid level instead of three)
 static int knn_self_interp_impl(const float *cloud, int B, int N, int K, int n_sub, int32_t *out_neigh, int32_t *out_interp,
-                                void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                                unsigned *out_unresolved, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     if (!cloud || !out_neigh || !out_interp || n_sub < 0 || n_sub > N) return PU_ERR_INVALID_ARG;
     int rc = knn_impl(cloud, cloud, B, N, N, K, out_neigh, nullptr, workspace, workspace_bytes, st);
     if (rc != PU_OK) return rc;
     if (B == 0 || N == 0) return PU_OK;
     if (n_sub == 0) {
         PU_CUDA_TRY(cudaMemsetAsync(out_interp, 0, (size_t)B * N * sizeof(int32_t), st));
+        if (out_unresolved) PU_CUDA_TRY(cudaMemsetAsync(out_unresolved, 0, (size_t)B * sizeof(unsigned), st));
         return PU_OK;
     }
     const Layout L = make_layout(B, N, N);
@@ -1048,14 +1070,24 @@ static int knn_self_interp_impl(const float *cloud, int B, int N, int K, int n_s
         (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), L.NSB, L.NCB, B, (float4 *)(ws + L.cb_lo),
         (float4 *)(ws + L.cb_hi));
     PU_LAUNCH_CHECK();
-    int gx = ceil_div(N, NP_WARPS * 16);   // a warp per 16 rows would cover a list of ALL rows; ~1 % of them are expected
-    const int cap = kNumSMs * 2 / (B > 0 ? B : 1) + 1;
+    int *bk_min = (int *)(ws + L.qkeys_b), *sb_min = bk_min + (size_t)B * L.NB, *cb_min = sb_min + (size_t)B * L.NSB;
+    box_min_idx_kernel<<<ceil_div((long long)B * L.NB * 32, 128), 128, 0, st>>>((const float4 *)(ws + L.sp), nullptr, N, L.NB, B,
+                                                                               bk_min);
+    PU_LAUNCH_CHECK();
+    box_min_idx_kernel<<<ceil_div((long long)B * L.NSB * 32, 128), 128, 0, st>>>(nullptr, bk_min, L.NB, L.NSB, B, sb_min);
+    PU_LAUNCH_CHECK();
+    box_min_idx_kernel<<<ceil_div((long long)B * L.NCB * 32, 128), 128, 0, st>>>(nullptr, sb_min, L.NSB, L.NCB, B, cb_min);
+    PU_LAUNCH_CHECK();
+    int gx = ceil_div(N, NP_WARPS * 4);    // rows of the list per warp: few when the prefix is a random subset (~1 % of N)
+    const int cap = kNumSMs * 8 / (B > 0 ? B : 1) + 1;
     if (gx > cap) gx = cap;
     knn_nearest_prefix_kernel<<<dim3(gx, B), NP_WARPS * 32, 0, st>>>(
         cloud, (const float4 *)(ws + L.sp), (const float4 *)(ws + L.bk_lo), (const float4 *)(ws + L.bk_hi),
         (const float4 *)(ws + L.sb_lo), (const float4 *)(ws + L.sb_hi), (const float4 *)(ws + L.cb_lo),
-        (const float4 *)(ws + L.cb_hi), N, L.NB, L.NSB, L.NCB, n_sub, cnt, list, out_interp);
+        (const float4 *)(ws + L.cb_hi), bk_min, sb_min, cb_min, N, L.NB, L.NSB, L.NCB, n_sub, cnt, list, out_interp);
     PU_LAUNCH_CHECK();
+    if (out_unresolved)
+        PU_CUDA_TRY(cudaMemcpyAsync(out_unresolved, cnt, (size_t)B * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     return PU_OK;
 }
 
@@ -1084,8 +1116,8 @@ int pu_knn_batch_dist(const float *support, const float *query, int B, int N1, i
 }
 
 int pu_knn_self_interp(const float *cloud, int B, int N, int K, int n_sub, int32_t *out_neigh, int32_t *out_interp,
-                       void *workspace, size_t workspace_bytes, pu_stream_t stream) {
-    return pu::knn::knn_self_interp_impl(cloud, B, N, K, n_sub, out_neigh, out_interp, workspace, workspace_bytes,
+                       unsigned *out_unresolved, void *workspace, size_t workspace_bytes, pu_stream_t stream) {
+    return pu::knn::knn_self_interp_impl(cloud, B, N, K, n_sub, out_neigh, out_interp, out_unresolved, workspace, workspace_bytes,
                                          (cudaStream_t)stream);
 }
 

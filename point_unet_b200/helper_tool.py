@@ -109,11 +109,20 @@ def knn_search_cuda(support: torch.Tensor, query: torch.Tensor, k: int, return_d
     return out
 
 
+# Fraction of the rows of a level whose K neighbours held no sub-cloud point, as seen by the most recent finished
+# pu_knn_self_interp call for that (N, n_sub): with a random prefix it is ~1 %; when the prefix is a spatial region (a volume
+# listed organ first) it is most rows, and two separate searches are the faster way.  Both are exact, so this only picks speed.
+_interp_unresolved: dict = {}
+_interp_pending: dict = {}
+FUSED_INTERP_MAX_UNRESOLVED = 0.125
+
+
 def knn_self_interp_cuda(points: torch.Tensor, k: int, n_sub: int, out_neigh: torch.Tensor | None = None,
-                         out_interp: torch.Tensor | None = None):
-    """One pyramid level of ``tf_map`` (runPancreas.py:131-137) from a single search structure: returns
-    ``(knn_search(points, points, k) [B,N,k], knn_search(points[:, :n_sub], points, 1) [B,N,1])``, both int32 and
-    bit-identical to the two separate searches (C-ABI ``pu_knn_self_interp``)."""
+                         out_interp: torch.Tensor | None = None, adaptive: bool = True):
+    """One pyramid level of ``tf_map`` (runPancreas.py:131-137): returns
+    ``(knn_search(points, points, k) [B,N,k], knn_search(points[:, :n_sub], points, 1) [B,N,1])``, both int32.  By default from a
+    single search structure (C-ABI ``pu_knn_self_interp``, bit-identical to the two searches); ``adaptive``: if the previous
+    call for this shape found that most rows needed the filtered search (prefix = spatial region), run the two searches."""
     if not points.is_cuda:
         raise _lib.PointUnetError("knn_self_interp_cuda needs CUDA tensors (there is no CPU fallback)")
     if points.dim() != 3 or points.shape[2] != 3:
@@ -130,12 +139,30 @@ def knn_self_interp_cuda(points: torch.Tensor, k: int, n_sub: int, out_neigh: to
         if t.dtype != torch.int32 or tuple(t.shape) != shape or not t.is_contiguous() or t.device != dev:
             raise ValueError("knn_self_interp_cuda: outputs must be contiguous int32 [B,N,k] / [B,N,1] tensors on the inputs' device")
         ops.drop_inverse(t.data_ptr())   # rewritten through the raw pointer: cached inverse lists of it are stale
+    key = (dev.index, B, N, int(n_sub), int(k))
+    pend = _interp_pending.get(key)
+    if pend is not None and pend[1].query():   # the count of an earlier call has arrived on the host
+        _interp_unresolved[key] = float(pend[0].sum()) / max(B * N, 1)
+        _interp_pending.pop(key)
+    if adaptive and _interp_unresolved.get(key, 0.0) > FUSED_INTERP_MAX_UNRESOLVED and n_sub >= 1:
+        knn_search_cuda(points, points, k, out=out_neigh)
+        knn_search_cuda(points[:, :n_sub].contiguous(), points, 1, out=out_interp)
+        return out_neigh, out_interp
     L = _lib.lib()
     ws = workspace(L.pu_knn_workspace_bytes(B, N, N, k), dev)
+    capturing = torch.cuda.is_current_stream_capturing()
+    track = adaptive and not capturing and key not in _interp_pending and key not in _interp_unresolved
+    cnt = torch.empty(B, dtype=torch.int32, device=dev) if track else None
     with torch.cuda.device(dev):
         st = L.pu_knn_self_interp(points.data_ptr(), B, N, int(k), int(n_sub), out_neigh.data_ptr(), out_interp.data_ptr(),
-                                  ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                                  cnt.data_ptr() if track else None, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         _lib.check(st, "pu_knn_self_interp")
+    if track:   # fetched without a synchronisation; read by a later call once the copy has completed
+        host = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        host.copy_(cnt, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        _interp_pending[key] = (host, ev, cnt)
     return out_neigh, out_interp
 
 

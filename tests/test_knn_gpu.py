@@ -169,7 +169,7 @@ def test_deterministic_and_numpy_boundary():
 
 @pytest.mark.parametrize("kind,N,ratio,K", [("uniform", 20000, 4, 16), ("uniform", 5000, 2, 16), ("lattice", 30000, 4, 16),
                                             ("uniform", 703, 2, 16), ("uniform", 3000, 4, 3), ("dup", 8000, 4, 16),
-                                            ("uniform", 12, 4, 16), ("uniform", 4096, 64, 16)])
+                                            ("uniform", 12, 4, 16), ("uniform", 4096, 64, 16), ("sorted", 20000, 4, 16)])
 def test_self_interp_equals_two_searches(kind, N, ratio, K):
     """pu_knn_self_interp: neigh_idx and interp_idx of a pyramid level from one structure == the two separate searches of
     tf_map (runPancreas.py:131-137), bit for bit -- including rows whose K neighbours hold no sub-cloud point (forced by a
@@ -182,15 +182,22 @@ def test_self_interp_equals_two_searches(kind, N, ratio, K):
         pts = rng.integers(0, 40, size=(B, N, 3)).astype(np.float32)          # many exact ties and coincident points
     else:
         pts = rng.random((B, N, 3)).astype(np.float32)
+        if kind == "sorted":                                                  # the prefix is a spatial slab, not a random subset
+            pts = np.stack([c[np.argsort(c[:, 0])] for c in pts])
         if kind == "dup":
             pts[:, N // 2:] = pts[:, :N - N // 2]                             # every point of the second half duplicates one
     x = torch.from_numpy(pts).cuda()
     n_sub = max(N // ratio, 1)
-    neigh, interp = knn_self_interp_cuda(x, K, n_sub)
+    neigh, interp = knn_self_interp_cuda(x, K, n_sub, adaptive=False)   # always the single-structure path
     want_neigh = knn_search_cuda(x, x, K)
     want_interp = knn_search_cuda(x[:, :n_sub].contiguous(), x, 1)
     assert torch.equal(neigh, want_neigh)
     assert torch.equal(interp, want_interp)
     # deterministic (the unresolved-row list is filled in arbitrary order)
-    neigh2, interp2 = knn_self_interp_cuda(x, K, n_sub)
+    neigh2, interp2 = knn_self_interp_cuda(x, K, n_sub, adaptive=False)
     assert torch.equal(interp, interp2) and torch.equal(neigh, neigh2)
+    # the adaptive front end (switches to two searches once it has seen that most rows need the filtered search)
+    for _ in range(3):
+        neigh3, interp3 = knn_self_interp_cuda(x, K, n_sub)
+        torch.cuda.synchronize()
+        assert torch.equal(interp, interp3) and torch.equal(neigh, neigh3)
