@@ -954,12 +954,16 @@ class _LocSEMlpConcatFn(torch.autograd.Function):
         else:
             dg = torch.empty(h, dtype=torch.float32, device=dev)
             dbeta = torch.empty(h, dtype=torch.float32, device=dev)
-        db = None if gb is not None else torch.empty(h, dtype=torch.float32, device=dev)
+        # training mode: the bias gradient is identically zero (nothing to add to a sink); with moving statistics it is not
+        db = None if (gb is not None and ctx.training) else torch.empty(h, dtype=torch.float32, device=dev)
         ws = workspace(_L().pu_locse_mlp_workspace_bytes(h), dev, slot=6)
         _call("pu_locse_mlp_bwd", xyz.data_ptr(), ctx.idx.data_ptr(), B, N, K, w.data_ptr(), h, coef.data_ptr(), gamma.data_ptr(),
               bias.data_ptr(), int(bool(ctx.training)), LEAKY_SLOPE, dz.data_ptr(), ldz, d2ptr, ld2, dw.data_ptr(), int(gw is not None),
               db.data_ptr() if db is not None else None, dg.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(),
               _stream(xyz), tag=(B * N * K, h))
+        if gb is not None and db is not None:
+            gb.add_(db)
+            db = None
         return (d_fpc, None, None, None if gw is not None else dw, db, None if sk is not None else dg,
                 None if sk is not None else dbeta, None, None, None, None, None, None)
 
