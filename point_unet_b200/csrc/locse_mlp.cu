@@ -527,51 +527,63 @@ __global__ void __launch_bounds__(256, 2) locse_mlp_bwd_kernel(const float4 *__r
 // index -> coordinates round trip (ncu: 37 % issue utilisation, long-scoreboard + barrier stalls).  Here every thread
 // recomputes the LocSE channels of its own row (CQ-fold redundant, ~35 instructions) and nothing is shared: no staging, no
 // barrier, and the loads of a thread are pipelined across ITS rows (index four rows ahead, coordinates two rows ahead).
+// forward of the narrow layers: ONE thread per row, all h = 4 CQ channels (the pipeline bookkeeping of a row -- ~110 of the
+// ~210 instructions a (row, column group) cost with CQ threads per row -- is paid once per row); the weights are read from
+// shared memory, every lane the same address (broadcast), the two or four float4 stores of a row are contiguous.
 template <int CQ>
 __global__ void __launch_bounds__(256, 3) locse_mlp_fwd_direct_kernel(const float4 *__restrict__ xyz, const int32_t *__restrict__ idx,
                                                                       int N, int K, int shiftK, unsigned rpc,
                                                                       const float *__restrict__ w, const float *__restrict__ coef,
                                                                       float slope, float *__restrict__ out, int ldo,
                                                                       float *__restrict__ out2, int ldo2) {
-    constexpr int h = CQ * 4, RPB = 256 / CQ;
+    constexpr int h = CQ * 4;
     extern __shared__ __align__(16) unsigned char s_rows[];   // ROWS_SMEM
-    const int c = (threadIdx.x % CQ) * 4;
-    float wr[10][4];
-#pragma unroll
-    for (int j = 0; j < 10; ++j) {
-        const float4 v = *reinterpret_cast<const float4 *>(w + (size_t)j * h + c);
-        wr[j][0] = v.x; wr[j][1] = v.y; wr[j][2] = v.z; wr[j][3] = v.w;
-    }
-    const float4 sc = *reinterpret_cast<const float4 *>(coef + c), tt = *reinterpret_cast<const float4 *>(coef + h + c);
-    float xbar[10];
-#pragma unroll
-    for (int j = 0; j < 10; ++j) xbar[j] = coef[5 * h + j];
+    __shared__ __align__(16) float s_w[10 * h];
+    __shared__ __align__(16) float s_c[2 * h];                // scale | t
+    __shared__ float s_xbar[10];
+    for (int i = threadIdx.x; i < 10 * h; i += 256) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < 2 * h; i += 256) s_c[i] = coef[i];
+    if (threadIdx.x < 10) s_xbar[threadIdx.x] = coef[5 * h + threadIdx.x];
+    __syncthreads();
     const size_t cloud_row0 = (size_t)blockIdx.y * rpc;
     AsyncRows rp;
     rp.xb = xyz + (size_t)blockIdx.y * N;
     rp.ib = idx + cloud_row0;
-    rp.rpc = rpc; rp.step = gridDim.x * (unsigned)RPB; rp.K = K; rp.shiftK = shiftK;
-    rp.start(s_rows, blockIdx.x * (unsigned)RPB + threadIdx.x / CQ, NoExtra{});
+    rp.rpc = rpc; rp.step = gridDim.x * 256u; rp.K = K; rp.shiftK = shiftK;
+    rp.start(s_rows, blockIdx.x * 256u + threadIdx.x, NoExtra{});
     for (; rp.r < rpc; rp.advance(NoExtra{})) {
         const unsigned ru = rp.r;
         const RowPts pts = rp.current();
         float x[10];
         locse_from_pts(pts, x);
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        float a[CQ][4];
+#pragma unroll
+        for (int q = 0; q < CQ; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[q][k] = 0.f;
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
-            const float xc = x[j] - xbar[j];
+            const float xc = x[j] - s_xbar[j];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = fmaf(xc, wr[j][k], a[k]);
+            for (int q = 0; q < CQ; ++q) {
+                const float4 wv = *reinterpret_cast<const float4 *>(s_w + j * h + q * 4);
+                a[q][0] = fmaf(xc, wv.x, a[q][0]); a[q][1] = fmaf(xc, wv.y, a[q][1]);
+                a[q][2] = fmaf(xc, wv.z, a[q][2]); a[q][3] = fmaf(xc, wv.w, a[q][3]);
+            }
         }
-        float4 z = make_float4(fmaf(a[0], sc.x, tt.x), fmaf(a[1], sc.y, tt.y), fmaf(a[2], sc.z, tt.z), fmaf(a[3], sc.w, tt.w));
-        z.x = z.x > 0.f ? z.x : z.x * slope;
-        z.y = z.y > 0.f ? z.y : z.y * slope;
-        z.z = z.z > 0.f ? z.z : z.z * slope;
-        z.w = z.w > 0.f ? z.w : z.w * slope;
         const size_t row = cloud_row0 + ru;
-        *reinterpret_cast<float4 *>(out + row * ldo + c) = z;
-        if (out2) *reinterpret_cast<float4 *>(out2 + row * ldo2 + c) = z;
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+            const float4 sc = *reinterpret_cast<const float4 *>(s_c + q * 4), tt = *reinterpret_cast<const float4 *>(s_c + h + q * 4);
+            float4 z = make_float4(fmaf(a[q][0], sc.x, tt.x), fmaf(a[q][1], sc.y, tt.y), fmaf(a[q][2], sc.z, tt.z),
+                                   fmaf(a[q][3], sc.w, tt.w));
+            z.x = z.x > 0.f ? z.x : z.x * slope;
+            z.y = z.y > 0.f ? z.y : z.y * slope;
+            z.z = z.z > 0.f ? z.z : z.z * slope;
+            z.w = z.w > 0.f ? z.w : z.w * slope;
+            *reinterpret_cast<float4 *>(out + row * ldo + q * 4) = z;
+            if (out2) *reinterpret_cast<float4 *>(out2 + row * ldo2 + q * 4) = z;
+        }
     }
 }
 
@@ -807,8 +819,8 @@ int pu_locse_mlp_fwd(const float *xyz4, const int32_t *idx, int B, int N, int K,
     if (rc != PU_OK) return rc;
     if (B == 0 || g.rpc == 0) return PU_OK;
     if (h <= 16) {   // narrow layers: one row per thread group, no staging
-        const int rpb = 1024 / h;   // rows per CTA iteration (256 threads, h/4 threads per row)
-        unsigned gx = (unsigned)((g.rpc + rpb - 1) / rpb), cap = (unsigned)(kNumSMs * 2 * 4 / B);
+        const int rpb = 256;        // rows per CTA iteration: one thread per row
+        unsigned gx = (unsigned)((g.rpc + rpb - 1) / rpb), cap = (unsigned)(kNumSMs * 3 * 4 / B);
         if (cap < 1) cap = 1;
         const dim3 grid(gx < cap ? gx : cap, (unsigned)B);
         cudaStream_t st = (cudaStream_t)stream;
